@@ -1,0 +1,102 @@
+/*
+ * mimeo_b200.h -- C ABI of libmimeo_b200.so, the B200 (sm_100a) implementation of mimeo's
+ * alignment-to-annotation hot path.
+ *
+ * The reference (Adamtaranto/mimeo) has NO FFI for this path: its "plugin interface" is two
+ * executable-path flags whose argv contracts are literal strings inside generated bash
+ *   --lzpath   -> `lastz T.fa Q.fa --entropy --format=general:... --chain --gapped ...`
+ *                 (src/mimeo/wrappers.py:1025-1037 self, 786-798 x, 645-653 map)
+ *   --bedtools -> `bedtools genomecov -bg -i BED -g LENS` / `bedtools merge -i BED`
+ *                 (src/mimeo/wrappers.py:1131-1150, 847-866, 1223-1250)
+ * executed by utils.run_cmd (src/mimeo/utils.py:213-254). Each entry point below names the piece
+ * of that script it replaces. Plain pointers and sizes only; no torch types. All functions return
+ * 0 on success or a negative error code, with the message available from mb2_last_error().
+ *
+ * Threading: one process per GPU, calls are not re-entrant; every kernel is launched on the
+ * library's own stream (mb2_stream()).
+ */
+#ifndef MIMEO_B200_H
+#define MIMEO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MB2_API __attribute__((visibility("default")))
+#else
+#define MB2_API
+#endif
+
+#define MB2_OK 0
+#define MB2_ERR_INVALID_ARG (-2)
+#define MB2_ERR_TOO_LARGE (-3)
+#define MB2_ERR_BAD_HIT (-4)
+#define MB2_ERR_INTERNAL (-5)
+#define MB2_ERR_CUDA (-100)
+
+/* ---- library / device -------------------------------------------------------------------- */
+/* Bind the calling process to one CUDA device and create the library stream + memory pool.
+ * Replaces nothing in the reference (it has no device); called once by the host layer that
+ * replaces utils.run_cmd (utils.py:213). */
+MB2_API int mb2_init(int device);
+MB2_API void mb2_shutdown(void);
+MB2_API const char* mb2_last_error(void);
+/* cudaStream_t of the library as an opaque pointer (for CUDA-event timing by the caller). */
+MB2_API void* mb2_stream(void);
+/* Number of kernels of this library launched since mb2_init (the bench's `gpu_launches`). */
+MB2_API unsigned long long mb2_launch_count(void);
+MB2_API int mb2_sm_count(void);
+/* Block the host until the library stream is idle. */
+MB2_API int mb2_sync(void);
+
+/* Per-kernel timing with CUDA events on the library stream (used by bench.py for the roofline
+ * of the dominant kernel). mb2_prof_enable(1) starts recording; mb2_prof_get() synchronises and
+ * returns accumulated milliseconds and launch count for a kernel tag (e.g. "cov_tile"), 0/0 if
+ * the tag never ran; mb2_prof_reset() clears the accumulators. */
+MB2_API int mb2_prof_enable(int on);
+MB2_API int mb2_prof_get(const char* tag, double* ms_total, unsigned long long* count);
+MB2_API int mb2_prof_reset(void);
+
+/* ---- (d) coverage -> threshold -> merged segments ----------------------------------------- */
+/* Output of the coverage stage: merged runs of depth >= min_cov with end-start >= min_len, ordered
+ * by scaffold index then start. Coordinates are the raw BED-style numbers the reference prints into
+ * GFF3 columns 4/5 (wrappers.py:1169-1171). Arrays are owned by the library; free with
+ * mb2_free_segments. `on_device` tells whether the three arrays are host or device memory. */
+typedef struct mb2_segments {
+    int32_t* chrom;
+    int32_t* start;
+    int32_t* end;
+    uint64_t n;
+    int on_device;
+} mb2_segments;
+
+/* Replaces: awk BED projection + sort + `bedtools genomecov -bg` + awk '0+$4 >= cov' + sort +
+ * `bedtools merge` + awk minLen filter  (wrappers.py:1120-1167; x: 827-885; self intra: 1201-1258).
+ * Inputs are HOST arrays: one (scaffold index, start1, end1) triple per non-'#' line of the .tab file
+ * (columns 1,3,4), scaffold sizes as in A_gen_lens.txt (utils.py:552-555), indexed in the byte order
+ * `sort -k 1,1` produces. Host->device and device->host copies happen inside the call. */
+MB2_API int mb2_coverage_segments(const int32_t* chrom, const int32_t* start, const int32_t* end, uint64_t nhits,
+                          const int64_t* chrom_sizes, int nchrom, int min_cov, int min_len, mb2_segments* out);
+
+/* Same computation with the three hit arrays already resident in device memory (e.g. torch
+ * tensors' data_ptr()); the result arrays stay on the device (out->on_device = 1). */
+MB2_API int mb2_coverage_segments_dev(const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, uint64_t nhits,
+                              const int64_t* chrom_sizes, int nchrom, int min_cov, int min_len, mb2_segments* out);
+
+MB2_API void mb2_free_segments(mb2_segments* seg);
+
+/* ---- device primitives exposed for parity tests ------------------------------------------- */
+/* Stable LSD radix sort of HOST arrays on bits [begin_bit, end_bit) (vals may be NULL). */
+MB2_API int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);
+MB2_API int mb2_test_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);
+/* Exclusive prefix sum of a HOST array, in place; *total receives the grand total. */
+MB2_API int mb2_test_scan_u32(uint32_t* data, uint64_t n, uint32_t* total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMEO_B200_H */

@@ -1,0 +1,112 @@
+"""ctypes binding of libmimeo_b200.so (C ABI declared in include/mimeo_b200.h).
+
+The product path must fail loudly when the CUDA extension is missing: `lib()` raises if the shared
+library is not built, and `init()` raises if no B200-class device is present. Nothing here falls
+back to a CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libmimeo_b200.so')
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u32p = C.POINTER(C.c_uint32)
+c_u64p = C.POINTER(C.c_uint64)
+
+
+class Segments(C.Structure):
+    _fields_ = [('chrom', c_i32p), ('start', c_i32p), ('end', c_i32p), ('n', C.c_uint64), ('on_device', C.c_int)]
+
+
+# every symbol include/mimeo_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    'mb2_init': (C.c_int, [C.c_int]),
+    'mb2_shutdown': (None, []),
+    'mb2_last_error': (C.c_char_p, []),
+    'mb2_stream': (C.c_void_p, []),
+    'mb2_launch_count': (C.c_ulonglong, []),
+    'mb2_sm_count': (C.c_int, []),
+    'mb2_sync': (C.c_int, []),
+    'mb2_prof_enable': (C.c_int, [C.c_int]),
+    'mb2_prof_get': (C.c_int, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    'mb2_prof_reset': (C.c_int, []),
+    'mb2_coverage_segments': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.POINTER(Segments)]),
+    'mb2_coverage_segments_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int,
+                                            C.c_int, C.c_int, C.POINTER(Segments)]),
+    'mb2_free_segments': (None, [C.POINTER(Segments)]),
+    'mb2_test_sort_u32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
+    'mb2_test_sort_u64': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
+    'mb2_test_scan_u32': (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+}
+
+_lib = None
+_inited_device = None
+
+
+class Mb2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f'libmimeo_b200 error {code}: {msg}')
+        self.code = code
+
+
+def lib():
+    """Load the shared library (no GPU needed for loading)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is not built; run `python -m mimeo_b200.build` (there is no CPU fallback)')
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise Mb2Error(rc, lib().mb2_last_error().decode('utf-8', 'replace'))
+
+
+def init(device=None):
+    """Bind this process to one GPU (LOCAL_RANK under torchrun, else 0). Raises without a device."""
+    global _inited_device
+    if device is None:
+        device = int(os.environ.get('LOCAL_RANK', '0'))
+    if _inited_device != device:
+        check(lib().mb2_init(device))
+        _inited_device = device
+    return device
+
+
+def launch_count():
+    return int(lib().mb2_launch_count())
+
+
+def stream_handle():
+    return lib().mb2_stream()
+
+
+def sync():
+    check(lib().mb2_sync())
+
+
+def prof_enable(on=True):
+    check(lib().mb2_prof_enable(1 if on else 0))
+
+
+def prof_reset():
+    check(lib().mb2_prof_reset())
+
+
+def prof_get(tag):
+    """(total milliseconds, number of timed regions) accumulated for a kernel tag since the last reset."""
+    ms, cnt = C.c_double(0), C.c_ulonglong(0)
+    check(lib().mb2_prof_get(tag.encode(), C.byref(ms), C.byref(cnt)))
+    return ms.value, int(cnt.value)

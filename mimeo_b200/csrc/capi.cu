@@ -1,0 +1,213 @@
+// capi.cu -- extern "C" boundary of libmimeo_b200.so (see include/mimeo_b200.h).
+#include <cstring>
+#include <vector>
+
+#include "primitives.cuh"
+#include "internal.cuh"
+#include "mimeo_b200.h"
+
+namespace mb2 {
+
+static Ctx g_ctx;
+static thread_local std::string g_err;
+
+Ctx& ctx() { return g_ctx; }
+
+void ensure_init() {
+    if (!g_ctx.ready) throw Error(MB2_ERR_INVALID_ARG, "mb2_init() has not been called");
+}
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return MB2_OK;
+    } catch (const Error& e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return MB2_ERR_INTERNAL;
+    }
+}
+
+}  // namespace mb2
+
+using namespace mb2;
+
+template <typename K>
+static void test_sort(K* keys, uint32_t* vals, uint64_t n, int b0, int b1) {
+    ensure_init();
+    DevBuf<K> k0(n), k1(n);
+    DevBuf<uint32_t> v0(vals ? n : 0), v1(vals ? n : 0);
+    if (n == 0) return;
+    MB2_CUDA(cudaMemcpyAsync(k0.get(), keys, n * sizeof(K), cudaMemcpyHostToDevice, g_ctx.stream));
+    int w;
+    if (vals) {
+        MB2_CUDA(cudaMemcpyAsync(v0.get(), vals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, g_ctx.stream));
+        w = radix_sort_bits<K, uint32_t>(k0.get(), k1.get(), v0.get(), v1.get(), n, b0, b1);
+        MB2_CUDA(cudaMemcpyAsync(vals, w ? v1.get() : v0.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+    } else {
+        NoVal* nv = nullptr;
+        w = radix_sort_bits<K, NoVal>(k0.get(), k1.get(), nv, nv, n, b0, b1);
+    }
+    MB2_CUDA(cudaMemcpyAsync(keys, w ? k1.get() : k0.get(), n * sizeof(K), cudaMemcpyDeviceToHost, g_ctx.stream));
+    MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+}
+
+extern "C" {
+
+int mb2_init(int device) {
+    return guarded([&] {
+        if (g_ctx.ready && g_ctx.device == device) return;
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error(MB2_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                                          " -- libmimeo_b200 has no CPU fallback");
+        MB2_REQUIRE(device >= 0 && device < ndev, MB2_ERR_INVALID_ARG, "mb2_init: device index out of range");
+        MB2_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        MB2_CUDA(cudaGetDeviceProperties(&prop, device));
+        MB2_REQUIRE(prop.major >= 10, MB2_ERR_CUDA,
+                    std::string("libmimeo_b200 is built for sm_100a only; found ") + prop.name);
+        g_ctx.device = device;
+        g_ctx.sm_count = prop.multiProcessorCount;
+        MB2_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        MB2_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thresh = UINT64_MAX;   // keep freed scratch cached in the pool between calls
+        MB2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        g_ctx.launches = 0;
+        g_ctx.ready = true;
+    });
+}
+
+void mb2_shutdown(void) {
+    if (g_ctx.ready) {
+        cudaStreamSynchronize(g_ctx.stream);
+        cudaStreamDestroy(g_ctx.stream);
+        g_ctx.stream = nullptr;
+        g_ctx.ready = false;
+    }
+}
+
+const char* mb2_last_error(void) { return g_err.c_str(); }
+void* mb2_stream(void) { return (void*)g_ctx.stream; }
+unsigned long long mb2_launch_count(void) { return g_ctx.launches; }
+int mb2_sm_count(void) { return g_ctx.sm_count; }
+int mb2_sync(void) {
+    return guarded([&] { ensure_init(); MB2_CUDA(cudaStreamSynchronize(g_ctx.stream)); });
+}
+
+static void prof_drain() {
+    if (g_ctx.prof_recs.empty()) return;
+    MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    for (auto& r : g_ctx.prof_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& acc = g_ctx.prof_acc[r.tag];
+        acc.first += ms; acc.second += 1;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_ctx.prof_recs.clear();
+}
+
+int mb2_prof_enable(int on) {
+    return guarded([&] { ensure_init(); prof_drain(); g_ctx.prof = on != 0; });
+}
+int mb2_prof_get(const char* tag, double* ms_total, unsigned long long* count) {
+    return guarded([&] {
+        ensure_init();
+        prof_drain();
+        auto it = g_ctx.prof_acc.find(tag ? tag : "");
+        if (ms_total) *ms_total = it == g_ctx.prof_acc.end() ? 0.0 : it->second.first;
+        if (count) *count = it == g_ctx.prof_acc.end() ? 0ull : it->second.second;
+    });
+}
+int mb2_prof_reset(void) {
+    return guarded([&] { ensure_init(); prof_drain(); g_ctx.prof_acc.clear(); });
+}
+
+// ------------------------------------------------------------------------------------------ coverage
+int mb2_coverage_segments_dev(const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, uint64_t nhits,
+                              const int64_t* chrom_sizes, int nchrom, int min_cov, int min_len, mb2_segments* out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(out != nullptr && chrom_sizes != nullptr, MB2_ERR_INVALID_ARG, "coverage: null argument");
+        MB2_REQUIRE(nhits == 0 || (d_chrom && d_start && d_end), MB2_ERR_INVALID_ARG, "coverage: null hit arrays");
+        std::memset(out, 0, sizeof(*out));
+        CoverageResult res;
+        coverage_segments_device(d_chrom, d_start, d_end, nhits, chrom_sizes, nchrom, min_cov, min_len, res);
+        MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        out->n = res.n;
+        out->on_device = 1;
+        // hand the buffers over to the caller (freed by mb2_free_segments)
+        out->chrom = res.chrom.p; res.chrom.p = nullptr;
+        out->start = res.start.p; res.start.p = nullptr;
+        out->end = res.end.p; res.end.p = nullptr;
+    });
+}
+
+int mb2_coverage_segments(const int32_t* chrom, const int32_t* start, const int32_t* end, uint64_t nhits,
+                          const int64_t* chrom_sizes, int nchrom, int min_cov, int min_len, mb2_segments* out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(out != nullptr && chrom_sizes != nullptr, MB2_ERR_INVALID_ARG, "coverage: null argument");
+        MB2_REQUIRE(nhits == 0 || (chrom && start && end), MB2_ERR_INVALID_ARG, "coverage: null hit arrays");
+        std::memset(out, 0, sizeof(*out));
+        DevBuf<int32_t> dc(nhits), ds(nhits), de(nhits);
+        if (nhits) {
+            MB2_CUDA(cudaMemcpyAsync(dc.get(), chrom, nhits * sizeof(int32_t), cudaMemcpyHostToDevice, g_ctx.stream));
+            MB2_CUDA(cudaMemcpyAsync(ds.get(), start, nhits * sizeof(int32_t), cudaMemcpyHostToDevice, g_ctx.stream));
+            MB2_CUDA(cudaMemcpyAsync(de.get(), end, nhits * sizeof(int32_t), cudaMemcpyHostToDevice, g_ctx.stream));
+        }
+        CoverageResult res;
+        coverage_segments_device(dc.get(), ds.get(), de.get(), nhits, chrom_sizes, nchrom, min_cov, min_len, res);
+        out->n = res.n;
+        out->on_device = 0;
+        if (res.n) {
+            out->chrom = (int32_t*)malloc(res.n * sizeof(int32_t));
+            out->start = (int32_t*)malloc(res.n * sizeof(int32_t));
+            out->end = (int32_t*)malloc(res.n * sizeof(int32_t));
+            MB2_REQUIRE(out->chrom && out->start && out->end, MB2_ERR_INTERNAL, "coverage: host allocation failed");
+            MB2_CUDA(cudaMemcpyAsync(out->chrom, res.chrom.get(), res.n * sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+            MB2_CUDA(cudaMemcpyAsync(out->start, res.start.get(), res.n * sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+            MB2_CUDA(cudaMemcpyAsync(out->end, res.end.get(), res.n * sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+        }
+        MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    });
+}
+
+void mb2_free_segments(mb2_segments* seg) {
+    if (!seg) return;
+    if (seg->on_device) {
+        if (seg->chrom) cudaFreeAsync(seg->chrom, g_ctx.stream);
+        if (seg->start) cudaFreeAsync(seg->start, g_ctx.stream);
+        if (seg->end) cudaFreeAsync(seg->end, g_ctx.stream);
+    } else {
+        free(seg->chrom); free(seg->start); free(seg->end);
+    }
+    std::memset(seg, 0, sizeof(*seg));
+}
+
+// ------------------------------------------------------------------------------------------ test hooks
+int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit) {
+    return guarded([&] { test_sort<uint32_t>(keys, vals, n, begin_bit, end_bit); });
+}
+int mb2_test_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit) {
+    return guarded([&] { test_sort<uint64_t>(keys, vals, n, begin_bit, end_bit); });
+}
+int mb2_test_scan_u32(uint32_t* data, uint64_t n, uint32_t* total) {
+    return guarded([&] {
+        ensure_init();
+        DevBuf<uint32_t> d(n), t(1);
+        if (n) MB2_CUDA(cudaMemcpyAsync(d.get(), data, n * sizeof(uint32_t), cudaMemcpyHostToDevice, g_ctx.stream));
+        exclusive_scan_u32(d.get(), d.get(), n, t.get());
+        if (n) MB2_CUDA(cudaMemcpyAsync(data, d.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+        if (total) MB2_CUDA(cudaMemcpyAsync(total, t.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+        MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    });
+}
+
+}  // extern "C"

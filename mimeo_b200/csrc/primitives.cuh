@@ -1,0 +1,219 @@
+// primitives.cuh -- device-wide exclusive scan and LSD radix sort, hand-written for sm_100a.
+//
+// Both are global-atomic-free: the radix pass is histogram -> scan -> stable scatter with
+// per-warp digit counters in shared memory (warp match/ballot ranking), so results are
+// deterministic. Used by the coverage stage (bin interval events by genome tile) and by the
+// alignment stage (group seed hits by diagonal, HSPs by scaffold pair).
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace mb2 {
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan (uint32), any n; out may alias in. If total != nullptr the grand total is
+// written there (device pointer).
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// Block-wide exclusive scan of one value per thread; returns exclusive prefix, total via ref.
+// NT = threads per block (multiple of 32, <= 1024). sh must hold NT/32 uint32.
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* sh, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = warp_incl_scan(v, lane);
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < NT / 32) ? sh[lane] : 0;
+        uint32_t wi = warp_incl_scan(w, lane);
+        if (lane < NT / 32) sh[lane] = wi - w;
+        if (lane == NT / 32 - 1) sh[NT / 32] = wi;
+    }
+    __syncthreads();
+    uint32_t res = incl - v + sh[warp];
+    total = sh[NT / 32];
+    __syncthreads();
+    return res;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS)
+scan_block_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t sh[SCAN_THREADS / 32 + 1];
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        sum += v[i];
+    }
+    uint32_t total;
+    uint32_t run = block_excl_scan<SCAN_THREADS>(sum, sh, total);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+    if (threadIdx.x == 0 && block_sums) block_sums[blockIdx.x] = total;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS)
+scan_add_kernel(uint32_t* __restrict__ out, size_t n, const uint32_t* __restrict__ block_offsets) {
+    const uint32_t off = block_offsets[blockIdx.x];
+    const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++)
+        if (base + i < n) out[base + i] += off;
+}
+
+static __global__ void scan_total_kernel(const uint32_t* __restrict__ last_excl, const uint32_t* __restrict__ last_in, uint32_t* __restrict__ total) {
+    *total = *last_excl + *last_in;
+}
+
+inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total = nullptr) {
+    if (n == 0) {
+        if (total) MB2_CUDA(cudaMemsetAsync(total, 0, sizeof(uint32_t), ctx().stream));
+        return;
+    }
+    // total must be derived before `in` is overwritten when aliasing: keep the last input element.
+    DevBuf<uint32_t> last_in;
+    if (total) {
+        last_in.alloc(1);
+        MB2_CUDA(cudaMemcpyAsync(last_in.get(), in + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx().stream));
+    }
+    const unsigned nb = cdiv(n, SCAN_TILE);
+    if (nb == 1) {
+        launch(scan_block_kernel, 1, SCAN_THREADS, 0, in, out, n, (uint32_t*)nullptr);
+    } else {
+        DevBuf<uint32_t> sums(nb);
+        launch(scan_block_kernel, nb, SCAN_THREADS, 0, in, out, n, sums.get());
+        exclusive_scan_u32(sums.get(), sums.get(), nb, nullptr);
+        launch(scan_add_kernel, nb, SCAN_THREADS, 0, out, n, sums.get());
+    }
+    if (total) launch(scan_total_kernel, 1, 1, 0, out + (n - 1), last_in.get(), total);
+}
+
+// ------------------------------------------------------------------------------------------
+// LSD radix sort on a bit range of the key. K = uint32_t or uint64_t, V = payload type
+// (use NoVal for keys only). Stable. n < 2^32.
+// ------------------------------------------------------------------------------------------
+struct NoVal {};
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 keys per CTA, 512 contiguous keys per warp
+
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS)
+radix_hist_kernel(const K* __restrict__ keys, uint32_t n, int shift, int bits, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[256];
+    const int nbins = 1 << bits;
+    for (int i = threadIdx.x; i < nbins; i += RS_THREADS) sh[i] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+    const uint32_t mask = nbins - 1;
+#pragma unroll 4
+    for (int i = 0; i < RS_ITEMS; i++) {
+        uint32_t idx = base + i * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&sh[(uint32_t)(keys[idx] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += RS_THREADS) hist[(size_t)i * gridDim.x + blockIdx.x] = sh[i];
+}
+
+template <typename K, typename V, bool HAS_V>
+__global__ void __launch_bounds__(RS_THREADS)
+radix_scatter_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, const V* __restrict__ vals_in,
+                     V* __restrict__ vals_out, uint32_t n, int shift, int bits, const uint32_t* __restrict__ hist_scanned) {
+    __shared__ uint32_t wcount[RS_WARPS][256];   // per-warp running digit counters, then warp prefixes
+    __shared__ uint32_t gbase[256];
+    const int nbins = 1 << bits;
+    const uint32_t mask = nbins - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+
+    const uint32_t wbase = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
+    K key[RS_ITEMS];
+    uint16_t rank[RS_ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t idx = wbase + r * 32 + lane;
+        const bool valid = idx < n;
+        const uint32_t act = __ballot_sync(0xffffffffu, valid);
+        uint32_t rk = 0;
+        if (valid) {
+            key[r] = keys_in[idx];
+            const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+            const uint32_t peers = __match_any_sync(act, d);
+            const uint32_t prev = wcount[warp][d];
+            __syncwarp(act);
+            if ((peers & lt) == 0) wcount[warp][d] = prev + __popc(peers);
+            rk = prev + __popc(peers & lt);
+        }
+        __syncwarp();
+        rank[r] = (uint16_t)rk;
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over warps, plus the block's global base
+    for (int d = threadIdx.x; d < nbins; d += RS_THREADS) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) { uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
+        gbase[d] = hist_scanned[(size_t)d * gridDim.x + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t idx = wbase + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+            const uint32_t pos = gbase[d] + wcount[warp][d] + rank[r];
+            keys_out[pos] = key[r];
+            if (HAS_V) vals_out[pos] = vals_in[idx];
+        }
+    }
+}
+
+// Sort keys (and payload) on bits [begin_bit, end_bit). Ping-pongs between (k0,v0) and (k1,v1);
+// returns 0 if the result is in (k0,v0), 1 if in (k1,v1).
+template <typename K, typename V>
+inline int radix_sort_bits(K* k0, K* k1, V* v0, V* v1, size_t n, int begin_bit, int end_bit) {
+    constexpr bool HAS_V = !std::is_same<V, NoVal>::value;
+    if (n == 0 || end_bit <= begin_bit) return 0;
+    MB2_REQUIRE(n < 0xffffffffull, -3, "radix sort: n must be < 2^32");
+    const int total_bits = end_bit - begin_bit;
+    const int passes = (total_bits + 7) / 8;
+    const unsigned nb = cdiv(n, RS_TILE);
+    DevBuf<uint32_t> hist((size_t)256 * nb);
+    int cur = 0;
+    int bit = begin_bit;
+    for (int p = 0; p < passes; p++) {
+        const int bits = (total_bits - (bit - begin_bit) + (passes - p) - 1) / (passes - p);   // spread evenly
+        K* kin = cur ? k1 : k0; K* kout = cur ? k0 : k1;
+        V* vin = cur ? v1 : v0; V* vout = cur ? v0 : v1;
+        launch(radix_hist_kernel<K>, nb, RS_THREADS, 0, kin, (uint32_t)n, bit, bits, hist.get());
+        exclusive_scan_u32(hist.get(), hist.get(), (size_t)(1 << bits) * nb);
+        launch(radix_scatter_kernel<K, V, HAS_V>, nb, RS_THREADS, 0, kin, kout, vin, vout, (uint32_t)n, bit, bits, hist.get());
+        cur ^= 1;
+        bit += bits;
+    }
+    return cur;
+}
+
+}  // namespace mb2

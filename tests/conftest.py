@@ -7,7 +7,6 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 
 def pytest_configure(config):
@@ -19,8 +18,3 @@ def oracle_build():
     """Compile the C oracle (test infrastructure) once per session."""
     subprocess.check_call(['make', '-C', os.path.join(ROOT, 'oracle'), 'all'], stdout=subprocess.DEVNULL)
     return os.path.join(ROOT, 'oracle', '_build')
-
-
-def read_golden(name, mode='r'):
-    with open(os.path.join(GOLDEN, name), mode) as f:
-        return f.read()

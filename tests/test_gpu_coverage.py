@@ -1,0 +1,138 @@
+"""GPU parity: coverage -> threshold -> merged segments through the C ABI, bit-exact against the oracle,
+the reference-generated goldens and the SURVEY 9.3 known answers."""
+import json
+
+import numpy as np
+import pytest
+
+from tests.helpers import read_golden
+from oracle import annot_oracle as ao
+from tests.helpers import tab_to_arrays, segments_to_gff_rows, synth_hits
+
+pytestmark = pytest.mark.gpu
+MAN = json.loads(read_golden('manifest.json'))
+
+
+@pytest.fixture(scope='module')
+def cov():
+    from mimeo_b200 import coverage
+    return coverage
+
+
+def run(cov, chrom, start, end, sizes, c, ml):
+    got = cov.coverage_segments(chrom, start, end, sizes, c, ml)
+    want = ao.coverage_segments_arrays(np.asarray(chrom), np.asarray(start), np.asarray(end), sizes, max(c, 1), ml)
+    for g, w in zip(got, want):
+        assert g.dtype == np.int32 and (g == w).all(), (got, want)
+    return got
+
+
+def test_known_answers(cov):
+    c, s, e = run(cov, [0, 0, 0], [100, 200, 250], [300, 400, 500], [1000], 2, 100)
+    assert (c.tolist(), s.tolist(), e.tolist()) == ([0], [200], [400])                       # KAT 1
+    c, s, e = run(cov, [0] * 4, [0, 0, 150, 150], [150, 150, 300, 300], [1000], 2, 1)
+    assert (s.tolist(), e.tolist()) == ([0], [300])                                            # KAT 2 book-ended
+    c, s, e = run(cov, [0] * 3, [200] * 3, [400] * 3, [250], 3, 50)
+    assert (s.tolist(), e.tolist()) == ([200], [250])                                          # KAT 3 clipped
+    assert len(run(cov, [0, 0], [10, 10], [110, 110], [500], 2, 100)[0]) == 1                  # KAT 4 inclusive
+    assert len(run(cov, [0, 0], [10, 10], [110, 110], [500], 2, 101)[0]) == 0
+
+
+def test_edge_cases(cov):
+    z = np.zeros(0, np.int32)
+    assert len(cov.coverage_segments(z, z, z, [100], 1, 1)[0]) == 0                           # empty input
+    run(cov, [0], [10], [10], [100], 1, 0)                                                     # zero-length hit invisible
+    run(cov, [0], [0], [0], [100], 1, 0)                                                       # (0,0) quirk of the restated sweep
+    run(cov, [0], [100], [120], [100], 1, 0)                                                   # start beyond scaffold end
+    run(cov, [0, 1], [90, 0], [500, 10], [100, 50], 1, 1)                                      # run at scaffold end + next scaffold start never join
+    run(cov, [1, 1, 0], [0, 0, 99], [50, 50, 100], [100, 50], 2, 1)
+    run(cov, [0], [5], [9], [8192 * 3 + 1], 1, 1)
+    run(cov, [0, 0], [8191, 8190], [8193, 16385], [8192 * 3], 1, 1)                           # runs crossing tile borders
+    run(cov, [0], [3], [7], [10], 0, 0)                                                        # cov <= 0 behaves as 1 (rows of depth 0 never exist)
+    run(cov, [0], [3], [7], [10], -3, -5)
+
+
+def test_invalid_hits_raise(cov):
+    from mimeo_b200._lib import Mb2Error
+    for bad in ([[0], [5], [3]], [[2], [1], [3]], [[0], [-1], [3]], [[-1], [1], [3]]):
+        with pytest.raises(Mb2Error):
+            cov.coverage_segments(bad[0], bad[1], bad[2], [100, 100], 1, 1)
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_random_small(cov, seed):
+    rng = np.random.default_rng(seed)
+    nchrom = int(rng.integers(1, 7))
+    sizes = rng.integers(1, 40000, nchrom).astype(np.int64)
+    n = int(rng.integers(1, 3000))
+    chrom = rng.integers(0, nchrom, n).astype(np.int32)
+    start = (rng.random(n) * (sizes[chrom] + 30)).astype(np.int32)
+    end = (start + rng.integers(0, 2000, n)).astype(np.int32)
+    run(cov, chrom, start, end, sizes, int(rng.integers(0, 6)), int(rng.integers(0, 300)))
+
+
+def test_dense_hotspots_many_events_per_tile(cov):
+    rng = np.random.default_rng(99)
+    n = 200000
+    start = (5000 + rng.normal(0, 300, n)).astype(np.int32).clip(0)
+    end = start + rng.integers(1, 900, n).astype(np.int32)
+    run(cov, np.zeros(n, np.int32), start, end, [20000], 1000, 10)
+    run(cov, np.zeros(n, np.int32), start, end, [20000], 3, 100)
+
+
+@pytest.mark.parametrize('case', ['cov_order', 'cov_dense', 'cov_nointra'])
+def test_goldens_bit_exact_gff(cov, case):
+    m = MAN[case]
+    sizes = {l.split('\t')[0]: int(l.split('\t')[1]) for l in read_golden(case + '.lens').splitlines()}
+    names = sorted(sizes, key=lambda s: s.encode())
+    text = ao.GFF_HEADER_SELF
+    blocks = [(case + '.tab', m['minCov'], m['label'])]
+    if m['has_intra']:
+        blocks.append((case + '.tab_intra.tab', m['intraCov'], m['label'] + '_intra'))
+    for fn, c, label in blocks:
+        chrom, start, end = tab_to_arrays(read_golden(fn).splitlines(), names)
+        seg = cov.coverage_segments(chrom, start, end, [sizes[n] for n in names], c, m['minLen'])
+        text += ''.join(segments_to_gff_rows(seg, names, 'mimeo-self', label, m['prefix']))
+    assert text == read_golden(case + '.gff3')
+
+
+def test_config2_shape_scaled_against_c_oracle(cov, oracle_build):
+    """C2-shaped input (hotspots + uniform, 50 scaffolds) at 1/20 scale: 500 k hits over 5 Mbp."""
+    import ctypes, os
+    chrom, start, end, sizes = synth_hits(seed=1002, nchrom=50, chrom_size=100_000, nhits=500_000, hotspots=100)
+    got = cov.coverage_segments(chrom, start, end, sizes, 3, 100)
+    lib = ctypes.CDLL(os.path.join(oracle_build, 'libannot_oracle.so'))
+    lib.ora_coverage_segments.restype = ctypes.c_long
+    cap = len(chrom) + 8
+    oc, os_, oe = (np.zeros(cap, np.int32) for _ in range(3))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    k = lib.ora_coverage_segments(P(chrom), P(start), P(end), ctypes.c_long(len(chrom)), P(sizes), ctypes.c_int(len(sizes)),
+                                  ctypes.c_int(3), ctypes.c_int(100), P(oc), P(os_), P(oe), ctypes.c_long(cap))
+    assert k == len(got[0]) and k > 100
+    assert (got[0] == oc[:k]).all() and (got[1] == os_[:k]).all() and (got[2] == oe[:k]).all()
+
+
+def test_full_size_properties(cov):
+    """BASELINE config 2 at full size (10 M hits / 100 Mbp): size-independent properties."""
+    chrom, start, end, sizes = synth_hits(seed=1002, nchrom=50, chrom_size=2_000_000, nhits=10_000_000, hotspots=2000)
+    c1, s1, e1 = cov.coverage_segments(chrom, start, end, sizes, 3, 100)
+    assert len(c1) > 1000
+    key = c1.astype(np.int64) * (1 << 32) + s1
+    assert (np.diff(key) > 0).all()                                  # sorted, strictly increasing
+    assert ((e1 - s1) >= 100).all() and (e1 <= sizes[c1]).all()
+    same = c1[1:] == c1[:-1]
+    assert (s1[1:][same] > e1[:-1][same]).all()                      # merged: no overlap, no book-ends
+    # permutation invariance (hit order must not matter)
+    p = np.random.default_rng(1).permutation(len(chrom))
+    c2, s2, e2 = cov.coverage_segments(chrom[p], start[p], end[p], sizes, 3, 100)
+    assert (c1 == c2).all() and (s1 == s2).all() and (e1 == e2).all()
+    # monotone in cov: covered bases shrink as the threshold rises; every cov=4 run lies inside a cov=3 run
+    c4, s4, e4 = cov.coverage_segments(chrom, start, end, sizes, 4, 1)
+    c3, s3, e3 = cov.coverage_segments(chrom, start, end, sizes, 3, 1)
+    assert (e4 - s4).sum() <= (e3 - s3).sum()
+    k3s = c3.astype(np.int64) * (1 << 32) + s3
+    idx = np.searchsorted(k3s, c4.astype(np.int64) * (1 << 32) + s4, side='right') - 1
+    assert (idx >= 0).all() and (c3[idx] == c4).all() and (s3[idx] <= s4).all() and (e3[idx] >= e4).all()
+    # duplicating every hit doubles the depth: cov=6 on doubled input == cov=3 on the original
+    cd, sd, ed = cov.coverage_segments(np.tile(chrom, 2), np.tile(start, 2), np.tile(end, 2), sizes, 6, 1)
+    assert (cd == c3).all() and (sd == s3).all() and (ed == e3).all()

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, read_golden
+from tests.helpers import GOLDEN, read_golden
 from oracle import annot_oracle as ao
 
 MAN = json.loads(read_golden('manifest.json'))
