@@ -100,14 +100,14 @@ def test_config2_shape_scaled_against_c_oracle(cov, oracle_build):
     """C2-shaped input (hotspots + uniform, 50 scaffolds) at 1/20 scale: 500 k hits over 5 Mbp."""
     import ctypes, os
     chrom, start, end, sizes = synth_hits(seed=1002, nchrom=50, chrom_size=100_000, nhits=500_000, hotspots=100)
-    got = cov.coverage_segments(chrom, start, end, sizes, 3, 100)
+    got = cov.coverage_segments(chrom, start, end, sizes, 21, 100)
     lib = ctypes.CDLL(os.path.join(oracle_build, 'libannot_oracle.so'))
     lib.ora_coverage_segments.restype = ctypes.c_long
     cap = len(chrom) + 8
     oc, os_, oe = (np.zeros(cap, np.int32) for _ in range(3))
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     k = lib.ora_coverage_segments(P(chrom), P(start), P(end), ctypes.c_long(len(chrom)), P(sizes), ctypes.c_int(len(sizes)),
-                                  ctypes.c_int(3), ctypes.c_int(100), P(oc), P(os_), P(oe), ctypes.c_long(cap))
+                                  ctypes.c_int(21), ctypes.c_int(100), P(oc), P(os_), P(oe), ctypes.c_long(cap))
     assert k == len(got[0]) and k > 100
     assert (got[0] == oc[:k]).all() and (got[1] == os_[:k]).all() and (got[2] == oe[:k]).all()
 
@@ -115,7 +115,7 @@ def test_config2_shape_scaled_against_c_oracle(cov, oracle_build):
 def test_full_size_properties(cov):
     """BASELINE config 2 at full size (10 M hits / 100 Mbp): size-independent properties."""
     chrom, start, end, sizes = synth_hits(seed=1002, nchrom=50, chrom_size=2_000_000, nhits=10_000_000, hotspots=2000)
-    c1, s1, e1 = cov.coverage_segments(chrom, start, end, sizes, 3, 100)
+    c1, s1, e1 = cov.coverage_segments(chrom, start, end, sizes, 21, 100)
     assert len(c1) > 1000
     key = c1.astype(np.int64) * (1 << 32) + s1
     assert (np.diff(key) > 0).all()                                  # sorted, strictly increasing
@@ -124,15 +124,15 @@ def test_full_size_properties(cov):
     assert (s1[1:][same] > e1[:-1][same]).all()                      # merged: no overlap, no book-ends
     # permutation invariance (hit order must not matter)
     p = np.random.default_rng(1).permutation(len(chrom))
-    c2, s2, e2 = cov.coverage_segments(chrom[p], start[p], end[p], sizes, 3, 100)
+    c2, s2, e2 = cov.coverage_segments(chrom[p], start[p], end[p], sizes, 21, 100)
     assert (c1 == c2).all() and (s1 == s2).all() and (e1 == e2).all()
-    # monotone in cov: covered bases shrink as the threshold rises; every cov=4 run lies inside a cov=3 run
-    c4, s4, e4 = cov.coverage_segments(chrom, start, end, sizes, 4, 1)
-    c3, s3, e3 = cov.coverage_segments(chrom, start, end, sizes, 3, 1)
+    # monotone in cov: covered bases shrink as the threshold rises; every cov=24 run lies inside a cov=21 run
+    c4, s4, e4 = cov.coverage_segments(chrom, start, end, sizes, 24, 1)
+    c3, s3, e3 = cov.coverage_segments(chrom, start, end, sizes, 21, 1)
     assert (e4 - s4).sum() <= (e3 - s3).sum()
     k3s = c3.astype(np.int64) * (1 << 32) + s3
     idx = np.searchsorted(k3s, c4.astype(np.int64) * (1 << 32) + s4, side='right') - 1
     assert (idx >= 0).all() and (c3[idx] == c4).all() and (s3[idx] <= s4).all() and (e3[idx] >= e4).all()
-    # duplicating every hit doubles the depth: cov=6 on doubled input == cov=3 on the original
-    cd, sd, ed = cov.coverage_segments(np.tile(chrom, 2), np.tile(start, 2), np.tile(end, 2), sizes, 6, 1)
+    # duplicating every hit doubles the depth: cov=42 on doubled input == cov=21 on the original
+    cd, sd, ed = cov.coverage_segments(np.tile(chrom, 2), np.tile(start, 2), np.tile(end, 2), sizes, 42, 1)
     assert (cd == c3).all() and (sd == s3).all() and (ed == e3).all()
