@@ -1,0 +1,236 @@
+"""
+lastz_oracle.py -- TEST INFRASTRUCTURE ONLY: ctypes front-end of oracle/lastz_oracle.c (the
+"LASTZ-restatement", PARITY UNPINNED against a real LASTZ binary -- see the C file header) plus the
+glue that turns its alignments into the text LASTZ would have written for mimeo's command line
+(--format=general:name1,strand1,start1,end1,length1,name2,strand2,start2+,end2+,length2,score,identity
+--markend; wrappers.py:1031) and the whole `mimeo self / x / map` reference pipeline on top of it
+(oracle/annot_oracle.py restates the shell stages).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import annot_oracle as ao
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('hspthresh', 'xdrop', 'ydrop', 'gap_open', 'gap_extend', 'gappedthresh',
+                                         'entropy', 'chain', 'gapped', 'transition')]
+
+
+class Hsp(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('s1', 's2', 'len', 'score')]
+
+
+class Aln(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('s1', 'e1', 's2', 'e2', 'score', 'nmatch', 'ncols', 'a1', 'a2')]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ('seed_hits', 'leaders', 'extended', 'ungapped_cells', 'hsps_raw', 'hsps_kept',
+                                         'chained', 'anchors_extended', 'gapped_cells')]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+    def add(self, o):
+        for n, _ in self._fields_:
+            setattr(self, n, getattr(self, n) + getattr(o, n))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(HERE, '_build', 'liblastz_oracle.so')
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(HERE, 'lastz_oracle.c')):
+            subprocess.check_call(['make', '-C', HERE, '_build/liblastz_oracle.so'], stdout=subprocess.DEVNULL)
+        l = C.CDLL(so)
+        l.lzo_index_build.restype = C.c_void_p
+        l.lzo_index_build.argtypes = [C.c_void_p, C.c_long]
+        l.lzo_index_free.argtypes = [C.c_void_p]
+        l.lzo_hsps_ix.restype = C.c_long
+        l.lzo_hsps_ix.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(Params), C.c_void_p,
+                                  C.c_long, C.POINTER(Stats)]
+        l.lzo_chain.restype = C.c_long
+        l.lzo_chain.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+        l.lzo_gapped.restype = C.c_long
+        l.lzo_gapped.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(Params),
+                                 C.c_void_p, C.c_long, C.POINTER(Stats)]
+        l.lzo_align_tile_ix.restype = C.c_long
+        l.lzo_align_tile_ix.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(Params),
+                                        C.c_void_p, C.c_long, C.POINTER(Stats)]
+        l.lzo_anchor.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Hsp), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        l.lzo_seed_at.restype = C.c_int
+        l.lzo_seed_at.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_int]
+        l.lzo_entropy_q24.restype = C.c_uint32
+        l.lzo_entropy_q24.argtypes = [C.c_void_p]
+        l.lzo_default_params.argtypes = [C.POINTER(Params)]
+        _LIB = l
+    return _LIB
+
+
+def default_params(hspthresh=3000, **kw) -> Params:
+    p = Params()
+    lib().lzo_default_params(C.byref(p))
+    p.hspthresh = int(hspthresh)
+    p.gappedthresh = int(hspthresh)
+    for k, v in kw.items():
+        setattr(p, k, int(v))
+    return p
+
+
+_ENC = np.full(256, 4, dtype=np.uint8)
+for _i, _c in enumerate('ACGT'):
+    _ENC[ord(_c)] = _i
+    _ENC[ord(_c.lower())] = _i          # D6: soft-masking is ignored
+
+
+def encode(seq) -> np.ndarray:
+    """str / bytes / uint8 ASCII array -> codes 0..3 (ACGT), 4 (anything else)."""
+    if isinstance(seq, str):
+        seq = seq.encode()
+    if isinstance(seq, (bytes, bytearray)):
+        seq = np.frombuffer(bytes(seq), dtype=np.uint8)
+    return _ENC[np.asarray(seq, dtype=np.uint8)]
+
+
+def revcomp_codes(codes: np.ndarray) -> np.ndarray:
+    r = codes[::-1].copy()
+    m = r < 4
+    r[m] = 3 - r[m]
+    return r
+
+
+class TargetIndex:
+    """Seed position table of one target scaffold (LASTZ rebuilds this per process; tests share it)."""
+
+    def __init__(self, codes: np.ndarray):
+        self.codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        self.h = lib().lzo_index_build(self.codes.ctypes.data, len(self.codes))
+
+    def __del__(self):
+        if getattr(self, 'h', None):
+            lib().lzo_index_free(self.h)
+            self.h = None
+
+
+def hsps(t: TargetIndex, q: np.ndarray, p: Params, stats: Optional[Stats] = None) -> np.ndarray:
+    """Kept ungapped HSPs of one (target, query-strand) tile as an (n,4) int32 array [s1,s2,len,score]."""
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    st = Stats()
+    cap = 1 << 16
+    while True:
+        out = np.zeros((cap, 4), dtype=np.int32)
+        st = Stats()
+        n = lib().lzo_hsps_ix(t.h, t.codes.ctypes.data, len(t.codes), q.ctypes.data, len(q), C.byref(p), out.ctypes.data, cap, C.byref(st))
+        if n >= 0:
+            break
+        cap *= 4
+    if stats is not None:
+        stats.add(st)
+    return out[:n].copy()
+
+
+def chain(h: np.ndarray) -> np.ndarray:
+    """Best collinear chain; returns the member rows in canonical (s1,s2,len,score) order."""
+    h = np.ascontiguousarray(h, dtype=np.int32).copy()
+    if len(h) == 0:
+        return h
+    flag = np.zeros(len(h), dtype=np.uint8)
+    lib().lzo_chain(h.ctypes.data, len(h), flag.ctypes.data)
+    return h[flag.astype(bool)]
+
+
+def align_tile(t: TargetIndex, q: np.ndarray, p: Params, stats: Optional[Stats] = None) -> np.ndarray:
+    """Full pipeline for one tile-strand; (n,9) int32 rows [s1,e1,s2,e2,score,nmatch,ncols,a1,a2] (strand-local)."""
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    cap = 1 << 14
+    while True:
+        out = np.zeros((cap, 9), dtype=np.int32)
+        st = Stats()
+        n = lib().lzo_align_tile_ix(t.h, t.codes.ctypes.data, len(t.codes), q.ctypes.data, len(q), C.byref(p), out.ctypes.data, cap, C.byref(st))
+        if n >= 0:
+            break
+        cap *= 4
+    if stats is not None:
+        stats.add(st)
+    return out[:n].copy()
+
+
+def pct_str(nmatch: int, ncols: int) -> str:
+    """LASTZ prints identity as '%.1f%%' of 100*n/d computed in double precision."""
+    return '%.1f' % (100.0 * nmatch / ncols) if ncols else '0.0'
+
+
+def lastz_general(tname: str, t: TargetIndex, qname: str, qcodes: np.ndarray, p: Params, stats: Optional[Stats] = None) -> List[str]:
+    """The text `lastz T Q ... --format=general:... --markend --strand=both` writes (13 columns, '%' present)."""
+    out = ['#name1\tstrand1\tstart1\tend1\tlength1\tname2\tstrand2\tstart2+\tend2+\tlength2\tscore\tidentity\tidPct\n']
+    m = len(qcodes)
+    for strand in '+-':
+        q = qcodes if strand == '+' else revcomp_codes(qcodes)
+        for (s1, e1, s2, e2, score, nm, nc, _a1, _a2) in align_tile(t, q, p, stats).tolist():
+            if strand == '+':
+                qs, qe = s2 + 1, e2
+            else:
+                qs, qe = m - e2 + 1, m - s2
+            out.append('\t'.join(map(str, (tname, '+', s1 + 1, e1, e1 - s1, qname, strand, qs, qe, e2 - s2, score,
+                                           f'{nm}/{nc}', pct_str(nm, nc) + '%'))) + '\n')
+    out.append('# lastz end-of-file\n')
+    return out
+
+
+# ------------------------------------------------------------------------------------------ whole reference pipelines
+def _pairs(anames: Sequence[str], bnames: Optional[Sequence[str]]):
+    """get_all_pairs (utils.py:92-102) with sorted() instead of glob order."""
+    return [(a, b) for a in sorted(anames) for b in sorted(bnames if bnames is not None else anames)]
+
+
+def mimeo_self(genome: Dict[str, np.ndarray], minIdt=60, minLen=100, minCov=3, intraCov=5, hspthresh=3000, strictSelf=False,
+               label='Self_Repeat', prefix='Self_Repeat', stats: Optional[Stats] = None) -> Tuple[str, Optional[str], str]:
+    """Reference pipeline of `mimeo self` (run_self.py:169-255 + wrappers.py:899-1271) on encoded scaffolds.
+    Returns (tab text, intra tab text or None, gff3 text)."""
+    p = default_params(hspthresh)
+    idx = {n: TargetIndex(c) for n, c in genome.items()}
+    tab, intra = ao.TAB_HEADER, (ao.TAB_HEADER if strictSelf else None)
+    for a, b in _pairs(list(genome), None):
+        rows = ''.join(ao.filter_lastz_general(lastz_general(a, idx[a], b, genome[b], p, stats), minLen, minIdt))
+        if a == b and strictSelf:
+            intra += rows
+        else:
+            tab += rows
+    sizes = {n: len(c) for n, c in genome.items()}
+    gff = ao.self_gff3(tab.splitlines(True), intra.splitlines(True) if strictSelf else None, sizes, minCov, intraCov, minLen, label, prefix)
+    return tab, intra, gff
+
+
+def mimeo_x(agenome, bgenome, minIdt=60, minLen=100, minCov=5, label='B_Repeat', prefix='B_Repeat', stats=None):
+    """Reference pipeline of `mimeo x` (run_interspecies.py:173-258; hspthresh is always 3000 there)."""
+    p = default_params(3000)
+    idx = {n: TargetIndex(c) for n, c in agenome.items()}
+    tab = ao.TAB_HEADER
+    for a, b in _pairs(list(agenome), list(bgenome)):
+        tab += ''.join(ao.filter_lastz_general(lastz_general(a, idx[a], b, bgenome[b], p, stats), minLen, minIdt))
+    sizes = {n: len(c) for n, c in agenome.items()}
+    return tab, ao.x_gff3(tab.splitlines(True), sizes, minCov, minLen, label, prefix)
+
+
+def mimeo_map(agenome, bgenome, minIdt=90, minLen=100, hspthresh=3000, label='BHit', prefix='BHit', stats=None):
+    """Reference pipeline of `mimeo map` without TRF (run_map.py:190-328)."""
+    p = default_params(hspthresh)
+    idx = {n: TargetIndex(c) for n, c in agenome.items()}
+    tab = ao.TAB_HEADER
+    for a, b in _pairs(list(agenome), list(bgenome)):
+        tab += ''.join(ao.filter_lastz_general(lastz_general(a, idx[a], b, bgenome[b], p, stats), minLen, minIdt))
+    hits = ao.import_align_rows(tab.splitlines(True), prefix, minLen, minIdt)
+    chrlens = sorted((n, str(len(c))) for n, c in agenome.items())
+    return tab, ''.join(ao.write_gff_lines(hits, chrlens, label))

@@ -45,3 +45,64 @@ def synth_hits(seed, nchrom, chrom_size, nhits, hotspots):
     length = np.minimum(100 + rng.exponential(600, nhits), 20000).astype(np.int32)
     end = np.minimum(start + length, chrom_size).astype(np.int32)
     return chrom, start, end, sizes
+
+
+# ----------------------------------------------------------------------------------------- synthetic genomes
+def mutate(rng, seq, sub, indel):
+    """Copy of `seq` (uint8 ASCII) with per-base substitution prob `sub` and indel prob `indel` (length 1-3)."""
+    out = []
+    bases = np.frombuffer(b'ACGT', dtype=np.uint8)
+    i = 0
+    n = len(seq)
+    r = rng.random(n)
+    r2 = rng.random(n)
+    while i < n:
+        if r2[i] < indel:
+            ln = int(rng.integers(1, 4))
+            if rng.random() < 0.5:
+                i += ln                       # deletion
+                continue
+            out.append(bases[rng.integers(0, 4, ln)])   # insertion
+        b = seq[i]
+        if r[i] < sub:
+            b = bases[(int(np.searchsorted(bases, b)) + int(rng.integers(1, 4))) % 4]
+        out.append(np.array([b], dtype=np.uint8))
+        i += 1
+    return np.concatenate(out) if out else np.zeros(0, np.uint8)
+
+
+_COMP = np.zeros(256, dtype=np.uint8)
+for _a, _b in zip(b'ACGTN', b'TGCAN'):
+    _COMP[_a] = _b
+
+
+def revcomp_ascii(seq):
+    return _COMP[seq[::-1]]
+
+
+def synth_genome(seed, nscaf, scaf_len, nfam, copies=(5, 30), fam_len=(300, 3000), sub=0.106, indel=0.005, n_runs=0):
+    """SURVEY 8(d) config-1 shaped generator: uniform random scaffolds with planted repeat families; each copy is the
+    family consensus with per-base substitutions/indels on a random strand at a random non-overlapping place.
+    Returns {name: uint8 ASCII array}."""
+    rng = np.random.default_rng(seed)
+    bases = np.frombuffer(b'ACGT', dtype=np.uint8)
+    scafs = [bases[rng.integers(0, 4, scaf_len)].copy() for _ in range(nscaf)]
+    used = [[] for _ in range(nscaf)]
+    for _ in range(nfam):
+        L = int(rng.integers(fam_len[0], fam_len[1] + 1))
+        cons = bases[rng.integers(0, 4, L)]
+        for _c in range(int(rng.integers(copies[0], copies[1] + 1))):
+            cp = mutate(rng, cons, sub, indel)
+            if rng.random() < 0.5:
+                cp = revcomp_ascii(cp)
+            for _try in range(50):
+                s = int(rng.integers(0, nscaf))
+                p = int(rng.integers(0, scaf_len - len(cp)))
+                if all(p + len(cp) <= a or p >= b for a, b in used[s]):
+                    scafs[s][p:p + len(cp)] = cp
+                    used[s].append((p, p + len(cp)))
+                    break
+    for _ in range(n_runs):                       # a few N runs to exercise non-ACGT handling
+        s = int(rng.integers(0, nscaf)); p = int(rng.integers(0, scaf_len - 50))
+        scafs[s][p:p + int(rng.integers(1, 40))] = ord('N')
+    return {f'scaf{i:03d}': scafs[i] for i in range(nscaf)}
