@@ -89,6 +89,40 @@ MB2_API int mb2_coverage_segments_dev(const int32_t* d_chrom, const int32_t* d_s
 
 MB2_API void mb2_free_segments(mb2_segments* seg);
 
+/* ---- genomes --------------------------------------------------------------------------- */
+/* A genome resident in HBM: every scaffold 2-bit packed + a non-ACGT mask, one padded coordinate
+ * space. Replaces the per-scaffold FASTA files mimeo writes for LASTZ (utils.py:274-309) and
+ * LASTZ's own sequence loading. `seqs[i]` is the ASCII sequence of scaffold i (no header, no
+ * newlines), `lens[i]` its length; scaffold order defines the scaffold index used everywhere. */
+typedef struct mb2_genome mb2_genome;
+MB2_API int mb2_genome_create(const uint8_t* const* seqs, const uint64_t* lens, int n, mb2_genome** out);
+/* Reverse complement of every scaffold (what LASTZ aligns for strand2 = '-'). */
+MB2_API int mb2_genome_revcomp(const mb2_genome* g, mb2_genome** out);
+MB2_API void mb2_genome_free(mb2_genome* g);
+/* Test hook: scaffold `scaf` decoded back to codes 0..3 = ACGT, 4 = other (HOST buffer of its length). */
+MB2_API int mb2_genome_decode(const mb2_genome* g, int scaf, uint8_t* out);
+
+/* ---- alignment parameters --------------------------------------------------------------- */
+/* The knobs of the one LASTZ command line mimeo issues (wrappers.py:1031): --hspthresh is the only
+ * one mimeo exposes (run_self.py:142-147); the rest are LASTZ defaults. */
+typedef struct mb2_align_params {
+    int32_t hspthresh, xdrop, ydrop, gap_open, gap_extend, gappedthresh;
+    int32_t entropy, chain, gapped, transition;
+} mb2_align_params;
+MB2_API void mb2_default_align_params(mb2_align_params* p);
+
+/* Ungapped HSPs (stage b), canonical order (tile, s1, s2, len); tile = t_scaffold * nQ + q_scaffold;
+ * coordinates 0-based, local to the scaffolds, on the strand Q is oriented in. HOST arrays. */
+typedef struct mb2_hsps {
+    uint32_t* tile;
+    int32_t *s1, *s2, *len, *score;
+    uint64_t n;
+} mb2_hsps;
+MB2_API void mb2_free_hsps(mb2_hsps* h);
+/* Test hook: stage (a)+(b) only. `stats` (may be NULL) receives 16 counters:
+ * [0] survivors [1] seed hits [2] run leaders [3] stage-1 cells [4] HSPs [5] extensions [6] stage-2 cells. */
+MB2_API int mb2_test_hsps(const mb2_genome* T, const mb2_genome* Q, const mb2_align_params* p, mb2_hsps* out, uint64_t* stats);
+
 /* ---- device primitives exposed for parity tests ------------------------------------------- */
 /* Stable LSD radix sort of HOST arrays on bits [begin_bit, end_bit) (vals may be NULL). */
 MB2_API int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);

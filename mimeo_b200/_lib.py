@@ -18,6 +18,15 @@ c_u32p = C.POINTER(C.c_uint32)
 c_u64p = C.POINTER(C.c_uint64)
 
 
+class AlignParams(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ('hspthresh', 'xdrop', 'ydrop', 'gap_open', 'gap_extend', 'gappedthresh',
+                                         'entropy', 'chain', 'gapped', 'transition')]
+
+
+class Hsps(C.Structure):
+    _fields_ = [('tile', c_u32p), ('s1', c_i32p), ('s2', c_i32p), ('len', c_i32p), ('score', c_i32p), ('n', C.c_uint64)]
+
+
 class Segments(C.Structure):
     _fields_ = [('chrom', c_i32p), ('start', c_i32p), ('end', c_i32p), ('n', C.c_uint64), ('on_device', C.c_int)]
 
@@ -39,6 +48,13 @@ SIGNATURES = {
     'mb2_coverage_segments_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int, C.POINTER(Segments)]),
     'mb2_free_segments': (None, [C.POINTER(Segments)]),
+    'mb2_genome_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    'mb2_genome_revcomp': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'mb2_genome_free': (None, [C.c_void_p]),
+    'mb2_genome_decode': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    'mb2_default_align_params': (None, [C.POINTER(AlignParams)]),
+    'mb2_free_hsps': (None, [C.POINTER(Hsps)]),
+    'mb2_test_hsps': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(AlignParams), C.POINTER(Hsps), C.c_void_p]),
     'mb2_test_sort_u32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     'mb2_test_sort_u64': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     'mb2_test_scan_u32': (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),

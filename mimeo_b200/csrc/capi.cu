@@ -4,6 +4,7 @@
 
 #include "primitives.cuh"
 #include "internal.cuh"
+#include "seq.cuh"
 #include "mimeo_b200.h"
 
 namespace mb2 {
@@ -189,6 +190,86 @@ void mb2_free_segments(mb2_segments* seg) {
         free(seg->chrom); free(seg->start); free(seg->end);
     }
     std::memset(seg, 0, sizeof(*seg));
+}
+
+// ------------------------------------------------------------------------------------------ genomes
+struct mb2_genome { Genome* g; };
+
+int mb2_genome_create(const uint8_t* const* seqs, const uint64_t* lens, int n, mb2_genome** out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(seqs && lens && out, MB2_ERR_INVALID_ARG, "genome_create: null argument");
+        Genome* g = genome_from_ascii(seqs, lens, n);
+        *out = new mb2_genome{g};
+    });
+}
+int mb2_genome_revcomp(const mb2_genome* g, mb2_genome** out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(g && g->g && out, MB2_ERR_INVALID_ARG, "genome_revcomp: null argument");
+        *out = new mb2_genome{genome_revcomp(*g->g)};
+    });
+}
+void mb2_genome_free(mb2_genome* g) {
+    if (!g) return;
+    delete g->g;
+    delete g;
+}
+int mb2_genome_decode(const mb2_genome* g, int scaf, uint8_t* out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(g && g->g && out, MB2_ERR_INVALID_ARG, "genome_decode: null argument");
+        genome_decode(*g->g, scaf, out);
+    });
+}
+
+void mb2_default_align_params(mb2_align_params* p) {
+    if (!p) return;
+    AlignParams d;
+    p->hspthresh = d.hspthresh; p->xdrop = d.xdrop; p->ydrop = d.ydrop; p->gap_open = d.gap_open; p->gap_extend = d.gap_extend;
+    p->gappedthresh = d.gappedthresh; p->entropy = d.entropy; p->chain = d.chain; p->gapped = d.gapped; p->transition = d.transition;
+}
+static AlignParams to_params(const mb2_align_params* p) {
+    AlignParams a;
+    if (p) {
+        a.hspthresh = p->hspthresh; a.xdrop = p->xdrop; a.ydrop = p->ydrop; a.gap_open = p->gap_open; a.gap_extend = p->gap_extend;
+        a.gappedthresh = p->gappedthresh; a.entropy = p->entropy; a.chain = p->chain; a.gapped = p->gapped; a.transition = p->transition;
+    }
+    MB2_REQUIRE(a.xdrop > 0 && a.ydrop > 0 && a.gap_open >= 0 && a.gap_extend > 0 && a.hspthresh > 0, MB2_ERR_INVALID_ARG,
+                "align params out of range");
+    return a;
+}
+
+}  // extern "C"
+template <typename Tp>
+static Tp* to_host(const DevBuf<Tp>& d, size_t n) {
+    Tp* h = (Tp*)malloc((n ? n : 1) * sizeof(Tp));
+    MB2_REQUIRE(h != nullptr, MB2_ERR_INTERNAL, "host allocation failed");
+    if (n) MB2_CUDA(cudaMemcpyAsync(h, d.get(), n * sizeof(Tp), cudaMemcpyDeviceToHost, g_ctx.stream));
+    return h;
+}
+extern "C" {
+
+void mb2_free_hsps(mb2_hsps* h) {
+    if (!h) return;
+    free(h->tile); free(h->s1); free(h->s2); free(h->len); free(h->score);
+    std::memset(h, 0, sizeof(*h));
+}
+
+int mb2_test_hsps(const mb2_genome* T, const mb2_genome* Q, const mb2_align_params* p, mb2_hsps* out, uint64_t* stats) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(T && Q && out, MB2_ERR_INVALID_ARG, "test_hsps: null argument");
+        std::memset(out, 0, sizeof(*out));
+        HspSet h;
+        unsigned long long cnt[CNT_N];
+        align_hsps(*T->g, *Q->g, to_params(p), h, cnt);
+        out->n = h.n;
+        out->tile = to_host(h.tile, h.n); out->s1 = to_host(h.s1, h.n); out->s2 = to_host(h.s2, h.n);
+        out->len = to_host(h.len, h.n); out->score = to_host(h.score, h.n);
+        MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        if (stats) for (int k = 0; k < CNT_N; k++) stats[k] = cnt[k];
+    });
 }
 
 // ------------------------------------------------------------------------------------------ test hooks

@@ -1,0 +1,137 @@
+// genome.cu -- build the device genome (2-bit pack + N mask) from ASCII, and its reverse complement.
+// Replaces the FASTA -> per-scaffold files -> LASTZ sequence loading of the reference
+// (utils.py:274-309 splitFasta, LASTZ's own reader) for the hot path.
+#include "seq.cuh"
+#include "internal.cuh"
+
+namespace mb2 {
+
+// one thread packs 32 bases -> one uint64 of 2-bit codes + one uint32 of N flags
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    const uint4* src = reinterpret_cast<const uint4*>(ascii + (size_t)w * 32);
+    uint64_t bits = 0;
+    uint32_t nflag = 0;
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+        const uint4 x = src[v];
+        const uint32_t words[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t c = ((words[k] >> (8 * b)) & 0xFFu) & 0xDFu;   // fold to upper case (soft-masking ignored)
+                uint32_t code = 0, bad = 0;
+                if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3; else bad = 1;
+                const int idx = v * 16 + k * 4 + b;
+                bits |= (uint64_t)code << (2 * idx);
+                nflag |= bad << idx;
+            }
+        }
+    }
+    pk[w] = bits;
+    nm[w] = nflag;
+}
+
+// reverse complement every scaffold in place of its own slot (same offsets, same lengths)
+__global__ void __launch_bounds__(256)
+revcomp_kernel(GenomeView src, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm, uint32_t nwords) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    const uint32_t p0 = w * 32;
+    // find the scaffold containing (or following) p0: last s with off[s] <= p0 + 31
+    int lo = 0, hi = src.nscaf;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (src.off[mid] <= p0 + 31) lo = mid; else hi = mid; }
+    const uint32_t so = src.off[lo], sl = src.len[lo];
+    uint64_t bits = 0;
+    uint32_t nflag = 0;
+    for (int c = 0; c < 32; c++) {
+        const uint32_t p = p0 + c;
+        uint32_t code = 0, bad = 1;
+        if (p >= so && p < so + sl) {
+            const uint32_t sp = so + (sl - 1 - (p - so));
+            bad = isn_at(src.nm, sp);
+            code = bad ? 0u : 3u - base_at(src.pk, sp);
+        }
+        bits |= (uint64_t)code << (2 * c);
+        nflag |= bad << c;
+    }
+    pk[w] = bits;
+    nm[w] = nflag;
+}
+
+static void layout(Genome& g, const uint64_t* lens, int n) {
+    g.nscaf = n;
+    g.off.resize(n); g.len.resize(n);
+    uint64_t pos = GENOME_PAD;
+    g.nbases = 0;
+    for (int s = 0; s < n; s++) {
+        MB2_REQUIRE(lens[s] < 0x7fffffffull, -3, "scaffold longer than 2^31-1 bases");
+        g.off[s] = (uint32_t)pos; g.len[s] = (uint32_t)lens[s];
+        g.nbases += lens[s];
+        pos = (pos + lens[s] + GENOME_PAD + 63) & ~63ull;
+        MB2_REQUIRE(pos < 0xfff00000ull, -3, "genome exceeds 2^32 padded positions; load it as several genomes");
+    }
+    g.G = pos;
+}
+
+Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int n) {
+    MB2_REQUIRE(n > 0, -2, "genome: need at least one scaffold");
+    Genome* g = new Genome();
+    try {
+        layout(*g, lens, n);
+        Ctx& cx = ctx();
+        // stage ASCII with 'N' padding in pinned host memory, one H2D copy, pack on the device
+        const size_t nbytes = g->G + 64;
+        uint8_t* h = nullptr;
+        MB2_CUDA(cudaMallocHost((void**)&h, nbytes));
+        memset(h, 'N', nbytes);
+        for (int s = 0; s < n; s++) memcpy(h + g->off[s], seqs[s], lens[s]);
+        DevBuf<uint8_t> d_ascii(nbytes);
+        MB2_CUDA(cudaMemcpyAsync(d_ascii.get(), h, nbytes, cudaMemcpyHostToDevice, cx.stream));
+        const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
+        g->pk.alloc(nwords); g->nm.alloc(nwords);
+        g->d_off.alloc(n); g->d_len.alloc(n);
+        MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), g->off.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
+        MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), g->len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
+        launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get());
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));
+        cudaFreeHost(h);
+    } catch (...) { delete g; throw; }
+    return g;
+}
+
+Genome* genome_revcomp(const Genome& src) {
+    Genome* g = new Genome();
+    try {
+        g->nscaf = src.nscaf; g->off = src.off; g->len = src.len; g->G = src.G; g->nbases = src.nbases; g->is_rc = !src.is_rc;
+        const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
+        g->pk.alloc(nwords); g->nm.alloc(nwords);
+        g->d_off.alloc(src.nscaf); g->d_len.alloc(src.nscaf);
+        Ctx& cx = ctx();
+        MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), src.d_off.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
+        MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), src.d_len.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
+        launch(revcomp_kernel, cdiv(nwords, 256), 256, 0, view(src), g->pk.get(), g->nm.get(), nwords);
+    } catch (...) { delete g; throw; }
+    return g;
+}
+
+// test hook: decode a range back to codes 0..3 / 4
+__global__ void decode_kernel(GenomeView g, uint32_t p0, uint32_t n, uint8_t* __restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t p = p0 + k;
+    out[k] = isn_at(g.nm, p) ? 4 : (uint8_t)base_at(g.pk, p);
+}
+void genome_decode(const Genome& g, int scaf, uint8_t* h_out) {
+    MB2_REQUIRE(scaf >= 0 && scaf < g.nscaf, -2, "decode: scaffold index out of range");
+    const uint32_t n = g.len[scaf];
+    DevBuf<uint8_t> d(n);
+    if (n) launch(decode_kernel, cdiv(n, 256), 256, 0, view(g), g.off[scaf], n, d.get());
+    if (n) MB2_CUDA(cudaMemcpyAsync(h_out, d.get(), n, cudaMemcpyDeviceToHost, ctx().stream));
+    MB2_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
+}  // namespace mb2

@@ -14,4 +14,54 @@ struct CoverageResult {
 void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, uint64_t nhits,
                               const int64_t* h_sizes, int nchrom, int min_cov, int min_len, CoverageResult& res);
 
+// ---- alignment half
+struct Genome;
+struct AlignParams {   // LASTZ defaults for mimeo's command line
+    int hspthresh = 3000, xdrop = 910, ydrop = 9400, gap_open = 400, gap_extend = 30, gappedthresh = 3000;
+    int entropy = 1, chain = 1, gapped = 1, transition = 1;
+};
+
+// genome.cu
+Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int n);
+Genome* genome_revcomp(const Genome& src);
+void genome_decode(const Genome& g, int scaf, uint8_t* h_out);
+
+// seed.cu
+struct SeedTable {
+    DevBuf<uint32_t> off;   // 2^24+1 bucket offsets
+    DevBuf<uint32_t> pos;   // target positions sorted by seed key
+    uint32_t p_lo = 0, p_hi = 0;
+};
+void build_seed_table(const Genome& T, uint32_t p_lo, uint32_t p_hi, SeedTable& tab);
+void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t q_lo, uint32_t q_hi, const AlignParams& p,
+               uint64_t* surv, uint32_t surv_cap, unsigned long long* counters);
+
+// hsp.cu : survivors -> kept HSPs in canonical order (tile, s1, s2, len); coordinates local to the scaffolds
+struct HspSet {
+    DevBuf<uint32_t> tile;              // tscaf * nQ + qscaf
+    DevBuf<int32_t> s1, s2, len, score;
+    uint32_t n = 0;
+};
+void find_hsps(const Genome& T, const Genome& Q, uint64_t* surv0, uint64_t* surv1, uint32_t nsurv, const AlignParams& p,
+               HspSet& out, unsigned long long* counters);
+
+// chain.cu : flags the members of the best collinear chain of every tile
+void chain_hsps(const HspSet& h, int max_len_bits, DevBuf<uint8_t>& in_chain);
+
+// gapped.cu
+struct AlnSet {   // strand-local, scaffold-local, 0-based half-open
+    DevBuf<uint32_t> tile;
+    DevBuf<int32_t> s1, e1, s2, e2, score, nmatch, ncols;
+    uint32_t n = 0;
+};
+void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevBuf<uint8_t>& in_chain, const AlignParams& p,
+                   AlnSet& out, unsigned long long* counters);
+
+// align.cu
+void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& hsps, unsigned long long* h_counters);
+
+// counters layout (device, unsigned long long[16])
+enum { CNT_SURV = 0, CNT_SEED_HITS = 1, CNT_LEADERS = 2, CNT_S1_CELLS = 3, CNT_HSPS = 4, CNT_EXTENDED = 5, CNT_S2_CELLS = 6,
+       CNT_GAPPED_CELLS = 7, CNT_ALNS = 8, CNT_ANCHORS = 9, CNT_ERR = 10, CNT_WORK = 11, CNT_N = 16 };
+
 }  // namespace mb2
