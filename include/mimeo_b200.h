@@ -123,6 +123,26 @@ MB2_API void mb2_free_hsps(mb2_hsps* h);
  * [0] survivors [1] seed hits [2] run leaders [3] stage-1 cells [4] HSPs [5] extensions [6] stage-2 cells. */
 MB2_API int mb2_test_hsps(const mb2_genome* T, const mb2_genome* Q, const mb2_align_params* p, mb2_hsps* out, uint64_t* stats);
 
+/* ---- (a)+(b)+(b')+(c): the whole LASTZ stage ------------------------------------------------ */
+/* One row per gapped alignment, i.e. per line of LASTZ's --format=general output before mimeo's
+ * awk filters (wrappers.py:1044-1056). start1/end1/start2/end2 are what LASTZ prints: origin-one,
+ * closed, start2/end2 on the query's + strand (start2+/end2+); strand: 0 = '+', 1 = '-';
+ * length1 = end1-start1+1; identity = nmatch/ncols. HOST arrays owned by the library.
+ * stats: [0] survivors [1] seed hits [2] run leaders [3] stage-1 cells [4] HSPs [5] stage-2 extensions
+ * [6] stage-2 cells [7] gapped DP cells [8] alignments [9] anchors extended (summed over strands). */
+typedef struct mb2_hits {
+    int32_t *t_id, *q_id, *strand, *start1, *end1, *start2, *end2, *score, *nmatch, *ncols;
+    uint64_t n;
+    uint64_t stats[16];
+} mb2_hits;
+/* Replaces every `lastz T Q ...` process of mimeo's script (wrappers.py:1025-1037, 1070-1082, 786-798,
+ * 645-653): aligns every scaffold of T against every scaffold of Q, both strands when strands == 3
+ * (1 = plus only, 2 = minus only). Q_rc may be NULL (the reverse complement is then built and freed
+ * inside the call). Multi-GPU: each rank passes its own subset of target scaffolds as T. */
+MB2_API int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_rc, const mb2_align_params* p, int strands,
+                      mb2_hits* out);
+MB2_API void mb2_free_hits(mb2_hits* h);
+
 /* ---- device primitives exposed for parity tests ------------------------------------------- */
 /* Stable LSD radix sort of HOST arrays on bits [begin_bit, end_bit) (vals may be NULL). */
 MB2_API int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);

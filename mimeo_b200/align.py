@@ -1,0 +1,67 @@
+"""Host side of the alignment stage: device genomes in, LASTZ-style hit rows out.
+
+`align()` replaces every `lastz T Q ...` process of the reference's generated script
+(wrappers.py:1025-1037 et al.); `tab_blocks()` replaces the sed/awk/awk/awk/sed/sort filter that follows
+each of them (wrappers.py:1040-1056): keep length1 >= minLen and idPct >= minIdt, print the 10 columns,
+sort each pair's rows by `sort -k 1,1 -k 3n,4n` (C locale, whole-line tie-break).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .genome import Genome, align_params
+
+HIT_FIELDS = ('t_id', 'q_id', 'strand', 'start1', 'end1', 'start2', 'end2', 'score', 'nmatch', 'ncols')
+STAT_NAMES = ('survivors', 'seed_hits', 'leaders', 'stage1_cells', 'hsps', 'stage2_extensions', 'stage2_cells',
+              'gapped_cells', 'alignments', 'anchors_extended')
+
+
+def align(T: Genome, Q: Genome, params: Optional[_lib.AlignParams] = None, strands: int = 3,
+          Q_rc: Optional[Genome] = None) -> Tuple[Dict[str, np.ndarray], Dict[str, int]]:
+    """All scaffolds of T against all scaffolds of Q on the GPU. Returns (hit columns, stage counters)."""
+    if params is None:
+        params = align_params()
+    h = _lib.Hits()
+    _lib.check(_lib.lib().mb2_align(T.handle, Q.handle, Q_rc.handle if Q_rc is not None else None, C.byref(params),
+                                    int(strands), C.byref(h)))
+    try:
+        n = int(h.n)
+        cols = {f: (np.ctypeslib.as_array(getattr(h, f), shape=(n,)).copy() if n else np.zeros(0, np.int32)) for f in HIT_FIELDS}
+        stats = {name: int(h.stats[i]) for i, name in enumerate(STAT_NAMES)}
+    finally:
+        _lib.lib().mb2_free_hits(C.byref(h))
+    return cols, stats
+
+
+def pct_text(nmatch: int, ncols: int) -> str:
+    """LASTZ prints the identity percentage with '%.1f' of 100*n/d evaluated in double precision."""
+    return '%.1f' % (100.0 * nmatch / ncols) if ncols else '0.0'
+
+
+def _sort_n(s: str) -> float:
+    return float(s)
+
+
+def tab_blocks(hits: Dict[str, np.ndarray], tnames: List[str], qnames: List[str], minLen, minIdt) -> Dict[Tuple[int, int], List[str]]:
+    """Filtered, sorted 10-column rows (with newline) per (t_id, q_id) pair."""
+    out: Dict[Tuple[int, int], List[str]] = {}
+    n = len(hits['t_id'])
+    for k in range(n):
+        s1, e1 = int(hits['start1'][k]), int(hits['end1'][k])
+        if e1 - s1 + 1 < minLen:                               # awk '0+$5 >= minLen' on length1
+            continue
+        pct = pct_text(int(hits['nmatch'][k]), int(hits['ncols'][k]))
+        if float(pct) < float(minIdt):                         # awk '0+$13 >= minIdt' on the printed percentage
+            continue
+        t, q = int(hits['t_id'][k]), int(hits['q_id'][k])
+        row = '\t'.join((tnames[t], '+', str(s1), str(e1), qnames[q], '-' if hits['strand'][k] else '+',
+                         str(int(hits['start2'][k])), str(int(hits['end2'][k])), str(int(hits['score'][k])), pct))
+        out.setdefault((t, q), []).append(row)
+    for key, rows in out.items():
+        rows.sort(key=lambda r: (float(r.split('\t')[2]), r.encode()))   # sort -k 3n,4n then whole line (name1 equal inside a pair)
+        out[key] = [r + '\n' for r in rows]
+    return out

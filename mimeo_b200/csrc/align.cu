@@ -35,4 +35,36 @@ void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& 
     }
 }
 
+// Full pipeline for one strand orientation of Q: alignments in strand-local, scaffold-local coordinates.
+void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, AlnSet& alns, unsigned long long* h_counters) {
+    Ctx& cx = ctx();
+    HspSet hsps;
+    unsigned long long c1[CNT_N];
+    align_hsps(T, Q, p, hsps, c1);
+    uint32_t maxlen = 0;
+    for (int s = 0; s < T.nscaf; s++) maxlen = std::max(maxlen, T.len[s]);
+    for (int s = 0; s < Q.nscaf; s++) maxlen = std::max(maxlen, Q.len[s]);
+    int lb = 1; while (lb < 32 && (maxlen >> lb)) lb++;
+    lb += 1;   // e = s + len can reach maxlen exactly
+    int tb = 1; while (tb < 33 && (((uint64_t)T.nscaf * (uint64_t)Q.nscaf) >> tb)) tb++;
+    DevBuf<uint8_t> in_chain;
+    if (p.chain) chain_hsps(hsps, lb, tb, in_chain);
+    else {
+        in_chain.alloc(hsps.n ? hsps.n : 1);
+        if (hsps.n) MB2_CUDA(cudaMemsetAsync(in_chain.get(), 1, hsps.n, cx.stream));
+    }
+    DevBuf<unsigned long long> counters(CNT_N);
+    MB2_CUDA(cudaMemsetAsync(counters.get(), 0, CNT_N * sizeof(unsigned long long), cx.stream));
+    gapped_extend(T, Q, hsps, in_chain, p, alns, counters.get());
+    unsigned long long c2[CNT_N];
+    MB2_CUDA(cudaMemcpyAsync(c2, counters.get(), sizeof(c2), cudaMemcpyDeviceToHost, cx.stream));
+    MB2_CUDA(cudaStreamSynchronize(cx.stream));
+    if (h_counters) {
+        for (int k = 0; k < CNT_N; k++) h_counters[k] = c1[k];
+        h_counters[CNT_GAPPED_CELLS] = c2[CNT_GAPPED_CELLS];
+        h_counters[CNT_ANCHORS] = c2[CNT_ANCHORS];
+        h_counters[CNT_ALNS] = alns.n;
+    }
+}
+
 }  // namespace mb2

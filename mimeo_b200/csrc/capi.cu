@@ -272,6 +272,71 @@ int mb2_test_hsps(const mb2_genome* T, const mb2_genome* Q, const mb2_align_para
     });
 }
 
+void mb2_free_hits(mb2_hits* h) {
+    if (!h) return;
+    free(h->t_id); free(h->q_id); free(h->strand); free(h->start1); free(h->end1); free(h->start2); free(h->end2);
+    free(h->score); free(h->nmatch); free(h->ncols);
+    std::memset(h, 0, sizeof(*h));
+}
+
+int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_rc, const mb2_align_params* p, int strands,
+              mb2_hits* out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(T && Q && out && T->g && Q->g, MB2_ERR_INVALID_ARG, "align: null argument");
+        MB2_REQUIRE(strands >= 1 && strands <= 3, MB2_ERR_INVALID_ARG, "align: strands must be 1, 2 or 3");
+        std::memset(out, 0, sizeof(*out));
+        const AlignParams ap = to_params(p);
+        std::vector<int32_t> cols[10];
+        Genome* own_rc = nullptr;
+        try {
+            for (int st = 0; st < 2; st++) {
+                if (!(strands & (1 << st))) continue;
+                const Genome* q = Q->g;
+                if (st == 1) {
+                    if (Q_rc && Q_rc->g) q = Q_rc->g;
+                    else { own_rc = genome_revcomp(*Q->g); q = own_rc; }
+                }
+                AlnSet a;
+                unsigned long long cnt[CNT_N];
+                align_strand(*T->g, *q, ap, a, cnt);
+                for (int k = 0; k < CNT_N; k++) out->stats[k] += cnt[k];
+                const size_t n = a.n;
+                if (!n) continue;
+                std::vector<uint32_t> tile(n);
+                std::vector<int32_t> s1(n), e1(n), s2(n), e2(n), sc(n), nm(n), nc(n);
+                auto d2h = [&](void* dst, const void* src, size_t bytes) {
+                    MB2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+                };
+                d2h(tile.data(), a.tile.get(), n * 4); d2h(s1.data(), a.s1.get(), n * 4); d2h(e1.data(), a.e1.get(), n * 4);
+                d2h(s2.data(), a.s2.get(), n * 4); d2h(e2.data(), a.e2.get(), n * 4); d2h(sc.data(), a.score.get(), n * 4);
+                d2h(nm.data(), a.nmatch.get(), n * 4); d2h(nc.data(), a.ncols.get(), n * 4);
+                MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+                const uint32_t nq = (uint32_t)q->nscaf;
+                for (size_t k = 0; k < n; k++) {
+                    const int32_t qi = (int32_t)(tile[k] % nq), ti = (int32_t)(tile[k] / nq);
+                    const int32_t m = (int32_t)q->len[qi];
+                    cols[0].push_back(ti); cols[1].push_back(qi); cols[2].push_back(st);
+                    cols[3].push_back(s1[k] + 1); cols[4].push_back(e1[k]);
+                    if (st == 0) { cols[5].push_back(s2[k] + 1); cols[6].push_back(e2[k]); }
+                    else { cols[5].push_back(m - e2[k] + 1); cols[6].push_back(m - s2[k]); }   // back to the + strand of the query
+                    cols[7].push_back(sc[k]); cols[8].push_back(nm[k]); cols[9].push_back(nc[k]);
+                }
+            }
+        } catch (...) { delete own_rc; throw; }
+        delete own_rc;
+        const size_t n = cols[0].size();
+        out->n = n;
+        int32_t** dst[10] = {&out->t_id, &out->q_id, &out->strand, &out->start1, &out->end1, &out->start2, &out->end2,
+                             &out->score, &out->nmatch, &out->ncols};
+        for (int c = 0; c < 10; c++) {
+            *dst[c] = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
+            MB2_REQUIRE(*dst[c] != nullptr, MB2_ERR_INTERNAL, "align: host allocation failed");
+            if (n) std::memcpy(*dst[c], cols[c].data(), n * sizeof(int32_t));
+        }
+    });
+}
+
 // ------------------------------------------------------------------------------------------ test hooks
 int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit) {
     return guarded([&] { test_sort<uint32_t>(keys, vals, n, begin_bit, end_bit); });

@@ -46,7 +46,7 @@ void find_hsps(const Genome& T, const Genome& Q, uint64_t* surv0, uint64_t* surv
                HspSet& out, unsigned long long* counters);
 
 // chain.cu : flags the members of the best collinear chain of every tile
-void chain_hsps(const HspSet& h, int max_len_bits, DevBuf<uint8_t>& in_chain);
+void chain_hsps(const HspSet& h, int len_bits, int tile_bits, DevBuf<uint8_t>& in_chain);
 
 // gapped.cu
 struct AlnSet {   // strand-local, scaffold-local, 0-based half-open
@@ -59,6 +59,8 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
 
 // align.cu
 void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& hsps, unsigned long long* h_counters);
+
+void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, AlnSet& alns, unsigned long long* h_counters);
 
 // counters layout (device, unsigned long long[16])
 enum { CNT_SURV = 0, CNT_SEED_HITS = 1, CNT_LEADERS = 2, CNT_S1_CELLS = 3, CNT_HSPS = 4, CNT_EXTENDED = 5, CNT_S2_CELLS = 6,

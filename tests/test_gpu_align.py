@@ -1,0 +1,90 @@
+"""GPU parity: the whole LASTZ stage (seeds -> HSPs -> chain -> gapped) and the self/x/map outputs, against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import annot_oracle as ao
+from oracle import lastz_oracle as lo
+from tests.helpers import synth_genome
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def M():
+    import mimeo_b200.align as A
+    import mimeo_b200.genome as G
+    return A, G
+
+
+def oracle_rows(tg, qg, p):
+    """Every alignment of every tile and strand as tuples in LASTZ output coordinates."""
+    rows = set()
+    qn = list(qg)
+    for ti, (tname, t) in enumerate(tg.items()):
+        tix = lo.TargetIndex(lo.encode(t))
+        for qi, qname in enumerate(qn):
+            qc = lo.encode(qg[qname])
+            m = len(qc)
+            for st in (0, 1):
+                q = qc if st == 0 else lo.revcomp_codes(qc)
+                for (s1, e1, s2, e2, sc, nm, nc, _a, _b) in lo.align_tile(tix, q, p).tolist():
+                    qs, qe = (s2 + 1, e2) if st == 0 else (m - e2 + 1, m - s2)
+                    rows.add((ti, qi, st, s1 + 1, e1, qs, qe, sc, nm, nc))
+    return rows
+
+
+def gpu_rows(hits):
+    from mimeo_b200.align import HIT_FIELDS
+    return set(zip(*[hits[f].tolist() for f in HIT_FIELDS]))
+
+
+@pytest.mark.parametrize('seed', [41, 42])
+def test_alignments_bit_exact_vs_oracle(M, seed):
+    A, G = M
+    g = synth_genome(seed, 3, 25_000, 3, copies=(3, 6), fam_len=(300, 2000), sub=0.10, indel=0.006, n_runs=2)
+    T = G.Genome.from_dict(g)
+    hits, stats = A.align(T, T, G.align_params(3000))
+    want = oracle_rows(g, g, lo.default_params(3000))
+    assert len(want) > 10
+    assert gpu_rows(hits) == want
+    assert stats['alignments'] == len(want) and stats['gapped_cells'] > 0
+
+
+def test_flags_chain_and_gapped_off(M):
+    A, G = M
+    g = synth_genome(43, 2, 20_000, 2, copies=(4, 5), fam_len=(500, 900), sub=0.08, indel=0.004)
+    T = G.Genome.from_dict(g)
+    for kw in (dict(chain=0), dict(gapped=0), dict(chain=0, gapped=0)):
+        hits, _ = A.align(T, T, G.align_params(3000, **kw))
+        assert gpu_rows(hits) == oracle_rows(g, g, lo.default_params(3000, **kw)), kw
+
+
+def test_self_pipeline_text_identical(M):
+    """`mimeo self --strictSelf` end to end: .tab, _intra.tab and GFF3 byte-identical to the oracle pipeline."""
+    A, G = M
+    from mimeo_b200 import coverage
+    g = synth_genome(44, 4, 30_000, 3, copies=(6, 10), fam_len=(300, 1500), sub=0.09, indel=0.005)
+    enc = {k: lo.encode(v) for k, v in g.items()}
+    tab_o, intra_o, gff_o = lo.mimeo_self(enc, minIdt=80, minLen=100, minCov=2, intraCov=2, strictSelf=True)
+    names = sorted(g)
+    T = G.Genome(names, [g[n] for n in names])
+    hits, _ = A.align(T, T, G.align_params(3000))
+    blocks = A.tab_blocks(hits, names, names, 100, 80)
+    tab, intra = ao.TAB_HEADER, ao.TAB_HEADER
+    for a in range(len(names)):
+        for b in range(len(names)):
+            rows = ''.join(blocks.get((a, b), []))
+            if a == b:
+                intra += rows
+            else:
+                tab += rows
+    assert tab == tab_o and intra == intra_o
+    assert len(tab.splitlines()) > 20
+    sizes = [len(g[n]) for n in names]
+    from tests.helpers import tab_to_arrays, segments_to_gff_rows
+    text = ao.GFF_HEADER_SELF
+    for txt, cov, label in ((tab, 2, 'Self_Repeat'), (intra, 2, 'Self_Repeat_intra')):
+        c, s, e = tab_to_arrays(txt.splitlines(), names)
+        text += ''.join(segments_to_gff_rows(coverage.coverage_segments(c, s, e, sizes, cov, 100), names, 'mimeo-self', label, 'Self_Repeat'))
+    assert text == gff_o
+    assert len(text.splitlines()) > 4
