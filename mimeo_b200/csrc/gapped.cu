@@ -19,11 +19,14 @@
 
 namespace mb2 {
 
-constexpr int GAP_W = 2048;            // circular capacity (cells) of one anti-diagonal buffer; band must stay below it
-constexpr int GAP_WM = GAP_W - 1;
+constexpr int GP_NT = 256;             // threads per CTA: one cell per thread for bands up to 512, 4 warps per scheduler hide latency
+constexpr int GP_WARPS = GP_NT / 32;
+constexpr int GP_CAP = 1024;           // circular row capacity of one anti-diagonal; the y-drop band must stay below it
+constexpr int GP_MASK = GP_CAP - 1;
 constexpr int NEG_INF = INT_MIN / 4;
-constexpr int GAP_FIELDS = 9;          // h,d,i,hm,hc,dm,dc,im,ic
-constexpr size_t GAP_SCRATCH_INTS = (size_t)3 * GAP_FIELDS * GAP_W;   // three rotating anti-diagonals
+// shared memory: A={h,hm,hc,d} for three anti-diagonals, B={i,dm,dc,im} and C={ic} for two
+constexpr int GP_SMEM_INTS = (3 * 4 + 2 * 4 + 2 * 1) * GP_CAP;
+constexpr size_t GP_SMEM_BYTES = (size_t)GP_SMEM_INTS * sizeof(int);
 
 __device__ __forceinline__ int sub_lut3(uint32_t idx) {
     const uint64_t lo = 0xE183648E85E18E5Bull, hi = 0x5B8EE1858E6483E1ull;
@@ -63,105 +66,122 @@ anchor_starts_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restri
 
 struct Ext { int score, di, dj, nmatch, ncols; };
 
-// One-sided y-drop extension. DIR=+1: cell (i,j) consumes T[ta + i - 1], Q[qa + j - 1]; DIR=-1: T[ta - i], Q[qa - j].
-// ta/qa are padded-genome coordinates of the anchor, tn/qn the bases available in that direction.
+struct WarpRec { int wmax, wi, hm, hc, alo, ahi, pad0, pad1; };
+
+// One-sided y-drop extension by the whole CTA. DIR=+1: cell (i,j) consumes T[ta+i-1], Q[qa+j-1]; DIR=-1: T[ta-i], Q[qa-j].
+// All DP state lives in shared memory, indexed circularly by the row i, as 16-byte records so that one cell costs
+// 6 vector loads and 3 vector stores:  A = {h, hm, hc, d} (three anti-diagonals kept: k, k-1, k-2),
+// B = {i, dm, dc, im} and C = {ic} (two kept). One __syncthreads per anti-diagonal.
 template <int DIR>
-__device__ Ext ydrop_extend(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E, int Y,
-                            int* __restrict__ scratch, int lane, unsigned long long& cells, int& err) {
-    int* buf[3] = {scratch, scratch + GAP_FIELDS * GAP_W, scratch + 2 * GAP_FIELDS * GAP_W};
-    int* p2 = buf[0]; int* p1 = buf[1]; int* cur = buf[2];
-#define F(b, f, i) (b)[(f) * GAP_W + ((i) & GAP_WM)]
+__device__ Ext ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E, int Y,
+                                int* __restrict__ sm, WarpRec (*rec)[GP_WARPS], const int* __restrict__ sub5,
+                                unsigned long long& cells, int& err) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int4* As = reinterpret_cast<int4*>(sm);                       // [3][CAP]
+    int4* Bs = reinterpret_cast<int4*>(sm + 12 * GP_CAP);         // [2][CAP]
+    int* Cs = sm + 20 * GP_CAP;                                   // [2][CAP]
     Ext r = {0, 0, 0, 0, 0};
-    int lo2 = 0, hi2 = -1, lo1 = 0, hi1 = 0;
-    if (lane == 0) {
-        F(p1, 0, 0) = 0; F(p1, 1, 0) = NEG_INF; F(p1, 2, 0) = NEG_INF;
-        for (int f = 3; f < GAP_FIELDS; f++) F(p1, f, 0) = 0;
+    __syncthreads();                    // previous users of the buffers are done
+    if (tid == 0) {                     // anti-diagonal 0 = the single cell (0,0), generation 0
+        As[0] = make_int4(0, 0, 0, NEG_INF); Bs[0] = make_int4(NEG_INF, 0, 0, 0); Cs[0] = 0;
     }
-    __syncwarp();
+    __syncthreads();
+    int lo2 = 0, hi2 = -1, lo1 = 0, hi1 = 0;
     int best = 0;
-    const long long kmax = (long long)tn + (long long)qn;
-    for (long long k = 1; k <= kmax; k++) {
+    const uint32_t kmax = (uint32_t)tn + (uint32_t)qn;
+    int g0 = 1, g1 = 0, g2 = 2;         // generation slots of anti-diagonals k, k-1, k-2
+    for (uint32_t k = 1; k <= kmax; k++) {
         int clo = INT_MAX, chi = INT_MIN;
         if (hi1 >= lo1) { clo = lo1; chi = hi1 + 1; }
         if (hi2 >= lo2) { clo = min(clo, lo2 + 1); chi = max(chi, hi2 + 1); }
-        if (clo == INT_MAX) break;
+        if (clo == INT_MAX) break;                                   // two dead anti-diagonals in a row
         clo = max(clo, 0);
-        if ((long long)clo < k - qn) clo = (int)(k - qn);
-        if ((long long)chi > k) chi = (int)k;
-        chi = min(chi, tn);
-        int nlo = INT_MAX, nhi = INT_MIN;
-        if (chi >= clo) {
-            if (chi - clo + 1 > GAP_W - 2) { err = 1; break; }
-            const int thr = best - Y;
-            int curbest = best;
-            for (int base = clo; base <= chi; base += 32) {
-                const int i = base + lane;
-                const int j = (int)(k - i);
-                int h = NEG_INF, d = NEG_INF, ii = NEG_INF, hm = 0, hc = 0, dm = 0, dc = 0, im = 0, ic = 0;
-                const bool in = i <= chi;
-                if (in) {
-                    if (i - 1 >= lo1 && i - 1 <= hi1) {           // up: (i-1, j) on k-1
-                        const int uh = F(p1, 0, i - 1);
-                        if (uh > NEG_INF) {
-                            const int ud = F(p1, 1, i - 1);
-                            const int open = uh - O - E, ext = ud > NEG_INF ? ud - E : NEG_INF;
-                            if (open >= ext) { d = open; dm = F(p1, 3, i - 1); dc = F(p1, 4, i - 1); }
-                            else { d = ext; dm = F(p1, 5, i - 1); dc = F(p1, 6, i - 1); }
-                        }
-                    }
-                    if (i >= lo1 && i <= hi1) {                   // left: (i, j-1) on k-1
-                        const int lh = F(p1, 0, i);
-                        if (lh > NEG_INF) {
-                            const int li = F(p1, 2, i);
-                            const int open = lh - O - E, ext = li > NEG_INF ? li - E : NEG_INF;
-                            if (open >= ext) { ii = open; im = F(p1, 3, i); ic = F(p1, 4, i); }
-                            else { ii = ext; im = F(p1, 7, i); ic = F(p1, 8, i); }
-                        }
-                    }
-                    int mval = NEG_INF, mm = 0, mc = 0;
-                    if (i >= 1 && j >= 1 && i - 1 >= lo2 && i - 1 <= hi2) {   // diagonal: (i-1, j-1) on k-2
-                        const int dh = F(p2, 0, i - 1);
-                        if (dh > NEG_INF) {
-                            const uint32_t ct = DIR > 0 ? ta + (uint32_t)i - 1u : ta - (uint32_t)i;
-                            const uint32_t cq = DIR > 0 ? qa + (uint32_t)j - 1u : qa - (uint32_t)j;
-                            const uint32_t an = isn_at(T.nm, ct) | isn_at(Q.nm, cq);
-                            const uint32_t tb = base_at(T.pk, ct), qb = base_at(Q.pk, cq);
-                            mval = dh + (an ? SCORE_N : sub_lut3((tb << 2) | qb));
-                            mm = F(p2, 3, i - 1) + ((!an && tb == qb) ? 1 : 0);
-                            mc = F(p2, 4, i - 1) + 1;
-                        }
-                    }
-                    if (mval >= d && mval >= ii) { h = mval; hm = mm; hc = mc; }
-                    else if (d >= ii) { h = d; hm = dm; hc = dc; }
-                    else { h = ii; hm = im; hc = ic; }
-                    if (h <= NEG_INF || h < thr) { h = NEG_INF; d = NEG_INF; ii = NEG_INF; }
-                    F(cur, 0, i) = h; F(cur, 1, i) = d; F(cur, 2, i) = ii;
-                    F(cur, 3, i) = hm; F(cur, 4, i) = hc; F(cur, 5, i) = dm; F(cur, 6, i) = dc; F(cur, 7, i) = im; F(cur, 8, i) = ic;
-                }
-                const bool alive = in && h > NEG_INF;
-                const uint32_t amask = __ballot_sync(0xffffffffu, alive);
-                if (amask) {
-                    if (nlo == INT_MAX) nlo = base + __ffs(amask) - 1;
-                    nhi = base + 31 - __clz(amask);
-                    const int mx = __reduce_max_sync(0xffffffffu, alive ? h : INT_MIN);
-                    if (mx > curbest) {
-                        const int src = __ffs(__ballot_sync(0xffffffffu, alive && h == mx)) - 1;
-                        curbest = mx;
-                        r.score = mx; r.di = base + src; r.dj = (int)(k - (base + src));
-                        r.nmatch = __shfl_sync(0xffffffffu, hm, src); r.ncols = __shfl_sync(0xffffffffu, hc, src);
-                    }
+        if (k > (uint32_t)qn) clo = max(clo, (int)(k - (uint32_t)qn));
+        chi = min(chi, (int)min(k, (uint32_t)tn));
+        if (chi - clo + 1 > GP_CAP - 2) { err = 1; break; }
+        const int e0 = (int)(k & 1), e1 = e0 ^ 1;
+        int4* Ac = As + g0 * GP_CAP; const int4* A1 = As + g1 * GP_CAP; const int4* A2 = As + g2 * GP_CAP;
+        int4* Bc = Bs + e0 * GP_CAP; const int4* B1 = Bs + e1 * GP_CAP;
+        int* Cc = Cs + e0 * GP_CAP; const int* C1 = Cs + e1 * GP_CAP;
+        const int thr = best - Y;
+        int tmax = INT_MIN, ti = 0, thm = 0, thc = 0, talo = INT_MAX, tahi = INT_MIN;
+        for (int i = clo + tid; i <= chi; i += GP_NT) {
+            const int j = (int)k - i;
+            const int x = i & GP_MASK, xu = (i - 1) & GP_MASK;
+            // the substitution score does not depend on the DP state: fetch it first (padding keeps these reads in bounds)
+            const uint32_t ct = DIR > 0 ? ta + (uint32_t)i - 1u : ta - (uint32_t)i;
+            const uint32_t cq = DIR > 0 ? qa + (uint32_t)j - 1u : qa - (uint32_t)j;
+            const uint32_t tb = T.codes[ct], qb = Q.codes[cq];
+            const int sc = sub5[tb * 5 + qb];
+            const int ismatch = (tb == qb && tb < 4) ? 1 : 0;
+            int h, d = NEG_INF, ii = NEG_INF, hm, hc, dm = 0, dc = 0, im = 0, ic = 0;
+            if (i - 1 >= lo1 && i - 1 <= hi1) {                       // up: (i-1, j) on k-1
+                const int4 ua = A1[xu];                               // {h, hm, hc, d}
+                if (ua.x > NEG_INF) {
+                    const int open = ua.x - O - E, ext = ua.w > NEG_INF ? ua.w - E : NEG_INF;
+                    if (open >= ext) { d = open; dm = ua.y; dc = ua.z; }
+                    else { const int4 ub = B1[xu]; d = ext; dm = ub.y; dc = ub.z; }
                 }
             }
-            cells += (unsigned long long)(chi - clo + 1);
-            best = curbest;
+            if (i >= lo1 && i <= hi1) {                               // left: (i, j-1) on k-1
+                const int4 la = A1[x];
+                if (la.x > NEG_INF) {
+                    const int4 lb = B1[x];                            // {i, dm, dc, im}
+                    const int open = la.x - O - E, ext = lb.x > NEG_INF ? lb.x - E : NEG_INF;
+                    if (open >= ext) { ii = open; im = la.y; ic = la.z; }
+                    else { ii = ext; im = lb.w; ic = C1[x]; }
+                }
+            }
+            int mval = NEG_INF, mm = 0, mc = 0;
+            if (i >= 1 && j >= 1 && i - 1 >= lo2 && i - 1 <= hi2) {   // diagonal: (i-1, j-1) on k-2
+                const int4 da = A2[xu];
+                if (da.x > NEG_INF) { mval = da.x + sc; mm = da.y + ismatch; mc = da.z + 1; }
+            }
+            if (mval >= d && mval >= ii) { h = mval; hm = mm; hc = mc; }
+            else if (d >= ii) { h = d; hm = dm; hc = dc; }
+            else { h = ii; hm = im; hc = ic; }
+            if (h <= NEG_INF || h < thr) { h = NEG_INF; d = NEG_INF; ii = NEG_INF; }
+            else {
+                talo = min(talo, i); tahi = max(tahi, i);
+                if (h > tmax) { tmax = h; ti = i; thm = hm; thc = hc; }   // i increases along the loop: first = smallest row
+            }
+            Ac[x] = make_int4(h, hm, hc, d); Bc[x] = make_int4(ii, dm, dc, im); Cc[x] = ic;
         }
-        __syncwarp();
-        int* tmp = p2; p2 = p1; p1 = cur; cur = tmp;
+        // per-warp summary: best cell (max h, then smallest row) and alive row range
+        const int wmax = __reduce_max_sync(0xffffffffu, tmax);
+        const int walo = __reduce_min_sync(0xffffffffu, talo), wahi = __reduce_max_sync(0xffffffffu, tahi);
+        int wi = 0, whm = 0, whc = 0;
+        if (wmax > best) {
+            wi = __reduce_min_sync(0xffffffffu, tmax == wmax ? ti : INT_MAX);
+            const int src = __ffs(__ballot_sync(0xffffffffu, tmax == wmax && ti == wi)) - 1;
+            whm = __shfl_sync(0xffffffffu, thm, src); whc = __shfl_sync(0xffffffffu, thc, src);
+        }
+        const int par = (int)(k & 1);
+        if (lane == 0) {
+            int4* rp = reinterpret_cast<int4*>(&rec[par][warp]);
+            rp[0] = make_int4(wmax, wi, whm, whc); rp[1] = make_int4(walo, wahi, 0, 0);
+        }
+        __syncthreads();
+        // every warp combines the per-warp records lane-parallel (lane w reads record w)
+        int4 q0 = make_int4(INT_MIN, INT_MAX, 0, 0), q1 = make_int4(INT_MAX, INT_MIN, 0, 0);
+        if (lane < GP_WARPS) {
+            const int4* rp = reinterpret_cast<const int4*>(&rec[par][lane]);
+            q0 = rp[0]; q1 = rp[1];
+        }
+        const int alo = __reduce_min_sync(0xffffffffu, q1.x), ahi = __reduce_max_sync(0xffffffffu, q1.y);
+        const int bmax = __reduce_max_sync(0xffffffffu, q0.x);
+        int bi = 0, bhm = 0, bhc = 0;
+        if (bmax > best) {
+            bi = __reduce_min_sync(0xffffffffu, q0.x == bmax ? q0.y : INT_MAX);
+            const int src = __ffs(__ballot_sync(0xffffffffu, q0.x == bmax && q0.y == bi)) - 1;
+            bhm = __shfl_sync(0xffffffffu, q0.z, src); bhc = __shfl_sync(0xffffffffu, q0.w, src);
+        }
+        if (bmax > best) { best = bmax; r.score = bmax; r.di = bi; r.dj = (int)k - bi; r.nmatch = bhm; r.ncols = bhc; }
+        cells += (unsigned long long)(chi >= clo ? chi - clo + 1 : 0);
         lo2 = lo1; hi2 = hi1;
-        if (nhi >= nlo && nlo != INT_MAX) { lo1 = nlo; hi1 = nhi; } else { lo1 = 0; hi1 = -1; }
+        if (ahi >= alo && alo != INT_MAX) { lo1 = alo; hi1 = ahi; } else { lo1 = 0; hi1 = -1; }
+        const int gt = g2; g2 = g1; g1 = g0; g0 = gt;
     }
-#undef F
-    __syncwarp();
     return r;
 }
 
@@ -205,24 +225,31 @@ __device__ int anchor_offset(const GenomeView& T, const GenomeView& Q, uint32_t 
     return bw + 15;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(GP_NT, 1)
 gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, const int32_t* __restrict__ hs1, const int32_t* __restrict__ hs2,
               const int32_t* __restrict__ hlen, const uint32_t* __restrict__ order, uint32_t nmember,
               const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
-              int O, int E, int Y, int gthr, int* __restrict__ scratch_all,
+              int O, int E, int Y, int gthr,
               int32_t* __restrict__ o_s1, int32_t* __restrict__ o_e1, int32_t* __restrict__ o_s2, int32_t* __restrict__ o_e2,
               int32_t* __restrict__ o_score, int32_t* __restrict__ o_nm, int32_t* __restrict__ o_nc, uint32_t* __restrict__ o_tile,
               uint32_t* __restrict__ o_keep, unsigned long long* __restrict__ counters) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int* scratch = scratch_all + (size_t)gwarp * GAP_SCRATCH_INTS;
+    extern __shared__ __align__(16) int gp_smem[];
+    __shared__ __align__(16) WarpRec rec[2][GP_WARPS];
+    __shared__ uint32_t sh_seg;
+    __shared__ int sh_off;
+    __shared__ int sub5[25];
+    if (threadIdx.x < 25) {
+        const int a = threadIdx.x / 5, b = threadIdx.x % 5;
+        sub5[threadIdx.x] = (a == 4 || b == 4) ? SCORE_N : c_sub[a * 4 + b];
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nseg = *nseg_p;
     unsigned long long cells = 0, anchors = 0;
     int err = 0;
     for (;;) {
-        uint32_t seg = 0;
-        if (lane == 0) seg = (uint32_t)atomicAdd(&counters[CNT_WORK], 1ull);
-        seg = __shfl_sync(0xffffffffu, seg, 0);
+        if (tid == 0) sh_seg = (uint32_t)atomicAdd(&counters[CNT_WORK], 1ull);
+        __syncthreads();
+        const uint32_t seg = sh_seg;
         if (seg >= nseg) break;
         const uint32_t a = seg_start[seg];
         const uint32_t b = (seg + 1 < nseg) ? seg_start[seg + 1] : nmember;
@@ -234,30 +261,33 @@ gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, con
         for (uint32_t x = a; x < b; x++) {
             const uint32_t g = order[x];
             const int s1 = hs1[g], s2 = hs2[g], len = hlen[g];
-            const int off = anchor_offset(T, Q, toff + s1, qoff + s2, len, lane);
-            const int a1 = s1 + off, a2 = s2 + off;
-            bool covered = false;                                 // spec D5: bounding-box test against reported alignments
-            for (uint32_t kb = 0; kb < nkept; kb += 32) {
-                const uint32_t kk = kb + lane;
-                const bool c = kk < nkept && a1 >= o_s1[a + kk] && a1 < o_e1[a + kk] && a2 >= o_s2[a + kk] && a2 < o_e2[a + kk];
-                if (__any_sync(0xffffffffu, c)) { covered = true; break; }
+            if (warp == 0) {
+                const int off = anchor_offset(T, Q, toff + s1, qoff + s2, len, lane);
+                if (lane == 0) sh_off = off;
             }
-            if (covered) continue;
+            __syncthreads();
+            const int a1 = s1 + sh_off, a2 = s2 + sh_off;
+            int cov = 0;                                          // spec D5: bounding-box test against reported alignments
+            for (uint32_t kk = tid; kk < nkept; kk += GP_NT)
+                cov |= (a1 >= o_s1[a + kk] && a1 < o_e1[a + kk] && a2 >= o_s2[a + kk] && a2 < o_e2[a + kk]) ? 1 : 0;
+            if (__syncthreads_or(cov)) continue;
             anchors++;
-            const Ext f = ydrop_extend<+1>(T, Q, toff + a1, qoff + a2, tlen - a1, qlen - a2, O, E, Y, scratch, lane, cells, err);
-            const Ext r = ydrop_extend<-1>(T, Q, toff + a1, qoff + a2, a1, a2, O, E, Y, scratch, lane, cells, err);
+            const Ext f = ydrop_extend_cta<+1>(T, Q, toff + a1, qoff + a2, tlen - a1, qlen - a2, O, E, Y, gp_smem, rec, sub5, cells, err);
+            const Ext r = ydrop_extend_cta<-1>(T, Q, toff + a1, qoff + a2, a1, a2, O, E, Y, gp_smem, rec, sub5, cells, err);
             const int score = f.score + r.score;
             if (score < gthr) continue;
-            if (lane == 0) {
+            if (tid == 0) {
                 const uint32_t o = a + nkept;
                 o_s1[o] = a1 - r.di; o_e1[o] = a1 + f.di; o_s2[o] = a2 - r.dj; o_e2[o] = a2 + f.dj;
                 o_score[o] = score; o_nm[o] = f.nmatch + r.nmatch; o_nc[o] = f.ncols + r.ncols; o_tile[o] = tl; o_keep[o] = 1;
+                __threadfence_block();
             }
             nkept++;
-            __syncwarp();
+            __syncthreads();
         }
+        __syncthreads();
     }
-    if (lane == 0) {
+    if (tid == 0) {
         if (cells) atomicAdd(&counters[CNT_GAPPED_CELLS], cells);
         if (anchors) atomicAdd(&counters[CNT_ANCHORS], anchors);
         if (err) atomicAdd(&counters[CNT_ERR], 1ull);
@@ -339,13 +369,16 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
         MB2_CUDA(cudaMemcpyAsync(&h_nmember, d_nmember.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
         if (h_nmember) {
-            const unsigned blocks = std::min<unsigned>((unsigned)cx.sm_count * 4, std::max<unsigned>(1u, (h_nseg + 3) / 4));
-            const unsigned nwarps = blocks * 4;
-            DevBuf<int> scratch((size_t)nwarps * GAP_SCRATCH_INTS);
+            static bool attr_set = false;
+            if (!attr_set) {
+                MB2_CUDA(cudaFuncSetAttribute(gapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM_BYTES));
+                attr_set = true;
+            }
+            const unsigned blocks = std::min<unsigned>((unsigned)cx.sm_count * 2, std::max<unsigned>(1u, h_nseg));   // 88 KB smem + 512 threads: 2 CTAs/SM
             MB2_CUDA(cudaMemsetAsync(counters + CNT_WORK, 0, sizeof(unsigned long long), cx.stream));
             ProfScope ps("gapped");
-            launch(gapped_kernel, blocks, 128, 0, view(T), view(Q), h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(), order, h_nmember,
-                   seg_start.get(), d_nseg.get(), p.gap_open, p.gap_extend, p.ydrop, p.gappedthresh, scratch.get(),
+            launch(gapped_kernel, blocks, GP_NT, GP_SMEM_BYTES, view(T), view(Q), h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(),
+                   order, h_nmember, seg_start.get(), d_nseg.get(), p.gap_open, p.gap_extend, p.ydrop, p.gappedthresh,
                    r_s1.get(), r_e1.get(), r_s2.get(), r_e2.get(), r_score.get(), r_nm.get(), r_nc.get(), r_tile.get(), keep.get(), counters);
         }
     }

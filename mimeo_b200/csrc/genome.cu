@@ -8,7 +8,8 @@ namespace mb2 {
 
 // one thread packs 32 bases -> one uint64 of 2-bit codes + one uint32 of N flags
 __global__ void __launch_bounds__(256)
-pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm) {
+pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm,
+            uint8_t* __restrict__ codes) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     const uint4* src = reinterpret_cast<const uint4*>(ascii + (size_t)w * 32);
@@ -33,11 +34,26 @@ pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __rest
     }
     pk[w] = bits;
     nm[w] = nflag;
+    uint32_t out[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int idx = k * 4 + b;
+            const uint32_t c = ((nflag >> idx) & 1u) ? 4u : (uint32_t)((bits >> (2 * idx)) & 3u);
+            v |= c << (8 * b);
+        }
+        out[k] = v;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(codes + (size_t)w * 32);
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
 }
 
 // reverse complement every scaffold in place of its own slot (same offsets, same lengths)
 __global__ void __launch_bounds__(256)
-revcomp_kernel(GenomeView src, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm, uint32_t nwords) {
+revcomp_kernel(GenomeView src, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm, uint8_t* __restrict__ codes, uint32_t nwords) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     const uint32_t p0 = w * 32;
@@ -57,6 +73,7 @@ revcomp_kernel(GenomeView src, uint64_t* __restrict__ pk, uint32_t* __restrict__
         }
         bits |= (uint64_t)code << (2 * c);
         nflag |= bad << c;
+        codes[(size_t)p0 + c] = bad ? 4 : (uint8_t)code;
     }
     pk[w] = bits;
     nm[w] = nflag;
@@ -84,7 +101,7 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         layout(*g, lens, n);
         Ctx& cx = ctx();
         // stage ASCII with 'N' padding in pinned host memory, one H2D copy, pack on the device
-        const size_t nbytes = g->G + 64;
+        const size_t nbytes = g->G + 64;   // = (G/32 + 2) * 32
         uint8_t* h = nullptr;
         MB2_CUDA(cudaMallocHost((void**)&h, nbytes));
         memset(h, 'N', nbytes);
@@ -92,11 +109,11 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         DevBuf<uint8_t> d_ascii(nbytes);
         MB2_CUDA(cudaMemcpyAsync(d_ascii.get(), h, nbytes, cudaMemcpyHostToDevice, cx.stream));
         const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
-        g->pk.alloc(nwords); g->nm.alloc(nwords);
+        g->pk.alloc(nwords); g->nm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
         g->d_off.alloc(n); g->d_len.alloc(n);
         MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), g->off.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
         MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), g->len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
-        launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get());
+        launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get(), g->codes.get());
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
         cudaFreeHost(h);
     } catch (...) { delete g; throw; }
@@ -108,12 +125,12 @@ Genome* genome_revcomp(const Genome& src) {
     try {
         g->nscaf = src.nscaf; g->off = src.off; g->len = src.len; g->G = src.G; g->nbases = src.nbases; g->is_rc = !src.is_rc;
         const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
-        g->pk.alloc(nwords); g->nm.alloc(nwords);
+        g->pk.alloc(nwords); g->nm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
         g->d_off.alloc(src.nscaf); g->d_len.alloc(src.nscaf);
         Ctx& cx = ctx();
         MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), src.d_off.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
         MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), src.d_len.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
-        launch(revcomp_kernel, cdiv(nwords, 256), 256, 0, view(src), g->pk.get(), g->nm.get(), nwords);
+        launch(revcomp_kernel, cdiv(nwords, 256), 256, 0, view(src), g->pk.get(), g->nm.get(), g->codes.get(), nwords);
     } catch (...) { delete g; throw; }
     return g;
 }

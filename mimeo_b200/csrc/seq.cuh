@@ -23,6 +23,7 @@ struct Genome {
     uint64_t nbases = 0;              // sum of scaffold lengths
     DevBuf<uint64_t> pk;              // G/32 + 2 words
     DevBuf<uint32_t> nm;              // G/32 + 2 words
+    DevBuf<uint8_t> codes;            // 1 byte/base: 0..3 = ACGT, 4 = other/pad (gapped DP reads single bases)
     DevBuf<uint32_t> d_off, d_len;
     bool is_rc = false;
 };
@@ -30,12 +31,13 @@ struct Genome {
 struct GenomeView {   // what kernels receive
     const uint64_t* __restrict__ pk;
     const uint32_t* __restrict__ nm;
+    const uint8_t* __restrict__ codes;
     const uint32_t* __restrict__ off;
     const uint32_t* __restrict__ len;
     int nscaf;
     uint32_t G;
 };
-inline GenomeView view(const Genome& g) { return GenomeView{g.pk.get(), g.nm.get(), g.d_off.get(), g.d_len.get(), g.nscaf, (uint32_t)g.G}; }
+inline GenomeView view(const Genome& g) { return GenomeView{g.pk.get(), g.nm.get(), g.codes.get(), g.d_off.get(), g.d_len.get(), g.nscaf, (uint32_t)g.G}; }
 
 // HOXD70 as LASTZ's default, row = target base, col = query base (index t*4+q)
 static __constant__ int c_sub[16] = {91, -114, -31, -123, -114, 100, -125, -31, -31, -125, 100, -114, -123, -31, -114, 91};
