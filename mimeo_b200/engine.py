@@ -1,0 +1,138 @@
+"""
+engine.py -- the replacement of mimeo's generated bash script (wrappers.py:899-1271, 683-896, 525-680
+executed by utils.run_cmd, utils.py:213-254): the same stages, run through libmimeo_b200 on the GPU.
+
+    align_pairs()      = every `lastz T Q ...` + sed/awk/awk/awk/sed/sort >> outtab     (wrappers.py:1015-1104)
+    coverage_to_gff()  = awk BED | sort | genomecov | awk cov | sort | merge | awk GFF  (wrappers.py:1106-1177)
+
+Text in / text out is byte-compatible with the reference (10-column .tab, GFF3); everything between
+is device arrays. There is no CPU fallback: without the CUDA library these functions raise.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import align as _align
+from . import coverage as _coverage
+from .fasta import read_fasta
+from .genome import Genome, align_params
+
+TAB_HEADER = '#name1\tstrand1\tstart1\tend1\tname2\tstrand2\tstart2+\tend2+\tscore\tidentity\n'
+GFF_HEADER = '##gff-version 3\n#seqid\tsource\ttype\tstart\tend\tscore\tstrand\tphase\tattributes\n'
+
+
+def c_sorted(names: Iterable[str]) -> List[str]:
+    """`sort -k 1,1` order in the C locale (byte order)."""
+    return sorted(names, key=lambda s: s.encode())
+
+
+# ------------------------------------------------------------------------------------------ alignment -> .tab
+def load_files(paths: Sequence[str]) -> Tuple[List[str], List[np.ndarray], Dict[str, int]]:
+    """One scaffold per file as LASTZ sees it: name = first word of the first header. Returns names, seqs, path->index."""
+    names, seqs, index = [], [], {}
+    for p in paths:
+        recs = read_fasta(p)
+        if not recs:
+            raise RuntimeError(f'no FASTA record in {p}')
+        if len(recs) > 1:
+            logging.warning('%s holds %d records; only the first is aligned (mimeo expects one per file)', p, len(recs))
+        index[p] = len(names)
+        names.append(recs[0][0])
+        seqs.append(recs[0][2])
+    return names, seqs, index
+
+
+def align_genomes(tnames, tseqs, qnames, qseqs, hspthresh=3000, same=False):
+    """Device genomes + all-pairs alignment. Returns (hits dict, stats dict)."""
+    T = Genome(tnames, tseqs)
+    Q = T if same else Genome(qnames, qseqs)
+    try:
+        return _align.align(T, Q, align_params(hspthresh))
+    finally:
+        if Q is not T:
+            Q.close()
+        T.close()
+
+
+def align_pairs(pairs: Sequence[Tuple[str, str]], outtab: str, minIdt, minLen, hspthresh=3000,
+                outtab_intra: Optional[str] = None) -> Dict[str, int]:
+    """All (target file, query file) pairs -> filtered, per-pair sorted rows appended to outtab in pair order.
+    With outtab_intra, pairs whose two paths are identical go there instead (--strictSelf, wrappers.py:1016)."""
+    tpaths = list(dict.fromkeys(a for a, _ in pairs))
+    qpaths = list(dict.fromkeys(b for _, b in pairs))
+    same = tpaths == qpaths
+    tnames, tseqs, tidx = load_files(tpaths)
+    if same:
+        qnames, qseqs, qidx = tnames, tseqs, tidx
+    else:
+        qnames, qseqs, qidx = load_files(qpaths)
+    hits, stats = align_genomes(tnames, tseqs, qnames, qseqs, hspthresh, same)
+    blocks = _align.tab_blocks(hits, tnames, qnames, minLen, minIdt)
+    with open(outtab, 'a') as ft:
+        fi = open(outtab_intra, 'a') if outtab_intra else None
+        try:
+            for a, b in pairs:
+                rows = blocks.get((tidx[a], qidx[b]))
+                if rows:
+                    (fi if (fi is not None and a == b) else ft).write(''.join(rows))
+        finally:
+            if fi is not None:
+                fi.close()
+    return stats
+
+
+# ------------------------------------------------------------------------------------------ .tab -> GFF3
+def read_lens(path: str) -> Dict[str, int]:
+    sizes = {}
+    with open(path) as f:
+        for line in f:
+            p = line.rstrip('\n').split('\t')
+            if len(p) >= 2 and p[0]:
+                sizes[p[0]] = int(p[1])
+    return sizes
+
+
+def parse_tab_hits(path: str):
+    """Columns 1,3,4 of every non-'#' line (what awk '!/^#/ {print $1,$3,$4;}' projects, wrappers.py:1121)."""
+    import pandas as pd
+    try:
+        df = pd.read_csv(path, sep='\t', comment='#', header=None, usecols=[0, 2, 3], dtype={0: str, 2: np.int64, 3: np.int64},
+                         skip_blank_lines=True, engine='c')
+    except pd.errors.EmptyDataError:
+        return [], np.zeros(0, np.int64), np.zeros(0, np.int64)
+    except (ValueError, pd.errors.ParserError):
+        df = pd.read_csv(path, sep=r'\s+', comment='#', header=None, usecols=[0, 2, 3], dtype={0: str, 2: np.int64, 3: np.int64},
+                         skip_blank_lines=True, engine='python')
+    return df[0].tolist(), df[2].to_numpy(), df[3].to_numpy()
+
+
+def coverage_rows(tab_path: str, sizes: Dict[str, int], cov, minLen, source: str, label: str, prefix) -> List[str]:
+    """GFF3 feature rows of one coverage block."""
+    names, start, end = parse_tab_hits(tab_path)
+    if not len(names):
+        return []
+    order = c_sorted(set(names))
+    missing = [n for n in order if n not in sizes]
+    if missing:
+        raise RuntimeError(f'chromosome {missing[0]!r} found in {tab_path} but not in the genome length file')
+    if (start < 0).any() or (start > end).any() or (end > 0x7fffffff).any():
+        raise RuntimeError(f'malformed hit in {tab_path}: start must be >= 0 and <= end')
+    idx = {n: i for i, n in enumerate(order)}
+    chrom = np.fromiter((idx[n] for n in names), dtype=np.int32, count=len(names))
+    c, s, e = _coverage.coverage_segments(chrom, start.astype(np.int32), end.astype(np.int32), [sizes[n] for n in order],
+                                          int(cov), int(minLen))
+    return [f'{order[int(c[k])]}\t{source}\t{label}\t{int(s[k])}\t{int(e[k])}\t.\t+\t.\tID={prefix}_{k + 1:05d}\n' for k in range(len(c))]
+
+
+def coverage_to_gff(tab_path: str, lens_path: str, outgff: str, cov, minLen, source: str, label: str, prefix,
+                    write_header: bool = True) -> int:
+    rows = coverage_rows(tab_path, read_lens(lens_path), cov, minLen, source, label, prefix)
+    with open(outgff, 'w' if write_header else 'a') as f:
+        if write_header:
+            f.write(GFF_HEADER)
+        f.write(''.join(rows))
+    return len(rows)

@@ -1,0 +1,60 @@
+"""`mimeo x` (host mirror of src/mimeo/run_interspecies.py)."""
+import argparse
+import logging
+import os
+import shutil
+from typing import List
+
+from ._cli_common import add_loglevel, add_version
+from .logs import init_logging
+from .utils import chromlens, get_all_pairs, run_cmd, set_paths
+from .wrappers import xspecies_LZ_cmds
+
+
+def mainArgs() -> argparse.Namespace:
+    parser = argparse.ArgumentParser(
+        description='Cross-species repeat finder. Mimeo-x searches for features which are abundant in an external reference genome.',
+        prog='mimeo-x')
+    add_version(parser)
+    parser.add_argument('--adir', type=str, default=None, help='Name of directory containing sequences from A genome.')
+    parser.add_argument('--bdir', type=str, default=None, help='Name of directory containing sequences from B genome.')
+    parser.add_argument('--afasta', type=str, default=None, help='A genome as multifasta.')
+    parser.add_argument('--bfasta', type=str, default=None, help='B genome as multifasta.')
+    parser.add_argument('-r', '--recycle', action='store_true', help='Use existing alignment "--outfile" if found.')
+    parser.add_argument('-d', '--outdir', type=str, default=None, help='Write output files to this directory. (Default: cwd)')
+    parser.add_argument('--gffout', type=str, default='mimeo_B_in_A.gff3', help='Name of GFF3 annotation file.')
+    parser.add_argument('--outfile', type=str, default='mimeo_alignment.tab', help='Name of alignment result file.')
+    parser.add_argument('--verbose', action='store_true', default=False, help='If set report alignment stage counters.')
+    parser.add_argument('--label', type=str, default='B_Repeat', help='Set annotation TYPE field in gff.')
+    parser.add_argument('--prefix', type=str, default='B_Repeat', help='ID prefix for B-genome repeats annotated in A-genome.')
+    parser.add_argument('--keeptemp', action='store_true', default=False, help='If set do not remove temp files.')
+    parser.add_argument('--lzpath', type=str, default='lastz', help='Accepted for compatibility; alignment runs on the GPU.')
+    parser.add_argument('--bedtools', type=str, default='bedtools', help='Accepted for compatibility; coverage runs on the GPU.')
+    parser.add_argument('--minIdt', type=int, default=60, help='Minimum alignment identity to report.')
+    parser.add_argument('--minLen', type=int, default=100, help='Minimum alignment length to report.')
+    parser.add_argument('--minCov', type=int, default=5, help='Minimum depth of B-genome hits to report feature in A-genome.')
+    parser.add_argument('--hspthresh', type=int, default=3000, help='Set HSP min score threshold.')
+    add_loglevel(parser)
+    return parser.parse_args()
+
+
+def main() -> None:
+    args = mainArgs()
+    init_logging(loglevel=args.loglevel)
+    logging.info('Starting interspecies comparison workflow.')
+    adir_path, bdir_path, outdir, outtab, gffout, tempdir = set_paths(
+        adir=args.adir, bdir=args.bdir, afasta=args.afasta, bfasta=args.bfasta, outdir=args.outdir, outtab=args.outfile,
+        gffout=args.gffout)
+    pairs = get_all_pairs(Adir=adir_path, Bdir=bdir_path)
+    lenPathA = os.path.join(outdir, 'A_gen_lens.txt')
+    chromlens(seqDir=adir_path, outfile=lenPathA)
+    # like the reference (run_interspecies.py:233-248) --hspthresh is NOT forwarded: mimeo x always uses 3000
+    cmds: List[str] = xspecies_LZ_cmds(
+        lzpath=args.lzpath, bdtlsPath=args.bedtools, pairs=pairs, Adir=adir_path, Bdir=bdir_path, outtab=outtab, outgff=gffout,
+        minIdt=args.minIdt, minLen=args.minLen, minCov=args.minCov, AchrmLens=lenPathA, reuseTab=args.recycle, label=args.label,
+        prefix=args.prefix)
+    logging.info('Running alignments...')
+    run_cmd(cmds, verbose=args.verbose, keeptemp=args.keeptemp)
+    if tempdir and os.path.isdir(tempdir) and not args.keeptemp:
+        shutil.rmtree(tempdir)
+    logging.info('Finished!')

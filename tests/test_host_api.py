@@ -1,0 +1,140 @@
+"""CPU tests of the host mirror of the reference's Python interface (no GPU work is triggered here)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from mimeo_b200 import fasta, utils, wrappers
+from tests.helpers import GOLDEN, read_golden
+
+MAN = json.loads(read_golden('manifest.json'))
+
+
+def test_import_align_and_gff_match_reference_pandas_output():
+    m = MAN['map']
+    df = wrappers.import_Align(infile=os.path.join(GOLDEN, 'map.tab'), prefix=m['prefix'], minLen=m['minLen'], minIdt=m['minIdt'])
+    assert list(df.columns) == ['tName', 'tStrand', 'tStart', 'tEnd', 'qName', 'qStrand', 'qStart', 'qEnd', 'score', 'pID', 'UID']
+    assert df.index[0] == 1
+    got = ''.join(wrappers.writeGFFlines(alnDF=df, chrlens=[tuple(x) for x in m['chrlens']], ftype=m['ftype']))
+    assert got == read_golden('map.gff3')
+
+
+def test_import_align_string_sort_and_default_prefix():
+    df = wrappers.import_Align(infile=os.path.join(GOLDEN, 'map_kat7.tab'), prefix=None, minLen=100, minIdt=95)
+    assert ''.join(wrappers.writeGFFlines(alnDF=df, chrlens=None, ftype='HGT')) == read_golden('map_kat7.gff3')
+    assert df['tStart'].tolist() == ['1000', '200', '200', '99']          # strings, lexicographic
+
+
+def test_import_align_exits_when_empty(tmp_path):
+    p = tmp_path / 'e.tab'
+    p.write_text('#h\nc\t+\t5\t104\tq\t+\t1\t100\t9000\t96.0\n')
+    with pytest.raises(SystemExit) as e:
+        wrappers.import_Align(infile=str(p), prefix='x', minLen=100, minIdt=95)     # 104-5 = 99
+    assert e.value.code == 1
+
+
+def test_split_fasta_chromlens_pairs(tmp_path):
+    fa = tmp_path / 'g.fa'
+    fa.write_text('>s2 desc here\nACGTACGTAC\nGT\n>S3\n' + 'A' * 130 + '\n>s10\nNNNN\n')
+    d = tmp_path / 'split'
+    d.mkdir()
+    utils.splitFasta(str(fa), str(d))
+    assert sorted(os.listdir(d)) == ['S3.fa', 's10.fa', 's2.fa']
+    assert (d / 's2.fa').read_text() == '>s2 desc here\nACGTACGTACGT\n'
+    assert (d / 'S3.fa').read_text() == '>S3\n' + 'A' * 60 + '\n' + 'A' * 60 + '\n' + 'A' * 10 + '\n'
+    lens = utils.chromlens(str(d), str(tmp_path / 'lens.txt'))
+    assert lens == [('S3', '130'), ('s10', '4'), ('s2', '12')]
+    assert (tmp_path / 'lens.txt').read_text() == 'S3\t130\ns10\t4\ns2\t12\n'
+    pairs = utils.get_all_pairs(str(d))
+    assert len(pairs) == 9 and pairs[0][0] == pairs[0][1]
+    pairs = utils.get_all_pairs(str(d), str(d))
+    assert len(pairs) == 9
+    with pytest.raises(SystemExit):
+        utils.get_all_pairs(None, None)
+
+
+def test_split_fasta_rejects_duplicate_ids(tmp_path):
+    fa = tmp_path / 'g.fa'
+    fa.write_text('>a\nAC\n>a\nGT\n')
+    (tmp_path / 'o').mkdir()
+    with pytest.raises(SystemExit):
+        utils.splitFasta(str(fa), str(tmp_path / 'o'))
+
+
+def test_set_paths_layout(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    fa = tmp_path / 'g.fa'
+    fa.write_text('>a\nACGT\n')
+    adir, bdir, outdir, outtab, gffout, tempdir = utils.set_paths(afasta=str(fa), outtab='o.tab', gffout='o.gff3', suppresBdir=True)
+    assert bdir is None and tempdir and adir == os.path.join(tempdir, 'A_genome_split') and os.path.isfile(os.path.join(adir, 'a.fa'))
+    assert outdir == str(tmp_path) and outtab == str(tmp_path / 'o.tab') and gffout == str(tmp_path / 'o.gff3')
+    adir2, bdir2, *_ = utils.set_paths(adir=str(tmp_path / 'A'), afasta=str(fa), bdir=str(tmp_path / 'B'), bfasta=str(fa))
+    assert os.path.isfile(os.path.join(adir2, 'a.fa')) and os.path.isfile(os.path.join(bdir2, 'a.fa'))
+
+
+def ops(cmds):
+    return [json.loads(c[len(utils.OP_PREFIX):]) for c in cmds]
+
+
+def test_self_cmds_mirror_reference_stage_structure(tmp_path):
+    """Same stage sequence as the reference's command list (golden: tests/golden/self_cmds.json)."""
+    ref = json.loads(read_golden('self_cmds.json'))
+    n_lastz = sum(1 for c in ref if c.startswith('lastz '))
+    n_cov = sum(1 for c in ref if 'genomecov' in c)
+    pairs = [('A/x.fa', 'A/x.fa'), ('A/x.fa', 'A/y.fa')]
+    o = ops(wrappers.self_LZ_cmds(splitSelf=True, pairs=pairs, outtab=str(tmp_path / 'o.tab'), outgff='o.gff3', AchrmLens='lens.txt', prefix='P'))
+    assert [x['op'] for x in o] == ['write', 'write', 'align', 'echo', 'coverage', 'echo', 'coverage']
+    assert len(o[2]['pairs']) == n_lastz and sum(1 for x in o if x['op'] == 'coverage') == n_cov
+    assert o[2]['outtab_intra'] == str(tmp_path / 'o.tab') + '_intra.tab'
+    assert (o[4]['cov'], o[4]['label'], o[4]['write_header']) == (3, 'Self_repeats', True)
+    assert (o[6]['cov'], o[6]['label'], o[6]['write_header'], o[6]['tab']) == (5, 'Self_repeats_intra', False, o[2]['outtab_intra'])
+    assert o[0]['text'] == '#name1\tstrand1\tstart1\tend1\tname2\tstrand2\tstart2+\tend2+\tscore\tidentity\n'
+
+
+def test_recycle_skips_alignment_and_warns_without_intra(tmp_path, caplog):
+    tab = tmp_path / 'o.tab'
+    tab.write_text('#h\n')
+    o = ops(wrappers.self_LZ_cmds(splitSelf=True, pairs=[('a', 'a')], outtab=str(tab), outgff='g', AchrmLens='l', reuseTab=True, prefix='P'))
+    assert [x['op'] for x in o] == ['echo', 'coverage']                   # intra file missing -> warning, no intra block
+    assert 'Could not find intra-chrom results file' in caplog.text
+    o = ops(wrappers.xspecies_LZ_cmds(pairs=[('a', 'b')], outtab=str(tab), outgff='g', AchrmLens='l', reuseTab=True, prefix='P'))
+    assert [x['op'] for x in o] == ['echo', 'coverage'] and o[1]['source'] == 'mimeo' and o[1]['cov'] == 5
+    o = ops(wrappers.xspecies_LZ_cmds(pairs=[('a', 'b')], outtab=str(tmp_path / 'new.tab'), outgff='g', AchrmLens='l', reuseTab=True, prefix='P'))
+    assert [x['op'] for x in o] == ['write', 'align', 'echo', 'coverage'] and o[1]['hspthresh'] == 3000
+
+
+def test_map_cmds_validation():
+    with pytest.raises(ValueError):
+        wrappers.map_LZ_cmds(pairs=[], outfile='x')
+    with pytest.raises(ValueError):
+        wrappers.map_LZ_cmds(pairs=[('a', 'b')], outfile=None)
+    o = ops(wrappers.map_LZ_cmds(pairs=[('a', 'b')], outfile='x.tab', minIdt=90))
+    assert [x['op'] for x in o] == ['write', 'align'] and o[1]['minIdt'] == 90
+
+
+def test_run_cmd_never_shells_out(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    with pytest.raises(RuntimeError):
+        utils.run_cmd(['echo pwned > x'])
+    assert not (tmp_path / 'x').exists()
+    assert [d for d in os.listdir(tmp_path) if d.startswith('tmp.')] == []      # temp dir removed
+    utils.run_cmd([wrappers._op(op='write', path=str(tmp_path / 'h.tab'), text='hi\n')], keeptemp=True)
+    assert (tmp_path / 'h.tab').read_text() == 'hi\n'
+    assert len([d for d in os.listdir(tmp_path) if d.startswith('tmp.')]) == 1
+
+
+def test_cli_surfaces_match_reference_defaults(monkeypatch):
+    from mimeo_b200 import run_interspecies, run_map, run_self
+    monkeypatch.setattr(sys, 'argv', ['mimeo-self'])
+    a = run_self.mainArgs()
+    assert (a.minIdt, a.minLen, a.minCov, a.hspthresh, a.intraCov, a.strictSelf, a.gffout, a.outfile, a.label, a.prefix, a.lzpath, a.bedtools) == \
+        (60, 100, 3, 3000, 5, False, 'mimeo-self_repeats.gff3', 'mimeo_alignment.tab', 'Self_Repeat', 'Self_Repeat', 'lastz', 'bedtools')
+    monkeypatch.setattr(sys, 'argv', ['mimeo-x', '--minIdt', '80'])
+    a = run_interspecies.mainArgs()
+    assert (a.minIdt, a.minCov, a.gffout, a.label, a.prefix) == (80, 5, 'mimeo_B_in_A.gff3', 'B_Repeat', 'B_Repeat') and isinstance(a.minIdt, int)
+    monkeypatch.setattr(sys, 'argv', ['mimeo-map'])
+    a = run_map.mainArgs()
+    assert (a.gffout, a.label, a.prefix, a.maxtandem, a.tmaxperiod) == (None, 'BHit', 'BHit', None, 50)
