@@ -137,7 +137,114 @@ class CoverageWorkload:
         return dt, 1, 'full workload (10M hits / 100 Mbp), arrays already parsed; single-threaded C port of genomecov+merge'
 
 
-WORKLOADS = {'cov': CoverageWorkload}
+
+def _oracle_pair_job(args):
+    """One (target, query) scaffold pair through the CPU LASTZ-restatement (both strands) -- runs in a worker process."""
+    tcodes, qcodes, hspthresh = args
+    from oracle import lastz_oracle as lo
+    st = lo.Stats()
+    t0 = time.perf_counter()
+    tix = lo.TargetIndex(tcodes)          # LASTZ rebuilds its seed table for every pair: that cost belongs to the baseline
+    p = lo.default_params(hspthresh)
+    n = 0
+    for q in (qcodes, lo.revcomp_codes(qcodes)):
+        n += len(lo.align_tile(tix, q, p, st))
+    return time.perf_counter() - t0, n, st.as_dict()
+
+
+class SelfWorkload:
+    """BASELINE config 1: `mimeo self` on a synthetic 5 Mbp genome (10 scaffolds x 500 kbp, 20 planted repeat families of
+    5-30 copies at ~80 % pairwise identity), minIdt 80, minLen 100, minCov 3, intraCov 4, --strictSelf.
+    Under N ranks every rank annotates its own genome of the batch (weak scaling: one genome per GPU, no collective)."""
+    name = 'C1: mimeo self, synthetic 5 Mbp genome (10 x 500 kbp, 20 repeat families at ~80% identity), minIdt 80 minLen 100 minCov 3 intraCov 4 strictSelf'
+    NSCAF, SCAF_LEN, NFAM = 10, 500_000, 20
+    MIN_IDT, MIN_LEN, MIN_COV, INTRA_COV, HSPTHRESH = 80, 100, 3, 4, 3000
+    dtype = 'int32'
+
+    def __init__(self, rank):
+        from tests.helpers import synth_genome
+        g = synth_genome(1001 + rank, self.NSCAF, self.SCAF_LEN, self.NFAM, copies=(5, 30), fam_len=(300, 3000), sub=0.106, indel=0.005)
+        self.names = sorted(g, key=lambda s: s.encode())
+        self.seqs = [g[n] for n in self.names]
+        self.sizes = [len(x) for x in self.seqs]
+        self.mbp = sum(self.sizes) / 1e6
+
+    def to_device(self, torch, dev):
+        from mimeo_b200.genome import Genome
+        self.pinned = [torch.from_numpy(x.copy()).pin_memory() for x in self.seqs]
+        self.T = Genome(self.names, self.seqs)
+        self.Trc = self.T.revcomp()
+        self.h2d_bytes = sum(self.sizes)
+
+    def step_resident(self):
+        from mimeo_b200 import engine
+        inter, intra, hits, stats = engine.self_segments(self.T, self.Trc, self.sizes, self.MIN_IDT, self.MIN_LEN, self.MIN_COV,
+                                                         self.INTRA_COV, self.HSPTHRESH, True)
+        self.stats, self.nhits, self.nseg = stats, len(hits['t_id']), len(inter[0]) + len(intra[0])
+        return inter, intra
+
+    def step_e2e(self):
+        """Host ASCII (pinned) in -> .tab rows and GFF3 rows out, every copy inside."""
+        from mimeo_b200 import align as A, engine
+        from mimeo_b200.genome import Genome
+        T = Genome(self.names, [t.numpy() for t in self.pinned])
+        try:
+            inter, intra, hits, stats = engine.self_segments(T, None, self.sizes, self.MIN_IDT, self.MIN_LEN, self.MIN_COV,
+                                                             self.INTRA_COV, self.HSPTHRESH, True)
+        finally:
+            T.close()
+        blocks = A.tab_blocks(hits, self.names, self.names, self.MIN_LEN, self.MIN_IDT)
+        ntab = sum(len(v) for v in blocks.values())
+        gff = [f'{self.names[int(c)]}\tmimeo-self\tSelf_Repeat\t{int(s)}\t{int(e)}\t.\t+\t.\tID=Self_Repeat_{k + 1:05d}\n'
+               for k, (c, s, e) in enumerate(zip(*inter))]
+        self.d2h_bytes = 40 * len(hits['t_id']) + 12 * (len(inter[0]) + len(intra[0]))
+        return ntab, len(gff)
+
+    def kernel_bytes(self):
+        """Algorithmic bytes of the HBM-bound seeding kernels, per strand-launch."""
+        Q = T = sum(self.sizes)
+        S = self.stats['seed_hits'] / 2.0
+        S_out = self.stats['survivors'] / 2.0
+        return {
+            'seed_table_build': T // 4 * 2 + 4 * T + 2 * 4 * (1 << 24),
+            'seed_scan': Q // 4 + Q * 13 * 4 + 4 * S + 8 * S_out,
+        }
+
+    def int_cells(self):
+        return {'seed_scan': self.stats['stage1_cells'], 'hsp_extend': self.stats['stage2_cells'], 'gapped': self.stats['gapped_cells']}
+
+    def cpu_reference(self, threads, npairs=None):
+        """CPU LASTZ-restatement on a bounded, stratified sample of the 100 ordered scaffold pairs (always includes self
+        pairs in proportion), extrapolated by pair count; plus nothing else (annotation stages are negligible here)."""
+        from concurrent.futures import ProcessPoolExecutor
+        from oracle import lastz_oracle as lo
+        enc = [lo.encode(x) for x in self.seqs]
+        n = len(enc)
+        if npairs is None:
+            npairs = max(2, min(n * n, 2 * threads))
+        # stratified: one self pair per ceil(n) sampled pairs, like the full schedule (n self pairs of n*n)
+        rng = np.random.default_rng(7)
+        pairs = [(0, 0)] + [tuple(map(int, rng.integers(0, n, 2))) for _ in range(npairs - 1)]
+        pairs = [(a, b if (k == 0 or a != b) else (b + 1) % n) for k, (a, b) in enumerate(pairs)]
+        jobs = [(enc[a], enc[b], self.HSPTHRESH) for a, b in pairs]
+        t0 = time.perf_counter()
+        if threads > 1:
+            with ProcessPoolExecutor(max_workers=threads) as ex:
+                res = list(ex.map(_oracle_pair_job, jobs))
+        else:
+            res = [_oracle_pair_job(j) for j in jobs]
+        wall = time.perf_counter() - t0
+        n_self = sum(1 for a, b in pairs if a == b)
+        t_self = np.mean([r[0] for (a, b), r in zip(pairs, res) if a == b])
+        t_cross = np.mean([r[0] for (a, b), r in zip(pairs, res) if a != b])
+        cpu_seconds_full = n * t_self + n * (n - 1) * t_cross           # all n*n ordered pairs, one core
+        est = cpu_seconds_full / threads if threads > 1 else cpu_seconds_full
+        sample = (f'{len(pairs)} of {n * n} ordered scaffold pairs ({n_self} self) through the C LASTZ-restatement incl. per-pair seed-table '
+                  f'build, both strands; {wall:.1f} s wall on {threads} process(es); full-genome time extrapolated by pair class: '
+                  f'{cpu_seconds_full:.0f} core-seconds')
+        return est, threads, sample
+
+WORKLOADS = {'self': SelfWorkload, 'cov': CoverageWorkload}
 
 
 # ------------------------------------------------------------------------------------------------- arms
@@ -219,19 +326,40 @@ def run_b200(args):
     ms_step = maxreduce(total_ms / args.steps)
     value = world * wl.mbp / (ms_step / 1e3)
 
-    # ---- roofline of the dominant kernel (same timed region, CUDA events on the library stream)
+    # ---- roofline of the dominant HBM-bound kernel (same timed region, CUDA events on the library stream)
     peak, peak_src = measured_peaks()
     kb = wl.kernel_bytes()
-    prof = {t: _lib.prof_get(t) for t in kb if not t.startswith('_')}
-    dom = max(prof, key=lambda t: prof[t][0])
+    tags = [t for t in kb if not t.startswith('_')]
+    all_tags = tags + [t for t in ('surv_sort', 'hsp_extend', 'hsp_sort', 'chain', 'gapped', 'cov_events', 'cov_bin_events', 'cov_tile') if t not in tags]
+    prof = {t: _lib.prof_get(t) for t in all_tags}
+    dom = max(tags, key=lambda t: prof[t][0])
     dms, dcnt = prof[dom]
     per_launch_ms = dms / max(dcnt, 1)
     achieved = kb[dom] / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'ms_per_launch': per_launch_ms,
-                'kernels_ms_per_step': {t: prof[t][0] / args.steps for t in prof},
-                'stage_survey_model': {'bytes': kb['_stage_survey'], 'achieved': kb['_stage_survey'] / (ms_step / 1e3) / 1e9,
-                                       'frac': kb['_stage_survey'] / (ms_step / 1e3) / 1e9 / peak}}
+                'traffic': None, 'peak_source': peak_src, 'ms_per_launch': per_launch_ms, 'algorithmic_bytes_per_launch': kb[dom],
+                'kernels_ms_per_step': {t: prof[t][0] / args.steps for t in all_tags if prof[t][1]}}
+    if '_stage_survey' in kb:
+        roofline['stage_survey_model'] = {'bytes': kb['_stage_survey'], 'achieved': kb['_stage_survey'] / (ms_step / 1e3) / 1e9,
+                                          'frac': kb['_stage_survey'] / (ms_step / 1e3) / 1e9 / peak}
+    extra = {}
+    if hasattr(wl, 'int_cells'):
+        # integer-pipe kernels: GCUPS = DP/extension cells actually evaluated / kernel seconds
+        cells = wl.int_cells()
+        sm = _lib.lib().mb2_sm_count()
+        int_peak = sm * 128 * 1.965e9                                   # INT32 lane-ops/s at max clock
+        budget = {'seed_scan': 6, 'hsp_extend': 6, 'gapped': 12}
+        gc = {}
+        for t, c in cells.items():
+            ms = prof[t][0] / args.steps
+            if ms > 0:
+                g = c / (ms / 1e3) / 1e9
+                gc[t] = {'gcups': g, 'cells_per_step': c, 'ms_per_step': ms, 'frac_of_int_roofline': g * 1e9 * budget[t] / int_peak}
+        tot_cells = sum(cells.values())
+        tot_ms = sum(prof[t][0] for t in cells) / args.steps
+        extra['gcups'] = {'value': tot_cells / (tot_ms / 1e3) / 1e9 if tot_ms > 0 else 0.0, 'unit': 'GCUPS (ungapped + gapped cells / kernel seconds)',
+                          'per_kernel': gc, 'int_roofline_ops_per_s': int_peak, 'ops_per_cell_budget': budget}
+        extra['stage_counters'] = wl.stats
 
     # ---- end-to-end arm through the host-buffer C ABI (H2D + D2H inside the timed region)
     for _ in range(max(1, args.warmup // 2)):
@@ -258,8 +386,8 @@ def run_b200(args):
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': wl.dtype, 'data': 'synthetic',
             'config': {'workload': wl.name, 'l2': 'flushed between timed steps (256 MiB memset, outside the timed interval)',
-                       'sharding': 'one scaffold group per rank, no data-path collective'},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+                       'sharding': 'one genome (scaffold group) of the batch per rank, no data-path collective'},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, **extra,
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -271,7 +399,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='cov', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='self', choices=sorted(WORKLOADS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

@@ -85,6 +85,38 @@ def align_pairs(pairs: Sequence[Tuple[str, str]], outtab: str, minIdt, minLen, h
     return stats
 
 
+def filter_hits(hits: Dict[str, np.ndarray], minLen, minIdt) -> np.ndarray:
+    """Boolean mask of the rows the reference's awk filters keep (wrappers.py:1049-1052): length1 >= minLen and the
+    PRINTED identity ('%.1f') >= minIdt. Vectorised; rows within 1e-6 of a rounding tie are decided by real formatting."""
+    n = len(hits['t_id'])
+    if n == 0:
+        return np.zeros(0, dtype=bool)
+    keep = (hits['end1'].astype(np.int64) - hits['start1'] + 1) >= minLen
+    nm, nc = hits['nmatch'].astype(np.float64), hits['ncols'].astype(np.float64)
+    t = 1000.0 * nm / np.maximum(nc, 1.0)
+    tenths = np.floor(t + 0.5)
+    near_tie = np.abs((t + 0.5) - np.round(t + 0.5)) < 1e-6
+    for k in np.flatnonzero(near_tie & keep):
+        tenths[k] = round(float(_align.pct_text(int(hits['nmatch'][k]), int(hits['ncols'][k]))) * 10)
+    return keep & (tenths >= 10.0 * float(minIdt))
+
+
+def self_segments(T: Genome, T_rc: Optional[Genome], sizes: Sequence[int], minIdt, minLen, minCov, intraCov, hspthresh=3000,
+                  strictSelf=True):
+    """`mimeo self` without any text: device genome in, (inter segments, intra segments or None, hits, stats) out.
+    Scaffold index order must already be the C-locale name order (it defines the GFF row order)."""
+    hits, stats = _align.align(T, T, align_params(hspthresh), Q_rc=T_rc)
+    keep = filter_hits(hits, minLen, minIdt)
+    intra_mask = (hits['t_id'] == hits['q_id']) & keep if strictSelf else np.zeros(len(keep), dtype=bool)
+    inter_mask = keep & ~intra_mask
+
+    def seg(mask, cov):
+        return _coverage.coverage_segments(hits['t_id'][mask], hits['start1'][mask], hits['end1'][mask], sizes, cov, minLen)
+    inter = seg(inter_mask, minCov)
+    intra = seg(intra_mask, intraCov) if strictSelf else None
+    return inter, intra, hits, stats
+
+
 # ------------------------------------------------------------------------------------------ .tab -> GFF3
 def read_lens(path: str) -> Dict[str, int]:
     sizes = {}
