@@ -20,7 +20,7 @@ void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& 
     for (int attempt = 0; attempt < 2; attempt++) {
         s0.alloc(cap);
         MB2_CUDA(cudaMemsetAsync(counters.get(), 0, 4 * sizeof(unsigned long long), cx.stream));
-        seed_scan(T, Q, tab, GENOME_PAD, (uint32_t)Q.G, p, s0.get(), cap, counters.get());
+        seed_scan(T, Q, tab, GENOME_END_PAD, (uint32_t)Q.G - GENOME_END_PAD, p, s0.get(), cap, counters.get());
         MB2_CUDA(cudaMemcpyAsync(&nsurv, counters.get() + CNT_SURV, sizeof(nsurv), cudaMemcpyDeviceToHost, cx.stream));
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
         if (nsurv <= cap) break;

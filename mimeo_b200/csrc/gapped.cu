@@ -185,6 +185,38 @@ __device__ Ext ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32
     return r;
 }
 
+// Exact shortcut for the trivial alignment of a scaffold with itself. When target and query are the SAME N-free
+// sequence and the anchor lies on the main diagonal, the y-drop DP has a closed form: every column (x,x) is a match
+// scoring s(b,b) > 0, and any other path to an anti-diagonal k uses at most min(i,j) <= k/2 aligned columns, each
+// worth at most s(b,b) of its row base, minus gap costs -- so the main-diagonal cell is the strict maximum of every
+// even anti-diagonal, is never pruned, and the extension ends at the scaffold end with score = sum of s(b,b),
+// matches = columns = length. (Proof in DESIGN.md; sequences with any non-ACGT base take the general DP.)
+__device__ Ext selfdiag_extend_cta(const GenomeView& T, uint32_t p0, uint32_t p1, int* __restrict__ sm) {
+    // count C/G bases in padded-coordinate range [p0, p1): 2-bit code has exactly one bit set for C (01) and G (10)
+    int cg = 0;
+    if (p1 > p0) {
+        const uint32_t w0 = p0 >> 5, w1 = (p1 - 1) >> 5;
+        for (uint32_t w = w0 + threadIdx.x; w <= w1; w += blockDim.x) {
+            uint64_t x = T.pk[w];
+            uint64_t m = (x ^ (x >> 1)) & 0x5555555555555555ull;
+            if (w == w0 && (p0 & 31)) m &= ~0ull << (2 * (p0 & 31));
+            if (w == w1 && (p1 & 31)) m &= ~0ull >> (64 - 2 * (p1 & 31));
+            cg += __popcll(m);
+        }
+    }
+    cg = __reduce_add_sync(0xffffffffu, cg);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cg;
+    __syncthreads();
+    int tot = 0;
+    for (int w = 0; w < GP_WARPS; w++) tot += sm[w];
+    __syncthreads();
+    const int n = (int)(p1 - p0);
+    Ext r;
+    r.score = 91 * (n - tot) + 100 * tot; r.di = n; r.dj = n; r.nmatch = n; r.ncols = n;
+    return r;
+}
+
 // best 31-column window of an HSP (first maximum); returns the anchor offset inside the HSP
 __device__ int anchor_offset(const GenomeView& T, const GenomeView& Q, uint32_t ts, uint32_t qs, int len, int lane) {
     if (len <= 31) return len / 2;
@@ -272,8 +304,14 @@ gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, con
                 cov |= (a1 >= o_s1[a + kk] && a1 < o_e1[a + kk] && a2 >= o_s2[a + kk] && a2 < o_e2[a + kk]) ? 1 : 0;
             if (__syncthreads_or(cov)) continue;
             anchors++;
-            const Ext f = ydrop_extend_cta<+1>(T, Q, toff + a1, qoff + a2, tlen - a1, qlen - a2, O, E, Y, gp_smem, rec, sub5, cells, err);
-            const Ext r = ydrop_extend_cta<-1>(T, Q, toff + a1, qoff + a2, a1, a2, O, E, Y, gp_smem, rec, sub5, cells, err);
+            Ext f, r;
+            if (T.pk == Q.pk && tsc == qsc && a1 == a2 && T.nfree[tsc]) {
+                f = selfdiag_extend_cta(T, toff + a1, toff + tlen, gp_smem);
+                r = selfdiag_extend_cta(T, toff, toff + a1, gp_smem);
+            } else {
+                f = ydrop_extend_cta<+1>(T, Q, toff + a1, qoff + a2, tlen - a1, qlen - a2, O, E, Y, gp_smem, rec, sub5, cells, err);
+                r = ydrop_extend_cta<-1>(T, Q, toff + a1, qoff + a2, a1, a2, O, E, Y, gp_smem, rec, sub5, cells, err);
+            }
             const int score = f.score + r.score;
             if (score < gthr) continue;
             if (tid == 0) {

@@ -79,10 +79,26 @@ revcomp_kernel(GenomeView src, uint64_t* __restrict__ pk, uint32_t* __restrict__
     nm[w] = nflag;
 }
 
+// nfree[s] = 1 iff scaffold s has no non-ACGT base (one CTA per scaffold scans its mask words)
+__global__ void __launch_bounds__(256)
+nfree_kernel(const uint32_t* __restrict__ nm, const uint32_t* __restrict__ off, const uint32_t* __restrict__ len, uint32_t* __restrict__ nfree) {
+    const uint32_t s = blockIdx.x;
+    const uint32_t o = off[s], l = len[s];
+    const uint32_t w0 = o >> 5, nw = (l + 31) >> 5;          // scaffolds start word-aligned (multiple of 64 bases)
+    int bad = 0;
+    for (uint32_t w = threadIdx.x; w < nw; w += blockDim.x) {
+        uint32_t m = nm[w0 + w];
+        if (w == nw - 1 && (l & 31)) m &= (1u << (l & 31)) - 1u;
+        bad |= m != 0;
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) nfree[s] = bad ? 0u : 1u;
+}
+
 static void layout(Genome& g, const uint64_t* lens, int n) {
     g.nscaf = n;
     g.off.resize(n); g.len.resize(n);
-    uint64_t pos = GENOME_PAD;
+    uint64_t pos = GENOME_END_PAD;
     g.nbases = 0;
     for (int s = 0; s < n; s++) {
         MB2_REQUIRE(lens[s] < 0x7fffffffull, -3, "scaffold longer than 2^31-1 bases");
@@ -91,7 +107,7 @@ static void layout(Genome& g, const uint64_t* lens, int n) {
         pos = (pos + lens[s] + GENOME_PAD + 63) & ~63ull;
         MB2_REQUIRE(pos < 0xfff00000ull, -3, "genome exceeds 2^32 padded positions; load it as several genomes");
     }
-    g.G = pos;
+    g.G = pos + GENOME_END_PAD;
 }
 
 Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int n) {
@@ -114,6 +130,8 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), g->off.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
         MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), g->len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
         launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get(), g->codes.get());
+        g->d_nfree.alloc(n);
+        launch(nfree_kernel, n, 256, 0, g->nm.get(), g->d_off.get(), g->d_len.get(), g->d_nfree.get());
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
         cudaFreeHost(h);
     } catch (...) { delete g; throw; }
@@ -130,6 +148,8 @@ Genome* genome_revcomp(const Genome& src) {
         Ctx& cx = ctx();
         MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), src.d_off.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
         MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), src.d_len.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
+        g->d_nfree.alloc(src.nscaf);
+        MB2_CUDA(cudaMemcpyAsync(g->d_nfree.get(), src.d_nfree.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
         launch(revcomp_kernel, cdiv(nwords, 256), 256, 0, view(src), g->pk.get(), g->nm.get(), g->codes.get(), nwords);
     } catch (...) { delete g; throw; }
     return g;

@@ -37,35 +37,86 @@ __device__ __forceinline__ int col_score(const GenomeView& T, const GenomeView& 
     return an ? SCORE_N : sub_lut2((base_at(T.pk, ct) << 2) | base_at(Q.pk, cq));
 }
 
-// dir = +1: columns ct0, ct0+1, ... ; returns best score and the exclusive end of the best prefix.
-// dir = -1: columns ct0, ct0-1, ... ; returns best score and the inclusive start of the best prefix.
+// Exact x-drop extension, 1024 columns per warp step: lane l scores its own block of 32 consecutive columns from
+// registers (two unaligned 64-bit windows + N masks), then two warp scans stitch the blocks together.
+//   phase 1 (per lane): block sum, block prefix maximum (+ its first position), the deepest drop below the block's own
+//            running maximum and the lowest prefix value;
+//   phase 2 (warp):     S_in = exclusive sum, M_in = exclusive running best; a block can contain the termination column
+//            iff  min_prefix < (M_in - S_in) - X  or  deepest_drop < -X; the first such lane replays its 32 columns with
+//            the true incoming state to find the exact column.
+// DIR=+1: columns ct0, ct0+1, ... -> best score and exclusive end of the best prefix.
+// DIR=-1: columns ct0, ct0-1, ... -> best score and inclusive start of the best prefix.
 template <int DIR>
 __device__ __forceinline__ void xdrop_side(const GenomeView& T, const GenomeView& Q, uint32_t ct0, uint32_t cq0, int X, int lane,
                                            int& best_out, uint32_t& bpos_out, unsigned long long& cells) {
     int run0 = 0, best = 0;
     uint32_t bpos = DIR > 0 ? ct0 : ct0 + 1;
-    for (uint32_t base = 0;; base += 32) {
-        const uint32_t ct = DIR > 0 ? ct0 + base + lane : ct0 - base - lane;
-        const uint32_t cq = DIR > 0 ? cq0 + base + lane : cq0 - base - lane;
-        const int s = col_score(T, Q, ct, cq);
-        const int ps = warp_incl_sum_i(s, lane) + run0;
-        const int pm = warp_incl_max_i(ps, lane);
-        int pm_excl = __shfl_up_sync(0xffffffffu, pm, 1);
-        if (lane == 0) pm_excl = INT_MIN;
-        const int best_prev = max(best, pm_excl);
-        const uint32_t tmask = __ballot_sync(0xffffffffu, ps < best_prev - X);
-        const int nvalid = tmask ? __ffs(tmask) - 1 : 32;
-        const int cand = lane < nvalid ? ps : INT_MIN;
-        const int mx = __reduce_max_sync(0xffffffffu, cand);
+    for (uint32_t base = 0;; base += 1024) {
+        // block of this lane: DIR>0 columns [ct0+base+32l, +32) ascending; DIR<0 columns (ct0-base-32l) descending
+        const uint32_t wt_pos = DIR > 0 ? ct0 + base + 32u * lane : ct0 - base - 32u * lane - 31u;
+        const uint32_t wq_pos = DIR > 0 ? cq0 + base + 32u * lane : cq0 - base - 32u * lane - 31u;
+        const uint64_t wt = window32(T.pk, wt_pos), wq = window32(Q.pk, wq_pos);
+        const uint32_t an = nwindow32(T.nm, wt_pos) | nwindow32(Q.nm, wq_pos);
+        int sc[32];
+        int p = 0, lmax = INT_MIN, lmax_at = 0, mind = INT_MAX, minp = INT_MAX;
+#pragma unroll
+        for (int c = 0; c < 32; c++) {
+            const int k = DIR > 0 ? c : 31 - c;                       // bit position inside the windows
+            const int s = ((an >> k) & 1u) ? SCORE_N : sub_lut2((uint32_t)(((wt >> (2 * k)) & 3) << 2 | ((wq >> (2 * k)) & 3)));
+            sc[c] = s;
+            p += s;
+            if (c > 0) mind = min(mind, p - lmax);
+            minp = min(minp, p);
+            if (p > lmax) { lmax = p; lmax_at = c; }
+        }
+        const int sum_incl = warp_incl_sum_i(p, lane);
+        const int s_in = sum_incl - p + run0;                          // running sum entering this lane's block
+        const int cand = s_in + lmax;                                  // best running value reached inside the block
+        const int cm = warp_incl_max_i(cand, lane);
+        int m_in = __shfl_up_sync(0xffffffffu, cm, 1);
+        if (lane == 0) m_in = INT_MIN;
+        m_in = max(m_in, best);                                        // best seen before this block
+        const int dgap = m_in - s_in;
+        const bool may_term = (minp < dgap - X) || (mind < -X);
+        const uint32_t tmask = __ballot_sync(0xffffffffu, may_term);
+        const int lt = tmask ? __ffs(tmask) - 1 : 32;
+        // the terminating lane replays its block with the true incoming state
+        int tcol = 32, tbest = INT_MIN, tbest_at = 0;
+        if (lane == lt) {
+            int q = 0, lm = INT_MIN;
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                q += sc[c];
+                const int ref = max(dgap, lm);
+                if (tcol == 32 && q < ref - X) tcol = c;
+                if (tcol == 32 && q > lm) { lm = q; if (q > tbest) { tbest = q; tbest_at = c; } }
+            }
+        }
+        // candidates for a new best: whole blocks of lanes < lt, and the prefix of lane lt before its termination column
+        int v = INT_MIN, vat = 0;
+        if (lane < lt) { v = cand; vat = lmax_at; }
+        else if (lane == lt && tbest != INT_MIN) { v = s_in + tbest; vat = tbest_at; }
+        const int mx = __reduce_max_sync(0xffffffffu, v);
         if (mx > best) {
-            const uint32_t eq = __ballot_sync(0xffffffffu, cand == mx);
-            const uint32_t first = __ffs(eq) - 1;
-            bpos = DIR > 0 ? ct0 + base + first + 1 : ct0 - base - first;
+            const int src = __ffs(__ballot_sync(0xffffffffu, v == mx)) - 1;
+            const int at = __shfl_sync(0xffffffffu, vat, src);
+            const uint32_t col = base + 32u * src + at;                // columns consumed before + this one
+            bpos = DIR > 0 ? ct0 + col + 1 : ct0 - col;
             best = mx;
         }
-        cells += tmask ? nvalid + 1 : 32;
-        if (tmask) break;
-        run0 = __shfl_sync(0xffffffffu, ps, 31);
+        if (tmask) {
+            const int tc = __shfl_sync(0xffffffffu, tcol, lt);
+            cells += 32ull * lt + tc + 1;
+            if (tc < 32) break;
+            // the flagged lane did not actually terminate (conservative test): continue with the lanes after it
+            // by restarting the step right after that lane's block
+            run0 = __shfl_sync(0xffffffffu, s_in + p, lt);
+            // shift so that the next step starts at the block following lane lt
+            base += 32u * (lt + 1) - 1024u;
+            continue;
+        }
+        cells += 1024;
+        run0 = __shfl_sync(0xffffffffu, sum_incl, 31) + run0;
     }
     best_out = best; bpos_out = bpos;
 }
@@ -144,14 +195,26 @@ hsp_extend_kernel(GenomeView T, GenomeView Q, const uint64_t* __restrict__ surv,
             const uint32_t qs = bs - (i - j);
             if (entropy) {
                 uint32_t cnt[4] = {0, 0, 0, 0};
-                for (uint32_t c = bs; c < be; c += 32) {
-                    const uint32_t ct = c + lane, cq = qs + (c - bs) + lane;
-                    const bool in = ct < be;
-                    const uint32_t tb = in ? base_at(T.pk, ct) : 0u, qb = in ? base_at(Q.pk, cq) : 1u;
-                    const bool m = in && tb == qb && !(isn_at(T.nm, ct) | isn_at(Q.nm, cq));
+                for (uint32_t c = bs + 32u * lane; c < be; c += 1024u) {      // each lane owns 32-column words
+                    const uint64_t wt = window32(T.pk, c), wq = window32(Q.pk, qs + (c - bs));
+                    const uint32_t an = nwindow32(T.nm, c) | nwindow32(Q.nm, qs + (c - bs));
+                    const uint64_t x = wt ^ wq;
+                    uint64_t m = ~(x | (x >> 1)) & 0x5555555555555555ull;      // bit 2k set iff column k matches
+                    // drop N columns and columns beyond the HSP end
+                    if (an) {
+                        uint64_t nsp = 0;
 #pragma unroll
-                    for (uint32_t bb = 0; bb < 4; bb++) cnt[bb] += __popc(__ballot_sync(0xffffffffu, m && tb == bb));
+                        for (int k = 0; k < 32; k++) nsp |= (uint64_t)((an >> k) & 1u) << (2 * k);
+                        m &= ~nsp;
+                    }
+                    const uint32_t left = be - c;
+                    if (left < 32) m &= (~0ull) >> (64 - 2 * left);
+                    const uint64_t lo = wt & 0x5555555555555555ull, hi = (wt >> 1) & 0x5555555555555555ull;
+                    cnt[0] += __popcll(m & ~lo & ~hi); cnt[1] += __popcll(m & lo & ~hi);
+                    cnt[2] += __popcll(m & ~lo & hi);  cnt[3] += __popcll(m & lo & hi);
                 }
+#pragma unroll
+                for (int bb = 0; bb < 4; bb++) cnt[bb] = __reduce_add_sync(0xffffffffu, cnt[bb]);
                 const uint32_t h = entropy_q24(cnt);
                 score = (int)(((long long)score * (long long)h) >> 24);
                 if (score < K) continue;

@@ -1,7 +1,7 @@
 // seq.cuh -- device genome layout and sequence access helpers.
 //
 // A genome is one concatenated coordinate space. Every scaffold starts at a multiple of 64 bases
-// and is surrounded by at least 64 pad bases that are flagged non-ACGT, so that
+// and is surrounded by at least 64 pad bases (2048 at both ends of the genome) that are flagged non-ACGT, so that
 //   * a 19-mer seed window can never span two scaffolds,
 //   * gap-free x-drop extension needs no bounds checks: a pad column scores -100 like any
 //     non-ACGT character, so ten of them end the extension without changing its maximum,
@@ -14,7 +14,8 @@
 namespace mb2 {
 
 constexpr int SEED_SPAN = 19;
-constexpr uint32_t GENOME_PAD = 64;
+constexpr uint32_t GENOME_PAD = 64;       // between scaffolds
+constexpr uint32_t GENOME_END_PAD = 2048;  // before the first and after the last scaffold: wide x-drop steps read 1024 columns ahead
 
 struct Genome {
     int nscaf = 0;
@@ -25,6 +26,7 @@ struct Genome {
     DevBuf<uint32_t> nm;              // G/32 + 2 words
     DevBuf<uint8_t> codes;            // 1 byte/base: 0..3 = ACGT, 4 = other/pad (gapped DP reads single bases)
     DevBuf<uint32_t> d_off, d_len;
+    DevBuf<uint32_t> d_nfree;         // per scaffold: 1 = every base is A/C/G/T
     bool is_rc = false;
 };
 
@@ -34,10 +36,11 @@ struct GenomeView {   // what kernels receive
     const uint8_t* __restrict__ codes;
     const uint32_t* __restrict__ off;
     const uint32_t* __restrict__ len;
+    const uint32_t* __restrict__ nfree;
     int nscaf;
     uint32_t G;
 };
-inline GenomeView view(const Genome& g) { return GenomeView{g.pk.get(), g.nm.get(), g.codes.get(), g.d_off.get(), g.d_len.get(), g.nscaf, (uint32_t)g.G}; }
+inline GenomeView view(const Genome& g) { return GenomeView{g.pk.get(), g.nm.get(), g.codes.get(), g.d_off.get(), g.d_len.get(), g.d_nfree.get(), g.nscaf, (uint32_t)g.G}; }
 
 // HOXD70 as LASTZ's default, row = target base, col = query base (index t*4+q)
 static __constant__ int c_sub[16] = {91, -114, -31, -123, -114, 100, -125, -31, -31, -125, 100, -114, -123, -31, -114, 91};
