@@ -19,13 +19,14 @@
 
 namespace mb2 {
 
-constexpr int GP_NT = 256;             // threads per CTA: one cell per thread for bands up to 512, 4 warps per scheduler hide latency
+constexpr int GP_NT = 256;             // threads per CTA
 constexpr int GP_WARPS = GP_NT / 32;
-constexpr int GP_CAP = 1024;           // circular row capacity of one anti-diagonal; the y-drop band must stay below it
-constexpr int GP_MASK = GP_CAP - 1;
+constexpr int GP_ND = 4 * GP_NT;         // circular diagonal slots: thread t owns slots 4t..4t+3, slot = (i - j) & (GP_ND - 1)
+constexpr int GP_DMASK = GP_ND - 1;
+constexpr int GP_MAXBAND = GP_ND - 64;   // widest alive diagonal range the circular window can hold
 constexpr int NEG_INF = INT_MIN / 4;
-// shared memory: A={h,hm,hc,d} for three anti-diagonals, B={i,dm,dc,im} and C={ic} for two
-constexpr int GP_SMEM_INTS = (3 * 4 + 2 * 4 + 2 * 1) * GP_CAP;
+// shared memory: only the two boundary slots of every thread are exchanged: A = {h, hm, hc, d}, B = {i, dm, dc, im}, C = {ic}
+constexpr int GP_SMEM_INTS = 2 * (4 + 4 + 1) * GP_NT;
 constexpr size_t GP_SMEM_BYTES = (size_t)GP_SMEM_INTS * sizeof(int);
 
 __device__ __forceinline__ int sub_lut3(uint32_t idx) {
@@ -66,90 +67,118 @@ anchor_starts_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restri
 
 struct Ext { int score, di, dj, nmatch, ncols; };
 
-struct WarpRec { int wmax, wi, hm, hc, alo, ahi, pad0, pad1; };
 
-// One-sided y-drop extension by the whole CTA. DIR=+1: cell (i,j) consumes T[ta+i-1], Q[qa+j-1]; DIR=-1: T[ta-i], Q[qa-j].
-// All DP state lives in shared memory, indexed circularly by the row i, as 16-byte records so that one cell costs
-// 6 vector loads and 3 vector stores:  A = {h, hm, hc, d} (three anti-diagonals kept: k, k-1, k-2),
-// B = {i, dm, dc, im} and C = {ic} (two kept). One __syncthreads per anti-diagonal.
+struct CellState { int h, d, i, hm, hc, dm, dc, im, ic; };
+__device__ __forceinline__ void cs_dead(CellState& c) { c.h = c.d = c.i = NEG_INF; c.hm = c.hc = c.dm = c.dc = c.im = c.ic = 0; }
+
+// One DP cell (i,j) of anti-diagonal k on diagonal delta = i - j.  self = this diagonal's cell two anti-diagonals ago
+// (updated in place), up = cell (i-1,j) and left = cell (i,j-1) of the previous anti-diagonal.
+template <int DIR>
+__device__ __forceinline__ void gp_cell(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E,
+                                        int thr, int k, int delta, CellState& self, const CellState& up, const CellState& left,
+                                        const int* __restrict__ sub5, int& tmax, int& ti, int& thm, int& thc, int& dlo, int& dhi,
+                                        unsigned& ncell) {
+    const int i2 = k + delta, j2 = k - delta;                    // 2i, 2j
+    CellState n; cs_dead(n);
+    const bool inb = i2 >= 0 && j2 >= 0 && (i2 >> 1) <= tn && (j2 >> 1) <= qn;
+    if (inb && (self.h > NEG_INF || up.h > NEG_INF || left.h > NEG_INF)) {
+        const int i = i2 >> 1, j = j2 >> 1;
+        if (i >= 1 && up.h > NEG_INF) {
+            const int open = up.h - O - E, ext = up.d > NEG_INF ? up.d - E : NEG_INF;
+            if (open >= ext) { n.d = open; n.dm = up.hm; n.dc = up.hc; } else { n.d = ext; n.dm = up.dm; n.dc = up.dc; }
+        }
+        if (j >= 1 && left.h > NEG_INF) {
+            const int open = left.h - O - E, ext = left.i > NEG_INF ? left.i - E : NEG_INF;
+            if (open >= ext) { n.i = open; n.im = left.hm; n.ic = left.hc; } else { n.i = ext; n.im = left.im; n.ic = left.ic; }
+        }
+        int mval = NEG_INF, mm = 0, mc = 0;
+        if (i >= 1 && j >= 1 && self.h > NEG_INF) {
+            const uint32_t ct = DIR > 0 ? ta + (uint32_t)i - 1u : ta - (uint32_t)i;
+            const uint32_t cq = DIR > 0 ? qa + (uint32_t)j - 1u : qa - (uint32_t)j;
+            const uint32_t tb = T.codes[ct], qb = Q.codes[cq];
+            mval = self.h + sub5[tb * 5 + qb];
+            mm = self.hm + ((tb == qb && tb < 4) ? 1 : 0);
+            mc = self.hc + 1;
+        }
+        if (mval >= n.d && mval >= n.i) { n.h = mval; n.hm = mm; n.hc = mc; }
+        else if (n.d >= n.i) { n.h = n.d; n.hm = n.dm; n.hc = n.dc; }
+        else { n.h = n.i; n.hm = n.im; n.hc = n.ic; }
+        ncell++;
+        if (n.h <= NEG_INF || n.h < thr) { n.h = n.d = n.i = NEG_INF; }
+        else {
+            if (n.h > tmax) { tmax = n.h; ti = i; thm = n.hm; thc = n.hc; }
+            dlo = min(dlo, delta); dhi = max(dhi, delta);
+        }
+    }
+    self = n;
+}
+
+struct WarpRec { int wmax, wi, hm, hc, dlo, dhi, pad0, pad1; };
+
+// One-sided y-drop extension by the whole CTA in diagonal-major coordinates. DIR=+1: cell (i,j) consumes T[ta+i-1],
+// Q[qa+j-1]; DIR=-1: T[ta-i], Q[qa-j]. Diagonals delta = i-j live in a circular window of GP_ND slots, slot = delta mod
+// GP_ND; thread t owns slots 4t..4t+3 for the whole extension, so every cell and three of its four neighbours stay in
+// registers. Per anti-diagonal a thread computes its two cells of the right parity, reads ONE cell of a neighbouring
+// thread from shared memory and publishes one; one __syncthreads per anti-diagonal. Dead cells are -inf by value, so the
+// window follows the alignment without any bookkeeping: a slot that re-enters the band on another diagonal is already dead.
 template <int DIR>
 __device__ Ext ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E, int Y,
                                 int* __restrict__ sm, WarpRec (*rec)[GP_WARPS], const int* __restrict__ sub5,
                                 unsigned long long& cells, int& err) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int4* As = reinterpret_cast<int4*>(sm);                       // [3][CAP]
-    int4* Bs = reinterpret_cast<int4*>(sm + 12 * GP_CAP);         // [2][CAP]
-    int* Cs = sm + 20 * GP_CAP;                                   // [2][CAP]
+    int4* A0 = reinterpret_cast<int4*>(sm);                 // published slot 0 of every thread
+    int4* B0 = A0 + GP_NT;
+    int4* A3 = B0 + GP_NT;                                  // published slot 3
+    int4* B3 = A3 + GP_NT;
+    int* C0 = reinterpret_cast<int*>(B3 + GP_NT);
+    int* C3 = C0 + GP_NT;
     Ext r = {0, 0, 0, 0, 0};
-    __syncthreads();                    // previous users of the buffers are done
-    if (tid == 0) {                     // anti-diagonal 0 = the single cell (0,0), generation 0
-        As[0] = make_int4(0, 0, 0, NEG_INF); Bs[0] = make_int4(NEG_INF, 0, 0, 0); Cs[0] = 0;
-    }
+    CellState s0, s1, s2, s3;
+    cs_dead(s0); cs_dead(s1); cs_dead(s2); cs_dead(s3);
+    if (tid == 0) s0.h = 0;                 // the cell (0,0): delta 0 -> slot 0 of thread 0
+    __syncthreads();                        // previous users of the buffers are done
+    A0[tid] = make_int4(s0.h, 0, 0, NEG_INF); B0[tid] = make_int4(NEG_INF, 0, 0, 0); C0[tid] = 0;
+    A3[tid] = make_int4(NEG_INF, 0, 0, NEG_INF); B3[tid] = make_int4(NEG_INF, 0, 0, 0); C3[tid] = 0;
     __syncthreads();
-    int lo2 = 0, hi2 = -1, lo1 = 0, hi1 = 0;
-    int best = 0;
+    int best = 0, dead_steps = 0;
+    int lo1 = 0, hi1 = 0, lo2 = 1, hi2 = 0;     // alive diagonal ranges of anti-diagonals k-1 and k-2 (empty when lo > hi)
+    unsigned ncell = 0;
     const uint32_t kmax = (uint32_t)tn + (uint32_t)qn;
-    int g0 = 1, g1 = 0, g2 = 2;         // generation slots of anti-diagonals k, k-1, k-2
     for (uint32_t k = 1; k <= kmax; k++) {
+        // candidate diagonals of this anti-diagonal and the window position: delta of slot s is base + ((s - base) & mask)
         int clo = INT_MAX, chi = INT_MIN;
-        if (hi1 >= lo1) { clo = lo1; chi = hi1 + 1; }
-        if (hi2 >= lo2) { clo = min(clo, lo2 + 1); chi = max(chi, hi2 + 1); }
-        if (clo == INT_MAX) break;                                   // two dead anti-diagonals in a row
-        clo = max(clo, 0);
-        if (k > (uint32_t)qn) clo = max(clo, (int)(k - (uint32_t)qn));
-        chi = min(chi, (int)min(k, (uint32_t)tn));
-        if (chi - clo + 1 > GP_CAP - 2) { err = 1; break; }
-        const int e0 = (int)(k & 1), e1 = e0 ^ 1;
-        int4* Ac = As + g0 * GP_CAP; const int4* A1 = As + g1 * GP_CAP; const int4* A2 = As + g2 * GP_CAP;
-        int4* Bc = Bs + e0 * GP_CAP; const int4* B1 = Bs + e1 * GP_CAP;
-        int* Cc = Cs + e0 * GP_CAP; const int* C1 = Cs + e1 * GP_CAP;
+        if (hi1 >= lo1) { clo = lo1 - 1; chi = hi1 + 1; }
+        if (hi2 >= lo2) { clo = min(clo, lo2); chi = max(chi, hi2); }
+        if (chi - clo > GP_MAXBAND) { err = 1; break; }
+        const int base = clo - 16;
         const int thr = best - Y;
-        int tmax = INT_MIN, ti = 0, thm = 0, thc = 0, talo = INT_MAX, tahi = INT_MIN;
-        for (int i = clo + tid; i <= chi; i += GP_NT) {
-            const int j = (int)k - i;
-            const int x = i & GP_MASK, xu = (i - 1) & GP_MASK;
-            // the substitution score does not depend on the DP state: fetch it first (padding keeps these reads in bounds)
-            const uint32_t ct = DIR > 0 ? ta + (uint32_t)i - 1u : ta - (uint32_t)i;
-            const uint32_t cq = DIR > 0 ? qa + (uint32_t)j - 1u : qa - (uint32_t)j;
-            const uint32_t tb = T.codes[ct], qb = Q.codes[cq];
-            const int sc = sub5[tb * 5 + qb];
-            const int ismatch = (tb == qb && tb < 4) ? 1 : 0;
-            int h, d = NEG_INF, ii = NEG_INF, hm, hc, dm = 0, dc = 0, im = 0, ic = 0;
-            if (i - 1 >= lo1 && i - 1 <= hi1) {                       // up: (i-1, j) on k-1
-                const int4 ua = A1[xu];                               // {h, hm, hc, d}
-                if (ua.x > NEG_INF) {
-                    const int open = ua.x - O - E, ext = ua.w > NEG_INF ? ua.w - E : NEG_INF;
-                    if (open >= ext) { d = open; dm = ua.y; dc = ua.z; }
-                    else { const int4 ub = B1[xu]; d = ext; dm = ub.y; dc = ub.z; }
-                }
+        int tmax = INT_MIN, ti = 0, thm = 0, thc = 0, dlo = INT_MAX, dhi = INT_MIN;
+        const int dA = base + ((4 * tid - base) & GP_DMASK);      // diagonal currently held by slot 0 (slots 1..3 follow unless they wrap)
+        const int d0 = dA, d1 = base + ((4 * tid + 1 - base) & GP_DMASK), d2 = base + ((4 * tid + 2 - base) & GP_DMASK),
+                  d3 = base + ((4 * tid + 3 - base) & GP_DMASK);
+        if (k & 1) {
+            // odd anti-diagonal: slots 1 and 3. slot1: up = slot0, left = slot2 (own); slot3: up = slot2 (own), left = slot 0 of thread t+1
+            if ((d1 >= clo && d1 <= chi) || (d3 >= clo && d3 <= chi)) {
+                const int f = (tid + 1) & (GP_NT - 1);
+                CellState fl; const int4 fa = A0[f]; const int4 fb = B0[f];
+                fl.h = fa.x; fl.hm = fa.y; fl.hc = fa.z; fl.d = fa.w; fl.i = fb.x; fl.dm = fb.y; fl.dc = fb.z; fl.im = fb.w; fl.ic = C0[f];
+                gp_cell<DIR>(T, Q, ta, qa, tn, qn, O, E, thr, (int)k, d1, s1, s0, s2, sub5, tmax, ti, thm, thc, dlo, dhi, ncell);
+                gp_cell<DIR>(T, Q, ta, qa, tn, qn, O, E, thr, (int)k, d3, s3, s2, fl, sub5, tmax, ti, thm, thc, dlo, dhi, ncell);
+                A3[tid] = make_int4(s3.h, s3.hm, s3.hc, s3.d); B3[tid] = make_int4(s3.i, s3.dm, s3.dc, s3.im); C3[tid] = s3.ic;
             }
-            if (i >= lo1 && i <= hi1) {                               // left: (i, j-1) on k-1
-                const int4 la = A1[x];
-                if (la.x > NEG_INF) {
-                    const int4 lb = B1[x];                            // {i, dm, dc, im}
-                    const int open = la.x - O - E, ext = lb.x > NEG_INF ? lb.x - E : NEG_INF;
-                    if (open >= ext) { ii = open; im = la.y; ic = la.z; }
-                    else { ii = ext; im = lb.w; ic = C1[x]; }
-                }
+        } else {
+            // even anti-diagonal: slots 0 and 2. slot0: up = slot 3 of thread t-1, left = slot1 (own); slot2: up = slot1, left = slot3 (own)
+            if ((d0 >= clo && d0 <= chi) || (d2 >= clo && d2 <= chi)) {
+                const int f = (tid - 1) & (GP_NT - 1);
+                CellState fu; const int4 fa = A3[f]; const int4 fb = B3[f];
+                fu.h = fa.x; fu.hm = fa.y; fu.hc = fa.z; fu.d = fa.w; fu.i = fb.x; fu.dm = fb.y; fu.dc = fb.z; fu.im = fb.w; fu.ic = C3[f];
+                gp_cell<DIR>(T, Q, ta, qa, tn, qn, O, E, thr, (int)k, d0, s0, fu, s1, sub5, tmax, ti, thm, thc, dlo, dhi, ncell);
+                gp_cell<DIR>(T, Q, ta, qa, tn, qn, O, E, thr, (int)k, d2, s2, s1, s3, sub5, tmax, ti, thm, thc, dlo, dhi, ncell);
+                A0[tid] = make_int4(s0.h, s0.hm, s0.hc, s0.d); B0[tid] = make_int4(s0.i, s0.dm, s0.dc, s0.im); C0[tid] = s0.ic;
             }
-            int mval = NEG_INF, mm = 0, mc = 0;
-            if (i >= 1 && j >= 1 && i - 1 >= lo2 && i - 1 <= hi2) {   // diagonal: (i-1, j-1) on k-2
-                const int4 da = A2[xu];
-                if (da.x > NEG_INF) { mval = da.x + sc; mm = da.y + ismatch; mc = da.z + 1; }
-            }
-            if (mval >= d && mval >= ii) { h = mval; hm = mm; hc = mc; }
-            else if (d >= ii) { h = d; hm = dm; hc = dc; }
-            else { h = ii; hm = im; hc = ic; }
-            if (h <= NEG_INF || h < thr) { h = NEG_INF; d = NEG_INF; ii = NEG_INF; }
-            else {
-                talo = min(talo, i); tahi = max(tahi, i);
-                if (h > tmax) { tmax = h; ti = i; thm = hm; thc = hc; }   // i increases along the loop: first = smallest row
-            }
-            Ac[x] = make_int4(h, hm, hc, d); Bc[x] = make_int4(ii, dm, dc, im); Cc[x] = ic;
         }
-        // per-warp summary: best cell (max h, then smallest row) and alive row range
         const int wmax = __reduce_max_sync(0xffffffffu, tmax);
-        const int walo = __reduce_min_sync(0xffffffffu, talo), wahi = __reduce_max_sync(0xffffffffu, tahi);
+        const int wlo = __reduce_min_sync(0xffffffffu, dlo), whi = __reduce_max_sync(0xffffffffu, dhi);
         int wi = 0, whm = 0, whc = 0;
         if (wmax > best) {
             wi = __reduce_min_sync(0xffffffffu, tmax == wmax ? ti : INT_MAX);
@@ -159,29 +188,28 @@ __device__ Ext ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32
         const int par = (int)(k & 1);
         if (lane == 0) {
             int4* rp = reinterpret_cast<int4*>(&rec[par][warp]);
-            rp[0] = make_int4(wmax, wi, whm, whc); rp[1] = make_int4(walo, wahi, 0, 0);
+            rp[0] = make_int4(wmax, wi, whm, whc); rp[1] = make_int4(wlo, whi, 0, 0);
         }
-        __syncthreads();
-        // every warp combines the per-warp records lane-parallel (lane w reads record w)
+        __syncthreads();                    // the one barrier of this anti-diagonal
         int4 q0 = make_int4(INT_MIN, INT_MAX, 0, 0), q1 = make_int4(INT_MAX, INT_MIN, 0, 0);
         if (lane < GP_WARPS) {
             const int4* rp = reinterpret_cast<const int4*>(&rec[par][lane]);
             q0 = rp[0]; q1 = rp[1];
         }
-        const int alo = __reduce_min_sync(0xffffffffu, q1.x), ahi = __reduce_max_sync(0xffffffffu, q1.y);
         const int bmax = __reduce_max_sync(0xffffffffu, q0.x);
-        int bi = 0, bhm = 0, bhc = 0;
+        const int alo = __reduce_min_sync(0xffffffffu, q1.x), ahi = __reduce_max_sync(0xffffffffu, q1.y);
         if (bmax > best) {
-            bi = __reduce_min_sync(0xffffffffu, q0.x == bmax ? q0.y : INT_MAX);
+            const int bi = __reduce_min_sync(0xffffffffu, q0.x == bmax ? q0.y : INT_MAX);
             const int src = __ffs(__ballot_sync(0xffffffffu, q0.x == bmax && q0.y == bi)) - 1;
-            bhm = __shfl_sync(0xffffffffu, q0.z, src); bhc = __shfl_sync(0xffffffffu, q0.w, src);
+            best = bmax; r.score = bmax; r.di = bi; r.dj = (int)k - bi;
+            r.nmatch = __shfl_sync(0xffffffffu, q0.z, src); r.ncols = __shfl_sync(0xffffffffu, q0.w, src);
         }
-        if (bmax > best) { best = bmax; r.score = bmax; r.di = bi; r.dj = (int)k - bi; r.nmatch = bhm; r.ncols = bhc; }
-        cells += (unsigned long long)(chi >= clo ? chi - clo + 1 : 0);
-        lo2 = lo1; hi2 = hi1;
-        if (ahi >= alo && alo != INT_MAX) { lo1 = alo; hi1 = ahi; } else { lo1 = 0; hi1 = -1; }
-        const int gt = g2; g2 = g1; g1 = g0; g0 = gt;
+        lo2 = lo1; hi2 = hi1; lo1 = alo; hi1 = ahi;          // empty ranges arrive as (INT_MAX, INT_MIN)
+        if (hi1 < lo1) { lo1 = 1; hi1 = 0; }
+        dead_steps = (hi1 < lo1) ? dead_steps + 1 : 0;
+        if (dead_steps >= 2) break;         // two dead anti-diagonals in a row: nothing can revive
     }
+    cells += ncell;                         // per-thread; summed by the caller
     return r;
 }
 
@@ -325,8 +353,8 @@ gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, con
         }
         __syncthreads();
     }
+    if (cells) atomicAdd(&counters[CNT_GAPPED_CELLS], cells);
     if (tid == 0) {
-        if (cells) atomicAdd(&counters[CNT_GAPPED_CELLS], cells);
         if (anchors) atomicAdd(&counters[CNT_ANCHORS], anchors);
         if (err) atomicAdd(&counters[CNT_ERR], 1ull);
     }
@@ -412,7 +440,7 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
                 MB2_CUDA(cudaFuncSetAttribute(gapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM_BYTES));
                 attr_set = true;
             }
-            const unsigned blocks = std::min<unsigned>((unsigned)cx.sm_count * 2, std::max<unsigned>(1u, h_nseg));   // 88 KB smem + 512 threads: 2 CTAs/SM
+            const unsigned blocks = std::min<unsigned>((unsigned)cx.sm_count * 2, std::max<unsigned>(1u, h_nseg));
             MB2_CUDA(cudaMemsetAsync(counters + CNT_WORK, 0, sizeof(unsigned long long), cx.stream));
             ProfScope ps("gapped");
             launch(gapped_kernel, blocks, GP_NT, GP_SMEM_BYTES, view(T), view(Q), h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(),
