@@ -64,93 +64,138 @@ __device__ __forceinline__ int sub_lut(uint32_t idx) {
     return (int)(int8_t)(v >> ((idx & 7) * 8));
 }
 
-struct S1Result { bool survivor; };
+// ---- load-balanced scan --------------------------------------------------------------------------------------
+// A CTA takes SC_NQ consecutive query positions per round. Phase A: every thread looks up the 13 buckets of its own
+// position and the CTA prefix-sums the 13*SC_NQ bucket sizes, which numbers the round's candidate hits 0..H-1.
+// Phase B: hit number h goes to thread h mod SC_NT, which locates the owning bucket by binary search in the prefix
+// array and runs the leader test and the bounded x-drop in a fixed, fully unrolled shape (32-column windows held in
+// registers); a warp skips the remaining windows as soon as all of its lanes have terminated.
+constexpr int SC_NT = 256;                 // threads per CTA
+constexpr int SC_NQ = 256;                 // query positions per round
+constexpr int SC_NPROBE = 13;
+constexpr int SC_NDESC = SC_NQ * SC_NPROBE;
 
-// exact gap-free x-drop extension of the seed hit (i,j), bounded; returns whether it may still yield an HSP
-__device__ __forceinline__ bool stage1_survives(const GenomeView& T, const GenomeView& Q, uint32_t i, uint32_t j, int X, int K,
-                                                unsigned long long& cells) {
-    // ---- right of the seed
-    int run = 0, best = 0;
-    bool term_r = false;
-#pragma unroll 1
-    for (int b = 0; b < S1_RIGHT_BLOCKS && !term_r; b++) {
-        const uint32_t ct = i + SEED_SPAN + 32 * b, cq = j + SEED_SPAN + 32 * b;
-        uint64_t wt = window32(T.pk, ct), wq = window32(Q.pk, cq);
-        uint32_t an = nwindow32(T.nm, ct) | nwindow32(Q.nm, cq);
-#pragma unroll 8
-        for (int c = 0; c < 32; c++) {
-            const int s = (an & 1u) ? SCORE_N : sub_lut((uint32_t)((wt & 3) << 2 | (wq & 3)));
-            wt >>= 2; wq >>= 2; an >>= 1;
-            run += s;
-            cells++;
-            if (run > best) best = run;
-            else if (run < best - X) { term_r = true; break; }
-        }
-    }
-    // ---- left, from the last seed column downwards
-    int runl = 0, bestl = 0;
-    bool term_l = false;
-#pragma unroll 1
-    for (int b = 0; b < S1_LEFT_BLOCKS && !term_l; b++) {
-        const uint32_t ct = i + SEED_SPAN - 32 * (b + 1), cq = j + SEED_SPAN - 32 * (b + 1);   // window = 32 columns ending at the previous start
-        uint64_t wt = window32(T.pk, ct), wq = window32(Q.pk, cq);
-        uint32_t an = nwindow32(T.nm, ct) | nwindow32(Q.nm, cq);
-#pragma unroll 8
-        for (int c = 31; c >= 0; c--) {
-            const int s = ((an >> c) & 1u) ? SCORE_N : sub_lut((uint32_t)(((wt >> (2 * c)) & 3) << 2 | ((wq >> (2 * c)) & 3)));
-            runl += s;
-            cells++;
-            if (runl > bestl) bestl = runl;
-            else if (runl < bestl - X) { term_l = true; break; }
-        }
-    }
-    if (term_r && term_l) return best + bestl >= K;
-    return true;
-}
-
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SC_NT)
 seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, const uint32_t* __restrict__ pos,
                  uint32_t q_lo, uint32_t q_n, int X, int K, int transition, uint32_t diag_bias,
                  uint64_t* __restrict__ surv, uint32_t surv_cap, unsigned long long* __restrict__ counters) {
-    // counters: [0] survivors, [1] seed hits, [2] leaders, [3] stage-1 cells
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long n_hits = 0, n_lead = 0, n_cells = 0;
-    if (k < q_n) {
-        const uint32_t j = q_lo + k;
-        const uint32_t nq = nwindow32(Q.nm, j) & SEED_WINDOW_MASK19;
-        if (nq == 0) {
-            const uint64_t wq = window32(Q.pk, j);
-            const uint32_t key = seed_key(wq);
-            const uint64_t wq1 = window32(Q.pk, j - 1);
-            const bool q1_clean = (nwindow32(Q.nm, j - 1) & SEED_WINDOW_MASK19) == 0;
-            const int nprobe = transition ? 13 : 1;
-            for (int pr = 0; pr < nprobe; pr++) {
+    __shared__ uint32_t d_start[SC_NDESC + 1];     // exclusive prefix of bucket sizes (hit number of each bucket's first entry)
+    __shared__ uint32_t d_b0[SC_NDESC];            // first index of each bucket in pos[]
+    __shared__ uint32_t sh_scan[SC_NT / 32 + 1];
+    __shared__ unsigned long long sh_stat[3];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nprobe = transition ? SC_NPROBE : 1;
+    if (tid < 3) sh_stat[tid] = 0;
+    unsigned long long n_lead = 0, n_cells = 0, n_hits_cta = 0;
+    const uint32_t nrounds = (q_n + SC_NQ - 1) / SC_NQ;
+    for (uint32_t round = blockIdx.x; round < nrounds; round += gridDim.x) {
+        // ---------------- phase A: bucket ranges of this thread's query position
+        const uint32_t j = q_lo + round * SC_NQ + tid;
+        uint32_t cnt[SC_NPROBE];
+        uint32_t mine = 0;
+        const bool jvalid = (round * SC_NQ + tid) < q_n && (nwindow32(Q.nm, j) & SEED_WINDOW_MASK19) == 0;
+        uint32_t key = 0;
+        if (jvalid) key = seed_key(window32(Q.pk, j));
+#pragma unroll
+        for (int pr = 0; pr < SC_NPROBE; pr++) {
+            uint32_t c = 0, b0 = 0;
+            if (jvalid && pr < nprobe) {
                 const uint32_t kk = pr == 0 ? key : key ^ (2u << (2 * (pr - 1)));
-                const uint32_t b0 = off[kk], b1 = off[kk + 1];
-                for (uint32_t x = b0; x < b1; x++) {
-                    const uint32_t i = pos[x];
-                    n_hits++;
-                    // spec D1: only run leaders are candidates
-                    if (q1_clean && (nwindow32(T.nm, i - 1) & SEED_WINDOW_MASK19) == 0 &&
-                        seed_match(window32(T.pk, i - 1), wq1, transition != 0))
-                        continue;
-                    n_lead++;
-                    if (!stage1_survives(T, Q, i, j, X, K, n_cells)) continue;
-                    const unsigned long long slot = atomicAdd(&counters[0], 1ull);
-                    if (slot < surv_cap) surv[slot] = ((uint64_t)(i - j + diag_bias) << 32) | j;
+                b0 = off[kk];
+                c = off[kk + 1] - b0;
+            }
+            cnt[pr] = c;
+            d_b0[tid * SC_NPROBE + pr] = b0;
+            mine += c;
+        }
+        uint32_t total;
+        uint32_t run = block_excl_scan<SC_NT>(mine, sh_scan, total);
+#pragma unroll
+        for (int pr = 0; pr < SC_NPROBE; pr++) { d_start[tid * SC_NPROBE + pr] = run; run += cnt[pr]; }
+        if (tid == 0) d_start[SC_NDESC] = total;
+        __syncthreads();
+        n_hits_cta += (tid == 0) ? total : 0;
+        // ---------------- phase B: hits of the round, strided over the CTA; fixed-shape, convergent extension
+        for (uint32_t hbase = 0; hbase < total; hbase += SC_NT) {
+            const uint32_t h = hbase + tid;
+            bool live = h < total;                                   // lane has a hit that still needs an answer
+            uint32_t hi = 0, hj = 0;
+            if (live) {
+                int lo = 0, hi_d = SC_NDESC;                          // bucket that owns hit h: last descriptor with d_start <= h
+                while (hi_d - lo > 1) { const int mid = (lo + hi_d) >> 1; if (d_start[mid] <= h) lo = mid; else hi_d = mid; }
+                hi = pos[d_b0[lo] + (h - d_start[lo])];
+                hj = q_lo + round * SC_NQ + (uint32_t)(lo / SC_NPROBE);
+                // spec D1: only run leaders are candidates
+                const bool prev_seed = (nwindow32(Q.nm, hj - 1) & SEED_WINDOW_MASK19) == 0 &&
+                                       (nwindow32(T.nm, hi - 1) & SEED_WINDOW_MASK19) == 0 &&
+                                       seed_match(window32(T.pk, hi - 1), window32(Q.pk, hj - 1), transition != 0);
+                if (prev_seed) live = false; else n_lead++;
+            }
+            // right of the seed: up to S1_RIGHT_BLOCKS windows of 32 columns; a warp stops early once all its lanes are done
+            int runv = 0, best_r = 0;
+            bool term_r = !live;
+#pragma unroll 1
+            for (int b = 0; b < S1_RIGHT_BLOCKS; b++) {
+                if (__all_sync(0xffffffffu, term_r)) break;
+                if (!term_r) {
+                    const uint32_t ct = hi + SEED_SPAN + 32 * b, cq = hj + SEED_SPAN + 32 * b;
+                    uint64_t wt = window32(T.pk, ct), wq = window32(Q.pk, cq);
+                    uint32_t an = nwindow32(T.nm, ct) | nwindow32(Q.nm, cq);
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int sc = (an & 1u) ? SCORE_N : sub_lut((uint32_t)((wt & 3) << 2 | (wq & 3)));
+                        wt >>= 2; wq >>= 2; an >>= 1;
+                        if (!term_r) {
+                            runv += sc; n_cells++;
+                            if (runv > best_r) best_r = runv; else if (runv < best_r - X) term_r = true;
+                        }
+                    }
+                }
+            }
+            const bool open_r = live && !term_r;
+            // left, from the last seed column downwards: up to S1_LEFT_BLOCKS windows
+            int best_l = 0;
+            runv = 0;
+            bool term_l = !live;
+#pragma unroll 1
+            for (int b = 0; b < S1_LEFT_BLOCKS; b++) {
+                if (__all_sync(0xffffffffu, term_l)) break;
+                if (!term_l) {
+                    const uint32_t ct = hi + SEED_SPAN - 32 * (b + 1), cq = hj + SEED_SPAN - 32 * (b + 1);
+                    uint64_t wt = window32(T.pk, ct), wq = window32(Q.pk, cq);
+                    uint32_t an = nwindow32(T.nm, ct) | nwindow32(Q.nm, cq);
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int sc = (an >> 31) ? SCORE_N : sub_lut((uint32_t)(((wt >> 62) & 3) << 2 | ((wq >> 62) & 3)));
+                        wt <<= 2; wq <<= 2; an <<= 1;
+                        if (!term_l) {
+                            runv += sc; n_cells++;
+                            if (runv > best_l) best_l = runv; else if (runv < best_l - X) term_l = true;
+                        }
+                    }
+                }
+            }
+            // dead iff both sides terminated inside their bounds with a total below K (spec D2: failed extensions leave no trace)
+            const bool survivor = live && (open_r || !term_l || (best_r + best_l >= K));
+            const uint32_t smask = __ballot_sync(0xffffffffu, survivor);
+            if (smask) {
+                unsigned long long basev = 0;
+                if (lane == __ffs(smask) - 1) basev = atomicAdd(&counters[0], (unsigned long long)__popc(smask));
+                basev = __shfl_sync(0xffffffffu, basev, __ffs(smask) - 1);
+                if (survivor) {
+                    const unsigned long long slot = basev + __popc(smask & ((1u << lane) - 1u));
+                    if (slot < surv_cap) surv[slot] = ((uint64_t)(hi - hj + diag_bias) << 32) | hj;
                 }
             }
         }
+        __syncthreads();
     }
-    // block-level reduction of the statistics
-    __shared__ unsigned long long sh[3];
-    if (threadIdx.x < 3) sh[threadIdx.x] = 0;
+    // statistics
+    if (n_lead) atomicAdd(&sh_stat[1], n_lead);
+    if (n_cells) atomicAdd(&sh_stat[2], n_cells);
+    if (n_hits_cta) atomicAdd(&sh_stat[0], n_hits_cta);
     __syncthreads();
-    if (n_hits) atomicAdd(&sh[0], n_hits);
-    if (n_lead) atomicAdd(&sh[1], n_lead);
-    if (n_cells) atomicAdd(&sh[2], n_cells);
-    __syncthreads();
-    if (threadIdx.x < 3 && sh[threadIdx.x]) atomicAdd(&counters[1 + threadIdx.x], sh[threadIdx.x]);
+    if (tid < 3 && sh_stat[tid]) atomicAdd(&counters[1 + tid], sh_stat[tid]);
 }
 
 // Enqueue the scan of query positions [q_lo, q_hi) against a built table. Survivors are appended to surv.
@@ -159,7 +204,9 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
     const uint32_t n = q_hi - q_lo;
     if (n == 0) return;
     ProfScope ps("seed_scan");
-    launch(seed_scan_kernel, cdiv(n, 256), 256, 0, view(T), view(Q), tab.off.get(), tab.pos.get(), q_lo, n, p.xdrop,
+    const unsigned nrounds = cdiv(n, SC_NQ);
+    const unsigned grid = std::min<unsigned>(nrounds, (unsigned)ctx().sm_count * 8);
+    launch(seed_scan_kernel, grid, SC_NT, 0, view(T), view(Q), tab.off.get(), tab.pos.get(), q_lo, n, p.xdrop,
            p.hspthresh, p.transition, (uint32_t)Q.G, surv, surv_cap, counters);
 }
 
