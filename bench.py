@@ -173,12 +173,12 @@ class SelfWorkload:
         from mimeo_b200.genome import Genome
         self.pinned = [torch.from_numpy(x.copy()).pin_memory() for x in self.seqs]
         self.T = Genome(self.names, self.seqs)
-        self.Trc = self.T.revcomp()
+        self.Tboth = self.T.both_strands()
         self.h2d_bytes = sum(self.sizes)
 
     def step_resident(self):
         from mimeo_b200 import engine
-        inter, intra, hits, stats = engine.self_segments(self.T, self.Trc, self.sizes, self.MIN_IDT, self.MIN_LEN, self.MIN_COV,
+        inter, intra, hits, stats = engine.self_segments(self.T, self.Tboth, self.sizes, self.MIN_IDT, self.MIN_LEN, self.MIN_COV,
                                                          self.INTRA_COV, self.HSPTHRESH, True)
         self.stats, self.nhits, self.nseg = stats, len(hits['t_id']), len(inter[0]) + len(intra[0])
         return inter, intra

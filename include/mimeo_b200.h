@@ -98,6 +98,9 @@ typedef struct mb2_genome mb2_genome;
 MB2_API int mb2_genome_create(const uint8_t* const* seqs, const uint64_t* lens, int n, mb2_genome** out);
 /* Reverse complement of every scaffold (what LASTZ aligns for strand2 = '-'). */
 MB2_API int mb2_genome_revcomp(const mb2_genome* g, mb2_genome** out);
+/* Scaffolds [0,n) of g followed by their reverse complements as scaffolds [n,2n): one pass of the pipeline then covers
+ * --strand=both. mb2_align accepts such a genome as Q_both. */
+MB2_API int mb2_genome_both_strands(const mb2_genome* g, mb2_genome** out);
 MB2_API void mb2_genome_free(mb2_genome* g);
 /* Test hook: scaffold `scaf` decoded back to codes 0..3 = ACGT, 4 = other (HOST buffer of its length). */
 MB2_API int mb2_genome_decode(const mb2_genome* g, int scaf, uint8_t* out);
@@ -137,9 +140,10 @@ typedef struct mb2_hits {
 } mb2_hits;
 /* Replaces every `lastz T Q ...` process of mimeo's script (wrappers.py:1025-1037, 1070-1082, 786-798,
  * 645-653): aligns every scaffold of T against every scaffold of Q, both strands when strands == 3
- * (1 = plus only, 2 = minus only). Q_rc may be NULL (the reverse complement is then built and freed
- * inside the call). Multi-GPU: each rank passes its own subset of target scaffolds as T. */
-MB2_API int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_rc, const mb2_align_params* p, int strands,
+ * (1 = plus only, 2 = minus only). Q_aux may be NULL; otherwise it is a prebuilt companion of Q that saves
+ * rebuilding it per call: for strands == 3 the mb2_genome_both_strands(Q) genome, for strands == 2 mb2_genome_revcomp(Q).
+ * Multi-GPU: each rank passes its own subset of target scaffolds as T. */
+MB2_API int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux, const mb2_align_params* p, int strands,
                       mb2_hits* out);
 MB2_API void mb2_free_hits(mb2_hits* h);
 

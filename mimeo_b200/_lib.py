@@ -55,6 +55,7 @@ SIGNATURES = {
     'mb2_free_segments': (None, [C.POINTER(Segments)]),
     'mb2_genome_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     'mb2_genome_revcomp': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'mb2_genome_both_strands': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     'mb2_genome_free': (None, [C.c_void_p]),
     'mb2_genome_decode': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'mb2_default_align_params': (None, [C.POINTER(AlignParams)]),

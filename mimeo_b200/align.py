@@ -21,12 +21,13 @@ STAT_NAMES = ('survivors', 'seed_hits', 'leaders', 'stage1_cells', 'hsps', 'stag
 
 
 def align(T: Genome, Q: Genome, params: Optional[_lib.AlignParams] = None, strands: int = 3,
-          Q_rc: Optional[Genome] = None) -> Tuple[Dict[str, np.ndarray], Dict[str, int]]:
-    """All scaffolds of T against all scaffolds of Q on the GPU. Returns (hit columns, stage counters)."""
+          Q_aux: Optional[Genome] = None) -> Tuple[Dict[str, np.ndarray], Dict[str, int]]:
+    """All scaffolds of T against all scaffolds of Q on the GPU. Q_aux: prebuilt Q.both_strands() (strands=3) or
+    Q.revcomp() (strands=2) to avoid rebuilding it per call. Returns (hit columns, stage counters)."""
     if params is None:
         params = align_params()
     h = _lib.Hits()
-    _lib.check(_lib.lib().mb2_align(T.handle, Q.handle, Q_rc.handle if Q_rc is not None else None, C.byref(params),
+    _lib.check(_lib.lib().mb2_align(T.handle, Q.handle, Q_aux.handle if Q_aux is not None else None, C.byref(params),
                                     int(strands), C.byref(h)))
     try:
         n = int(h.n)

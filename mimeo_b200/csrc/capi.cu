@@ -210,6 +210,13 @@ int mb2_genome_revcomp(const mb2_genome* g, mb2_genome** out) {
         *out = new mb2_genome{genome_revcomp(*g->g)};
     });
 }
+int mb2_genome_both_strands(const mb2_genome* g, mb2_genome** out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(g && g->g && out, MB2_ERR_INVALID_ARG, "genome_both_strands: null argument");
+        *out = new mb2_genome{genome_both_strands(*g->g)};
+    });
+}
 void mb2_genome_free(mb2_genome* g) {
     if (!g) return;
     delete g->g;
@@ -279,7 +286,7 @@ void mb2_free_hits(mb2_hits* h) {
     std::memset(h, 0, sizeof(*h));
 }
 
-int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_rc, const mb2_align_params* p, int strands,
+int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux, const mb2_align_params* p, int strands,
               mb2_hits* out) {
     return guarded([&] {
         ensure_init();
@@ -287,22 +294,27 @@ int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_rc, 
         MB2_REQUIRE(strands >= 1 && strands <= 3, MB2_ERR_INVALID_ARG, "align: strands must be 1, 2 or 3");
         std::memset(out, 0, sizeof(*out));
         const AlignParams ap = to_params(p);
+        const int nq = Q->g->nscaf;
+        // the query actually aligned: Q (+), revcomp(Q) (-), or both strands as one 2n-scaffold genome
+        const Genome* q = Q->g;
+        Genome* own = nullptr;
+        if (strands != 1) {
+            if (Q_aux && Q_aux->g) {
+                q = Q_aux->g;
+                MB2_REQUIRE(q->nscaf == (strands == 3 ? 2 * nq : nq), MB2_ERR_INVALID_ARG, "align: Q_aux does not match Q and strands");
+            } else {
+                own = strands == 3 ? genome_both_strands(*Q->g) : genome_revcomp(*Q->g);
+                q = own;
+            }
+        }
         std::vector<int32_t> cols[10];
-        Genome* own_rc = nullptr;
         try {
-            for (int st = 0; st < 2; st++) {
-                if (!(strands & (1 << st))) continue;
-                const Genome* q = Q->g;
-                if (st == 1) {
-                    if (Q_rc && Q_rc->g) q = Q_rc->g;
-                    else { own_rc = genome_revcomp(*Q->g); q = own_rc; }
-                }
-                AlnSet a;
-                unsigned long long cnt[CNT_N];
-                align_strand(*T->g, *q, ap, a, cnt);
-                for (int k = 0; k < CNT_N; k++) out->stats[k] += cnt[k];
-                const size_t n = a.n;
-                if (!n) continue;
+            AlnSet a;
+            unsigned long long cnt[CNT_N];
+            align_strand(*T->g, *q, ap, a, cnt);
+            for (int k = 0; k < CNT_N; k++) out->stats[k] = cnt[k];
+            const size_t n = a.n;
+            if (n) {
                 std::vector<uint32_t> tile(n);
                 std::vector<int32_t> s1(n), e1(n), s2(n), e2(n), sc(n), nm(n), nc(n);
                 auto d2h = [&](void* dst, const void* src, size_t bytes) {
@@ -312,10 +324,13 @@ int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_rc, 
                 d2h(s2.data(), a.s2.get(), n * 4); d2h(e2.data(), a.e2.get(), n * 4); d2h(sc.data(), a.score.get(), n * 4);
                 d2h(nm.data(), a.nmatch.get(), n * 4); d2h(nc.data(), a.ncols.get(), n * 4);
                 MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
-                const uint32_t nq = (uint32_t)q->nscaf;
+                const uint32_t nq2 = (uint32_t)q->nscaf;
+                for (int c = 0; c < 10; c++) cols[c].reserve(n);
                 for (size_t k = 0; k < n; k++) {
-                    const int32_t qi = (int32_t)(tile[k] % nq), ti = (int32_t)(tile[k] / nq);
-                    const int32_t m = (int32_t)q->len[qi];
+                    const int32_t q2 = (int32_t)(tile[k] % nq2), ti = (int32_t)(tile[k] / nq2);
+                    const int st = strands == 3 ? (q2 >= nq ? 1 : 0) : (strands == 2 ? 1 : 0);
+                    const int32_t qi = q2 >= nq ? q2 - nq : q2;
+                    const int32_t m = (int32_t)Q->g->len[qi];
                     cols[0].push_back(ti); cols[1].push_back(qi); cols[2].push_back(st);
                     cols[3].push_back(s1[k] + 1); cols[4].push_back(e1[k]);
                     if (st == 0) { cols[5].push_back(s2[k] + 1); cols[6].push_back(e2[k]); }
@@ -323,8 +338,8 @@ int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_rc, 
                     cols[7].push_back(sc[k]); cols[8].push_back(nm[k]); cols[9].push_back(nc[k]);
                 }
             }
-        } catch (...) { delete own_rc; throw; }
-        delete own_rc;
+        } catch (...) { delete own; throw; }
+        delete own;
         const size_t n = cols[0].size();
         out->n = n;
         int32_t** dst[10] = {&out->t_id, &out->q_id, &out->strand, &out->start1, &out->end1, &out->start2, &out->end2,

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(GP_NT, 1)
 gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, const int32_t* __restrict__ hs1, const int32_t* __restrict__ hs2,
               const int32_t* __restrict__ hlen, const uint32_t* __restrict__ order, uint32_t nmember,
               const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
-              int O, int E, int Y, int gthr,
+              int O, int E, int Y, int gthr, int self_n,
               int32_t* __restrict__ o_s1, int32_t* __restrict__ o_e1, int32_t* __restrict__ o_s2, int32_t* __restrict__ o_e2,
               int32_t* __restrict__ o_score, int32_t* __restrict__ o_nm, int32_t* __restrict__ o_nc, uint32_t* __restrict__ o_tile,
               uint32_t* __restrict__ o_keep, unsigned long long* __restrict__ counters) {
@@ -333,7 +333,7 @@ gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, con
             if (__syncthreads_or(cov)) continue;
             anchors++;
             Ext f, r;
-            if (T.pk == Q.pk && tsc == qsc && a1 == a2 && T.nfree[tsc]) {
+            if ((int)qsc < self_n && tsc == qsc && a1 == a2 && T.nfree[tsc]) {
                 f = selfdiag_extend_cta(T, toff + a1, toff + tlen, gp_smem);
                 r = selfdiag_extend_cta(T, toff, toff + a1, gp_smem);
             } else {
@@ -445,6 +445,7 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
             ProfScope ps("gapped");
             launch(gapped_kernel, blocks, GP_NT, GP_SMEM_BYTES, view(T), view(Q), h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(),
                    order, h_nmember, seg_start.get(), d_nseg.get(), p.gap_open, p.gap_extend, p.ydrop, p.gappedthresh,
+                   (Q.fwd_src_id != 0 && Q.fwd_src_id == T.id) ? Q.nfwd : 0,
                    r_s1.get(), r_e1.get(), r_s2.get(), r_e2.get(), r_score.get(), r_nm.get(), r_nc.get(), r_tile.get(), keep.get(), counters);
         }
     }

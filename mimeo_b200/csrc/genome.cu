@@ -95,6 +95,8 @@ nfree_kernel(const uint32_t* __restrict__ nm, const uint32_t* __restrict__ off, 
     if (threadIdx.x == 0) nfree[s] = bad ? 0u : 1u;
 }
 
+uint64_t next_genome_id() { static uint64_t c = 0; return ++c; }
+
 static void layout(Genome& g, const uint64_t* lens, int n) {
     g.nscaf = n;
     g.off.resize(n); g.len.resize(n);
@@ -134,6 +136,7 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         launch(nfree_kernel, n, 256, 0, g->nm.get(), g->d_off.get(), g->d_len.get(), g->d_nfree.get());
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
         cudaFreeHost(h);
+        g->id = next_genome_id(); g->fwd_src_id = g->id; g->nfwd = n;
     } catch (...) { delete g; throw; }
     return g;
 }
@@ -151,6 +154,65 @@ Genome* genome_revcomp(const Genome& src) {
         g->d_nfree.alloc(src.nscaf);
         MB2_CUDA(cudaMemcpyAsync(g->d_nfree.get(), src.d_nfree.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
         launch(revcomp_kernel, cdiv(nwords, 256), 256, 0, view(src), g->pk.get(), g->nm.get(), g->codes.get(), nwords);
+        g->id = next_genome_id(); g->fwd_src_id = 0; g->nfwd = 0;
+    } catch (...) { delete g; throw; }
+    return g;
+}
+
+// Both strands in one genome: scaffolds [0,n) = src, scaffolds [n,2n) = their reverse complements. Lets one pass of the
+// alignment pipeline cover --strand=both (tile = target x (scaffold, strand)), so the two strands share every launch.
+__global__ void __launch_bounds__(256)
+both_strands_kernel(GenomeView src, const uint32_t* __restrict__ noff, const uint32_t* __restrict__ nlen, int n2,
+                    uint64_t* __restrict__ pk, uint32_t* __restrict__ nm, uint8_t* __restrict__ codes, uint32_t nwords) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwords) return;
+    const uint32_t p0 = w * 32;
+    int lo = 0, hi = n2;                         // scaffold of the new layout containing (or preceding) this word
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (noff[mid] <= p0 + 31) lo = mid; else hi = mid; }
+    const uint32_t so = noff[lo], sl = nlen[lo];
+    const int n = n2 >> 1;
+    const bool rc = lo >= n;
+    const uint32_t srco = src.off[rc ? lo - n : lo];
+    uint64_t bits = 0; uint32_t nflag = 0;
+    uint32_t cw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < 32; c++) {
+        const uint32_t p = p0 + c;
+        uint32_t code = 0, bad = 1;
+        if (p >= so && p < so + sl) {
+            const uint32_t k = p - so;
+            const uint32_t sp = srco + (rc ? sl - 1 - k : k);
+            bad = isn_at(src.nm, sp);
+            code = bad ? 0u : (rc ? 3u - base_at(src.pk, sp) : base_at(src.pk, sp));
+        }
+        bits |= (uint64_t)code << (2 * c);
+        nflag |= bad << c;
+        cw[c >> 2] |= (bad ? 4u : code) << (8 * (c & 3));
+    }
+    pk[w] = bits; nm[w] = nflag;
+    uint4* dst = reinterpret_cast<uint4*>(codes + (size_t)w * 32);
+    dst[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+    dst[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
+}
+
+Genome* genome_both_strands(const Genome& src) {
+    Genome* g = new Genome();
+    try {
+        const int n = src.nscaf;
+        std::vector<uint64_t> lens(2 * n);
+        for (int s = 0; s < n; s++) lens[s] = lens[n + s] = src.len[s];
+        layout(*g, lens.data(), 2 * n);
+        const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
+        g->pk.alloc(nwords); g->nm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
+        g->d_off.alloc(2 * n); g->d_len.alloc(2 * n); g->d_nfree.alloc(2 * n);
+        Ctx& cx = ctx();
+        MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), g->off.data(), 2 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
+        MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), g->len.data(), 2 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
+        MB2_CUDA(cudaMemcpyAsync(g->d_nfree.get(), src.d_nfree.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
+        MB2_CUDA(cudaMemcpyAsync(g->d_nfree.get() + n, src.d_nfree.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
+        launch(both_strands_kernel, cdiv(nwords, 256), 256, 0, view(src), g->d_off.get(), g->d_len.get(), 2 * n, g->pk.get(), g->nm.get(),
+               g->codes.get(), nwords);
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));   // g->off/len host vectors were copy sources
+        g->id = next_genome_id(); g->fwd_src_id = src.fwd_src_id == src.id ? src.id : 0; g->nfwd = src.fwd_src_id == src.id ? n : 0;
     } catch (...) { delete g; throw; }
     return g;
 }

@@ -24,6 +24,7 @@ struct AlignParams {   // LASTZ defaults for mimeo's command line
 // genome.cu
 Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int n);
 Genome* genome_revcomp(const Genome& src);
+Genome* genome_both_strands(const Genome& src);
 void genome_decode(const Genome& g, int scaf, uint8_t* h_out);
 
 // seed.cu

@@ -28,7 +28,12 @@ struct Genome {
     DevBuf<uint32_t> d_off, d_len;
     DevBuf<uint32_t> d_nfree;         // per scaffold: 1 = every base is A/C/G/T
     bool is_rc = false;
+    // identity bookkeeping for the trivial self-alignment shortcut: scaffolds [0, nfwd) of this genome are byte-identical
+    // to the scaffolds of the genome whose id is fwd_src_id (a genome is its own source)
+    uint64_t id = 0, fwd_src_id = 0;
+    int nfwd = 0;
 };
+uint64_t next_genome_id();
 
 struct GenomeView {   // what kernels receive
     const uint64_t* __restrict__ pk;

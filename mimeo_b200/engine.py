@@ -101,11 +101,11 @@ def filter_hits(hits: Dict[str, np.ndarray], minLen, minIdt) -> np.ndarray:
     return keep & (tenths >= 10.0 * float(minIdt))
 
 
-def self_segments(T: Genome, T_rc: Optional[Genome], sizes: Sequence[int], minIdt, minLen, minCov, intraCov, hspthresh=3000,
+def self_segments(T: Genome, T_both: Optional[Genome], sizes: Sequence[int], minIdt, minLen, minCov, intraCov, hspthresh=3000,
                   strictSelf=True):
     """`mimeo self` without any text: device genome in, (inter segments, intra segments or None, hits, stats) out.
     Scaffold index order must already be the C-locale name order (it defines the GFF row order)."""
-    hits, stats = _align.align(T, T, align_params(hspthresh), Q_rc=T_rc)
+    hits, stats = _align.align(T, T, align_params(hspthresh), Q_aux=T_both)
     keep = filter_hits(hits, minLen, minIdt)
     intra_mask = (hits['t_id'] == hits['q_id']) & keep if strictSelf else np.zeros(len(keep), dtype=bool)
     inter_mask = keep & ~intra_mask

@@ -49,6 +49,12 @@ class Genome:
         _lib.check(_lib.lib().mb2_genome_revcomp(self.handle, C.byref(h)))
         return Genome(self.names, None, _handle=h, _lengths=self.lengths)
 
+    def both_strands(self) -> 'Genome':
+        """Scaffolds followed by their reverse complements (2n scaffolds): the companion mb2_align takes for strands=3."""
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mb2_genome_both_strands(self.handle, C.byref(h)))
+        return Genome(self.names + [n + '(-)' for n in self.names], None, _handle=h, _lengths=self.lengths + self.lengths)
+
     def decode(self, scaf: int) -> np.ndarray:
         out = np.zeros(self.lengths[scaf], dtype=np.uint8)
         _lib.check(_lib.lib().mb2_genome_decode(self.handle, scaf, out.ctypes.data))

@@ -10,13 +10,13 @@ print('synth', time.time() - t0)
 names = sorted(g)
 t0 = time.time()
 T = G.Genome(names, [g[n] for n in names])
-Trc = T.revcomp()
+Trc = T.both_strands()
 _lib.sync()
 print('upload', time.time() - t0)
 for it in range(3):
     _lib.prof_reset(); _lib.prof_enable(True)
     t0 = time.time()
-    hits, stats = A.align(T, T, G.align_params(3000), Q_rc=Trc)
+    hits, stats = A.align(T, T, G.align_params(3000), Q_aux=Trc)
     dt = time.time() - t0
     _lib.prof_enable(False)
     print('align secs', dt, 'hits', len(hits['t_id']))
