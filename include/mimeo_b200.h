@@ -142,9 +142,12 @@ typedef struct mb2_hits {
  * 645-653): aligns every scaffold of T against every scaffold of Q, both strands when strands == 3
  * (1 = plus only, 2 = minus only). Q_aux may be NULL; otherwise it is a prebuilt companion of Q that saves
  * rebuilding it per call: for strands == 3 the mb2_genome_both_strands(Q) genome, for strands == 2 mb2_genome_revcomp(Q).
- * Multi-GPU: each rank passes its own subset of target scaffolds as T. */
+ * Multi-GPU: each rank passes its own subset of target scaffolds as T.
+ * t_same_q (may be NULL): for every target scaffold the index of the query scaffold holding the IDENTICAL sequence, or -1.
+ * It only enables the exact closed form of the trivial self-alignment; results do not depend on it. When NULL
+ * the identity is inferred if Q (or the genome Q_aux was built from) is the very genome object T. */
 MB2_API int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux, const mb2_align_params* p, int strands,
-                      mb2_hits* out);
+                      const int32_t* t_same_q, mb2_hits* out);
 MB2_API void mb2_free_hits(mb2_hits* h);
 
 /* ---- device primitives exposed for parity tests ------------------------------------------- */

@@ -21,14 +21,19 @@ STAT_NAMES = ('survivors', 'seed_hits', 'leaders', 'stage1_cells', 'hsps', 'stag
 
 
 def align(T: Genome, Q: Genome, params: Optional[_lib.AlignParams] = None, strands: int = 3,
-          Q_aux: Optional[Genome] = None) -> Tuple[Dict[str, np.ndarray], Dict[str, int]]:
+          Q_aux: Optional[Genome] = None, t_same_q=None) -> Tuple[Dict[str, np.ndarray], Dict[str, int]]:
     """All scaffolds of T against all scaffolds of Q on the GPU. Q_aux: prebuilt Q.both_strands() (strands=3) or
-    Q.revcomp() (strands=2) to avoid rebuilding it per call. Returns (hit columns, stage counters)."""
+    Q.revcomp() (strands=2) to avoid rebuilding it per call. t_same_q[i] = index of the query scaffold identical to target
+    scaffold i (or -1): lets a rank that holds a SUBSET of a genome as T keep the closed-form trivial self-alignment.
+    Returns (hit columns, stage counters)."""
     if params is None:
         params = align_params()
     h = _lib.Hits()
+    same = None if t_same_q is None else np.ascontiguousarray(t_same_q, dtype=np.int32)
+    if same is not None and len(same) != len(T.names):
+        raise ValueError('t_same_q needs one entry per target scaffold')
     _lib.check(_lib.lib().mb2_align(T.handle, Q.handle, Q_aux.handle if Q_aux is not None else None, C.byref(params),
-                                    int(strands), C.byref(h)))
+                                    int(strands), same.ctypes.data if same is not None else None, C.byref(h)))
     try:
         n = int(h.n)
         cols = {f: (np.ctypeslib.as_array(getattr(h, f), shape=(n,)).copy() if n else np.zeros(0, np.int32)) for f in HIT_FIELDS}

@@ -36,7 +36,7 @@ void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& 
 }
 
 // Full pipeline for one strand orientation of Q: alignments in strand-local, scaffold-local coordinates.
-void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, AlnSet& alns, unsigned long long* h_counters) {
+void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, AlnSet& alns, unsigned long long* h_counters) {
     Ctx& cx = ctx();
     HspSet hsps;
     unsigned long long c1[CNT_N];
@@ -55,7 +55,7 @@ void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, AlnSet
     }
     DevBuf<unsigned long long> counters(CNT_N);
     MB2_CUDA(cudaMemsetAsync(counters.get(), 0, CNT_N * sizeof(unsigned long long), cx.stream));
-    gapped_extend(T, Q, hsps, in_chain, p, alns, counters.get());
+    gapped_extend(T, Q, hsps, in_chain, p, h_same_q, alns, counters.get());
     unsigned long long c2[CNT_N];
     MB2_CUDA(cudaMemcpyAsync(c2, counters.get(), sizeof(c2), cudaMemcpyDeviceToHost, cx.stream));
     MB2_CUDA(cudaStreamSynchronize(cx.stream));

@@ -16,6 +16,9 @@ Ctx& ctx() { return g_ctx; }
 
 void ensure_init() {
     if (!g_ctx.ready) throw Error(MB2_ERR_INVALID_ARG, "mb2_init() has not been called");
+    // other CUDA users in the process (torch, NCCL) may have changed the calling thread's current device
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != g_ctx.device) MB2_CUDA(cudaSetDevice(g_ctx.device));
 }
 
 template <typename F>
@@ -80,6 +83,7 @@ int mb2_init(int device) {
         uint64_t thresh = UINT64_MAX;   // keep freed scratch cached in the pool between calls
         MB2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
         g_ctx.launches = 0;
+        g_ctx.debug_sync = getenv("MB2_DEBUG_SYNC") != nullptr;
         g_ctx.ready = true;
     });
 }
@@ -287,7 +291,7 @@ void mb2_free_hits(mb2_hits* h) {
 }
 
 int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux, const mb2_align_params* p, int strands,
-              mb2_hits* out) {
+              const int32_t* t_same_q, mb2_hits* out) {
     return guarded([&] {
         ensure_init();
         MB2_REQUIRE(T && Q && out && T->g && Q->g, MB2_ERR_INVALID_ARG, "align: null argument");
@@ -311,7 +315,7 @@ int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux,
         try {
             AlnSet a;
             unsigned long long cnt[CNT_N];
-            align_strand(*T->g, *q, ap, a, cnt);
+            align_strand(*T->g, *q, ap, (strands & 1) ? t_same_q : nullptr, a, cnt);
             for (int k = 0; k < CNT_N; k++) out->stats[k] = cnt[k];
             const size_t n = a.n;
             if (n) {

@@ -38,6 +38,7 @@ struct Ctx {
     bool ready = false;
     unsigned long long launches = 0;   // kernels of THIS library launched so far
     // optional per-kernel timing with CUDA events on the library stream (bench.py's roofline leg)
+    bool debug_sync = false;
     bool prof = false;
     struct ProfRec { std::string tag; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;
@@ -81,6 +82,12 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
     kernel<<<grid, block, smem, ctx().stream>>>(static_cast<KArgs>(args)...);
     ctx().launches++;
     MB2_CUDA(cudaGetLastError());
+    if (ctx().debug_sync) {   // MB2_DEBUG_SYNC=1: localise asynchronous faults to the launch that caused them
+        cudaError_t e = cudaStreamSynchronize(ctx().stream);
+        if (e != cudaSuccess)
+            throw Error(-100, std::string("kernel fault after launch #") + std::to_string(ctx().launches) + " grid " +
+                                  std::to_string(grid.x) + " block " + std::to_string(block.x) + ": " + cudaGetErrorString(e));
+    }
 }
 
 // Times everything enqueued on the library stream during its lifetime (only when profiling is on).

@@ -209,6 +209,10 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
     res.n = 0;
     if (nhits == 0) return;
     Ctx& cx = ctx();
+    struct DebugScope {   // MB2_DEBUG_COV=1: synchronise after every launch of this stage only
+        bool prev; DebugScope() : prev(ctx().debug_sync) { if (getenv("MB2_DEBUG_COV")) { cudaError_t e = cudaStreamSynchronize(ctx().stream); if (e != cudaSuccess) throw Error(-100, std::string("fault BEFORE the coverage stage: ") + cudaGetErrorString(e)); ctx().debug_sync = true; } }
+        ~DebugScope() { ctx().debug_sync = prev; }
+    } debug_scope;
     DevBuf<uint32_t> d_off(nchrom);
     DevBuf<int32_t> d_size(nchrom);
     MB2_CUDA(cudaMemcpyAsync(d_off.get(), off.data(), nchrom * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));

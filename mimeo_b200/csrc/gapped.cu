@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(GP_NT, 1)
 gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, const int32_t* __restrict__ hs1, const int32_t* __restrict__ hs2,
               const int32_t* __restrict__ hlen, const uint32_t* __restrict__ order, uint32_t nmember,
               const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
-              int O, int E, int Y, int gthr, int self_n,
+              int O, int E, int Y, int gthr, const int32_t* __restrict__ same_q,
               int32_t* __restrict__ o_s1, int32_t* __restrict__ o_e1, int32_t* __restrict__ o_s2, int32_t* __restrict__ o_e2,
               int32_t* __restrict__ o_score, int32_t* __restrict__ o_nm, int32_t* __restrict__ o_nc, uint32_t* __restrict__ o_tile,
               uint32_t* __restrict__ o_keep, unsigned long long* __restrict__ counters) {
@@ -333,7 +333,7 @@ gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, con
             if (__syncthreads_or(cov)) continue;
             anchors++;
             Ext f, r;
-            if ((int)qsc < self_n && tsc == qsc && a1 == a2 && T.nfree[tsc]) {
+            if (same_q[tsc] == (int)qsc && a1 == a2 && T.nfree[tsc]) {
                 f = selfdiag_extend_cta(T, toff + a1, toff + tlen, gp_smem);
                 r = selfdiag_extend_cta(T, toff, toff + a1, gp_smem);
             } else {
@@ -398,7 +398,7 @@ ungapped_rows_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ ti
 }
 
 void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevBuf<uint8_t>& in_chain, const AlignParams& p,
-                   AlnSet& out, unsigned long long* counters) {
+                   const int32_t* h_same_q, AlnSet& out, unsigned long long* counters) {
     out.n = 0;
     const uint32_t n = h.n;
     if (n == 0) return;
@@ -435,6 +435,15 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
         MB2_CUDA(cudaMemcpyAsync(&h_nmember, d_nmember.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
         if (h_nmember) {
+            // same_q[t] = query scaffold that is the identical sequence as target scaffold t (or -1): enables the closed form
+            std::vector<int32_t> same(T.nscaf, -1);
+            for (int t = 0; t < T.nscaf; t++) {
+                if (h_same_q) same[t] = h_same_q[t];
+                else if (Q.fwd_src_id != 0 && Q.fwd_src_id == T.id && t < Q.nfwd) same[t] = t;
+            }
+            DevBuf<int32_t> d_same(T.nscaf);
+            MB2_CUDA(cudaMemcpyAsync(d_same.get(), same.data(), T.nscaf * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
+            MB2_CUDA(cudaStreamSynchronize(cx.stream));
             static bool attr_set = false;
             if (!attr_set) {
                 MB2_CUDA(cudaFuncSetAttribute(gapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM_BYTES));
@@ -445,7 +454,7 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
             ProfScope ps("gapped");
             launch(gapped_kernel, blocks, GP_NT, GP_SMEM_BYTES, view(T), view(Q), h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(),
                    order, h_nmember, seg_start.get(), d_nseg.get(), p.gap_open, p.gap_extend, p.ydrop, p.gappedthresh,
-                   (Q.fwd_src_id != 0 && Q.fwd_src_id == T.id) ? Q.nfwd : 0,
+                   d_same.get(),
                    r_s1.get(), r_e1.get(), r_s2.get(), r_e2.get(), r_score.get(), r_nm.get(), r_nc.get(), r_tile.get(), keep.get(), counters);
         }
     }

@@ -56,12 +56,12 @@ struct AlnSet {   // strand-local, scaffold-local, 0-based half-open
     uint32_t n = 0;
 };
 void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevBuf<uint8_t>& in_chain, const AlignParams& p,
-                   AlnSet& out, unsigned long long* counters);
+                   const int32_t* h_same_q, AlnSet& out, unsigned long long* counters);
 
 // align.cu
 void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& hsps, unsigned long long* h_counters);
 
-void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, AlnSet& alns, unsigned long long* h_counters);
+void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, AlnSet& alns, unsigned long long* h_counters);
 
 // counters layout (device, unsigned long long[16])
 enum { CNT_SURV = 0, CNT_SEED_HITS = 1, CNT_LEADERS = 2, CNT_S1_CELLS = 3, CNT_HSPS = 4, CNT_EXTENDED = 5, CNT_S2_CELLS = 6,

@@ -88,3 +88,37 @@ def test_self_pipeline_text_identical(M):
         text += ''.join(segments_to_gff_rows(coverage.coverage_segments(c, s, e, sizes, cov, 100), names, 'mimeo-self', label, 'Self_Repeat'))
     assert text == gff_o
     assert len(text.splitlines()) > 4
+
+
+def test_sharded_driver_world1_equals_engine(M):
+    """parallel.self_sharded on one rank (no process group) == engine.self_segments."""
+    A, G = M
+    from mimeo_b200 import engine, parallel
+    g = synth_genome(45, 3, 25_000, 2, copies=(5, 7), fam_len=(400, 1200), sub=0.07, indel=0.004)
+    names = sorted(g)
+    seqs = [g[n] for n in names]
+    T = G.Genome(names, seqs)
+    inter, intra, hits, _ = engine.self_segments(T, None, [len(s) for s in seqs], 80, 100, 2, 2, 3000, True)
+    h2, i2, j2 = parallel.self_sharded(names, seqs, 80, 100, 2, 2)
+    assert gpu_rows(h2) == gpu_rows(hits) and len(hits['t_id']) > 5
+    assert i2.tolist() == np.stack(inter, axis=1).tolist() and j2.tolist() == np.stack(intra, axis=1).tolist()
+
+
+def test_target_subset_with_identity_map_matches_full_run(M):
+    """A rank holding a subset of the genome as T (row-block sharding) must produce exactly its rows of the full run,
+    with or without the t_same_q hint (the hint only enables the closed-form trivial self-alignment)."""
+    A, G = M
+    g = synth_genome(46, 4, 20_000, 2, copies=(5, 7), fam_len=(400, 1200), sub=0.07, indel=0.004, n_runs=1)
+    names = sorted(g)
+    seqs = [g[n] for n in names]
+    Q = G.Genome(names, seqs)
+    full, _ = A.align(Q, Q, G.align_params(3000))
+    full_rows = gpu_rows(full)
+    sub = [1, 3]
+    T = G.Genome([names[i] for i in sub], [seqs[i] for i in sub])
+    for hint in (sub, None):
+        part, _ = A.align(T, Q, G.align_params(3000), Q_aux=Q.both_strands(), t_same_q=hint)
+        part = dict(part)
+        part['t_id'] = np.asarray(sub, dtype=np.int32)[part['t_id']]
+        want = {r for r in full_rows if r[0] in sub}
+        assert gpu_rows(part) == want and len(want) > 4
