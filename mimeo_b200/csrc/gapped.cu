@@ -13,15 +13,18 @@
 //     columns) of their arg-max path, so identity needs no traceback;
 //   * keep the alignment if forward + backward score >= gappedthresh.
 // One warp owns one tile (its anchors are inherently sequential); tiles are scheduled dynamically.
+#include <cooperative_groups.h>
+
 #include "primitives.cuh"
 #include "seq.cuh"
 #include "internal.cuh"
 
 namespace mb2 {
 
-constexpr int GP_NT = 256;             // threads per CTA
+constexpr int GP_NT = 256;             // threads per CTA (measured sweet spot between per-warp overhead and per-thread chain length)
 constexpr int GP_WARPS = GP_NT / 32;
-constexpr int GP_ND = 4 * GP_NT;         // circular diagonal slots: thread t owns slots 4t..4t+3, slot = (i - j) & (GP_ND - 1)
+constexpr int GP_SLOTS = 4;            // diagonals per thread: two independent cells per thread per anti-diagonal
+constexpr int GP_ND = GP_SLOTS * GP_NT;  // circular diagonal slots: thread t owns GP_SLOTS consecutive slots, slot = (i - j) & (GP_ND - 1)
 constexpr int GP_DMASK = GP_ND - 1;
 constexpr int GP_MAXBAND = GP_ND - 64;   // widest alive diagonal range the circular window can hold
 constexpr int NEG_INF = INT_MIN / 4;
@@ -69,126 +72,142 @@ struct Ext { int score, di, dj, nmatch, ncols; };
 
 
 struct CellState { int h, d, i, hm, hc, dm, dc, im, ic; };
+// A dead cell holds NEG_INF in all three scores; arithmetic on it stays far below any threshold (thr >= -ydrop), so the
+// recurrence needs no "is this predecessor alive" branches: a cell whose predecessors are all dead evaluates to ~NEG_INF,
+// fails H >= thr and is reset to exactly NEG_INF. Out-of-range cells (i or j outside the sequences) are forced dead, which
+// also makes the (i-1) / (j-1) predecessors of the first row and column dead without special cases.
 __device__ __forceinline__ void cs_dead(CellState& c) { c.h = c.d = c.i = NEG_INF; c.hm = c.hc = c.dm = c.dc = c.im = c.ic = 0; }
 
 // One DP cell (i,j) of anti-diagonal k on diagonal delta = i - j.  self = this diagonal's cell two anti-diagonals ago
-// (updated in place), up = cell (i-1,j) and left = cell (i,j-1) of the previous anti-diagonal.
+// (updated in place), up = cell (i-1,j) and left = cell (i,j-1) of the previous anti-diagonal. Returns alive.
 template <int DIR>
-__device__ __forceinline__ void gp_cell(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E,
-                                        int thr, int k, int delta, CellState& self, const CellState& up, const CellState& left,
-                                        const int* __restrict__ sub5, int& tmax, int& ti, int& thm, int& thc, int& dlo, int& dhi,
-                                        unsigned& ncell) {
-    const int i2 = k + delta, j2 = k - delta;                    // 2i, 2j
-    CellState n; cs_dead(n);
-    const bool inb = i2 >= 0 && j2 >= 0 && (i2 >> 1) <= tn && (j2 >> 1) <= qn;
-    if (inb && (self.h > NEG_INF || up.h > NEG_INF || left.h > NEG_INF)) {
-        const int i = i2 >> 1, j = j2 >> 1;
-        if (i >= 1 && up.h > NEG_INF) {
-            const int open = up.h - O - E, ext = up.d > NEG_INF ? up.d - E : NEG_INF;
-            if (open >= ext) { n.d = open; n.dm = up.hm; n.dc = up.hc; } else { n.d = ext; n.dm = up.dm; n.dc = up.dc; }
-        }
-        if (j >= 1 && left.h > NEG_INF) {
-            const int open = left.h - O - E, ext = left.i > NEG_INF ? left.i - E : NEG_INF;
-            if (open >= ext) { n.i = open; n.im = left.hm; n.ic = left.hc; } else { n.i = ext; n.im = left.im; n.ic = left.ic; }
-        }
-        int mval = NEG_INF, mm = 0, mc = 0;
-        if (i >= 1 && j >= 1 && self.h > NEG_INF) {
-            const uint32_t ct = DIR > 0 ? ta + (uint32_t)i - 1u : ta - (uint32_t)i;
-            const uint32_t cq = DIR > 0 ? qa + (uint32_t)j - 1u : qa - (uint32_t)j;
-            const uint32_t tb = T.codes[ct], qb = Q.codes[cq];
-            mval = self.h + sub5[tb * 5 + qb];
-            mm = self.hm + ((tb == qb && tb < 4) ? 1 : 0);
-            mc = self.hc + 1;
-        }
-        if (mval >= n.d && mval >= n.i) { n.h = mval; n.hm = mm; n.hc = mc; }
-        else if (n.d >= n.i) { n.h = n.d; n.hm = n.dm; n.hc = n.dc; }
-        else { n.h = n.i; n.hm = n.im; n.hc = n.ic; }
-        ncell++;
-        if (n.h <= NEG_INF || n.h < thr) { n.h = n.d = n.i = NEG_INF; }
-        else {
-            if (n.h > tmax) { tmax = n.h; ti = i; thm = n.hm; thc = n.hc; }
-            dlo = min(dlo, delta); dhi = max(dhi, delta);
-        }
-    }
-    self = n;
+__device__ __forceinline__ bool gp_cell(const uint8_t* __restrict__ tcodes, const uint8_t* __restrict__ qcodes, uint32_t ta, uint32_t qa,
+                                        int tn, int qn, int OE, int E, int thr, int k, int delta, CellState& self, const CellState& up,
+                                        const CellState& left, const int* __restrict__ sub5, int& tmax, int& ti, int& thm, int& thc) {
+    const int i2 = k + delta, j2 = k - delta;                    // 2i, 2j (same parity as k by construction)
+    const int i = i2 >> 1, j = j2 >> 1;
+    const bool inb = i2 >= 0 && j2 >= 0 && i <= tn && j <= qn;
+    // substitution score of (i,j); clamped addresses keep the loads in bounds for cells that are forced dead anyway
+    const int ic_ = min(max(i, 1), tn), jc_ = min(max(j, 1), qn);
+    const uint32_t ct = DIR > 0 ? ta + (uint32_t)ic_ - 1u : ta - (uint32_t)ic_;
+    const uint32_t cq = DIR > 0 ? qa + (uint32_t)jc_ - 1u : qa - (uint32_t)jc_;
+    const uint32_t tb = tcodes[ct], qb = qcodes[cq];
+    const int sc = sub5[tb * 5 + qb];
+    // D: vertical gap state, I: horizontal gap state (ties prefer opening from H, as in the oracle)
+    const int dopen = up.h - OE, dext = up.d - E;
+    const bool dsel = dopen >= dext;
+    const int nd = dsel ? dopen : dext, ndm = dsel ? up.hm : up.dm, ndc = dsel ? up.hc : up.dc;
+    const int iopen = left.h - OE, iext = left.i - E;
+    const bool isel = iopen >= iext;
+    const int ni = isel ? iopen : iext, nim = isel ? left.hm : left.im, nic = isel ? left.hc : left.ic;
+    const int mval = self.h + sc, mm = self.hm + ((tb == qb && tb < 4) ? 1 : 0), mc = self.hc + 1;
+    // H = max(M, D, I) with ties M > D > I
+    const bool pickm = mval >= nd && mval >= ni;
+    const bool pickd = nd >= ni;
+    const int nh = pickm ? mval : (pickd ? nd : ni);
+    const int nhm = pickm ? mm : (pickd ? ndm : nim);
+    const int nhc = pickm ? mc : (pickd ? ndc : nic);
+    const bool alive = inb && nh >= thr;
+    self.h = alive ? nh : NEG_INF; self.d = alive ? nd : NEG_INF; self.i = alive ? ni : NEG_INF;
+    self.hm = nhm; self.hc = nhc; self.dm = ndm; self.dc = ndc; self.im = nim; self.ic = nic;
+    if (alive && nh > tmax) { tmax = nh; ti = i; thm = nhm; thc = nhc; }
+    return alive;
 }
 
 struct WarpRec { int wmax, wi, hm, hc, dlo, dhi, pad0, pad1; };
 
 // One-sided y-drop extension by the whole CTA in diagonal-major coordinates. DIR=+1: cell (i,j) consumes T[ta+i-1],
 // Q[qa+j-1]; DIR=-1: T[ta-i], Q[qa-j]. Diagonals delta = i-j live in a circular window of GP_ND slots, slot = delta mod
-// GP_ND; thread t owns slots 4t..4t+3 for the whole extension, so every cell and three of its four neighbours stay in
-// registers. Per anti-diagonal a thread computes its two cells of the right parity, reads ONE cell of a neighbouring
-// thread from shared memory and publishes one; one __syncthreads per anti-diagonal. Dead cells are -inf by value, so the
-// window follows the alignment without any bookkeeping: a slot that re-enters the band on another diagonal is already dead.
+// GP_ND; thread t owns GP_SLOTS consecutive slots for the whole extension, so every cell and all but one of its neighbours stay in
+// registers. Per anti-diagonal a thread computes its four cells of the right parity (independent of each other), reads ONE
+// cell of a neighbouring thread from shared memory and publishes one; one __syncthreads per anti-diagonal. Dead cells are
+// -inf by value, so the window follows the alignment without bookkeeping: a slot that re-enters the band on another
+// diagonal is already dead.
 template <int DIR>
 __device__ Ext ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E, int Y,
                                 int* __restrict__ sm, WarpRec (*rec)[GP_WARPS], const int* __restrict__ sub5,
                                 unsigned long long& cells, int& err) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int4* A0 = reinterpret_cast<int4*>(sm);                 // published slot 0 of every thread
+    int4* A0 = reinterpret_cast<int4*>(sm);                 // published first slot of every thread
     int4* B0 = A0 + GP_NT;
-    int4* A3 = B0 + GP_NT;                                  // published slot 3
-    int4* B3 = A3 + GP_NT;
-    int* C0 = reinterpret_cast<int*>(B3 + GP_NT);
-    int* C3 = C0 + GP_NT;
+    int4* AL = B0 + GP_NT;                                  // published last slot
+    int4* BL = AL + GP_NT;
+    int* C0 = reinterpret_cast<int*>(BL + GP_NT);
+    int* CL = C0 + GP_NT;
+    const uint8_t* __restrict__ tcodes = T.codes;
+    const uint8_t* __restrict__ qcodes = Q.codes;
+    const int OE = O + E;
     Ext r = {0, 0, 0, 0, 0};
-    CellState s0, s1, s2, s3;
-    cs_dead(s0); cs_dead(s1); cs_dead(s2); cs_dead(s3);
-    if (tid == 0) s0.h = 0;                 // the cell (0,0): delta 0 -> slot 0 of thread 0
+    CellState st[GP_SLOTS];
+#pragma unroll
+    for (int s = 0; s < GP_SLOTS; s++) cs_dead(st[s]);
+    if (tid == 0) st[0].h = 0;              // the cell (0,0): delta 0 -> slot 0 of thread 0
     __syncthreads();                        // previous users of the buffers are done
-    A0[tid] = make_int4(s0.h, 0, 0, NEG_INF); B0[tid] = make_int4(NEG_INF, 0, 0, 0); C0[tid] = 0;
-    A3[tid] = make_int4(NEG_INF, 0, 0, NEG_INF); B3[tid] = make_int4(NEG_INF, 0, 0, 0); C3[tid] = 0;
+    A0[tid] = make_int4(st[0].h, 0, 0, NEG_INF); B0[tid] = make_int4(NEG_INF, 0, 0, 0); C0[tid] = 0;
+    AL[tid] = make_int4(NEG_INF, 0, 0, NEG_INF); BL[tid] = make_int4(NEG_INF, 0, 0, 0); CL[tid] = 0;
     __syncthreads();
     int best = 0, dead_steps = 0;
     int lo1 = 0, hi1 = 0, lo2 = 1, hi2 = 0;     // alive diagonal ranges of anti-diagonals k-1 and k-2 (empty when lo > hi)
     unsigned ncell = 0;
     const uint32_t kmax = (uint32_t)tn + (uint32_t)qn;
     for (uint32_t k = 1; k <= kmax; k++) {
-        // candidate diagonals of this anti-diagonal and the window position: delta of slot s is base + ((s - base) & mask)
+        // candidate diagonals of this anti-diagonal; the window base is a multiple of GP_SLOTS so a thread's slots stay consecutive
         int clo = INT_MAX, chi = INT_MIN;
         if (hi1 >= lo1) { clo = lo1 - 1; chi = hi1 + 1; }
         if (hi2 >= lo2) { clo = min(clo, lo2); chi = max(chi, hi2); }
         if (chi - clo > GP_MAXBAND) { err = 1; break; }
-        const int base = clo - 16;
+        const int base = (clo - 16) & ~(GP_SLOTS - 1);
+        const int d0 = base + ((GP_SLOTS * tid - base) & GP_DMASK);  // diagonal of slot 0; slot s holds d0 + s
         const int thr = best - Y;
         int tmax = INT_MIN, ti = 0, thm = 0, thc = 0, dlo = INT_MAX, dhi = INT_MIN;
-        const int dA = base + ((4 * tid - base) & GP_DMASK);      // diagonal currently held by slot 0 (slots 1..3 follow unless they wrap)
-        const int d0 = dA, d1 = base + ((4 * tid + 1 - base) & GP_DMASK), d2 = base + ((4 * tid + 2 - base) & GP_DMASK),
-                  d3 = base + ((4 * tid + 3 - base) & GP_DMASK);
-        if (k & 1) {
-            // odd anti-diagonal: slots 1 and 3. slot1: up = slot0, left = slot2 (own); slot3: up = slot2 (own), left = slot 0 of thread t+1
-            if ((d1 >= clo && d1 <= chi) || (d3 >= clo && d3 <= chi)) {
+        const bool active = d0 + GP_SLOTS - 1 >= clo && d0 <= chi;
+        if (active) {
+            if (k & 1) {
+                // odd anti-diagonal: odd slots; up = slot s-1 (own), left = slot s+1 (own, or slot 0 of thread t+1 for the last slot)
                 const int f = (tid + 1) & (GP_NT - 1);
                 CellState fl; const int4 fa = A0[f]; const int4 fb = B0[f];
                 fl.h = fa.x; fl.hm = fa.y; fl.hc = fa.z; fl.d = fa.w; fl.i = fb.x; fl.dm = fb.y; fl.dc = fb.z; fl.im = fb.w; fl.ic = C0[f];
-                gp_cell<DIR>(T, Q, ta, qa, tn, qn, O, E, thr, (int)k, d1, s1, s0, s2, sub5, tmax, ti, thm, thc, dlo, dhi, ncell);
-                gp_cell<DIR>(T, Q, ta, qa, tn, qn, O, E, thr, (int)k, d3, s3, s2, fl, sub5, tmax, ti, thm, thc, dlo, dhi, ncell);
-                A3[tid] = make_int4(s3.h, s3.hm, s3.hc, s3.d); B3[tid] = make_int4(s3.i, s3.dm, s3.dc, s3.im); C3[tid] = s3.ic;
-            }
-        } else {
-            // even anti-diagonal: slots 0 and 2. slot0: up = slot 3 of thread t-1, left = slot1 (own); slot2: up = slot1, left = slot3 (own)
-            if ((d0 >= clo && d0 <= chi) || (d2 >= clo && d2 <= chi)) {
+#pragma unroll
+                for (int s = 1; s < GP_SLOTS; s += 2) {
+                    const bool a = gp_cell<DIR>(tcodes, qcodes, ta, qa, tn, qn, OE, E, thr, (int)k, d0 + s, st[s], st[s - 1],
+                                                s + 1 < GP_SLOTS ? st[s + 1 < GP_SLOTS ? s + 1 : s] : fl, sub5, tmax, ti, thm, thc);
+                    if (a) { dlo = min(dlo, d0 + s); dhi = d0 + s; }
+                }
+                const CellState& e = st[GP_SLOTS - 1];
+                AL[tid] = make_int4(e.h, e.hm, e.hc, e.d); BL[tid] = make_int4(e.i, e.dm, e.dc, e.im); CL[tid] = e.ic;
+            } else {
+                // even anti-diagonal: even slots; up = slot s-1 (own, or the last slot of thread t-1 for slot 0), left = slot s+1 (own)
                 const int f = (tid - 1) & (GP_NT - 1);
-                CellState fu; const int4 fa = A3[f]; const int4 fb = B3[f];
-                fu.h = fa.x; fu.hm = fa.y; fu.hc = fa.z; fu.d = fa.w; fu.i = fb.x; fu.dm = fb.y; fu.dc = fb.z; fu.im = fb.w; fu.ic = C3[f];
-                gp_cell<DIR>(T, Q, ta, qa, tn, qn, O, E, thr, (int)k, d0, s0, fu, s1, sub5, tmax, ti, thm, thc, dlo, dhi, ncell);
-                gp_cell<DIR>(T, Q, ta, qa, tn, qn, O, E, thr, (int)k, d2, s2, s1, s3, sub5, tmax, ti, thm, thc, dlo, dhi, ncell);
-                A0[tid] = make_int4(s0.h, s0.hm, s0.hc, s0.d); B0[tid] = make_int4(s0.i, s0.dm, s0.dc, s0.im); C0[tid] = s0.ic;
+                CellState fu; const int4 fa = AL[f]; const int4 fb = BL[f];
+                fu.h = fa.x; fu.hm = fa.y; fu.hc = fa.z; fu.d = fa.w; fu.i = fb.x; fu.dm = fb.y; fu.dc = fb.z; fu.im = fb.w; fu.ic = CL[f];
+#pragma unroll
+                for (int s = 0; s < GP_SLOTS; s += 2) {
+                    const bool a = gp_cell<DIR>(tcodes, qcodes, ta, qa, tn, qn, OE, E, thr, (int)k, d0 + s, st[s], s > 0 ? st[s > 0 ? s - 1 : 0] : fu,
+                                                st[s + 1], sub5, tmax, ti, thm, thc);
+                    if (a) { dlo = min(dlo, d0 + s); dhi = d0 + s; }
+                }
+                const CellState& e = st[0];
+                A0[tid] = make_int4(e.h, e.hm, e.hc, e.d); B0[tid] = make_int4(e.i, e.dm, e.dc, e.im); C0[tid] = e.ic;
             }
-        }
-        const int wmax = __reduce_max_sync(0xffffffffu, tmax);
-        const int wlo = __reduce_min_sync(0xffffffffu, dlo), whi = __reduce_max_sync(0xffffffffu, dhi);
-        int wi = 0, whm = 0, whc = 0;
-        if (wmax > best) {
-            wi = __reduce_min_sync(0xffffffffu, tmax == wmax ? ti : INT_MAX);
-            const int src = __ffs(__ballot_sync(0xffffffffu, tmax == wmax && ti == wi)) - 1;
-            whm = __shfl_sync(0xffffffffu, thm, src); whc = __shfl_sync(0xffffffffu, thc, src);
+            ncell += GP_SLOTS / 2;
         }
         const int par = (int)(k & 1);
-        if (lane == 0) {
+        if (__any_sync(0xffffffffu, active)) {
+            const int wmax = __reduce_max_sync(0xffffffffu, tmax);
+            const int wlo = __reduce_min_sync(0xffffffffu, dlo), whi = __reduce_max_sync(0xffffffffu, dhi);
+            int wi = 0, whm = 0, whc = 0;
+            if (wmax > best) {
+                wi = __reduce_min_sync(0xffffffffu, tmax == wmax ? ti : INT_MAX);
+                const int src = __ffs(__ballot_sync(0xffffffffu, tmax == wmax && ti == wi)) - 1;
+                whm = __shfl_sync(0xffffffffu, thm, src); whc = __shfl_sync(0xffffffffu, thc, src);
+            }
+            if (lane == 0) {
+                int4* rp = reinterpret_cast<int4*>(&rec[par][warp]);
+                rp[0] = make_int4(wmax, wi, whm, whc); rp[1] = make_int4(wlo, whi, 0, 0);
+            }
+        } else if (lane == 0) {
             int4* rp = reinterpret_cast<int4*>(&rec[par][warp]);
-            rp[0] = make_int4(wmax, wi, whm, whc); rp[1] = make_int4(wlo, whi, 0, 0);
+            rp[0] = make_int4(INT_MIN, 0, 0, 0); rp[1] = make_int4(INT_MAX, INT_MIN, 0, 0);
         }
         __syncthreads();                    // the one barrier of this anti-diagonal
         int4 q0 = make_int4(INT_MIN, INT_MAX, 0, 0), q1 = make_int4(INT_MAX, INT_MIN, 0, 0);
@@ -285,7 +304,10 @@ __device__ int anchor_offset(const GenomeView& T, const GenomeView& Q, uint32_t 
     return bw + 15;
 }
 
-__global__ void __launch_bounds__(GP_NT, 1)
+// One thread-block CLUSTER of two CTAs owns one tile: CTA 0 extends every anchor forwards, CTA 1 backwards, concurrently.
+// They meet twice per anchor at a cluster barrier: once to swap their one-sided results through distributed shared memory,
+// once after CTA 0 has published the alignment record that later anchors of the tile are tested against.
+__global__ void __launch_bounds__(GP_NT, 3)
 gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, const int32_t* __restrict__ hs1, const int32_t* __restrict__ hs2,
               const int32_t* __restrict__ hlen, const uint32_t* __restrict__ order, uint32_t nmember,
               const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
@@ -293,10 +315,14 @@ gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, con
               int32_t* __restrict__ o_s1, int32_t* __restrict__ o_e1, int32_t* __restrict__ o_s2, int32_t* __restrict__ o_e2,
               int32_t* __restrict__ o_score, int32_t* __restrict__ o_nm, int32_t* __restrict__ o_nc, uint32_t* __restrict__ o_tile,
               uint32_t* __restrict__ o_keep, unsigned long long* __restrict__ counters) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = cluster.block_rank();          // 0: forward extension, 1: backward extension
     extern __shared__ __align__(16) int gp_smem[];
     __shared__ __align__(16) WarpRec rec[2][GP_WARPS];
     __shared__ uint32_t sh_seg;
     __shared__ int sh_off;
+    __shared__ Ext sh_ext;
     __shared__ int sub5[25];
     if (threadIdx.x < 25) {
         const int a = threadIdx.x / 5, b = threadIdx.x % 5;
@@ -307,9 +333,10 @@ gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, con
     unsigned long long cells = 0, anchors = 0;
     int err = 0;
     for (;;) {
-        if (tid == 0) sh_seg = (uint32_t)atomicAdd(&counters[CNT_WORK], 1ull);
-        __syncthreads();
-        const uint32_t seg = sh_seg;
+        if (crank == 0 && tid == 0) sh_seg = (uint32_t)atomicAdd(&counters[CNT_WORK], 1ull);
+        cluster.sync();
+        const uint32_t seg = *cluster.map_shared_rank(&sh_seg, 0);
+        cluster.sync();                                     // everyone has read it before CTA 0 may overwrite it
         if (seg >= nseg) break;
         const uint32_t a = seg_start[seg];
         const uint32_t b = (seg + 1 < nseg) ? seg_start[seg + 1] : nmember;
@@ -330,28 +357,31 @@ gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, con
             int cov = 0;                                          // spec D5: bounding-box test against reported alignments
             for (uint32_t kk = tid; kk < nkept; kk += GP_NT)
                 cov |= (a1 >= o_s1[a + kk] && a1 < o_e1[a + kk] && a2 >= o_s2[a + kk] && a2 < o_e2[a + kk]) ? 1 : 0;
-            if (__syncthreads_or(cov)) continue;
-            anchors++;
-            Ext f, r;
-            if (same_q[tsc] == (int)qsc && a1 == a2 && T.nfree[tsc]) {
-                f = selfdiag_extend_cta(T, toff + a1, toff + tlen, gp_smem);
-                r = selfdiag_extend_cta(T, toff, toff + a1, gp_smem);
-            } else {
-                f = ydrop_extend_cta<+1>(T, Q, toff + a1, qoff + a2, tlen - a1, qlen - a2, O, E, Y, gp_smem, rec, sub5, cells, err);
-                r = ydrop_extend_cta<-1>(T, Q, toff + a1, qoff + a2, a1, a2, O, E, Y, gp_smem, rec, sub5, cells, err);
-            }
+            if (__syncthreads_or(cov)) continue;                  // both CTAs take the same decision
+            if (crank == 0) anchors++;
+            Ext mine;
+            const bool closed = same_q[tsc] == (int)qsc && a1 == a2 && T.nfree[tsc];
+            if (crank == 0)
+                mine = closed ? selfdiag_extend_cta(T, toff + a1, toff + tlen, gp_smem)
+                              : ydrop_extend_cta<+1>(T, Q, toff + a1, qoff + a2, tlen - a1, qlen - a2, O, E, Y, gp_smem, rec, sub5, cells, err);
+            else
+                mine = closed ? selfdiag_extend_cta(T, toff, toff + a1, gp_smem)
+                              : ydrop_extend_cta<-1>(T, Q, toff + a1, qoff + a2, a1, a2, O, E, Y, gp_smem, rec, sub5, cells, err);
+            if (tid == 0) sh_ext = mine;
+            cluster.sync();                                       // swap the one-sided results
+            const Ext other = *cluster.map_shared_rank(&sh_ext, crank ^ 1);
+            const Ext f = crank == 0 ? mine : other, r = crank == 0 ? other : mine;
             const int score = f.score + r.score;
-            if (score < gthr) continue;
-            if (tid == 0) {
+            const bool keep = score >= gthr;
+            if (keep && crank == 0 && tid == 0) {
                 const uint32_t o = a + nkept;
                 o_s1[o] = a1 - r.di; o_e1[o] = a1 + f.di; o_s2[o] = a2 - r.dj; o_e2[o] = a2 + f.dj;
                 o_score[o] = score; o_nm[o] = f.nmatch + r.nmatch; o_nc[o] = f.ncols + r.ncols; o_tile[o] = tl; o_keep[o] = 1;
-                __threadfence_block();
+                __threadfence();
             }
-            nkept++;
-            __syncthreads();
+            if (keep) nkept++;
+            cluster.sync();                                       // record visible to both CTAs; sh_ext reusable
         }
-        __syncthreads();
     }
     if (cells) atomicAdd(&counters[CNT_GAPPED_CELLS], cells);
     if (tid == 0) {
@@ -449,13 +479,23 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
                 MB2_CUDA(cudaFuncSetAttribute(gapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM_BYTES));
                 attr_set = true;
             }
-            const unsigned blocks = std::min<unsigned>((unsigned)cx.sm_count * 2, std::max<unsigned>(1u, h_nseg));
+            // one cluster (2 CTAs) per tile in flight; 3 CTAs of 256 threads per SM
+            const unsigned nclusters = std::min<unsigned>((unsigned)cx.sm_count * 3 / 2, std::max<unsigned>(1u, h_nseg));
             MB2_CUDA(cudaMemsetAsync(counters + CNT_WORK, 0, sizeof(unsigned long long), cx.stream));
             ProfScope ps("gapped");
-            launch(gapped_kernel, blocks, GP_NT, GP_SMEM_BYTES, view(T), view(Q), h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(),
-                   order, h_nmember, seg_start.get(), d_nseg.get(), p.gap_open, p.gap_extend, p.ydrop, p.gappedthresh,
-                   d_same.get(),
-                   r_s1.get(), r_e1.get(), r_s2.get(), r_e2.get(), r_score.get(), r_nm.get(), r_nc.get(), r_tile.get(), keep.get(), counters);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * nclusters); cfg.blockDim = dim3(GP_NT); cfg.dynamicSmemBytes = GP_SMEM_BYTES; cfg.stream = cx.stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            const GenomeView tv = view(T), qv = view(Q);
+            MB2_CUDA(cudaLaunchKernelEx(&cfg, gapped_kernel, tv, qv, (const uint32_t*)h.tile.get(), (const int32_t*)h.s1.get(),
+                                        (const int32_t*)h.s2.get(), (const int32_t*)h.len.get(), (const uint32_t*)order, h_nmember,
+                                        (const uint32_t*)seg_start.get(), (const uint32_t*)d_nseg.get(), p.gap_open, p.gap_extend, p.ydrop,
+                                        p.gappedthresh, (const int32_t*)d_same.get(), r_s1.get(), r_e1.get(), r_s2.get(), r_e2.get(),
+                                        r_score.get(), r_nm.get(), r_nc.get(), r_tile.get(), keep.get(), counters));
+            cx.launches++;
         }
     }
     exclusive_scan_u32(keep.get(), keep_off.get(), n, d_nout.get());
