@@ -151,11 +151,22 @@ __device__ __forceinline__ int scaf_of(const uint32_t* __restrict__ off, int n, 
     return lo;
 }
 
+// A segment = consecutive survivors on one global diagonal inside one target scaffold. (Global diagonals are shared by
+// different scaffold pairs, e.g. every scaffold's trivial self-alignment lies on diagonal 0; splitting at scaffold
+// boundaries is exact because an HSP never crosses the pad between scaffolds, and it lets those walks run in parallel.)
 __global__ void __launch_bounds__(256)
-diag_heads_kernel(const uint64_t* __restrict__ surv, uint32_t n, uint32_t* __restrict__ flag) {
+diag_heads_kernel(const uint64_t* __restrict__ surv, uint32_t n, GenomeView T, uint32_t diag_bias, uint32_t* __restrict__ flag) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    flag[k] = (k == 0 || (uint32_t)(surv[k] >> 32) != (uint32_t)(surv[k - 1] >> 32)) ? 1u : 0u;
+    uint32_t head = 1;
+    if (k > 0) {
+        const uint32_t dg = (uint32_t)(surv[k] >> 32), dgp = (uint32_t)(surv[k - 1] >> 32);
+        if (dg == dgp) {
+            const uint32_t i = (uint32_t)surv[k] + dg - diag_bias, ip = (uint32_t)surv[k - 1] + dg - diag_bias;
+            head = scaf_of(T.off, T.nscaf, i) != scaf_of(T.off, T.nscaf, ip) ? 1u : 0u;
+        }
+    }
+    flag[k] = head;
 }
 __global__ void __launch_bounds__(256)
 diag_starts_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ flag_off, uint32_t n, uint32_t* __restrict__ seg_start) {
@@ -282,7 +293,7 @@ void find_hsps(const Genome& T, const Genome& Q, uint64_t* surv0, uint64_t* surv
         sorted = w ? b : a;
     }
     DevBuf<uint32_t> flag(nsurv), flag_off(nsurv), seg_start(nsurv), d_nseg(1);
-    launch(diag_heads_kernel, cdiv(nsurv, 256), 256, 0, sorted, nsurv, flag.get());
+    launch(diag_heads_kernel, cdiv(nsurv, 256), 256, 0, sorted, nsurv, view(T), (uint32_t)Q.G, flag.get());
     exclusive_scan_u32(flag.get(), flag_off.get(), nsurv, d_nseg.get());
     launch(diag_starts_kernel, cdiv(nsurv, 256), 256, 0, flag.get(), flag_off.get(), nsurv, seg_start.get());
 
