@@ -1,12 +1,69 @@
 // align.cu -- host driver of the alignment half: target table -> seed scan -> HSPs -> chain -> gapped.
-// One call handles one query strand; the C ABI layer runs both strands and converts coordinates.
+//
+// The target genome is indexed once; the (strand-oriented) query genome is processed in chunks of whole scaffolds so
+// that the survivor / HSP buffers stay bounded no matter how repeat-rich the input is. A chunk never splits a query
+// scaffold, so every (target scaffold, query scaffold, strand) tile -- the scope of LASTZ's --chain and of the gapped
+// stage -- is complete inside one chunk and the results are identical to a single pass (tests/test_gpu_align.py forces
+// tiny chunks and compares). Chunk size: MB2_CHUNK_MBP (default 128 Mbp of query per chunk).
+#include <algorithm>
+#include <cstdlib>
+
 #include "primitives.cuh"
 #include "seq.cuh"
 #include "internal.cuh"
 
 namespace mb2 {
 
-// Kept HSPs of every (target scaffold, query scaffold) tile of T x Q (Q already strand-oriented).
+static const uint64_t MAX_SURVIVORS = 1500000000ull;   // 12 GB of keys (x2 for the sort ping-pong)
+
+struct QChunk { int s_lo, s_hi; };   // query scaffolds [s_lo, s_hi)
+
+static std::vector<QChunk> make_chunks(const Genome& Q) {
+    uint64_t chunk_bases = 128ull << 20;
+    if (const char* e = getenv("MB2_CHUNK_MBP")) { const double v = atof(e); if (v > 0) chunk_bases = (uint64_t)(v * 1e6); }
+    std::vector<QChunk> out;
+    int lo = 0; uint64_t acc = 0;
+    for (int s = 0; s < Q.nscaf; s++) {
+        if (s > lo && acc + Q.len[s] > chunk_bases) { out.push_back({lo, s}); lo = s; acc = 0; }
+        acc += Q.len[s];
+    }
+    out.push_back({lo, Q.nscaf});
+    return out;
+}
+
+// query position range of scaffolds [s_lo, s_hi): from the first base of s_lo to the last base of s_hi-1 (windows that
+// start in the pad are invalid by construction)
+static void chunk_range(const Genome& Q, const QChunk& c, uint32_t& q_lo, uint32_t& q_hi) {
+    q_lo = Q.off[c.s_lo];
+    q_hi = Q.off[c.s_hi - 1] + Q.len[c.s_hi - 1];
+}
+
+// Seed scan of one chunk into a survivor buffer; grows the buffer once if it overflowed; returns false if the chunk must
+// be split because even MAX_SURVIVORS is not enough.
+static bool scan_chunk(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t q_lo, uint32_t q_hi, const AlignParams& p,
+                       DevBuf<uint64_t>& s0, uint64_t& cap, unsigned long long* counters, unsigned long long& nsurv,
+                       unsigned long long* stat_acc) {
+    Ctx& cx = ctx();
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (s0.n < cap) s0.alloc(cap);
+        MB2_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), cx.stream));
+        seed_scan(T, Q, tab, q_lo, q_hi, p, s0.get(), (uint32_t)std::min<uint64_t>(cap, 0xffffffffull), counters);
+        unsigned long long h[4];
+        MB2_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, cx.stream));
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));
+        nsurv = h[CNT_SURV];
+        if (nsurv <= cap) {
+            stat_acc[CNT_SURV] += h[CNT_SURV]; stat_acc[CNT_SEED_HITS] += h[CNT_SEED_HITS];
+            stat_acc[CNT_LEADERS] += h[CNT_LEADERS]; stat_acc[CNT_S1_CELLS] += h[CNT_S1_CELLS];
+            return true;
+        }
+        if (nsurv > MAX_SURVIVORS) return false;
+        cap = nsurv;
+    }
+    return false;
+}
+
+// Test hook (stage a+b only): kept HSPs of every tile of T x Q in canonical order, single chunk.
 void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& hsps, unsigned long long* h_counters) {
     Ctx& cx = ctx();
     MB2_REQUIRE(T.G + Q.G < 0xffffffffull, -3, "align: target + query exceed 2^32 padded positions");
@@ -14,57 +71,89 @@ void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& 
     MB2_CUDA(cudaMemsetAsync(counters.get(), 0, CNT_N * sizeof(unsigned long long), cx.stream));
     SeedTable tab;
     build_seed_table(T, 0, (uint32_t)T.G, tab);
-    uint32_t cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1u << 20, (T.nbases + Q.nbases) / 2), 0x7fffffffull);
+    uint64_t cap = std::max<uint64_t>(1u << 20, (T.nbases + Q.nbases) / 2);
     DevBuf<uint64_t> s0, s1;
-    unsigned long long nsurv = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        s0.alloc(cap);
-        MB2_CUDA(cudaMemsetAsync(counters.get(), 0, 4 * sizeof(unsigned long long), cx.stream));
-        seed_scan(T, Q, tab, GENOME_END_PAD, (uint32_t)Q.G - GENOME_END_PAD, p, s0.get(), cap, counters.get());
-        MB2_CUDA(cudaMemcpyAsync(&nsurv, counters.get() + CNT_SURV, sizeof(nsurv), cudaMemcpyDeviceToHost, cx.stream));
-        MB2_CUDA(cudaStreamSynchronize(cx.stream));
-        if (nsurv <= cap) break;
-        MB2_REQUIRE(nsurv < 0x7fffffffull && attempt == 0, -3, "align: too many surviving seed hits for one pass");
-        cap = (uint32_t)nsurv;
-    }
+    unsigned long long nsurv = 0, acc[CNT_N] = {0};
+    const bool ok = scan_chunk(T, Q, tab, GENOME_END_PAD, (uint32_t)Q.G - GENOME_END_PAD, p, s0, cap, counters.get(), nsurv, acc);
+    MB2_REQUIRE(ok, -3, "align: too many surviving seed hits for one pass");
     s1.alloc(nsurv ? nsurv : 1);
     find_hsps(T, Q, s0.get(), s1.get(), (uint32_t)nsurv, p, hsps, counters.get());
     if (h_counters) {
         MB2_CUDA(cudaMemcpyAsync(h_counters, counters.get(), CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, cx.stream));
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
+        for (int k = 0; k < 4; k++) h_counters[k] = acc[k];
     }
 }
 
-// Full pipeline for one strand orientation of Q: alignments in strand-local, scaffold-local coordinates.
-void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, AlnSet& alns, unsigned long long* h_counters) {
+static void append_alns(const AlnSet& a, HostAlns& out) {
+    const size_t n = a.n;
+    if (!n) return;
     Ctx& cx = ctx();
-    HspSet hsps;
-    unsigned long long c1[CNT_N];
-    align_hsps(T, Q, p, hsps, c1);
+    const size_t base = out.tile.size();
+    out.tile.resize(base + n); out.s1.resize(base + n); out.e1.resize(base + n); out.s2.resize(base + n); out.e2.resize(base + n);
+    out.score.resize(base + n); out.nmatch.resize(base + n); out.ncols.resize(base + n);
+    auto d2h = [&](void* dst, const void* src) { MB2_CUDA(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, cx.stream)); };
+    d2h(out.tile.data() + base, a.tile.get()); d2h(out.s1.data() + base, a.s1.get()); d2h(out.e1.data() + base, a.e1.get());
+    d2h(out.s2.data() + base, a.s2.get()); d2h(out.e2.data() + base, a.e2.get()); d2h(out.score.data() + base, a.score.get());
+    d2h(out.nmatch.data() + base, a.nmatch.get()); d2h(out.ncols.data() + base, a.ncols.get());
+    MB2_CUDA(cudaStreamSynchronize(cx.stream));
+}
+
+// Full pipeline for one strand-oriented query genome: alignments in strand-local, scaffold-local coordinates (host).
+void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, HostAlns& alns,
+                  unsigned long long* h_counters) {
+    Ctx& cx = ctx();
+    MB2_REQUIRE(T.G + Q.G < 0xffffffffull, -3, "align: target + query exceed 2^32 padded positions");
+    unsigned long long acc[CNT_N] = {0};
     uint32_t maxlen = 0;
     for (int s = 0; s < T.nscaf; s++) maxlen = std::max(maxlen, T.len[s]);
     for (int s = 0; s < Q.nscaf; s++) maxlen = std::max(maxlen, Q.len[s]);
     int lb = 1; while (lb < 32 && (maxlen >> lb)) lb++;
     lb += 1;   // e = s + len can reach maxlen exactly
     int tb = 1; while (tb < 33 && (((uint64_t)T.nscaf * (uint64_t)Q.nscaf) >> tb)) tb++;
-    DevBuf<uint8_t> in_chain;
-    if (p.chain) chain_hsps(hsps, lb, tb, in_chain);
-    else {
-        in_chain.alloc(hsps.n ? hsps.n : 1);
-        if (hsps.n) MB2_CUDA(cudaMemsetAsync(in_chain.get(), 1, hsps.n, cx.stream));
-    }
+
+    SeedTable tab;
+    build_seed_table(T, 0, (uint32_t)T.G, tab);
     DevBuf<unsigned long long> counters(CNT_N);
-    MB2_CUDA(cudaMemsetAsync(counters.get(), 0, CNT_N * sizeof(unsigned long long), cx.stream));
-    gapped_extend(T, Q, hsps, in_chain, p, h_same_q, alns, counters.get());
-    unsigned long long c2[CNT_N];
-    MB2_CUDA(cudaMemcpyAsync(c2, counters.get(), sizeof(c2), cudaMemcpyDeviceToHost, cx.stream));
-    MB2_CUDA(cudaStreamSynchronize(cx.stream));
-    if (h_counters) {
-        for (int k = 0; k < CNT_N; k++) h_counters[k] = c1[k];
-        h_counters[CNT_GAPPED_CELLS] = c2[CNT_GAPPED_CELLS];
-        h_counters[CNT_ANCHORS] = c2[CNT_ANCHORS];
-        h_counters[CNT_ALNS] = alns.n;
+    DevBuf<uint64_t> s0, s1;
+
+    std::vector<QChunk> todo = make_chunks(Q);
+    std::reverse(todo.begin(), todo.end());          // used as a stack; chunks are processed in scaffold order
+    while (!todo.empty()) {
+        const QChunk c = todo.back(); todo.pop_back();
+        uint32_t q_lo, q_hi;
+        chunk_range(Q, c, q_lo, q_hi);
+        uint64_t cbases = 0;
+        for (int s = c.s_lo; s < c.s_hi; s++) cbases += Q.len[s];
+        uint64_t cap = std::max<uint64_t>(1u << 20, std::min<uint64_t>(MAX_SURVIVORS, (T.nbases + cbases) / 2));
+        unsigned long long nsurv = 0;
+        MB2_CUDA(cudaMemsetAsync(counters.get(), 0, CNT_N * sizeof(unsigned long long), cx.stream));
+        if (!scan_chunk(T, Q, tab, q_lo, q_hi, p, s0, cap, counters.get(), nsurv, acc)) {
+            MB2_REQUIRE(c.s_hi - c.s_lo > 1, -3, "align: one query scaffold alone produces more surviving seed hits than fit in memory");
+            const int mid = (c.s_lo + c.s_hi) / 2;
+            todo.push_back({mid, c.s_hi}); todo.push_back({c.s_lo, mid});      // split and retry (lower half first)
+            continue;
+        }
+        if (nsurv == 0) continue;
+        if (s1.n < nsurv) s1.alloc(nsurv);
+        HspSet hsps;
+        find_hsps(T, Q, s0.get(), s1.get(), (uint32_t)nsurv, p, hsps, counters.get());
+        DevBuf<uint8_t> in_chain;
+        if (p.chain) chain_hsps(hsps, lb, tb, in_chain);
+        else {
+            in_chain.alloc(hsps.n ? hsps.n : 1);
+            if (hsps.n) MB2_CUDA(cudaMemsetAsync(in_chain.get(), 1, hsps.n, cx.stream));
+        }
+        AlnSet a;
+        gapped_extend(T, Q, hsps, in_chain, p, h_same_q, a, counters.get());
+        unsigned long long c2[CNT_N];
+        MB2_CUDA(cudaMemcpyAsync(c2, counters.get(), sizeof(c2), cudaMemcpyDeviceToHost, cx.stream));
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));
+        acc[CNT_HSPS] += hsps.n; acc[CNT_EXTENDED] += c2[CNT_EXTENDED]; acc[CNT_S2_CELLS] += c2[CNT_S2_CELLS];
+        acc[CNT_GAPPED_CELLS] += c2[CNT_GAPPED_CELLS]; acc[CNT_ANCHORS] += c2[CNT_ANCHORS]; acc[CNT_ALNS] += a.n;
+        append_alns(a, alns);
     }
+    if (h_counters) for (int k = 0; k < CNT_N; k++) h_counters[k] = acc[k];
 }
 
 }  // namespace mb2

@@ -313,21 +313,14 @@ int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux,
         }
         std::vector<int32_t> cols[10];
         try {
-            AlnSet a;
+            HostAlns a;
             unsigned long long cnt[CNT_N];
             align_strand(*T->g, *q, ap, (strands & 1) ? t_same_q : nullptr, a, cnt);
             for (int k = 0; k < CNT_N; k++) out->stats[k] = cnt[k];
-            const size_t n = a.n;
+            const size_t n = a.tile.size();
             if (n) {
-                std::vector<uint32_t> tile(n);
-                std::vector<int32_t> s1(n), e1(n), s2(n), e2(n), sc(n), nm(n), nc(n);
-                auto d2h = [&](void* dst, const void* src, size_t bytes) {
-                    MB2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
-                };
-                d2h(tile.data(), a.tile.get(), n * 4); d2h(s1.data(), a.s1.get(), n * 4); d2h(e1.data(), a.e1.get(), n * 4);
-                d2h(s2.data(), a.s2.get(), n * 4); d2h(e2.data(), a.e2.get(), n * 4); d2h(sc.data(), a.score.get(), n * 4);
-                d2h(nm.data(), a.nmatch.get(), n * 4); d2h(nc.data(), a.ncols.get(), n * 4);
-                MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+                const std::vector<uint32_t>& tile = a.tile;
+                const std::vector<int32_t>&s1 = a.s1, &e1 = a.e1, &s2 = a.s2, &e2 = a.e2, &sc = a.score, &nm = a.nmatch, &nc = a.ncols;
                 const uint32_t nq2 = (uint32_t)q->nscaf;
                 for (int c = 0; c < 10; c++) cols[c].reserve(n);
                 for (size_t k = 0; k < n; k++) {

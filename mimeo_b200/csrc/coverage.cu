@@ -72,7 +72,8 @@ __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
 __global__ void __launch_bounds__(COV_THREADS)
 cov_tile_kernel(const uint32_t* __restrict__ ev_start, const uint32_t* __restrict__ ev_stop, uint32_t nev,
                 uint32_t num_tiles, uint32_t tiles_per_cta, int cov,
-                uint32_t* __restrict__ flips_staging, uint32_t* __restrict__ cta_count, uint32_t* __restrict__ cta_base) {
+                uint32_t* __restrict__ flips_staging, uint32_t* __restrict__ cta_count, uint32_t* __restrict__ cta_base,
+                int* __restrict__ err) {
     __shared__ int diff[COV_PAD_TILE];
     __shared__ uint32_t sh_scan[COV_THREADS / 32 + 1];
     __shared__ uint32_t sh_idx[2];
@@ -107,7 +108,8 @@ cov_tile_kernel(const uint32_t* __restrict__ ev_start, const uint32_t* __restric
             const uint32_t idx = is + tid;
             const uint32_t k = (idx < nev) ? ev_start[idx] : COV_SENTINEL;
             const bool in = k < hi;
-            if (in) atomicAdd(&diff[pad_idx((int)(k - lo))], 1);
+            if (in && k < lo) atomicOr(err, 2);         // invariant: events of earlier tiles were consumed (never expected)
+            if (in && k >= lo) atomicAdd(&diff[pad_idx((int)(k - lo))], 1);
             const int cnt = __syncthreads_count(in);
             is += cnt;
             if (cnt < COV_THREADS) break;
@@ -116,7 +118,8 @@ cov_tile_kernel(const uint32_t* __restrict__ ev_start, const uint32_t* __restric
             const uint32_t idx = ie + tid;
             const uint32_t k = (idx < nev) ? ev_stop[idx] : COV_SENTINEL;
             const bool in = k < hi;
-            if (in) atomicAdd(&diff[pad_idx((int)(k - lo))], -1);
+            if (in && k < lo) atomicOr(err, 2);
+            if (in && k >= lo) atomicAdd(&diff[pad_idx((int)(k - lo))], -1);
             const int cnt = __syncthreads_count(in);
             ie += cnt;
             if (cnt < COV_THREADS) break;
@@ -140,11 +143,12 @@ cov_tile_kernel(const uint32_t* __restrict__ ev_start, const uint32_t* __restric
         }
         uint32_t ftotal;
         uint32_t off = block_excl_scan<COV_THREADS>((uint32_t)__popc(mask), sh_scan, ftotal);
-        uint32_t* dst = flips_staging + out_base + out_n + off;
+        uint32_t widx = out_base + out_n + off;
         while (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
-            *dst++ = lo + tid * COV_PER_THREAD + j;
+            if (widx < 2u * nev) flips_staging[widx] = lo + tid * COV_PER_THREAD + j; else atomicOr(err, 4);   // #flips <= #events
+            widx++;
         }
         out_n += ftotal;
         tile++;
@@ -155,17 +159,19 @@ cov_tile_kernel(const uint32_t* __restrict__ ev_start, const uint32_t* __restric
 
 __global__ void __launch_bounds__(256)
 cov_gather_kernel(const uint32_t* __restrict__ flips_staging, const uint32_t* __restrict__ cta_count,
-                  const uint32_t* __restrict__ cta_base, const uint32_t* __restrict__ cta_out, uint32_t* __restrict__ flips) {
+                  const uint32_t* __restrict__ cta_base, const uint32_t* __restrict__ cta_out, uint32_t* __restrict__ flips,
+                  uint32_t cap, int* __restrict__ err) {
     const uint32_t n = cta_count[blockIdx.x];
-    const uint32_t* src = flips_staging + cta_base[blockIdx.x];
-    uint32_t* dst = flips + cta_out[blockIdx.x];
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    const uint32_t b0 = cta_base[blockIdx.x], o0 = cta_out[blockIdx.x];
+    if ((uint64_t)b0 + n > cap || (uint64_t)o0 + n > cap) { if (threadIdx.x == 0) atomicOr(err, 8); return; }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) flips[o0 + i] = flips_staging[b0 + i];
 }
 
 // flips[2k], flips[2k+1] = rise/fall of run k in concatenated coordinates
 __global__ void __launch_bounds__(256)
-cov_runs_flag_kernel(const uint32_t* __restrict__ flips, const uint32_t* __restrict__ nflips_p, int min_len, uint32_t* __restrict__ keep) {
-    const uint32_t nruns = *nflips_p >> 1;
+cov_runs_flag_kernel(const uint32_t* __restrict__ flips, const uint32_t* __restrict__ nflips_p, int min_len, uint32_t* __restrict__ keep,
+                     uint32_t cap_runs) {
+    const uint32_t nruns = min(*nflips_p >> 1, cap_runs);
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nruns) return;
     keep[k] = ((int64_t)flips[2 * k + 1] - (int64_t)flips[2 * k] >= (int64_t)min_len) ? 1u : 0u;
@@ -174,8 +180,9 @@ cov_runs_flag_kernel(const uint32_t* __restrict__ flips, const uint32_t* __restr
 __global__ void __launch_bounds__(256)
 cov_runs_write_kernel(const uint32_t* __restrict__ flips, const uint32_t* __restrict__ nflips_p, int min_len,
                       const uint32_t* __restrict__ keep_off, const uint32_t* __restrict__ chrom_off, int nchrom,
-                      int32_t* __restrict__ seg_chrom, int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_end) {
-    const uint32_t nruns = *nflips_p >> 1;
+                      int32_t* __restrict__ seg_chrom, int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_end,
+                      uint32_t cap_runs, uint32_t cap_seg) {
+    const uint32_t nruns = min(*nflips_p >> 1, cap_runs);
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nruns) return;
     const uint32_t s = flips[2 * k], e = flips[2 * k + 1];
@@ -183,6 +190,7 @@ cov_runs_write_kernel(const uint32_t* __restrict__ flips, const uint32_t* __rest
     int lo = 0, hi = nchrom;            // last scaffold whose offset <= s
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (chrom_off[mid] <= s) lo = mid; else hi = mid; }
     const uint32_t o = keep_off[k];
+    if (o >= cap_seg) return;
     seg_chrom[o] = lo;
     seg_start[o] = (int32_t)(s - chrom_off[lo]);
     seg_end[o] = (int32_t)(e - chrom_off[lo]);
@@ -244,15 +252,15 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
     DevBuf<uint32_t> staging((size_t)2 * H), cta_count(nctas), cta_base(nctas), cta_out(nctas), d_nflips(1);
     { ProfScope ps("cov_tile");
     launch(cov_tile_kernel, nctas, COV_THREADS, 0, s_sorted, e_sorted, H, num_tiles, tiles_per_cta,
-           min_cov < 1 ? 1 : min_cov, staging.get(), cta_count.get(), cta_base.get()); }
+           min_cov < 1 ? 1 : min_cov, staging.get(), cta_count.get(), cta_base.get(), d_err.get()); }
     exclusive_scan_u32(cta_count.get(), cta_out.get(), nctas, d_nflips.get());
     DevBuf<uint32_t> flips((size_t)2 * H);
-    launch(cov_gather_kernel, nctas, 256, 0, staging.get(), cta_count.get(), cta_base.get(), cta_out.get(), flips.get());
+    launch(cov_gather_kernel, nctas, 256, 0, staging.get(), cta_count.get(), cta_base.get(), cta_out.get(), flips.get(), 2u * H, d_err.get());
 
     // runs: at most H of them (every run needs at least one start event)
     DevBuf<uint32_t> keep(H), keep_off(H), d_nseg(1);
     MB2_CUDA(cudaMemsetAsync(keep.get(), 0, (size_t)H * sizeof(uint32_t), cx.stream));
-    launch(cov_runs_flag_kernel, cdiv(H, 256), 256, 0, flips.get(), d_nflips.get(), min_len, keep.get());
+    launch(cov_runs_flag_kernel, cdiv(H, 256), 256, 0, flips.get(), d_nflips.get(), min_len, keep.get(), H);
     exclusive_scan_u32(keep.get(), keep_off.get(), H, d_nseg.get());
 
     uint32_t h_nseg = 0; int h_err = 0; uint32_t h_nflips = 0;
@@ -260,13 +268,14 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
     MB2_CUDA(cudaMemcpyAsync(&h_err, d_err.get(), sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
     MB2_CUDA(cudaMemcpyAsync(&h_nflips, d_nflips.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
     MB2_CUDA(cudaStreamSynchronize(cx.stream));
-    MB2_REQUIRE(h_err == 0, -4, "coverage: invalid hit (scaffold index out of range, negative start, or start > end)");
-    MB2_REQUIRE((h_nflips & 1u) == 0, -5, "coverage: internal error, odd number of depth-flag flips");
+    MB2_REQUIRE((h_err & 1) == 0, -4, "coverage: invalid hit (scaffold index out of range, negative start, or start > end)");
+    MB2_REQUIRE(h_err == 0, -5, std::string("coverage: internal invariant violated, code ") + std::to_string(h_err));
+    MB2_REQUIRE((h_nflips & 1u) == 0 && h_nflips <= 2ull * H, -5, std::string("coverage: internal error, inconsistent flip count ") + std::to_string(h_nflips));
     res.chrom.alloc(h_nseg); res.start.alloc(h_nseg); res.end.alloc(h_nseg);
     res.n = h_nseg;
     if (h_nseg)
         launch(cov_runs_write_kernel, cdiv(H, 256), 256, 0, flips.get(), d_nflips.get(), min_len, keep_off.get(),
-               d_off.get(), nchrom, res.chrom.get(), res.start.get(), res.end.get());
+               d_off.get(), nchrom, res.chrom.get(), res.start.get(), res.end.get(), H, h_nseg);
 }
 
 }  // namespace mb2

@@ -297,20 +297,32 @@ void find_hsps(const Genome& T, const Genome& Q, uint64_t* surv0, uint64_t* surv
     exclusive_scan_u32(flag.get(), flag_off.get(), nsurv, d_nseg.get());
     launch(diag_starts_kernel, cdiv(nsurv, 256), 256, 0, flag.get(), flag_off.get(), nsurv, seg_start.get());
 
-    DevBuf<uint32_t> r_tile(nsurv);
-    DevBuf<int32_t> r_s1(nsurv), r_s2(nsurv), r_len(nsurv), r_score(nsurv);
-    MB2_CUDA(cudaMemsetAsync(counters + CNT_WORK, 0, sizeof(unsigned long long), cx.stream));
-    MB2_CUDA(cudaMemsetAsync(counters + CNT_HSPS, 0, sizeof(unsigned long long), cx.stream));
-    {
-        ProfScope ps("hsp_extend");
-        const unsigned grid = (unsigned)cx.sm_count * 8;
-        launch(hsp_extend_kernel, grid, 128, 0, view(T), view(Q), sorted, nsurv, seg_start.get(), d_nseg.get(), (uint32_t)Q.G,
-               p.xdrop, p.hspthresh, p.entropy, nsurv, r_tile.get(), r_s1.get(), r_s2.get(), r_len.get(), r_score.get(), counters);
-    }
+    // every survivor yields at most one HSP, but usually far fewer: start with a quarter and redo the (deterministic)
+    // walk with the exact size if that was too small
+    uint32_t hcap = std::min<uint32_t>(nsurv, std::max<uint32_t>(1u << 20, nsurv / 4));
+    DevBuf<uint32_t> r_tile;
+    DevBuf<int32_t> r_s1, r_s2, r_len, r_score;
     unsigned long long h_n = 0;
-    MB2_CUDA(cudaMemcpyAsync(&h_n, counters + CNT_HSPS, sizeof(h_n), cudaMemcpyDeviceToHost, cx.stream));
-    MB2_CUDA(cudaStreamSynchronize(cx.stream));
-    MB2_REQUIRE(h_n <= nsurv, -5, "hsp stage: internal overflow");
+    for (int attempt = 0; attempt < 2; attempt++) {
+        r_tile.alloc(hcap); r_s1.alloc(hcap); r_s2.alloc(hcap); r_len.alloc(hcap); r_score.alloc(hcap);
+        MB2_CUDA(cudaMemsetAsync(counters + CNT_WORK, 0, sizeof(unsigned long long), cx.stream));
+        MB2_CUDA(cudaMemsetAsync(counters + CNT_HSPS, 0, sizeof(unsigned long long), cx.stream));
+        if (attempt) {   // the first walk already counted these
+            MB2_CUDA(cudaMemsetAsync(counters + CNT_S2_CELLS, 0, sizeof(unsigned long long), cx.stream));
+            MB2_CUDA(cudaMemsetAsync(counters + CNT_EXTENDED, 0, sizeof(unsigned long long), cx.stream));
+        }
+        {
+            ProfScope ps("hsp_extend");
+            const unsigned grid = (unsigned)cx.sm_count * 8;
+            launch(hsp_extend_kernel, grid, 128, 0, view(T), view(Q), sorted, nsurv, seg_start.get(), d_nseg.get(), (uint32_t)Q.G,
+                   p.xdrop, p.hspthresh, p.entropy, hcap, r_tile.get(), r_s1.get(), r_s2.get(), r_len.get(), r_score.get(), counters);
+        }
+        MB2_CUDA(cudaMemcpyAsync(&h_n, counters + CNT_HSPS, sizeof(h_n), cudaMemcpyDeviceToHost, cx.stream));
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));
+        if (h_n <= hcap) break;
+        MB2_REQUIRE(h_n <= nsurv && attempt == 0, -5, "hsp stage: internal overflow");
+        hcap = (uint32_t)h_n;
+    }
     const uint32_t n = (uint32_t)h_n;
     out.n = n;
     if (n == 0) return;

@@ -61,7 +61,8 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
 // align.cu
 void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& hsps, unsigned long long* h_counters);
 
-void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, AlnSet& alns, unsigned long long* h_counters);
+struct HostAlns { std::vector<uint32_t> tile; std::vector<int32_t> s1, e1, s2, e2, score, nmatch, ncols; };
+void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, HostAlns& alns, unsigned long long* h_counters);
 
 // counters layout (device, unsigned long long[16])
 enum { CNT_SURV = 0, CNT_SEED_HITS = 1, CNT_LEADERS = 2, CNT_S1_CELLS = 3, CNT_HSPS = 4, CNT_EXTENDED = 5, CNT_S2_CELLS = 6,

@@ -49,26 +49,35 @@ def synth_hits(seed, nchrom, chrom_size, nhits, hotspots):
 
 # ----------------------------------------------------------------------------------------- synthetic genomes
 def mutate(rng, seq, sub, indel):
-    """Copy of `seq` (uint8 ASCII) with per-base substitution prob `sub` and indel prob `indel` (length 1-3)."""
-    out = []
+    """Copy of `seq` (uint8 ASCII, ACGT) with per-base substitution prob `sub` and indel prob `indel` (length 1-3,
+    half deletions, half insertions of random bases). Vectorised: substitutions first, then indels at sampled sites."""
     bases = np.frombuffer(b'ACGT', dtype=np.uint8)
-    i = 0
-    n = len(seq)
-    r = rng.random(n)
-    r2 = rng.random(n)
-    while i < n:
-        if r2[i] < indel:
-            ln = int(rng.integers(1, 4))
-            if rng.random() < 0.5:
-                i += ln                       # deletion
-                continue
-            out.append(bases[rng.integers(0, 4, ln)])   # insertion
-        b = seq[i]
-        if r[i] < sub:
-            b = bases[(int(np.searchsorted(bases, b)) + int(rng.integers(1, 4))) % 4]
-        out.append(np.array([b], dtype=np.uint8))
-        i += 1
-    return np.concatenate(out) if out else np.zeros(0, np.uint8)
+    out = np.array(seq, dtype=np.uint8, copy=True)
+    n = len(out)
+    if n == 0:
+        return out
+    hit = np.flatnonzero(rng.random(n) < sub)
+    if len(hit):
+        code = np.searchsorted(bases, out[hit])
+        out[hit] = bases[(code + rng.integers(1, 4, len(hit))) % 4]
+    sites = np.flatnonzero(rng.random(n) < indel)
+    if len(sites) == 0:
+        return out
+    lens = rng.integers(1, 4, len(sites))
+    is_del = rng.random(len(sites)) < 0.5
+    keep = np.ones(n, dtype=bool)
+    for p, ln in zip(sites[is_del], lens[is_del]):
+        keep[p:p + ln] = False
+    ins_sites = sites[~is_del]
+    ins_lens = lens[~is_del]
+    if len(ins_sites):
+        ins_pos = np.repeat(ins_sites, ins_lens)
+        ins_val = bases[rng.integers(0, 4, len(ins_pos))]
+        # insert before the site; deleted bases are dropped afterwards by the shifted mask
+        out2 = np.insert(out, ins_pos, ins_val)
+        keep2 = np.insert(keep, ins_pos, True)
+        return out2[keep2]
+    return out[keep]
 
 
 _COMP = np.zeros(256, dtype=np.uint8)
@@ -87,7 +96,7 @@ def synth_genome(seed, nscaf, scaf_len, nfam, copies=(5, 30), fam_len=(300, 3000
     rng = np.random.default_rng(seed)
     bases = np.frombuffer(b'ACGT', dtype=np.uint8)
     scafs = [bases[rng.integers(0, 4, scaf_len)].copy() for _ in range(nscaf)]
-    used = [[] for _ in range(nscaf)]
+    used = [np.zeros(scaf_len // 64 + 2, dtype=bool) for _ in range(nscaf)]     # 64-base occupancy map
     for _ in range(nfam):
         L = int(rng.integers(fam_len[0], fam_len[1] + 1))
         cons = bases[rng.integers(0, 4, L)]
@@ -98,9 +107,9 @@ def synth_genome(seed, nscaf, scaf_len, nfam, copies=(5, 30), fam_len=(300, 3000
             for _try in range(50):
                 s = int(rng.integers(0, nscaf))
                 p = int(rng.integers(0, scaf_len - len(cp)))
-                if all(p + len(cp) <= a or p >= b for a, b in used[s]):
+                if not used[s][p // 64:(p + len(cp)) // 64 + 1].any():
                     scafs[s][p:p + len(cp)] = cp
-                    used[s].append((p, p + len(cp)))
+                    used[s][p // 64:(p + len(cp)) // 64 + 1] = True
                     break
     for _ in range(n_runs):                       # a few N runs to exercise non-ACGT handling
         s = int(rng.integers(0, nscaf)); p = int(rng.integers(0, scaf_len - 50))

@@ -122,3 +122,18 @@ def test_target_subset_with_identity_map_matches_full_run(M):
         part['t_id'] = np.asarray(sub, dtype=np.int32)[part['t_id']]
         want = {r for r in full_rows if r[0] in sub}
         assert gpu_rows(part) == want and len(want) > 4
+
+
+def test_query_chunking_is_invisible(M, monkeypatch):
+    """Processing the query in chunks of whole scaffolds (bounded buffers for big genomes) must not change a single row."""
+    A, G = M
+    g = synth_genome(47, 5, 20_000, 3, copies=(5, 8), fam_len=(400, 1500), sub=0.07, indel=0.004, n_runs=1)
+    names = sorted(g)
+    T = G.Genome(names, [g[n] for n in names])
+    monkeypatch.delenv('MB2_CHUNK_MBP', raising=False)
+    one, s1 = A.align(T, T, G.align_params(3000))
+    monkeypatch.setenv('MB2_CHUNK_MBP', '0.03')          # 30 kbp chunks: the 10 strand-scaffolds fall into ~7 chunks
+    many, s2 = A.align(T, T, G.align_params(3000))
+    assert gpu_rows(one) == gpu_rows(many) and len(one['t_id']) > 10
+    for k in ('seed_hits', 'leaders', 'survivors', 'hsps', 'alignments'):
+        assert s1[k] == s2[k], k
