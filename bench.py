@@ -301,7 +301,28 @@ class ShardedSelfWorkload(SelfWorkload):
     def cpu_reference(self, threads, npairs=None):
         return SelfWorkload.cpu_reference(self, threads, npairs=max(2, min(8, threads)))
 
-WORKLOADS = {'self': SelfWorkload, 'cov': CoverageWorkload, 'c5s': ShardedSelfWorkload}
+
+class C5Workload(ShardedSelfWorkload):
+    """BASELINE config 5: `mimeo self` on a 1 Gbp synthetic plant-like genome (40 % repeats, 500 scaffolds), one genome whose
+    target scaffolds are row-sharded over the ranks (strong scaling). MB2_C5_MBP scales the genome down for trial runs (the
+    workload name then says so)."""
+    NSCAF = 500
+    scaling = 'strong'
+
+    def __init__(self, rank):
+        from tests.helpers import synth_c5
+        mbp = float(os.environ.get('MB2_C5_MBP', '1000'))
+        nscaf = max(8, int(round(self.NSCAF * mbp / 1000.0)))
+        g = synth_c5(1005, int(mbp * 1e6), nscaf)
+        self.names = sorted(g, key=lambda s: s.encode())
+        self.seqs = [g[n] for n in self.names]
+        self.sizes = [len(x) for x in self.seqs]
+        self.mbp = sum(self.sizes) / 1e6
+        self.name = ('C5: mimeo self, synthetic plant-like genome %.0f Mbp, %d scaffolds (log-normal lengths), 40%% repeats (families of '
+                     '2-10 kbp, 50-2000 copies, 75-98%% identity), minIdt 80 minLen 100 minCov 3 intraCov 4 strictSelf, targets sharded over ranks'
+                     % (self.mbp, nscaf)) + ('' if mbp == 1000 else ' [SCALED-DOWN TRIAL of the 1 Gbp config]')
+
+WORKLOADS = {'self': SelfWorkload, 'cov': CoverageWorkload, 'c5s': ShardedSelfWorkload, 'c5': C5Workload}
 
 
 # ------------------------------------------------------------------------------------------------- arms

@@ -43,18 +43,58 @@ chain_rank_kernel(const uint32_t* __restrict__ ord2, const int32_t* __restrict__
     e2s[k] = s2[x] + len[x];
 }
 
-struct ChV { long long c; int idx; };
-__device__ __forceinline__ bool chv_better(long long ac, int ai, long long bc, int bi) {
-    return ac != bc ? ac > bc : ai < bi;
+// (chain score, index) packed so that "larger score, then smaller index" is plain unsigned max:
+// score in the top 40 bits, (0xFFFFFF - index) in the low 24. 0 = "no predecessor".
+__device__ __forceinline__ unsigned long long chv_pack(long long c, uint32_t idx) {
+    return ((unsigned long long)c << 24) | (unsigned long long)(0xFFFFFFu - idx);
 }
 
+// Per HSP g (parallel): upto1[g] = #HSPs of its tile with e1 <= s1[g] (how many are visible to it),
+//                       cnt2[g]  = #HSPs of its tile with e2 <= s2[g] (Fenwick prefix it may query).
+__global__ void __launch_bounds__(256)
+chain_bounds_kernel(const int32_t* __restrict__ s1, const int32_t* __restrict__ s2, uint32_t n,
+                    const uint32_t* __restrict__ flag, const uint32_t* __restrict__ flag_off,
+                    const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
+                    const int32_t* __restrict__ e1s, const int32_t* __restrict__ e2s,
+                    uint32_t* __restrict__ upto1, uint32_t* __restrict__ cnt2) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const uint32_t seg = flag_off[g] + flag[g] - 1;
+    const uint32_t a = seg_start[seg];
+    const uint32_t b = (seg + 1 < *nseg_p) ? seg_start[seg + 1] : n;
+    const uint32_t m = b - a;
+    uint32_t lo = 0, hi = m;
+    const int x1 = s1[g];
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (e1s[a + mid] <= x1) lo = mid + 1; else hi = mid; }
+    upto1[g] = lo;
+    lo = 0; hi = m;
+    const int x2 = s2[g];
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (e2s[a + mid] <= x2) lo = mid + 1; else hi = mid; }
+    cnt2[g] = lo;
+}
+
+// e1s[k] = e1 of the k-th HSP in (tile, e1) order
+__global__ void __launch_bounds__(256)
+chain_e1s_kernel(const uint32_t* __restrict__ ord1, const int32_t* __restrict__ s1, const int32_t* __restrict__ len, uint32_t n,
+                 int32_t* __restrict__ e1s) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t x = ord1[k];
+    e1s[k] = s1[x] + len[x];
+}
+
+// One warp per tile. The HSPs of a tile are visited sequentially (canonical order), but every Fenwick-tree operation is
+// done by the warp in ONE memory round trip: the positions of an update chain (p, p+lowbit(p), ...) and of a query chain
+// (q, q-lowbit(q), ...) do not depend on the stored values, so lane l takes the l-th position of the chain.
+constexpr int CHAIN_SMEM_ENTRIES = 1024;     // tiles up to this many HSPs keep their tree in shared memory
+
 __global__ void __launch_bounds__(128)
-chain_kernel(const int32_t* __restrict__ s1, const int32_t* __restrict__ s2, const int32_t* __restrict__ len,
-             const int32_t* __restrict__ score, uint32_t n, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
-             const uint32_t* __restrict__ ord1, const uint32_t* __restrict__ rank2, const int32_t* __restrict__ e2s,
-             long long* __restrict__ bitC, int* __restrict__ bitI, long long* __restrict__ C, int* __restrict__ pred,
-             uint8_t* __restrict__ in_chain, unsigned long long* __restrict__ work) {
-    const int lane = threadIdx.x & 31;
+chain_kernel(const int32_t* __restrict__ score, uint32_t n, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
+             const uint32_t* __restrict__ ord1, const uint32_t* __restrict__ rank2, const uint32_t* __restrict__ upto1,
+             const uint32_t* __restrict__ cnt2, unsigned long long* __restrict__ bit_g, long long* __restrict__ C, int* __restrict__ pred,
+             uint8_t* __restrict__ in_chain, unsigned long long* __restrict__ work, int* __restrict__ err) {
+    __shared__ unsigned long long bit_s[4][CHAIN_SMEM_ENTRIES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t nseg = *nseg_p;
     for (;;) {
         uint32_t seg = 0;
@@ -64,37 +104,39 @@ chain_kernel(const int32_t* __restrict__ s1, const int32_t* __restrict__ s2, con
         const uint32_t a = seg_start[seg];
         const uint32_t b = (seg + 1 < nseg) ? seg_start[seg + 1] : n;
         const uint32_t m = b - a;
-        for (uint32_t k = lane; k < m; k += 32) { bitC[a + k] = 0; bitI[a + k] = INT_MAX; in_chain[a + k] = 0; }
+        if (m >= 0xFFFFFFu) { if (lane == 0) atomicOr(err, 1); continue; }
+        unsigned long long* bit = m <= (uint32_t)CHAIN_SMEM_ENTRIES ? bit_s[warp] : bit_g + a;      // 1-based positions stored at [pos-1]
+        for (uint32_t k = lane; k < m; k += 32) { bit[k] = 0ull; in_chain[a + k] = 0; }
         __syncwarp();
-        if (lane == 0) {
-            uint32_t ins = 0;
-            for (uint32_t x = 0; x < m; x++) {              // canonical order inside the tile
-                const uint32_t g = a + x;
-                const int xs1 = s1[g], xs2 = s2[g];
-                while (ins < m) {
-                    const uint32_t y = ord1[a + ins];        // global idx, increasing e1 inside the tile
-                    if (s1[y] + len[y] > xs1) break;
-                    const long long cy = C[y];
-                    const int yi = (int)(y - a);
-                    for (uint32_t pos = rank2[y] - a + 1; pos <= m; pos += pos & (~pos + 1)) {
-                        if (chv_better(cy, yi, bitC[a + pos - 1], bitI[a + pos - 1])) { bitC[a + pos - 1] = cy; bitI[a + pos - 1] = yi; }
-                    }
-                    ins++;
-                }
-                // number of HSPs of the tile with e2 <= xs2
-                uint32_t lo = 0, hi = m;
-                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (e2s[a + mid] <= xs2) lo = mid + 1; else hi = mid; }
-                long long bc = 0; int bi = INT_MAX;
-                for (uint32_t pos = lo; pos > 0; pos -= pos & (~pos + 1)) {
-                    if (chv_better(bitC[a + pos - 1], bitI[a + pos - 1], bc, bi)) { bc = bitC[a + pos - 1]; bi = bitI[a + pos - 1]; }
-                }
-                pred[g] = bi == INT_MAX ? -1 : bi;
-                C[g] = (long long)score[g] + (bi == INT_MAX ? 0 : bc);
+        uint32_t ins = 0;
+        long long cbest = -1; uint32_t end = 0;
+        for (uint32_t x = 0; x < m; x++) {              // canonical order inside the tile
+            const uint32_t g = a + x;
+            const uint32_t upto = upto1[g];
+            for (; ins < upto; ins++) {                  // make every HSP with e1 <= s1_x visible
+                const uint32_t y = ord1[a + ins];
+                const unsigned long long key = chv_pack(C[y], y - a);
+                uint32_t pos = rank2[y] - a + 1;
+                for (int l = 0; l < lane && pos <= m; l++) pos += pos & (0u - pos);      // lane l takes the l-th node of the update chain
+                if (pos <= m && bit[pos - 1] < key) bit[pos - 1] = key;
+                __syncwarp();
             }
-            uint32_t end = 0;
-            for (uint32_t x = 1; x < m; x++) if (C[a + x] > C[a + end]) end = x;
-            for (int k = (int)end; k >= 0; k = pred[a + k]) in_chain[a + k] = 1;
+            uint32_t q = cnt2[g];
+            for (int l = 0; l < lane && q > 0; l++) q -= q & (0u - q);                   // l-th node of the query chain
+            unsigned long long v = q > 0 ? bit[q - 1] : 0ull;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d); v = o > v ? o : v; }
+            if (lane == 0) {
+                const long long bc = (long long)(v >> 24);
+                const long long c = (long long)score[g] + (v ? bc : 0);
+                C[g] = c;
+                pred[g] = v ? (int)(0xFFFFFFu - (uint32_t)(v & 0xFFFFFFu)) : -1;
+                if (c > cbest) { cbest = c; end = x; }
+            }
+            __syncwarp();
         }
+        if (lane == 0)
+            for (int k = (int)end; k >= 0; k = pred[a + k]) in_chain[a + k] = 1;
         __syncwarp();
     }
 }
@@ -123,12 +165,22 @@ void chain_hsps(const HspSet& h, int lb, int tb, DevBuf<uint8_t>& in_chain) {
     exclusive_scan_u32(flag.get(), flag_off.get(), n, d_nseg.get());
     launch(heads_scatter_kernel, cdiv(n, 256), 256, 0, flag.get(), flag_off.get(), n, seg_start.get());
 
-    DevBuf<long long> bitC(n), C(n);
-    DevBuf<int> bitI(n), pred(n);
-    DevBuf<unsigned long long> work(1);
+    DevBuf<int32_t> e1s(n);
+    launch(chain_e1s_kernel, cdiv(n, 256), 256, 0, ord1, h.s1.get(), h.len.get(), n, e1s.get());
+    DevBuf<uint32_t> upto1(n), cnt2(n);
+    launch(chain_bounds_kernel, cdiv(n, 256), 256, 0, h.s1.get(), h.s2.get(), n, flag.get(), flag_off.get(), seg_start.get(), d_nseg.get(),
+           e1s.get(), e2s.get(), upto1.get(), cnt2.get());
+    DevBuf<unsigned long long> bit(n), work(1);
+    DevBuf<long long> C(n);
+    DevBuf<int> pred(n), d_err(1);
     MB2_CUDA(cudaMemsetAsync(work.get(), 0, sizeof(unsigned long long), cx.stream));
-    launch(chain_kernel, (unsigned)cx.sm_count * 8, 128, 0, h.s1.get(), h.s2.get(), h.len.get(), h.score.get(), n, seg_start.get(),
-           d_nseg.get(), ord1, rank2.get(), e2s.get(), bitC.get(), bitI.get(), C.get(), pred.get(), in_chain.get(), work.get());
+    MB2_CUDA(cudaMemsetAsync(d_err.get(), 0, sizeof(int), cx.stream));
+    launch(chain_kernel, (unsigned)cx.sm_count * 4, 128, 0, h.score.get(), n, seg_start.get(), d_nseg.get(), ord1, rank2.get(), upto1.get(),
+           cnt2.get(), bit.get(), C.get(), pred.get(), in_chain.get(), work.get(), d_err.get());
+    int h_err = 0;
+    MB2_CUDA(cudaMemcpyAsync(&h_err, d_err.get(), sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
+    MB2_CUDA(cudaStreamSynchronize(cx.stream));
+    MB2_REQUIRE(h_err == 0, -3, "chain: a tile holds more than 2^24 HSPs");
 }
 
 }  // namespace mb2

@@ -115,3 +115,42 @@ def synth_genome(seed, nscaf, scaf_len, nfam, copies=(5, 30), fam_len=(300, 3000
         s = int(rng.integers(0, nscaf)); p = int(rng.integers(0, scaf_len - 50))
         scafs[s][p:p + int(rng.integers(1, 40))] = ord('N')
     return {f'scaf{i:03d}': scafs[i] for i in range(nscaf)}
+
+
+def synth_c5(seed, total_bp=1_000_000_000, nscaf=500, repeat_frac=0.40, fam_len=(2000, 10000), copies=(50, 2000),
+             identity=(0.75, 0.98), sigma=0.8):
+    """SURVEY 8(d) config-5 shaped generator: `nscaf` scaffolds with log-normal lengths summing to `total_bp`, uniform
+    random background, repeat families (LTR-like 2-10 kbp, 50-2000 copies, per-family identity 75-98 %) planted until
+    `repeat_frac` of the bases are repeats. Returns {name: uint8 ASCII array}."""
+    rng = np.random.default_rng(seed)
+    bases = np.frombuffer(b'ACGT', dtype=np.uint8)
+    w = rng.lognormal(0.0, sigma, nscaf)
+    lens = np.maximum((w / w.sum() * total_bp).astype(np.int64), 20_000)
+    scafs = [bases[rng.integers(0, 4, int(n))] for n in lens]
+    used = [np.zeros(int(n) // 64 + 2, dtype=bool) for n in lens]
+    cum = np.cumsum(lens) / lens.sum()
+    target = repeat_frac * lens.sum()
+    planted = 0
+    while planted < target:
+        L = int(rng.integers(fam_len[0], fam_len[1] + 1))
+        ncopy = int(np.exp(rng.uniform(np.log(copies[0]), np.log(copies[1]))))
+        ident = rng.uniform(identity[0], identity[1])
+        sub = 1.0 - np.sqrt(ident)                      # two copies each diverged from the consensus
+        cons = bases[rng.integers(0, 4, L)]
+        for _ in range(ncopy):
+            cp = mutate(rng, cons, sub, 0.004)
+            if rng.random() < 0.5:
+                cp = revcomp_ascii(cp)
+            for _try in range(20):
+                s = int(np.searchsorted(cum, rng.random()))
+                if len(cp) + 64 >= lens[s]:
+                    continue
+                p = int(rng.integers(0, lens[s] - len(cp)))
+                if not used[s][p // 64:(p + len(cp)) // 64 + 1].any():
+                    scafs[s][p:p + len(cp)] = cp
+                    used[s][p // 64:(p + len(cp)) // 64 + 1] = True
+                    planted += len(cp)
+                    break
+            if planted >= target:
+                break
+    return {f'scaf{i:04d}': scafs[i] for i in range(nscaf)}
