@@ -120,8 +120,13 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         Ctx& cx = ctx();
         // stage ASCII with 'N' padding in pinned host memory, one H2D copy, pack on the device
         const size_t nbytes = g->G + 64;   // = (G/32 + 2) * 32
-        uint8_t* h = nullptr;
-        MB2_CUDA(cudaMallocHost((void**)&h, nbytes));
+        if (cx.pinned_bytes < nbytes) {
+            if (cx.pinned) cudaFreeHost(cx.pinned);
+            cx.pinned = nullptr; cx.pinned_bytes = 0;
+            MB2_CUDA(cudaMallocHost((void**)&cx.pinned, nbytes + (nbytes >> 2)));
+            cx.pinned_bytes = nbytes + (nbytes >> 2);
+        }
+        uint8_t* h = cx.pinned;
         memset(h, 'N', nbytes);
         for (int s = 0; s < n; s++) memcpy(h + g->off[s], seqs[s], lens[s]);
         DevBuf<uint8_t> d_ascii(nbytes);
@@ -134,8 +139,7 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get(), g->codes.get());
         g->d_nfree.alloc(n);
         launch(nfree_kernel, n, 256, 0, g->nm.get(), g->d_off.get(), g->d_len.get(), g->d_nfree.get());
-        MB2_CUDA(cudaStreamSynchronize(cx.stream));
-        cudaFreeHost(h);
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));      // the staging buffer is reusable after this
         g->id = next_genome_id(); g->fwd_src_id = g->id; g->nfwd = n;
     } catch (...) { delete g; throw; }
     return g;
