@@ -1,36 +1,42 @@
-// gapped.cu -- kernel family (c): anchors + affine-gap y-drop extension, warp-shuffle anti-diagonal
-// dynamic programming, integer only (no tensor cores: this is not a dense contraction).
+// gapped.cu -- kernel family (c): anchors + affine-gap y-drop extension, anti-diagonal dynamic
+// programming, integer only (no tensor cores: this is not a dense contraction).
 //
 // Replaces LASTZ's --gapped stage under spec D4/D5 of oracle/lastz_oracle.c:
 //   * every chained HSP is reduced to an anchor = centre of its best 31-column window;
 //   * per tile, anchors are taken best-first; an anchor inside the bounding box of an alignment
 //     already reported for the tile is skipped;
 //   * from the anchor the alignment is extended forwards and backwards by an affine-gap DP
-//     (open 400, extend 30) evaluated one anti-diagonal at a time: a warp computes 32 cells of the
-//     anti-diagonal per step (each cell needs only its up/left neighbours on the previous anti-diagonal
-//     and its diagonal neighbour two back); a cell survives iff H >= best - ydrop, where best is the
-//     maximum over all earlier anti-diagonals. The three DP states each carry (matches, aligned
-//     columns) of their arg-max path, so identity needs no traceback;
+//     (open 400, extend 30) evaluated one anti-diagonal at a time; a cell survives iff
+//     H >= best - ydrop, where best is the maximum over all earlier anti-diagonals. The three DP
+//     states each carry (matches, aligned columns) of their arg-max path, so identity needs no
+//     traceback;
 //   * keep the alignment if forward + backward score >= gappedthresh.
-// One warp owns one tile (its anchors are inherently sequential); tiles are scheduled dynamically.
-#include <cooperative_groups.h>
-
+//
+// Schedule. Under spec D5 an extension depends only on its anchor, never on the alignments reported
+// before it; only the SKIP decision is sequential. So the stage runs in rounds:
+//   gp_select_kernel   one warp per tile walks the tile's anchors best-first as far as results exist
+//                      (accept / skip exactly as the sequential rule says), then schedules extensions
+//                      for anchors that are still undecided: the first undecided one, plus -- as
+//                      speculation -- the best anchor of every other "cluster" of the chain (run of
+//                      chain members with small gaps, which one alignment usually swallows whole);
+//   gp_extend_kernel   one CTA per (anchor, direction), all tiles in one launch.
+// Speculation changes which extensions are computed early, never the result: a speculative result is
+// only used when the sequential walk reaches its anchor and finds it uncovered.
 #include "primitives.cuh"
 #include "seq.cuh"
 #include "internal.cuh"
 
 namespace mb2 {
 
-constexpr int GP_NT = 256;             // threads per CTA (measured sweet spot between per-warp overhead and per-thread chain length)
-constexpr int GP_WARPS = GP_NT / 32;
-constexpr int GP_SLOTS = 4;            // diagonals per thread: two independent cells per thread per anti-diagonal
-constexpr int GP_ND = GP_SLOTS * GP_NT;  // circular diagonal slots: thread t owns GP_SLOTS consecutive slots, slot = (i - j) & (GP_ND - 1)
-constexpr int GP_DMASK = GP_ND - 1;
-constexpr int GP_MAXBAND = GP_ND - 64;   // widest alive diagonal range the circular window can hold
+// CTA shape of the extension kernel: NT threads, each owning SLOTS consecutive diagonals of a circular window of
+// ND = NT * SLOTS diagonal slots, slot = (i - j) & (ND - 1); a thread computes SLOTS/2 independent cells per anti-diagonal.
+template <int NT_, int SLOTS_> struct GpShape {
+    static constexpr int NT = NT_, SLOTS = SLOTS_, WARPS = NT_ / 32, ND = NT_ * SLOTS_, DMASK = ND - 1;
+    static constexpr int MAXBAND = ND - 64;   // widest alive diagonal range the circular window can hold
+};
 constexpr int NEG_INF = INT_MIN / 4;
-// shared memory: only the two boundary slots of every thread are exchanged: A = {h, hm, hc, d}, B = {i, dm, dc, im}, C = {ic}
-constexpr int GP_SMEM_INTS = 2 * (4 + 4 + 1) * GP_NT;
-constexpr size_t GP_SMEM_BYTES = (size_t)GP_SMEM_INTS * sizeof(int);
+constexpr int GP_CLUSTER_GAP = 300;      // chain members further apart than this (either axis) start a new speculation cluster
+constexpr int GP_NARROW_ABORT_K = 140000;  // 16-bit payload run: beyond this anti-diagonal every cell has >= 65536 columns behind it
 
 __device__ __forceinline__ int sub_lut3(uint32_t idx) {
     const uint64_t lo = 0xE183648E85E18E5Bull, hi = 0x5B8EE1858E6483E1ull;
@@ -41,12 +47,13 @@ __device__ __forceinline__ int sub_lut3(uint32_t idx) {
 // ---- ordering of the chain members: per tile, score descending, then canonical (s1, s2)
 __global__ void __launch_bounds__(256)
 anchor_keys_kernel(const uint32_t* __restrict__ tile, const int32_t* __restrict__ score, const uint8_t* __restrict__ in_chain,
-                   uint32_t n, uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
+                   uint32_t n, uint64_t* __restrict__ key, uint32_t* __restrict__ idx, uint32_t* __restrict__ mflag) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     // non-members sort behind every real tile
     key[k] = in_chain[k] ? (((uint64_t)tile[k] << 31) | (uint64_t)(0x7fffffff - score[k])) : ~0ull;
     idx[k] = k;
+    mflag[k] = in_chain[k] ? 1u : 0u;
 }
 __global__ void __launch_bounds__(256)
 anchor_heads_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ flag) {
@@ -56,101 +63,147 @@ anchor_heads_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __re
     flag[k] = (member && (k == 0 || (key[k] >> 31) != (key[k - 1] >> 31))) ? 1u : 0u;
 }
 __global__ void __launch_bounds__(256)
-anchor_member_kernel(const uint64_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ flag) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    flag[k] = key[k] != ~0ull ? 1u : 0u;
-}
-__global__ void __launch_bounds__(256)
 anchor_starts_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ flag_off, uint32_t n, uint32_t* __restrict__ seg_start) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     if (flag[k]) seg_start[flag_off[k]] = k;
 }
+// speculation clusters over the members in canonical (= chain) order: mlist[r] = HSP index of the r-th member
+__global__ void __launch_bounds__(256)
+member_list_kernel(const uint32_t* __restrict__ mflag, const uint32_t* __restrict__ mrank, uint32_t n, uint32_t* __restrict__ mlist) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || !mflag[k]) return;
+    mlist[mrank[k]] = k;
+}
+__global__ void __launch_bounds__(256)
+cluster_heads_kernel(const uint32_t* __restrict__ mlist, uint32_t nmember, const uint32_t* __restrict__ tile, const int32_t* __restrict__ hs1,
+                     const int32_t* __restrict__ hs2, const int32_t* __restrict__ hlen, uint32_t* __restrict__ head) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nmember) return;
+    uint32_t h = 1;
+    if (r > 0) {
+        const uint32_t g = mlist[r], pg = mlist[r - 1];
+        const int g1 = hs1[g] - (hs1[pg] + hlen[pg]), g2 = hs2[g] - (hs2[pg] + hlen[pg]);
+        h = (tile[g] != tile[pg] || g1 > GP_CLUSTER_GAP || g2 > GP_CLUSTER_GAP || g1 < -GP_CLUSTER_GAP || g2 < -GP_CLUSTER_GAP) ? 1u : 0u;
+    }
+    head[r] = h;
+}
+__global__ void __launch_bounds__(256)
+cluster_ids_kernel(const uint32_t* __restrict__ mlist, uint32_t nmember, const uint32_t* __restrict__ head, const uint32_t* __restrict__ head_off,
+                   uint32_t* __restrict__ cluster_of) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nmember) return;
+    cluster_of[mlist[r]] = head_off[r] + head[r] - 1u;
+}
 
 struct Ext { int score, di, dj, nmatch, ncols; };
 
+// ---- payload (matches, aligned columns) of a DP state, packed in one register (16+16 bits) or two (32+32)
+template <typename P> struct Pay;
+template <> struct Pay<uint32_t> {
+    static __device__ __forceinline__ uint32_t step(uint32_t p, int match) { return p + 0x10000u + (uint32_t)match; }
+    static __device__ __forceinline__ int nm(uint32_t p) { return (int)(p & 0xffffu); }
+    static __device__ __forceinline__ int nc(uint32_t p) { return (int)(p >> 16); }
+};
+template <> struct Pay<uint64_t> {
+    static __device__ __forceinline__ uint64_t step(uint64_t p, int match) { return p + (1ull << 32) + (uint64_t)(uint32_t)match; }
+    static __device__ __forceinline__ int nm(uint64_t p) { return (int)(uint32_t)p; }
+    static __device__ __forceinline__ int nc(uint64_t p) { return (int)(p >> 32); }
+};
 
-struct CellState { int h, d, i, hm, hc, dm, dc, im, ic; };
+template <typename P> struct Cell { int h, d, i; P hp, dp, ip; };
 // A dead cell holds NEG_INF in all three scores; arithmetic on it stays far below any threshold (thr >= -ydrop), so the
 // recurrence needs no "is this predecessor alive" branches: a cell whose predecessors are all dead evaluates to ~NEG_INF,
-// fails H >= thr and is reset to exactly NEG_INF. Out-of-range cells (i or j outside the sequences) are forced dead, which
-// also makes the (i-1) / (j-1) predecessors of the first row and column dead without special cases.
-__device__ __forceinline__ void cs_dead(CellState& c) { c.h = c.d = c.i = NEG_INF; c.hm = c.hc = c.dm = c.dc = c.im = c.ic = 0; }
+// fails H >= thr and is reset to exactly NEG_INF.
+template <typename P> __device__ __forceinline__ void cell_dead(Cell<P>& c) { c.h = c.d = c.i = NEG_INF; c.hp = c.dp = c.ip = 0; }
+
+// what a thread publishes for its neighbours: slot 0 is read as the LEFT neighbour (h, i) of thread t-1's last slot,
+// the last slot as the UP neighbour (h, d) of thread t+1's slot 0
+template <typename P> struct Edge { int h, x; P hp, xp; };
+template <typename P, int NT> struct EdgeBuf;
+template <int NT> struct EdgeBuf<uint32_t, NT> {
+    int4 v[NT];
+    __device__ __forceinline__ void put(int t, const Edge<uint32_t>& e) { v[t] = make_int4(e.h, e.x, (int)e.hp, (int)e.xp); }
+    __device__ __forceinline__ Edge<uint32_t> get(int t) const { const int4 a = v[t]; return Edge<uint32_t>{a.x, a.y, (uint32_t)a.z, (uint32_t)a.w}; }
+};
+template <int NT> struct EdgeBuf<uint64_t, NT> {
+    int4 v[NT]; int2 w[NT];
+    __device__ __forceinline__ void put(int t, const Edge<uint64_t>& e) {
+        v[t] = make_int4(e.h, e.x, (int)(uint32_t)e.hp, (int)(uint32_t)(e.hp >> 32)); w[t] = make_int2((int)(uint32_t)e.xp, (int)(uint32_t)(e.xp >> 32));
+    }
+    __device__ __forceinline__ Edge<uint64_t> get(int t) const {
+        const int4 a = v[t]; const int2 b = w[t];
+        return Edge<uint64_t>{a.x, a.y, (uint64_t)(uint32_t)a.z | ((uint64_t)(uint32_t)a.w << 32), (uint64_t)(uint32_t)b.x | ((uint64_t)(uint32_t)b.y << 32)};
+    }
+};
+
+template <typename P, typename S> struct GpShared {
+    EdgeBuf<P, S::NT> left;             // slot 0 of every thread: {h, i, hp, ip}
+    EdgeBuf<P, S::NT> up;               // last slot of every thread: {h, d, hp, dp}
+    int4 rng[2][S::WARPS];              // per parity, per warp: {warp max, alive diagonal lo, hi, -}
+    int4 top[2][S::WARPS];              // per parity, per warp: {row i of the warp max, payload lo, payload hi, -}
+    int2 lut[25];                       // {substitution score, is-match} for codes 0..4 x 0..4
+    int red[S::WARPS];
+};
 
 // One DP cell (i,j) of anti-diagonal k on diagonal delta = i - j.  self = this diagonal's cell two anti-diagonals ago
-// (updated in place), up = cell (i-1,j) and left = cell (i,j-1) of the previous anti-diagonal. Returns alive.
-template <int DIR>
-__device__ __forceinline__ bool gp_cell(const uint8_t* __restrict__ tcodes, const uint8_t* __restrict__ qcodes, uint32_t ta, uint32_t qa,
-                                        int tn, int qn, int OE, int E, int thr, int k, int delta, CellState& self, const CellState& up,
-                                        const CellState& left, const int* __restrict__ sub5, int& tmax, int& ti, int& thm, int& thc) {
-    const int i2 = k + delta, j2 = k - delta;                    // 2i, 2j (same parity as k by construction)
-    const int i = i2 >> 1, j = j2 >> 1;
-    const bool inb = i2 >= 0 && j2 >= 0 && i <= tn && j <= qn;
-    // substitution score of (i,j); clamped addresses keep the loads in bounds for cells that are forced dead anyway
-    const int ic_ = min(max(i, 1), tn), jc_ = min(max(j, 1), qn);
-    const uint32_t ct = DIR > 0 ? ta + (uint32_t)ic_ - 1u : ta - (uint32_t)ic_;
-    const uint32_t cq = DIR > 0 ? qa + (uint32_t)jc_ - 1u : qa - (uint32_t)jc_;
-    const uint32_t tb = tcodes[ct], qb = qcodes[cq];
-    const int sc = sub5[tb * 5 + qb];
+// (updated in place), (uh, ud) = H and D of cell (i-1,j), (lh, li) = H and I of cell (i,j-1), both of the previous anti-diagonal.
+// ok = cell lies inside both sequences (always true away from the sequence ends).
+template <typename P>
+__device__ __forceinline__ void gp_cell(Cell<P>& self, int uh, int ud, P uhp, P udp, int lh, int li, P lhp, P lip, int2 sc, bool ok,
+                                        int OE, int E, int thr, int c, int& tmax, int& tc, P& tp, int& hmax) {
     // D: vertical gap state, I: horizontal gap state (ties prefer opening from H, as in the oracle)
-    const int dopen = up.h - OE, dext = up.d - E;
+    const int dopen = uh - OE, dext = ud - E;
     const bool dsel = dopen >= dext;
-    const int nd = dsel ? dopen : dext, ndm = dsel ? up.hm : up.dm, ndc = dsel ? up.hc : up.dc;
-    const int iopen = left.h - OE, iext = left.i - E;
+    const int nd = dsel ? dopen : dext; const P ndp = dsel ? uhp : udp;
+    const int iopen = lh - OE, iext = li - E;
     const bool isel = iopen >= iext;
-    const int ni = isel ? iopen : iext, nim = isel ? left.hm : left.im, nic = isel ? left.hc : left.ic;
-    const int mval = self.h + sc, mm = self.hm + ((tb == qb && tb < 4) ? 1 : 0), mc = self.hc + 1;
+    const int ni = isel ? iopen : iext; const P nip = isel ? lhp : lip;
+    const int mval = self.h + sc.x; const P mp = Pay<P>::step(self.hp, sc.y);
     // H = max(M, D, I) with ties M > D > I
     const bool pickm = mval >= nd && mval >= ni;
     const bool pickd = nd >= ni;
     const int nh = pickm ? mval : (pickd ? nd : ni);
-    const int nhm = pickm ? mm : (pickd ? ndm : nim);
-    const int nhc = pickm ? mc : (pickd ? ndc : nic);
-    const bool alive = inb && nh >= thr;
+    const P nhp = pickm ? mp : (pickd ? ndp : nip);
+    const bool alive = ok && nh >= thr;
     self.h = alive ? nh : NEG_INF; self.d = alive ? nd : NEG_INF; self.i = alive ? ni : NEG_INF;
-    self.hm = nhm; self.hc = nhc; self.dm = ndm; self.dc = ndc; self.im = nim; self.ic = nic;
-    if (alive && nh > tmax) { tmax = nh; ti = i; thm = nhm; thc = nhc; }
-    return alive;
+    self.hp = nhp; self.dp = ndp; self.ip = nip;
+    if (self.h > tmax) { tmax = self.h; tc = c; tp = nhp; }     // tmax starts at best: only a new maximum registers
+    hmax = max(hmax, self.h);
 }
-
-struct WarpRec { int wmax, wi, hm, hc, dlo, dhi, pad0, pad1; };
 
 // One-sided y-drop extension by the whole CTA in diagonal-major coordinates. DIR=+1: cell (i,j) consumes T[ta+i-1],
 // Q[qa+j-1]; DIR=-1: T[ta-i], Q[qa-j]. Diagonals delta = i-j live in a circular window of GP_ND slots, slot = delta mod
-// GP_ND; thread t owns GP_SLOTS consecutive slots for the whole extension, so every cell and all but one of its neighbours stay in
-// registers. Per anti-diagonal a thread computes its four cells of the right parity (independent of each other), reads ONE
-// cell of a neighbouring thread from shared memory and publishes one; one __syncthreads per anti-diagonal. Dead cells are
-// -inf by value, so the window follows the alignment without bookkeeping: a slot that re-enters the band on another
-// diagonal is already dead.
-template <int DIR>
-__device__ Ext ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E, int Y,
-                                int* __restrict__ sm, WarpRec (*rec)[GP_WARPS], const int* __restrict__ sub5,
-                                unsigned long long& cells, int& err) {
+// GP_ND; thread t owns GP_SLOTS consecutive slots for the whole extension, so every cell and all but one of its neighbours
+// stay in registers. Per anti-diagonal a thread computes its four cells of the right parity (independent of each other),
+// reads ONE cell of a neighbouring thread from shared memory and publishes one; one __syncthreads per anti-diagonal. Dead
+// cells are -inf by value, so the window follows the alignment without bookkeeping: a slot that re-enters the band on
+// another diagonal is already dead. Alive ranges are tracked per thread (8 diagonals), a superset of the exact range.
+// Returns false if the payload type cannot represent the result (16-bit columns overflowed): rerun with P = uint64_t.
+template <typename P, typename S, int DIR>
+__device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E, int Y,
+                                 GpShared<P, S>& sm, Ext& r, unsigned& ncell, int& err) {
+    constexpr int GP_NT = S::NT, GP_SLOTS = S::SLOTS, GP_WARPS = S::WARPS, GP_DMASK = S::DMASK, GP_MAXBAND = S::MAXBAND;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int4* A0 = reinterpret_cast<int4*>(sm);                 // published first slot of every thread
-    int4* B0 = A0 + GP_NT;
-    int4* AL = B0 + GP_NT;                                  // published last slot
-    int4* BL = AL + GP_NT;
-    int* C0 = reinterpret_cast<int*>(BL + GP_NT);
-    int* CL = C0 + GP_NT;
     const uint8_t* __restrict__ tcodes = T.codes;
     const uint8_t* __restrict__ qcodes = Q.codes;
     const int OE = O + E;
-    Ext r = {0, 0, 0, 0, 0};
-    CellState st[GP_SLOTS];
+    r = Ext{0, 0, 0, 0, 0};
+    Cell<P> st[GP_SLOTS];
 #pragma unroll
-    for (int s = 0; s < GP_SLOTS; s++) cs_dead(st[s]);
-    if (tid == 0) st[0].h = 0;              // the cell (0,0): delta 0 -> slot 0 of thread 0
+    for (int s = 0; s < GP_SLOTS; s++) cell_dead(st[s]);
+    if (tid == 0) st[0].h = 0;             // cell (0,0) on diagonal 0 = slot 0 of thread 0
     __syncthreads();                        // previous users of the buffers are done
-    A0[tid] = make_int4(st[0].h, 0, 0, NEG_INF); B0[tid] = make_int4(NEG_INF, 0, 0, 0); C0[tid] = 0;
-    AL[tid] = make_int4(NEG_INF, 0, 0, NEG_INF); BL[tid] = make_int4(NEG_INF, 0, 0, 0); CL[tid] = 0;
+    sm.left.put(tid, Edge<P>{st[0].h, NEG_INF, 0, 0});
+    sm.up.put(tid, Edge<P>{NEG_INF, NEG_INF, 0, 0});
     __syncthreads();
     int best = 0, dead_steps = 0;
     int lo1 = 0, hi1 = 0, lo2 = 1, hi2 = 0;     // alive diagonal ranges of anti-diagonals k-1 and k-2 (empty when lo > hi)
-    unsigned ncell = 0;
+    P bestp = 0;
+    bool narrow_ok = true;
     const uint32_t kmax = (uint32_t)tn + (uint32_t)qn;
     for (uint32_t k = 1; k <= kmax; k++) {
+        if (sizeof(P) == 4 && k >= (uint32_t)GP_NARROW_ABORT_K) { narrow_ok = false; break; }
         // candidate diagonals of this anti-diagonal; the window base is a multiple of GP_SLOTS so a thread's slots stay consecutive
         int clo = INT_MAX, chi = INT_MIN;
         if (hi1 >= lo1) { clo = lo1 - 1; chi = hi1 + 1; }
@@ -159,77 +212,113 @@ __device__ Ext ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32
         const int base = (clo - 16) & ~(GP_SLOTS - 1);
         const int d0 = base + ((GP_SLOTS * tid - base) & GP_DMASK);  // diagonal of slot 0; slot s holds d0 + s
         const int thr = best - Y;
-        int tmax = INT_MIN, ti = 0, thm = 0, thc = 0, dlo = INT_MAX, dhi = INT_MIN;
+        const int par = (int)(k & 1);
+        int tmax = best, tc = 0, hmax = NEG_INF;
+        P tp = 0;
         const bool active = d0 + GP_SLOTS - 1 >= clo && d0 <= chi;
+        const int i0 = ((int)k + d0 + par) >> 1, j0 = ((int)k - d0 - par) >> 1;   // cell c of this thread: (i0 + c, j0 - c)
         if (active) {
-            if (k & 1) {
-                // odd anti-diagonal: odd slots; up = slot s-1 (own), left = slot s+1 (own, or slot 0 of thread t+1 for the last slot)
-                const int f = (tid + 1) & (GP_NT - 1);
-                CellState fl; const int4 fa = A0[f]; const int4 fb = B0[f];
-                fl.h = fa.x; fl.hm = fa.y; fl.hc = fa.z; fl.d = fa.w; fl.i = fb.x; fl.dm = fb.y; fl.dc = fb.z; fl.im = fb.w; fl.ic = C0[f];
+            // is any cell of this anti-diagonal near the end of a sequence? (uniform over the CTA)
+            const bool edge = (((int)k + chi + GP_SLOTS + 1) >> 1) > tn || (((int)k - clo + GP_SLOTS + 1) >> 1) > qn;
+            int2 sc[GP_SLOTS / 2];
+            bool ok[GP_SLOTS / 2];
+            if (!edge) {
+                const uint8_t* tp_ = DIR > 0 ? tcodes + ta + i0 - 1 : tcodes + ta - i0;
+                const uint8_t* qp_ = DIR > 0 ? qcodes + qa + j0 - 1 : qcodes + qa - j0;
 #pragma unroll
-                for (int s = 1; s < GP_SLOTS; s += 2) {
-                    const bool a = gp_cell<DIR>(tcodes, qcodes, ta, qa, tn, qn, OE, E, thr, (int)k, d0 + s, st[s], st[s - 1],
-                                                s + 1 < GP_SLOTS ? st[s + 1 < GP_SLOTS ? s + 1 : s] : fl, sub5, tmax, ti, thm, thc);
-                    if (a) { dlo = min(dlo, d0 + s); dhi = d0 + s; }
+                for (int c = 0; c < GP_SLOTS / 2; c++) {
+                    const uint32_t tb = DIR > 0 ? tp_[c] : tp_[-c], qb = DIR > 0 ? qp_[-c] : qp_[c];
+                    sc[c] = sm.lut[tb * 5 + qb]; ok[c] = true;
                 }
-                const CellState& e = st[GP_SLOTS - 1];
-                AL[tid] = make_int4(e.h, e.hm, e.hc, e.d); BL[tid] = make_int4(e.i, e.dm, e.dc, e.im); CL[tid] = e.ic;
+            } else {
+#pragma unroll
+                for (int c = 0; c < GP_SLOTS / 2; c++) {
+                    const int i = i0 + c, j = j0 - c;
+                    ok[c] = i >= 0 && j >= 0 && i <= tn && j <= qn;
+                    const int ic_ = min(max(i, 1), max(tn, 1)), jc_ = min(max(j, 1), max(qn, 1));
+                    const uint32_t tb = tcodes[DIR > 0 ? ta + (uint32_t)ic_ - 1u : ta - (uint32_t)ic_];
+                    const uint32_t qb = qcodes[DIR > 0 ? qa + (uint32_t)jc_ - 1u : qa - (uint32_t)jc_];
+                    sc[c] = sm.lut[tb * 5 + qb];
+                }
+            }
+            if (par) {
+                // odd anti-diagonal: odd slots; up = slot s-1 (own), left = slot s+1 (own, or slot 0 of thread t+1 for the last slot)
+                const Edge<P> fl = sm.left.get((tid + 1) & (GP_NT - 1));
+#pragma unroll
+                for (int c = 0; c < GP_SLOTS / 2; c++) {
+                    const int s = 2 * c + 1;
+                    if (s + 1 < GP_SLOTS) {
+                        const Cell<P>& L = st[s + 1 < GP_SLOTS ? s + 1 : s];
+                        gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, L.h, L.i, L.hp, L.ip, sc[c], ok[c], OE, E, thr, c, tmax, tc, tp, hmax);
+                    } else {
+                        gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, fl.h, fl.x, fl.hp, fl.xp, sc[c], ok[c], OE, E, thr, c, tmax, tc, tp, hmax);
+                    }
+                }
+                const Cell<P>& e = st[GP_SLOTS - 1];
+                sm.up.put(tid, Edge<P>{e.h, e.d, e.hp, e.dp});
             } else {
                 // even anti-diagonal: even slots; up = slot s-1 (own, or the last slot of thread t-1 for slot 0), left = slot s+1 (own)
-                const int f = (tid - 1) & (GP_NT - 1);
-                CellState fu; const int4 fa = AL[f]; const int4 fb = BL[f];
-                fu.h = fa.x; fu.hm = fa.y; fu.hc = fa.z; fu.d = fa.w; fu.i = fb.x; fu.dm = fb.y; fu.dc = fb.z; fu.im = fb.w; fu.ic = CL[f];
+                const Edge<P> fu = sm.up.get((tid - 1) & (GP_NT - 1));
 #pragma unroll
-                for (int s = 0; s < GP_SLOTS; s += 2) {
-                    const bool a = gp_cell<DIR>(tcodes, qcodes, ta, qa, tn, qn, OE, E, thr, (int)k, d0 + s, st[s], s > 0 ? st[s > 0 ? s - 1 : 0] : fu,
-                                                st[s + 1], sub5, tmax, ti, thm, thc);
-                    if (a) { dlo = min(dlo, d0 + s); dhi = d0 + s; }
+                for (int c = 0; c < GP_SLOTS / 2; c++) {
+                    const int s = 2 * c;
+                    if (s > 0) {
+                        const Cell<P>& U = st[s > 0 ? s - 1 : 0];
+                        gp_cell<P>(st[s], U.h, U.d, U.hp, U.dp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, c, tmax, tc, tp, hmax);
+                    } else {
+                        gp_cell<P>(st[s], fu.h, fu.x, fu.hp, fu.xp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, c, tmax, tc, tp, hmax);
+                    }
                 }
-                const CellState& e = st[0];
-                A0[tid] = make_int4(e.h, e.hm, e.hc, e.d); B0[tid] = make_int4(e.i, e.dm, e.dc, e.im); C0[tid] = e.ic;
+                const Cell<P>& e = st[0];
+                sm.left.put(tid, Edge<P>{e.h, e.i, e.hp, e.ip});
             }
             ncell += GP_SLOTS / 2;
         }
-        const int par = (int)(k & 1);
         if (__any_sync(0xffffffffu, active)) {
+            const bool any_alive = hmax > NEG_INF;
             const int wmax = __reduce_max_sync(0xffffffffu, tmax);
-            const int wlo = __reduce_min_sync(0xffffffffu, dlo), whi = __reduce_max_sync(0xffffffffu, dhi);
-            int wi = 0, whm = 0, whc = 0;
+            const int wlo = __reduce_min_sync(0xffffffffu, any_alive ? d0 : INT_MAX);
+            const int whi = __reduce_max_sync(0xffffffffu, any_alive ? d0 + GP_SLOTS - 1 : INT_MIN);
             if (wmax > best) {
-                wi = __reduce_min_sync(0xffffffffu, tmax == wmax ? ti : INT_MAX);
-                const int src = __ffs(__ballot_sync(0xffffffffu, tmax == wmax && ti == wi)) - 1;
-                whm = __shfl_sync(0xffffffffu, thm, src); whc = __shfl_sync(0xffffffffu, thc, src);
+                // first maximum in DIAGONAL order (= smallest row i): lanes at or after the window's wrap point come first
+                const uint32_t m = __ballot_sync(0xffffffffu, tmax == wmax);
+                const int wrap_t = (base / GP_SLOTS) & (GP_NT - 1);          // thread whose slot 0 holds diagonal `base`
+                uint32_t mh = m;
+                if ((wrap_t >> 5) == warp) { const uint32_t hi = m & (0xffffffffu << (wrap_t & 31)); if (hi) mh = hi; }
+                if (lane == __ffs(mh) - 1) {
+                    const uint64_t p64 = (uint64_t)tp;
+                    sm.top[par][warp] = make_int4(i0 + tc, (int)(uint32_t)p64, (int)(uint32_t)(p64 >> 32), 0);
+                }
             }
-            if (lane == 0) {
-                int4* rp = reinterpret_cast<int4*>(&rec[par][warp]);
-                rp[0] = make_int4(wmax, wi, whm, whc); rp[1] = make_int4(wlo, whi, 0, 0);
-            }
+            if (lane == 0) sm.rng[par][warp] = make_int4(wmax, wlo, whi, 0);
         } else if (lane == 0) {
-            int4* rp = reinterpret_cast<int4*>(&rec[par][warp]);
-            rp[0] = make_int4(INT_MIN, 0, 0, 0); rp[1] = make_int4(INT_MAX, INT_MIN, 0, 0);
+            sm.rng[par][warp] = make_int4(INT_MIN, INT_MAX, INT_MIN, 0);
         }
         __syncthreads();                    // the one barrier of this anti-diagonal
-        int4 q0 = make_int4(INT_MIN, INT_MAX, 0, 0), q1 = make_int4(INT_MAX, INT_MIN, 0, 0);
-        if (lane < GP_WARPS) {
-            const int4* rp = reinterpret_cast<const int4*>(&rec[par][lane]);
-            q0 = rp[0]; q1 = rp[1];
-        }
-        const int bmax = __reduce_max_sync(0xffffffffu, q0.x);
-        const int alo = __reduce_min_sync(0xffffffffu, q1.x), ahi = __reduce_max_sync(0xffffffffu, q1.y);
+        int bmax = INT_MIN, alo = INT_MAX, ahi = INT_MIN;
+        int4 q[GP_WARPS];
+#pragma unroll
+        for (int w = 0; w < GP_WARPS; w++) { q[w] = sm.rng[par][w]; bmax = max(bmax, q[w].x); alo = min(alo, q[w].y); ahi = max(ahi, q[w].z); }
         if (bmax > best) {
-            const int bi = __reduce_min_sync(0xffffffffu, q0.x == bmax ? q0.y : INT_MAX);
-            const int src = __ffs(__ballot_sync(0xffffffffu, q0.x == bmax && q0.y == bi)) - 1;
-            best = bmax; r.score = bmax; r.di = bi; r.dj = (int)k - bi;
-            r.nmatch = __shfl_sync(0xffffffffu, q0.z, src); r.ncols = __shfl_sync(0xffffffffu, q0.w, src);
+            int bi = INT_MAX; uint64_t bp = 0;
+#pragma unroll
+            for (int w = 0; w < GP_WARPS; w++) {
+                if (q[w].x == bmax) {
+                    const int4 t4 = sm.top[par][w];
+                    if (t4.x < bi) { bi = t4.x; bp = (uint64_t)(uint32_t)t4.y | ((uint64_t)(uint32_t)t4.z << 32); }
+                }
+            }
+            best = bmax; r.score = bmax; r.di = bi; r.dj = (int)k - bi; bestp = (P)bp;
         }
         lo2 = lo1; hi2 = hi1; lo1 = alo; hi1 = ahi;          // empty ranges arrive as (INT_MAX, INT_MIN)
         if (hi1 < lo1) { lo1 = 1; hi1 = 0; }
         dead_steps = (hi1 < lo1) ? dead_steps + 1 : 0;
         if (dead_steps >= 2) break;         // two dead anti-diagonals in a row: nothing can revive
     }
-    cells += ncell;                         // per-thread; summed by the caller
-    return r;
+    r.nmatch = Pay<P>::nm(bestp); r.ncols = Pay<P>::nc(bestp);
+    // 16-bit columns are exact iff the optimal path has fewer than 65536 columns, which min(di, dj) bounds from above
+    if (sizeof(P) == 4 && min(r.di, r.dj) >= 65536) narrow_ok = false;
+    return narrow_ok;
 }
 
 // Exact shortcut for the trivial alignment of a scaffold with itself. When target and query are the SAME N-free
@@ -238,7 +327,7 @@ __device__ Ext ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32
 // worth at most s(b,b) of its row base, minus gap costs -- so the main-diagonal cell is the strict maximum of every
 // even anti-diagonal, is never pruned, and the extension ends at the scaffold end with score = sum of s(b,b),
 // matches = columns = length. (Proof in DESIGN.md; sequences with any non-ACGT base take the general DP.)
-__device__ Ext selfdiag_extend_cta(const GenomeView& T, uint32_t p0, uint32_t p1, int* __restrict__ sm) {
+__device__ Ext selfdiag_extend_cta(const GenomeView& T, uint32_t p0, uint32_t p1, int* __restrict__ sm, int nwarps) {
     // count C/G bases in padded-coordinate range [p0, p1): 2-bit code has exactly one bit set for C (01) and G (10)
     int cg = 0;
     if (p1 > p0) {
@@ -256,7 +345,7 @@ __device__ Ext selfdiag_extend_cta(const GenomeView& T, uint32_t p0, uint32_t p1
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cg;
     __syncthreads();
     int tot = 0;
-    for (int w = 0; w < GP_WARPS; w++) tot += sm[w];
+    for (int w = 0; w < nwarps; w++) tot += sm[w];
     __syncthreads();
     const int n = (int)(p1 - p0);
     Ext r;
@@ -264,130 +353,203 @@ __device__ Ext selfdiag_extend_cta(const GenomeView& T, uint32_t p0, uint32_t p1
     return r;
 }
 
-// best 31-column window of an HSP (first maximum); returns the anchor offset inside the HSP
-__device__ int anchor_offset(const GenomeView& T, const GenomeView& Q, uint32_t ts, uint32_t qs, int len, int lane) {
-    if (len <= 31) return len / 2;
-    int best = INT_MIN, bw = 0;
-    for (int base = 0; base + 31 <= len; base += 32) {
-        // scores of columns base+lane and base+32+lane (the second only below len)
-        const int c0 = base + lane, c1 = base + 32 + lane;
-        int s0 = 0, s1 = 0;
-        if (c0 < len) {
-            const uint32_t an = isn_at(T.nm, ts + c0) | isn_at(Q.nm, qs + c0);
-            s0 = an ? SCORE_N : sub_lut3((base_at(T.pk, ts + c0) << 2) | base_at(Q.pk, qs + c0));
-        }
-        if (c1 < len) {
-            const uint32_t an = isn_at(T.nm, ts + c1) | isn_at(Q.nm, qs + c1);
-            s1 = an ? SCORE_N : sub_lut3((base_at(T.pk, ts + c1) << 2) | base_at(Q.pk, qs + c1));
-        }
-        int p0 = s0, p1 = s1;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t0 = __shfl_up_sync(0xffffffffu, p0, d), t1 = __shfl_up_sync(0xffffffffu, p1, d);
-            if (lane >= d) { p0 += t0; p1 += t1; }
-        }
-        p1 += __shfl_sync(0xffffffffu, p0, 31);
-        // window w = base + lane covers columns [w, w+30]: P[lane+30] - P[lane-1]
-        const int hi_idx = lane + 30;
-        const int a0 = __shfl_sync(0xffffffffu, p0, hi_idx & 31), a1 = __shfl_sync(0xffffffffu, p1, hi_idx & 31);
-        const int top = hi_idx < 32 ? a0 : a1;
-        int bot = __shfl_up_sync(0xffffffffu, p0, 1);
-        if (lane == 0) bot = 0;
-        const bool valid = base + lane + 31 <= len;
-        const int wsum = valid ? top - bot : INT_MIN;
-        const int mx = __reduce_max_sync(0xffffffffu, wsum);
-        if (mx > best) {
-            best = mx;
-            bw = base + __ffs(__ballot_sync(0xffffffffu, wsum == mx)) - 1;
+// Anchors of all chain members at once (slot x = position in the (tile, score desc) order): centre of the best
+// 31-column window of the HSP (first maximum), the whole HSP if it is shorter. One CTA per member; every thread slides a
+// window over its own contiguous share of the window positions, then the CTA keeps the first maximum.
+constexpr int AP_NT = 128;
+__global__ void __launch_bounds__(AP_NT)
+anchor_points_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, const int32_t* __restrict__ hs1, const int32_t* __restrict__ hs2,
+                     const int32_t* __restrict__ hlen, const uint32_t* __restrict__ order, uint32_t nmember,
+                     int32_t* __restrict__ a1, int32_t* __restrict__ a2) {
+    __shared__ int sh_best[AP_NT / 32], sh_w[AP_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t x = blockIdx.x;
+    const uint32_t g = order[x], tl = tile[g];
+    const uint32_t ts = T.off[tl / (uint32_t)Q.nscaf] + (uint32_t)hs1[g], qs = Q.off[tl % (uint32_t)Q.nscaf] + (uint32_t)hs2[g];
+    const int len = hlen[g];
+    if (len <= 31) {
+        if (tid == 0) { a1[x] = hs1[g] + len / 2; a2[x] = hs2[g] + len / 2; }
+        return;
+    }
+    auto col = [&](int c) -> int {
+        const uint32_t an = isn_at(T.nm, ts + c) | isn_at(Q.nm, qs + c);
+        return an ? SCORE_N : sub_lut3((base_at(T.pk, ts + c) << 2) | base_at(Q.pk, qs + c));
+    };
+    const int nwin = len - 30;                       // window w covers columns [w, w + 30]
+    const int chunk = (nwin + AP_NT - 1) / AP_NT;
+    const int w0 = tid * chunk, w1 = min(nwin, w0 + chunk);
+    int best = INT_MIN, bw = INT_MAX;
+    if (w0 < w1) {
+        int sum = 0;
+        for (int c = 0; c < 31; c++) sum += col(w0 + c);
+        best = sum; bw = w0;
+        for (int w = w0 + 1; w < w1; w++) {
+            sum += col(w + 30) - col(w - 1);
+            if (sum > best) { best = sum; bw = w; }
         }
     }
-    return bw + 15;
+    // first maximum over the CTA: highest sum, then lowest window
+    const int wbest = __reduce_max_sync(0xffffffffu, best);
+    const int wbw = __reduce_min_sync(0xffffffffu, best == wbest ? bw : INT_MAX);
+    if (lane == 0) { sh_best[warp] = wbest; sh_w[warp] = wbw; }
+    __syncthreads();
+    if (tid == 0) {
+        int b = sh_best[0], w = sh_w[0];
+        for (int k = 1; k < AP_NT / 32; k++)
+            if (sh_best[k] > b || (sh_best[k] == b && sh_w[k] < w)) { b = sh_best[k]; w = sh_w[k]; }
+        a1[x] = hs1[g] + w + 15; a2[x] = hs2[g] + w + 15;
+    }
 }
 
-// One thread-block CLUSTER of two CTAs owns one tile: CTA 0 extends every anchor forwards, CTA 1 backwards, concurrently.
-// They meet twice per anchor at a cluster barrier: once to swap their one-sided results through distributed shared memory,
-// once after CTA 0 has published the alignment record that later anchors of the tile are tested against.
-__global__ void __launch_bounds__(GP_NT, 3)
-gapped_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, const int32_t* __restrict__ hs1, const int32_t* __restrict__ hs2,
-              const int32_t* __restrict__ hlen, const uint32_t* __restrict__ order, uint32_t nmember,
-              const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
-              int O, int E, int Y, int gthr, const int32_t* __restrict__ same_q,
-              int32_t* __restrict__ o_s1, int32_t* __restrict__ o_e1, int32_t* __restrict__ o_s2, int32_t* __restrict__ o_e2,
-              int32_t* __restrict__ o_score, int32_t* __restrict__ o_nm, int32_t* __restrict__ o_nc, uint32_t* __restrict__ o_tile,
-              uint32_t* __restrict__ o_keep, unsigned long long* __restrict__ counters) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned crank = cluster.block_rank();          // 0: forward extension, 1: backward extension
-    extern __shared__ __align__(16) int gp_smem[];
-    __shared__ __align__(16) WarpRec rec[2][GP_WARPS];
-    __shared__ uint32_t sh_seg;
-    __shared__ int sh_off;
-    __shared__ Ext sh_ext;
-    __shared__ int sub5[25];
-    if (threadIdx.x < 25) {
-        const int a = threadIdx.x / 5, b = threadIdx.x % 5;
-        sub5[threadIdx.x] = (a == 4 || b == 4) ? SCORE_N : c_sub[a * 4 + b];
-    }
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nseg = *nseg_p;
-    unsigned long long cells = 0, anchors = 0;
-    int err = 0;
-    for (;;) {
-        if (crank == 0 && tid == 0) sh_seg = (uint32_t)atomicAdd(&counters[CNT_WORK], 1ull);
-        cluster.sync();
-        const uint32_t seg = *cluster.map_shared_rank(&sh_seg, 0);
-        cluster.sync();                                     // everyone has read it before CTA 0 may overwrite it
-        if (seg >= nseg) break;
-        const uint32_t a = seg_start[seg];
-        const uint32_t b = (seg + 1 < nseg) ? seg_start[seg + 1] : nmember;
-        const uint32_t tl = tile[order[a]];
-        const uint32_t tsc = tl / (uint32_t)Q.nscaf, qsc = tl % (uint32_t)Q.nscaf;
-        const uint32_t toff = T.off[tsc], qoff = Q.off[qsc];
-        const int tlen = (int)T.len[tsc], qlen = (int)Q.len[qsc];
-        uint32_t nkept = 0;                                      // kept alignments of this tile live in slots [a, a+nkept)
-        for (uint32_t x = a; x < b; x++) {
-            const uint32_t g = order[x];
-            const int s1 = hs1[g], s2 = hs2[g], len = hlen[g];
-            if (warp == 0) {
-                const int off = anchor_offset(T, Q, toff + s1, qoff + s2, len, lane);
-                if (lane == 0) sh_off = off;
+// Per (slot, direction) status of an extension.
+enum : uint8_t { GX_NONE = 0, GX_NARROW = 1, GX_NEED_WIDE = 2, GX_WIDE = 3 };
+
+struct GpWork {
+    // per slot x (position in the (tile, score desc) order of the chain members)
+    const uint32_t* order; const int32_t *a1, *a2; const uint32_t* cluster_of;
+    uint8_t* status;                 // [2 * nmember]: slot * 2 + direction (0 forward, 1 backward)
+    int32_t *e_score, *e_di, *e_dj, *e_nm, *e_nc;   // [2 * nmember] one-sided extension results
+    uint32_t* stamp;                 // per cluster: last round that scheduled one of its members
+    uint32_t *items_narrow, *items_wide;   // work lists of this round: slot * 2 + direction
+    uint32_t* counts;                // {narrow, wide}
+};
+
+constexpr int SEL_PEND = 64;         // pending (computed, not yet accepted) boxes a warp remembers while scheduling
+
+// One warp per tile. Phase 1 replays the sequential rule as far as results exist; phase 2 schedules.
+__global__ void __launch_bounds__(128)
+gp_select_kernel(GpWork W, const uint32_t* __restrict__ tile, uint32_t nmember, const uint32_t* __restrict__ seg_start, uint32_t nseg,
+                 uint32_t* __restrict__ resume, uint32_t* __restrict__ nkept_arr, uint32_t round, int gthr,
+                 int32_t* __restrict__ o_s1, int32_t* __restrict__ o_e1, int32_t* __restrict__ o_s2, int32_t* __restrict__ o_e2,
+                 int32_t* __restrict__ o_score, int32_t* __restrict__ o_nm, int32_t* __restrict__ o_nc, uint32_t* __restrict__ o_tile,
+                 uint32_t* __restrict__ o_keep, unsigned long long* __restrict__ counters) {
+    __shared__ int pend[128 / 32][SEL_PEND][4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (seg >= nseg) return;
+    const uint32_t a = seg_start[seg];
+    const uint32_t b = (seg + 1 < nseg) ? seg_start[seg + 1] : nmember;
+    uint32_t x = a + resume[seg];
+    uint32_t nk = nkept_arr[seg];
+    if (x >= b) return;
+    unsigned long long accepted = 0;
+    auto covered = [&](int p1, int p2) -> bool {                 // spec D5: bounding-box test against reported alignments
+        int cov = 0;
+        for (uint32_t kk = lane; kk < nk; kk += 32)
+            cov |= (p1 >= o_s1[a + kk] && p1 < o_e1[a + kk] && p2 >= o_s2[a + kk] && p2 < o_e2[a + kk]) ? 1 : 0;
+        return __any_sync(0xffffffffu, cov);
+    };
+    auto ready = [&](uint32_t y) -> bool {
+        const uint8_t f = W.status[2 * y], r = W.status[2 * y + 1];
+        return (f == GX_NARROW || f == GX_WIDE) && (r == GX_NARROW || r == GX_WIDE);
+    };
+    // ---------------- phase 1: resolve in best-first order while results exist
+    for (; x < b; x++) {
+        const int p1 = W.a1[x], p2 = W.a2[x];
+        if (covered(p1, p2)) continue;
+        if (!ready(x)) break;
+        accepted++;
+        const int score = W.e_score[2 * x] + W.e_score[2 * x + 1];
+        if (score >= gthr) {
+            if (lane == 0) {
+                const uint32_t o = a + nk;
+                o_s1[o] = p1 - W.e_di[2 * x + 1]; o_e1[o] = p1 + W.e_di[2 * x]; o_s2[o] = p2 - W.e_dj[2 * x + 1]; o_e2[o] = p2 + W.e_dj[2 * x];
+                o_score[o] = score; o_nm[o] = W.e_nm[2 * x] + W.e_nm[2 * x + 1]; o_nc[o] = W.e_nc[2 * x] + W.e_nc[2 * x + 1];
+                o_tile[o] = tile[W.order[x]]; o_keep[o] = 1;
             }
-            __syncthreads();
-            const int a1 = s1 + sh_off, a2 = s2 + sh_off;
-            int cov = 0;                                          // spec D5: bounding-box test against reported alignments
-            for (uint32_t kk = tid; kk < nkept; kk += GP_NT)
-                cov |= (a1 >= o_s1[a + kk] && a1 < o_e1[a + kk] && a2 >= o_s2[a + kk] && a2 < o_e2[a + kk]) ? 1 : 0;
-            if (__syncthreads_or(cov)) continue;                  // both CTAs take the same decision
-            if (crank == 0) anchors++;
-            Ext mine;
-            const bool closed = same_q[tsc] == (int)qsc && a1 == a2 && T.nfree[tsc];
-            if (crank == 0)
-                mine = closed ? selfdiag_extend_cta(T, toff + a1, toff + tlen, gp_smem)
-                              : ydrop_extend_cta<+1>(T, Q, toff + a1, qoff + a2, tlen - a1, qlen - a2, O, E, Y, gp_smem, rec, sub5, cells, err);
-            else
-                mine = closed ? selfdiag_extend_cta(T, toff, toff + a1, gp_smem)
-                              : ydrop_extend_cta<-1>(T, Q, toff + a1, qoff + a2, a1, a2, O, E, Y, gp_smem, rec, sub5, cells, err);
-            if (tid == 0) sh_ext = mine;
-            cluster.sync();                                       // swap the one-sided results
-            const Ext other = *cluster.map_shared_rank(&sh_ext, crank ^ 1);
-            const Ext f = crank == 0 ? mine : other, r = crank == 0 ? other : mine;
-            const int score = f.score + r.score;
-            const bool keep = score >= gthr;
-            if (keep && crank == 0 && tid == 0) {
-                const uint32_t o = a + nkept;
-                o_s1[o] = a1 - r.di; o_e1[o] = a1 + f.di; o_s2[o] = a2 - r.dj; o_e2[o] = a2 + f.dj;
-                o_score[o] = score; o_nm[o] = f.nmatch + r.nmatch; o_nc[o] = f.ncols + r.ncols; o_tile[o] = tl; o_keep[o] = 1;
-                __threadfence();
-            }
-            if (keep) nkept++;
-            cluster.sync();                                       // record visible to both CTAs; sh_ext reusable
+            nk++;
+            __syncwarp();
         }
     }
-    if (cells) atomicAdd(&counters[CNT_GAPPED_CELLS], cells);
+    if (lane == 0) {
+        resume[seg] = x - a; nkept_arr[seg] = nk;
+        if (accepted) atomicAdd(&counters[CNT_ANCHORS], accepted);
+    }
+    __syncwarp();
+    if (x >= b) return;
+    // ---------------- phase 2: schedule. Boxes of results that wait for their turn count as covered FOR SCHEDULING only.
+    int npend = 0;
+    for (uint32_t y0 = x; y0 < b; y0 += 32) {
+        const uint32_t y = y0 + lane;
+        const bool have = y < b && ready(y);
+        const uint32_t m = __ballot_sync(0xffffffffu, have);
+        if (have) {
+            const int slot = npend + __popc(m & ((1u << lane) - 1u));
+            if (slot < SEL_PEND) {
+                const int p1 = W.a1[y], p2 = W.a2[y];
+                pend[wib][slot][0] = p1 - W.e_di[2 * y + 1]; pend[wib][slot][1] = p1 + W.e_di[2 * y];
+                pend[wib][slot][2] = p2 - W.e_dj[2 * y + 1]; pend[wib][slot][3] = p2 + W.e_dj[2 * y];
+            }
+        }
+        npend = min(SEL_PEND, npend + __popc(m));
+    }
+    __syncwarp();
+    for (uint32_t y = x; y < b; y++) {
+        const uint8_t sf = W.status[2 * y], sr = W.status[2 * y + 1];
+        const bool is_ready = (sf == GX_NARROW || sf == GX_WIDE) && (sr == GX_NARROW || sr == GX_WIDE);
+        if (is_ready) continue;
+        const uint32_t cl = W.cluster_of[W.order[y]];
+        if (y != x && W.stamp[cl] == round) continue;             // one speculative extension per cluster and round
+        const int p1 = W.a1[y], p2 = W.a2[y];
+        if (y != x) {
+            if (covered(p1, p2)) continue;                        // will be skipped when its turn comes
+            int cov = 0;
+            for (int kk = lane; kk < npend; kk += 32)
+                cov |= (p1 >= pend[wib][kk][0] && p1 < pend[wib][kk][1] && p2 >= pend[wib][kk][2] && p2 < pend[wib][kk][3]) ? 1 : 0;
+            if (__any_sync(0xffffffffu, cov)) continue;           // probably inside an alignment that is waiting for its turn
+        }
+        if (lane < 2) {
+            const uint8_t s = lane == 0 ? sf : sr;
+            if (s == GX_NONE) {
+                W.items_narrow[atomicAdd(&W.counts[0], 1u)] = 2 * y + lane;
+                W.status[2 * y + lane] = GX_NARROW;
+            } else if (s == GX_NEED_WIDE) {
+                W.items_wide[atomicAdd(&W.counts[1], 1u)] = 2 * y + lane;
+                W.status[2 * y + lane] = GX_WIDE;
+            }
+        }
+        if (lane == 0) W.stamp[cl] = round;
+        __syncwarp();
+    }
+}
+
+// One CTA per work item = (anchor, direction). P = uint32_t: 16+16-bit payload (fast path); uint64_t: always exact.
+template <typename P, typename S, int MINB>
+__global__ void __launch_bounds__(S::NT, MINB)
+gp_extend_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restrict__ items, const uint32_t* __restrict__ tile,
+                 int O, int E, int Y, const int32_t* __restrict__ same_q, unsigned long long* __restrict__ counters) {
+    __shared__ __align__(16) GpShared<P, S> sm;
+    const int tid = threadIdx.x;
+    if (tid < 25) {
+        const int a = tid / 5, b = tid % 5;
+        sm.lut[tid] = make_int2((a == 4 || b == 4) ? SCORE_N : c_sub[a * 4 + b], (a == b && a < 4) ? 1 : 0);
+    }
+    const uint32_t item = items[blockIdx.x];
+    const uint32_t x = item >> 1, dir = item & 1u;
+    const uint32_t tl = tile[W.order[x]];
+    const uint32_t tsc = tl / (uint32_t)Q.nscaf, qsc = tl % (uint32_t)Q.nscaf;
+    const uint32_t toff = T.off[tsc], qoff = Q.off[qsc];
+    const int tlen = (int)T.len[tsc], qlen = (int)Q.len[qsc];
+    const int a1 = W.a1[x], a2 = W.a2[x];
+    const bool closed = same_q[tsc] == (int)qsc && a1 == a2 && T.nfree[tsc];
+    Ext r;
+    unsigned ncell = 0;
+    int err = 0;
+    bool ok = true;
+    if (closed) {
+        r = dir == 0 ? selfdiag_extend_cta(T, toff + a1, toff + tlen, sm.red, S::WARPS) : selfdiag_extend_cta(T, toff, toff + a1, sm.red, S::WARPS);
+    } else if (dir == 0) {
+        ok = ydrop_extend_cta<P, S, +1>(T, Q, toff + a1, qoff + a2, tlen - a1, qlen - a2, O, E, Y, sm, r, ncell, err);
+    } else {
+        ok = ydrop_extend_cta<P, S, -1>(T, Q, toff + a1, qoff + a2, a1, a2, O, E, Y, sm, r, ncell, err);
+    }
     if (tid == 0) {
-        if (anchors) atomicAdd(&counters[CNT_ANCHORS], anchors);
+        W.e_score[item] = r.score; W.e_di[item] = r.di; W.e_dj[item] = r.dj; W.e_nm[item] = r.nmatch; W.e_nc[item] = r.ncols;
+        if (!ok) W.status[item] = GX_NEED_WIDE;
         if (err) atomicAdd(&counters[CNT_ERR], 1ull);
     }
+    ncell = __reduce_add_sync(0xffffffffu, ncell);
+    if ((tid & 31) == 0 && ncell) atomicAdd(&counters[CNT_GAPPED_CELLS], (unsigned long long)ncell);
 }
 
 __global__ void __launch_bounds__(256)
@@ -441,11 +603,12 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
                h.len.get(), h.score.get(), in_chain.get(), n, r_s1.get(), r_e1.get(), r_s2.get(), r_e2.get(), r_score.get(),
                r_nm.get(), r_nc.get(), r_tile.get(), keep.get());
     } else {
+        ProfScope ps("gapped");
         // order the chain members: (tile, score desc), stable over the canonical order
         int tb = 1; while (tb < 33 && (((uint64_t)T.nscaf * (uint64_t)Q.nscaf) >> tb)) tb++;
         DevBuf<uint64_t> k0(n), k1(n);
-        DevBuf<uint32_t> i0(n), i1(n);
-        launch(anchor_keys_kernel, cdiv(n, 256), 256, 0, h.tile.get(), h.score.get(), in_chain.get(), n, k0.get(), i0.get());
+        DevBuf<uint32_t> i0(n), i1(n), mflag(n), mrank(n), d_nmember(1);
+        launch(anchor_keys_kernel, cdiv(n, 256), 256, 0, h.tile.get(), h.score.get(), in_chain.get(), n, k0.get(), i0.get(), mflag.get());
         const int w = radix_sort_bits<uint64_t, uint32_t>(k0.get(), k1.get(), i0.get(), i1.get(), n, 0, std::min(64, tb + 31));
         const uint64_t* skey = w ? k1.get() : k0.get();
         const uint32_t* order = w ? i1.get() : i0.get();
@@ -453,49 +616,79 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
         launch(anchor_heads_kernel, cdiv(n, 256), 256, 0, skey, n, flag.get());
         exclusive_scan_u32(flag.get(), flag_off.get(), n, d_nseg.get());
         launch(anchor_starts_kernel, cdiv(n, 256), 256, 0, flag.get(), flag_off.get(), n, seg_start.get());
-        // number of chain members = first index whose key is the non-member sentinel; computed on the device side by
-        // passing n and letting segments end at the next head; the last segment must stop at the member count:
-        uint32_t h_nseg = 0;
+        exclusive_scan_u32(mflag.get(), mrank.get(), n, d_nmember.get());
+        uint32_t h_nseg = 0, h_nmember = 0;
         MB2_CUDA(cudaMemcpyAsync(&h_nseg, d_nseg.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
-        // member count = number of in_chain flags; reuse scan on a temporary
-        DevBuf<uint32_t> mflag(n), moff(n), d_nmember(1);
-        launch(anchor_member_kernel, cdiv(n, 256), 256, 0, skey, n, mflag.get());
-        exclusive_scan_u32(mflag.get(), moff.get(), n, d_nmember.get());
-        uint32_t h_nmember = 0;
         MB2_CUDA(cudaMemcpyAsync(&h_nmember, d_nmember.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+        // same_q[t] = query scaffold that is the identical sequence as target scaffold t (or -1): enables the closed form
+        std::vector<int32_t> same(T.nscaf, -1);
+        for (int t = 0; t < T.nscaf; t++) {
+            if (h_same_q) same[t] = h_same_q[t];
+            else if (Q.fwd_src_id != 0 && Q.fwd_src_id == T.id && t < Q.nfwd) same[t] = t;
+        }
+        DevBuf<int32_t> d_same(T.nscaf);
+        MB2_CUDA(cudaMemcpyAsync(d_same.get(), same.data(), T.nscaf * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
         if (h_nmember) {
-            // same_q[t] = query scaffold that is the identical sequence as target scaffold t (or -1): enables the closed form
-            std::vector<int32_t> same(T.nscaf, -1);
-            for (int t = 0; t < T.nscaf; t++) {
-                if (h_same_q) same[t] = h_same_q[t];
-                else if (Q.fwd_src_id != 0 && Q.fwd_src_id == T.id && t < Q.nfwd) same[t] = t;
-            }
-            DevBuf<int32_t> d_same(T.nscaf);
-            MB2_CUDA(cudaMemcpyAsync(d_same.get(), same.data(), T.nscaf * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
-            MB2_CUDA(cudaStreamSynchronize(cx.stream));
-            static bool attr_set = false;
-            if (!attr_set) {
-                MB2_CUDA(cudaFuncSetAttribute(gapped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GP_SMEM_BYTES));
-                attr_set = true;
-            }
-            // one cluster (2 CTAs) per tile in flight; 3 CTAs of 256 threads per SM
-            const unsigned nclusters = std::min<unsigned>((unsigned)cx.sm_count * 3 / 2, std::max<unsigned>(1u, h_nseg));
-            MB2_CUDA(cudaMemsetAsync(counters + CNT_WORK, 0, sizeof(unsigned long long), cx.stream));
-            ProfScope ps("gapped");
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(2 * nclusters); cfg.blockDim = dim3(GP_NT); cfg.dynamicSmemBytes = GP_SMEM_BYTES; cfg.stream = cx.stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
+            const uint32_t nm = h_nmember;
+            // speculation clusters along the chains
+            DevBuf<uint32_t> mlist(nm), chead(nm), chead_off(nm), cluster_of(n), stamp(nm);
+            launch(member_list_kernel, cdiv(n, 256), 256, 0, mflag.get(), mrank.get(), n, mlist.get());
+            launch(cluster_heads_kernel, cdiv(nm, 256), 256, 0, mlist.get(), nm, h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(), chead.get());
+            exclusive_scan_u32(chead.get(), chead_off.get(), nm);
+            launch(cluster_ids_kernel, cdiv(nm, 256), 256, 0, mlist.get(), nm, chead.get(), chead_off.get(), cluster_of.get());
+            MB2_CUDA(cudaMemsetAsync(stamp.get(), 0, (size_t)nm * sizeof(uint32_t), cx.stream));
+            // anchors, per-slot state
+            DevBuf<int32_t> a1(nm), a2(nm), e_score(2 * (size_t)nm), e_di(2 * (size_t)nm), e_dj(2 * (size_t)nm), e_nm(2 * (size_t)nm), e_nc(2 * (size_t)nm);
+            DevBuf<uint8_t> status(2 * (size_t)nm);
+            DevBuf<uint32_t> items_n(2 * (size_t)nm), items_w(2 * (size_t)nm), counts(2), resume(h_nseg), nkept(h_nseg);
+            MB2_CUDA(cudaMemsetAsync(status.get(), 0, 2 * (size_t)nm, cx.stream));
+            MB2_CUDA(cudaMemsetAsync(resume.get(), 0, (size_t)h_nseg * sizeof(uint32_t), cx.stream));
+            MB2_CUDA(cudaMemsetAsync(nkept.get(), 0, (size_t)h_nseg * sizeof(uint32_t), cx.stream));
             const GenomeView tv = view(T), qv = view(Q);
-            MB2_CUDA(cudaLaunchKernelEx(&cfg, gapped_kernel, tv, qv, (const uint32_t*)h.tile.get(), (const int32_t*)h.s1.get(),
-                                        (const int32_t*)h.s2.get(), (const int32_t*)h.len.get(), (const uint32_t*)order, h_nmember,
-                                        (const uint32_t*)seg_start.get(), (const uint32_t*)d_nseg.get(), p.gap_open, p.gap_extend, p.ydrop,
-                                        p.gappedthresh, (const int32_t*)d_same.get(), r_s1.get(), r_e1.get(), r_s2.get(), r_e2.get(),
-                                        r_score.get(), r_nm.get(), r_nc.get(), r_tile.get(), keep.get(), counters));
-            cx.launches++;
+            launch(anchor_points_kernel, nm, AP_NT, 0, tv, qv, h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(), order, nm,
+                   a1.get(), a2.get());
+            GpWork W;
+            W.order = order; W.a1 = a1.get(); W.a2 = a2.get(); W.cluster_of = cluster_of.get(); W.status = status.get();
+            W.e_score = e_score.get(); W.e_di = e_di.get(); W.e_dj = e_dj.get(); W.e_nm = e_nm.get(); W.e_nc = e_nc.get();
+            W.stamp = stamp.get(); W.items_narrow = items_n.get(); W.items_wide = items_w.get(); W.counts = counts.get();
+            static const bool dbg = getenv("MB2_GP_DEBUG") != nullptr;
+            static const int shape = getenv("MB2_GP_SHAPE") ? atoi(getenv("MB2_GP_SHAPE")) : 0;
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (dbg) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); }
+            for (uint32_t round = 1;; round++) {
+                MB2_CUDA(cudaMemsetAsync(counts.get(), 0, 2 * sizeof(uint32_t), cx.stream));
+                launch(gp_select_kernel, cdiv((size_t)h_nseg * 32, 128), 128, 0, W, h.tile.get(), nm, seg_start.get(), h_nseg, resume.get(), nkept.get(),
+                       round, p.gappedthresh, r_s1.get(), r_e1.get(), r_s2.get(), r_e2.get(), r_score.get(), r_nm.get(), r_nc.get(), r_tile.get(),
+                       keep.get(), counters);
+                uint32_t h_counts[2] = {0, 0};
+                MB2_CUDA(cudaMemcpyAsync(h_counts, counts.get(), sizeof(h_counts), cudaMemcpyDeviceToHost, cx.stream));
+                MB2_CUDA(cudaStreamSynchronize(cx.stream));
+                if (dbg) {
+                    float ms = 0;
+                    if (round > 1) { cudaEventSynchronize(ev1); cudaEventElapsedTime(&ms, ev0, ev1); }
+                    fprintf(stderr, "[gapped] members %u tiles %u | extend of round %u took %.3f ms | round %u schedules narrow %u wide %u\n", nm, h_nseg,
+                            round - 1, ms, round, h_counts[0], h_counts[1]);
+                    cudaEventRecord(ev0, cx.stream);
+                }
+                if (h_counts[0] == 0 && h_counts[1] == 0) break;
+                auto go = [&](auto kern, uint32_t count, int nt, const uint32_t* items) {
+                    launch(kern, count, nt, 0, tv, qv, W, items, h.tile.get(), p.gap_open, p.gap_extend, p.ydrop, d_same.get(), counters);
+                };
+                using S0 = GpShape<128, 8>; using S1 = GpShape<64, 16>; using S2 = GpShape<256, 4>;
+                if (h_counts[0]) {
+                    if (shape == 1) go(gp_extend_kernel<uint32_t, S1, 6>, h_counts[0], S1::NT, items_n.get());
+                    else if (shape == 2) go(gp_extend_kernel<uint32_t, S2, 3>, h_counts[0], S2::NT, items_n.get());
+                    else go(gp_extend_kernel<uint32_t, S0, 4>, h_counts[0], S0::NT, items_n.get());
+                }
+                if (h_counts[1]) {
+                    if (shape == 1) go(gp_extend_kernel<uint64_t, S1, 4>, h_counts[1], S1::NT, items_w.get());
+                    else if (shape == 2) go(gp_extend_kernel<uint64_t, S2, 2>, h_counts[1], S2::NT, items_w.get());
+                    else go(gp_extend_kernel<uint64_t, S0, 3>, h_counts[1], S0::NT, items_w.get());
+                }
+                if (dbg) cudaEventRecord(ev1, cx.stream);
+            }
+            if (dbg) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
         }
     }
     exclusive_scan_u32(keep.get(), keep_off.get(), n, d_nout.get());
