@@ -21,8 +21,11 @@
 namespace mb2 {
 
 constexpr uint32_t KEY_INVALID = 1u << 24;
-constexpr int S1_RIGHT_BLOCKS = 2;   // 64 columns
-constexpr int S1_LEFT_BLOCKS = 3;    // 96 columns (19 of them are the seed itself)
+constexpr int S1_WINDOW = 30;        // columns per first-stage window = 10 table chunks of 3 columns
+constexpr uint32_t S1_WINDOW_MASK = (1u << S1_WINDOW) - 1u;
+constexpr int S1_RIGHT_WINDOWS = 2;  // 60 columns
+constexpr int S1_LEFT_WINDOWS = 3;   // 90 columns (19 of them are the seed itself)
+constexpr int S1_TAB = 4096;         // (3 target bases, 3 query bases) -> packed {sum, max prefix, min prefix}
 
 __global__ void __launch_bounds__(256)
 seed_keys_kernel(GenomeView T, uint32_t p_lo, uint32_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ pos) {
@@ -64,136 +67,227 @@ __device__ __forceinline__ int sub_lut(uint32_t idx) {
     return (int)(int8_t)(v >> ((idx & 7) * 8));
 }
 
+// ---- first-stage x-drop, three columns per table lookup -------------------------------------------------------
+// Entry for target bases t0 t1 t2 / query bases q0 q1 q2 (index = t6 << 6 | q6, first column in the low bits):
+// bits 18.. = 375 + s0+s1+s2, bits 9..17 = 125 + max prefix sum, bits 0..8 = 375 + min prefix sum.
+// Exactness of the chunked rule: prefix sums inside a chunk differ by at most 2*125 < xdrop, so a column can only
+// terminate the extension against the maximum reached BEFORE the chunk; hence "terminates in this chunk" is
+// run + min_prefix < best - X (and then no column of the chunk has raised best), otherwise best = max(best, run + max_prefix).
+__device__ __forceinline__ uint32_t s1_entry(uint32_t idx) {
+    const uint32_t t6 = idx >> 6, q6 = idx & 63;
+    int sum = 0, mx = INT_MIN, mn = INT_MAX;
+    for (int c = 0; c < 3; c++) {
+        sum += sub_lut((((t6 >> (2 * c)) & 3u) << 2) | ((q6 >> (2 * c)) & 3u));
+        mx = max(mx, sum); mn = min(mn, sum);
+    }
+    return ((uint32_t)(sum + 375) << 18) | ((uint32_t)(mx + 125) << 9) | (uint32_t)(mn + 375);
+}
+// reverse the order of the 32 two-bit groups of a word
+__device__ __forceinline__ uint64_t rev2groups(uint64_t x) {
+    x = __brevll(x);
+    return ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
+}
+// 30 columns (first column in the low bits of wt / wq / an); updates (run, best, term) of the lane exactly as the
+// column-by-column rule would. Lanes whose window holds a non-ACGT column take the per-column path.
+__device__ __forceinline__ void xdrop_window30(const uint32_t* __restrict__ tab, uint64_t wt, uint64_t wq, uint32_t an, int X,
+                                               int& run, int& best, bool& term, unsigned long long& ncells) {
+    bool fast = !term;
+    if (fast && an) {
+        fast = false;
+        for (int c = 0; c < S1_WINDOW && !term; c++) {
+            const int sc = (an & 1u) ? SCORE_N : sub_lut((uint32_t)((wt & 3) << 2 | (wq & 3)));
+            wt >>= 2; wq >>= 2; an >>= 1;
+            run += sc; ncells++;
+            if (run > best) best = run; else if (run < best - X) term = true;
+        }
+    }
+    const uint32_t tl = (uint32_t)wt, th = (uint32_t)(wt >> 32), ql = (uint32_t)wq, qh = (uint32_t)(wq >> 32);
+#pragma unroll
+    for (int k = 0; k < S1_WINDOW / 3; k++) {
+        if (k == 3 || k == 6 || k == 8) { if (__all_sync(0xffffffffu, !fast)) break; }
+        const int sh = 6 * k;
+        uint32_t t6, q6;
+        if (sh + 6 <= 32) { t6 = (tl >> sh) & 63u; q6 = (ql >> sh) & 63u; }
+        else if (sh >= 32) { t6 = (th >> (sh - 32)) & 63u; q6 = (qh >> (sh - 32)) & 63u; }
+        else { t6 = __funnelshift_r(tl, th, sh) & 63u; q6 = __funnelshift_r(ql, qh, sh) & 63u; }
+        const uint32_t e = tab[(t6 << 6) | q6];
+        if (fast) {
+            ncells += 3;
+            if (run + (int)(e & 511u) - 375 < best - X) { term = true; fast = false; }
+            else { best = max(best, run + (int)((e >> 9) & 511u) - 125); run += (int)(e >> 18) - 375; }
+        }
+    }
+}
+
 // ---- load-balanced scan --------------------------------------------------------------------------------------
-// A CTA takes SC_NQ consecutive query positions per round. Phase A: every thread looks up the 13 buckets of its own
-// position and the CTA prefix-sums the 13*SC_NQ bucket sizes, which numbers the round's candidate hits 0..H-1.
-// Phase B: hit number h goes to thread h mod SC_NT, which locates the owning bucket by binary search in the prefix
-// array and runs the leader test and the bounded x-drop in a fixed, fully unrolled shape (32-column windows held in
-// registers); a warp skips the remaining windows as soon as all of its lanes have terminated.
+// Every WARP works on its own: no CTA barrier after the table build. A warp takes 32 consecutive query positions per
+// round (lane = position). Phase A: the 13 bucket ranges of each position are looked up, the non-empty ones are
+// compacted (warp scans) into the warp's ring of descriptors {first hit number, first index in pos[], query position};
+// hit numbers are cumulative over the warp's whole life. Phase B: whenever 32 hits are pending, lane l takes hit
+// `consumed + l`, finds its descriptor by binary search in the ring, and runs the leader test and the bounded x-drop
+// (30-column windows, 3 columns per table lookup). Leftover hits (< 32) wait for the next round, so batches are always
+// full except for the very last one of a warp. All loads of a batch that do not depend on the x-drop outcome (leader
+// windows, first right and left windows) are issued together.
 constexpr int SC_NT = 256;                 // threads per CTA
-constexpr int SC_NQ = 256;                 // query positions per round
+constexpr int SC_WARPS = SC_NT / 32;
 constexpr int SC_NPROBE = 13;
-constexpr int SC_NDESC = SC_NQ * SC_NPROBE;
+constexpr int SC_HALF = 7;                 // probes appended per step: at most 7 * 32 = 224 descriptors
+constexpr int SC_RING = 256;               // descriptors per warp: < 32 pending (every descriptor holds >= 1 hit) + 224 new
 
 __global__ void __launch_bounds__(SC_NT)
 seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, const uint32_t* __restrict__ pos,
                  uint32_t q_lo, uint32_t q_n, int X, int K, int transition, uint32_t diag_bias,
                  uint64_t* __restrict__ surv, uint32_t surv_cap, unsigned long long* __restrict__ counters) {
-    __shared__ uint32_t d_start[SC_NDESC + 1];     // exclusive prefix of bucket sizes (hit number of each bucket's first entry)
-    __shared__ uint32_t d_b0[SC_NDESC];            // first index of each bucket in pos[]
-    __shared__ uint32_t sh_scan[SC_NT / 32 + 1];
+    __shared__ uint32_t s1tab[S1_TAB];
+    __shared__ uint32_t r_cum[SC_WARPS][SC_RING], r_b0[SC_WARPS][SC_RING], r_j[SC_WARPS][SC_RING];
     __shared__ unsigned long long sh_stat[3];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int nprobe = transition ? SC_NPROBE : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < S1_TAB; e += SC_NT) s1tab[e] = s1_entry((uint32_t)e);
     if (tid < 3) sh_stat[tid] = 0;
-    unsigned long long n_lead = 0, n_cells = 0, n_hits_cta = 0;
-    const uint32_t nrounds = (q_n + SC_NQ - 1) / SC_NQ;
-    for (uint32_t round = blockIdx.x; round < nrounds; round += gridDim.x) {
-        // ---------------- phase A: bucket ranges of this thread's query position
-        const uint32_t j = q_lo + round * SC_NQ + tid;
-        uint32_t cnt[SC_NPROBE];
-        uint32_t mine = 0;
-        const bool jvalid = (round * SC_NQ + tid) < q_n && (nwindow32(Q.nm, j) & SEED_WINDOW_MASK19) == 0;
-        uint32_t key = 0;
-        if (jvalid) key = seed_key(window32(Q.pk, j));
+    __syncthreads();
+    uint32_t* __restrict__ rc = r_cum[warp];
+    uint32_t* __restrict__ rb = r_b0[warp];
+    uint32_t* __restrict__ rj = r_j[warp];
+    const int nprobe = transition ? SC_NPROBE : 1;
+    const uint32_t nrounds = (q_n + 31) / 32;
+    const uint32_t nwarps = gridDim.x * SC_WARPS, gw = blockIdx.x * SC_WARPS + warp;
+    // a warp's step = (round, half): probes [0,7) then [7,13) of the round's 32 positions
+    const uint32_t my_rounds = gw < nrounds ? (nrounds - gw + nwarps - 1) / nwarps : 0;
+    const uint32_t nsteps = my_rounds * 2;
+    uint32_t step = 0;
+    uint32_t head = 0, tail = 0;            // ring positions (monotone, used modulo SC_RING)
+    uint32_t cum_tail = 0, consumed = 0;    // hits appended / processed so far (wrapping arithmetic)
+    unsigned long long n_lead = 0, n_cells = 0, n_hits = 0;
+    for (;;) {
+        // ---------------- phase A: append half rounds until a full batch is pending
+        while (cum_tail - consumed < 32u && step < nsteps) {
+            const uint32_t round = gw + (step >> 1) * nwarps;
+            const int p0 = (step & 1) ? SC_HALF : 0, p1 = (step & 1) ? SC_NPROBE : SC_HALF;
+            step++;
+            const uint32_t jrel = round * 32 + lane;
+            const uint32_t j = q_lo + jrel;
+            const bool jvalid = jrel < q_n && (nwindow32(Q.nm, j) & SEED_WINDOW_MASK19) == 0;
+            uint32_t key = 0;
+            if (jvalid) key = seed_key(window32(Q.pk, j));
+            uint32_t b0[SC_HALF], cnt[SC_HALF];
+            uint32_t mine = 0, nne = 0;
 #pragma unroll
-        for (int pr = 0; pr < SC_NPROBE; pr++) {
-            uint32_t c = 0, b0 = 0;
-            if (jvalid && pr < nprobe) {
-                const uint32_t kk = pr == 0 ? key : key ^ (2u << (2 * (pr - 1)));
-                b0 = off[kk];
-                c = off[kk + 1] - b0;
+            for (int q = 0; q < SC_HALF; q++) {
+                const int pr = p0 + q;
+                uint32_t c = 0, b = 0;
+                if (jvalid && pr < p1 && pr < nprobe) {
+                    const uint32_t kk = pr == 0 ? key : key ^ (2u << (2 * (pr - 1)));
+                    b = off[kk];
+                    c = off[kk + 1] - b;
+                }
+                b0[q] = b; cnt[q] = c;
+                mine += c; nne += c ? 1u : 0u;
             }
-            cnt[pr] = c;
-            d_b0[tid * SC_NPROBE + pr] = b0;
-            mine += c;
+            // exclusive scans over the lanes of (hits, non-empty descriptors); descriptor order = (lane, probe)
+            uint32_t sh = mine, sn = nne;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t th = __shfl_up_sync(0xffffffffu, sh, d), tn = __shfl_up_sync(0xffffffffu, sn, d);
+                if (lane >= d) { sh += th; sn += tn; }
+            }
+            const uint32_t tot_h = __shfl_sync(0xffffffffu, sh, 31), tot_n = __shfl_sync(0xffffffffu, sn, 31);
+            uint32_t run = cum_tail + sh - mine, slot = tail + sn - nne;
+#pragma unroll
+            for (int q = 0; q < SC_HALF; q++) {
+                if (cnt[q]) {
+                    const uint32_t w = slot & (SC_RING - 1);
+                    rc[w] = run; rb[w] = b0[q]; rj[w] = j;
+                    run += cnt[q]; slot++;
+                }
+            }
+            tail += tot_n; cum_tail += tot_h; n_hits += (lane == 0) ? tot_h : 0;
+            __syncwarp();
         }
-        uint32_t total;
-        uint32_t run = block_excl_scan<SC_NT>(mine, sh_scan, total);
-#pragma unroll
-        for (int pr = 0; pr < SC_NPROBE; pr++) { d_start[tid * SC_NPROBE + pr] = run; run += cnt[pr]; }
-        if (tid == 0) d_start[SC_NDESC] = total;
-        __syncthreads();
-        n_hits_cta += (tid == 0) ? total : 0;
-        // ---------------- phase B: hits of the round, strided over the CTA; fixed-shape, convergent extension
-        for (uint32_t hbase = 0; hbase < total; hbase += SC_NT) {
-            const uint32_t h = hbase + tid;
-            bool live = h < total;                                   // lane has a hit that still needs an answer
-            uint32_t hi = 0, hj = 0;
-            if (live) {
-                int lo = 0, hi_d = SC_NDESC;                          // bucket that owns hit h: last descriptor with d_start <= h
-                while (hi_d - lo > 1) { const int mid = (lo + hi_d) >> 1; if (d_start[mid] <= h) lo = mid; else hi_d = mid; }
-                hi = pos[d_b0[lo] + (h - d_start[lo])];
-                hj = q_lo + round * SC_NQ + (uint32_t)(lo / SC_NPROBE);
-                // spec D1: only run leaders are candidates
-                const bool prev_seed = (nwindow32(Q.nm, hj - 1) & SEED_WINDOW_MASK19) == 0 &&
-                                       (nwindow32(T.nm, hi - 1) & SEED_WINDOW_MASK19) == 0 &&
-                                       seed_match(window32(T.pk, hi - 1), window32(Q.pk, hj - 1), transition != 0);
-                if (prev_seed) live = false; else n_lead++;
+        const uint32_t pending = cum_tail - consumed;
+        if (pending == 0) break;
+        // ---------------- phase B: one batch of up to 32 hits, one per lane
+        const uint32_t nb = min(pending, 32u);
+        bool live = (uint32_t)lane < nb;
+        const uint32_t h = consumed + (uint32_t)lane;
+        uint32_t hi = 0, hj = 0, e_last = head;
+        if (live) {
+            uint32_t lo = head, hi_d = tail;                        // last descriptor with cum <= h (wrapping compare)
+            while (hi_d - lo > 1) {
+                const uint32_t mid = lo + ((hi_d - lo) >> 1);
+                if ((int32_t)(h - rc[mid & (SC_RING - 1)]) >= 0) lo = mid; else hi_d = mid;
             }
-            // right of the seed: up to S1_RIGHT_BLOCKS windows of 32 columns; a warp stops early once all its lanes are done
-            int runv = 0, best_r = 0;
-            bool term_r = !live;
+            e_last = lo;
+            hi = pos[rb[lo & (SC_RING - 1)] + (h - rc[lo & (SC_RING - 1)])];
+            hj = rj[lo & (SC_RING - 1)];
+        }
+        // everything the batch needs that does not depend on the x-drop outcome: leader windows, first right window,
+        // first left window (T side is a random gather; issue them back to back)
+        uint64_t lt = 0, lq = 0, rt = 0, rq = 0, ft = 0, fq = 0;
+        uint32_t ln = 1, rn = 0, fn = 0;
+        if (live) {
+            lt = window32(T.pk, hi - 1); lq = window32(Q.pk, hj - 1);
+            ln = (nwindow32(Q.nm, hj - 1) | nwindow32(T.nm, hi - 1)) & SEED_WINDOW_MASK19;
+            rt = window32(T.pk, hi + SEED_SPAN); rq = window32(Q.pk, hj + SEED_SPAN);
+            rn = (nwindow32(T.nm, hi + SEED_SPAN) | nwindow32(Q.nm, hj + SEED_SPAN)) & S1_WINDOW_MASK;
+            ft = window32(T.pk, hi + SEED_SPAN - 32); fq = window32(Q.pk, hj + SEED_SPAN - 32);
+            fn = __brev(nwindow32(T.nm, hi + SEED_SPAN - 32) | nwindow32(Q.nm, hj + SEED_SPAN - 32)) & S1_WINDOW_MASK;
+            // spec D1: only run leaders are candidates
+            if (ln == 0 && seed_match(lt, lq, transition != 0)) live = false; else n_lead++;
+        }
+        // right of the seed: up to S1_RIGHT_WINDOWS windows of 30 columns; a warp stops as soon as all its lanes are done
+        int runv = 0, best_r = 0;
+        bool term_r = !live;
 #pragma unroll 1
-            for (int b = 0; b < S1_RIGHT_BLOCKS; b++) {
-                if (__all_sync(0xffffffffu, term_r)) break;
-                if (!term_r) {
-                    const uint32_t ct = hi + SEED_SPAN + 32 * b, cq = hj + SEED_SPAN + 32 * b;
-                    uint64_t wt = window32(T.pk, ct), wq = window32(Q.pk, cq);
-                    uint32_t an = nwindow32(T.nm, ct) | nwindow32(Q.nm, cq);
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const int sc = (an & 1u) ? SCORE_N : sub_lut((uint32_t)((wt & 3) << 2 | (wq & 3)));
-                        wt >>= 2; wq >>= 2; an >>= 1;
-                        if (!term_r) {
-                            runv += sc; n_cells++;
-                            if (runv > best_r) best_r = runv; else if (runv < best_r - X) term_r = true;
-                        }
-                    }
-                }
+        for (int b = 0; b < S1_RIGHT_WINDOWS; b++) {
+            if (__all_sync(0xffffffffu, term_r)) break;
+            uint64_t wt = rt, wq = rq; uint32_t an = rn;
+            if (b > 0 && !term_r) {
+                const uint32_t ct = hi + SEED_SPAN + S1_WINDOW * b, cq = hj + SEED_SPAN + S1_WINDOW * b;
+                wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
+                an = (nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            const bool open_r = live && !term_r;
-            // left, from the last seed column downwards: up to S1_LEFT_BLOCKS windows
-            int best_l = 0;
-            runv = 0;
-            bool term_l = !live;
+            xdrop_window30(s1tab, wt, wq, an, X, runv, best_r, term_r, n_cells);
+        }
+        const bool open_r = live && !term_r;
+        // left, from the last seed column downwards: windows are reversed so that the same forward-order table applies
+        int best_l = 0;
+        runv = 0;
+        bool term_l = !live;
 #pragma unroll 1
-            for (int b = 0; b < S1_LEFT_BLOCKS; b++) {
-                if (__all_sync(0xffffffffu, term_l)) break;
-                if (!term_l) {
-                    const uint32_t ct = hi + SEED_SPAN - 32 * (b + 1), cq = hj + SEED_SPAN - 32 * (b + 1);
-                    uint64_t wt = window32(T.pk, ct), wq = window32(Q.pk, cq);
-                    uint32_t an = nwindow32(T.nm, ct) | nwindow32(Q.nm, cq);
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const int sc = (an >> 31) ? SCORE_N : sub_lut((uint32_t)(((wt >> 62) & 3) << 2 | ((wq >> 62) & 3)));
-                        wt <<= 2; wq <<= 2; an <<= 1;
-                        if (!term_l) {
-                            runv += sc; n_cells++;
-                            if (runv > best_l) best_l = runv; else if (runv < best_l - X) term_l = true;
-                        }
-                    }
-                }
+        for (int b = 0; b < S1_LEFT_WINDOWS; b++) {
+            if (__all_sync(0xffffffffu, term_l)) break;
+            uint64_t wt = ft, wq = fq; uint32_t an = fn;
+            if (b > 0 && !term_l) {
+                const uint32_t ct = hi + SEED_SPAN - S1_WINDOW * b - 32, cq = hj + SEED_SPAN - S1_WINDOW * b - 32;
+                wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
+                an = __brev(nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            // dead iff both sides terminated inside their bounds with a total below K (spec D2: failed extensions leave no trace)
-            const bool survivor = live && (open_r || !term_l || (best_r + best_l >= K));
-            const uint32_t smask = __ballot_sync(0xffffffffu, survivor);
-            if (smask) {
-                unsigned long long basev = 0;
-                if (lane == __ffs(smask) - 1) basev = atomicAdd(&counters[0], (unsigned long long)__popc(smask));
-                basev = __shfl_sync(0xffffffffu, basev, __ffs(smask) - 1);
-                if (survivor) {
-                    const unsigned long long slot = basev + __popc(smask & ((1u << lane) - 1u));
-                    if (slot < surv_cap) surv[slot] = ((uint64_t)(hi - hj + diag_bias) << 32) | hj;
-                }
+            xdrop_window30(s1tab, rev2groups(wt), rev2groups(wq), an, X, runv, best_l, term_l, n_cells);
+        }
+        const bool open_l = live && !term_l;
+        // dead iff both sides terminated inside their bounds with a total below K (spec D2: failed extensions leave no trace)
+        const bool survivor = live && (open_r || open_l || (best_r + best_l >= K));
+        const uint32_t smask = __ballot_sync(0xffffffffu, survivor);
+        if (smask) {
+            unsigned long long basev = 0;
+            if (lane == __ffs(smask) - 1) basev = atomicAdd(&counters[0], (unsigned long long)__popc(smask));
+            basev = __shfl_sync(0xffffffffu, basev, __ffs(smask) - 1);
+            if (survivor) {
+                const unsigned long long slot = basev + __popc(smask & ((1u << lane) - 1u));
+                if (slot < surv_cap) surv[slot] = ((uint64_t)(hi - hj + diag_bias) << 32) | hj;
             }
         }
-        __syncthreads();
+        // retire the batch: descriptors that are fully consumed leave the ring
+        consumed += nb;
+        uint32_t e = __shfl_sync(0xffffffffu, e_last, (int)nb - 1);
+        const uint32_t next_cum = (e + 1 < tail) ? rc[(e + 1) & (SC_RING - 1)] : cum_tail;
+        head = ((int32_t)(next_cum - consumed) > 0) ? e : e + 1;
+        __syncwarp();
     }
     // statistics
     if (n_lead) atomicAdd(&sh_stat[1], n_lead);
     if (n_cells) atomicAdd(&sh_stat[2], n_cells);
-    if (n_hits_cta) atomicAdd(&sh_stat[0], n_hits_cta);
+    if (n_hits) atomicAdd(&sh_stat[0], n_hits);
     __syncthreads();
     if (tid < 3 && sh_stat[tid]) atomicAdd(&counters[1 + tid], sh_stat[tid]);
 }
@@ -204,8 +298,11 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
     const uint32_t n = q_hi - q_lo;
     if (n == 0) return;
     ProfScope ps("seed_scan");
-    const unsigned nrounds = cdiv(n, SC_NQ);
-    const unsigned grid = std::min<unsigned>(nrounds, (unsigned)ctx().sm_count * 8);
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) MB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, seed_scan_kernel, SC_NT, 0));
+    const unsigned nrounds = cdiv(n, 32);
+    // persistent: exactly one resident wave of CTAs; every warp strides over the 32-position rounds
+    const unsigned grid = std::min<unsigned>(cdiv(nrounds, SC_WARPS), (unsigned)ctx().sm_count * (unsigned)std::max(1, ctas_per_sm));
     launch(seed_scan_kernel, grid, SC_NT, 0, view(T), view(Q), tab.off.get(), tab.pos.get(), q_lo, n, p.xdrop,
            p.hspthresh, p.transition, (uint32_t)Q.G, surv, surv_cap, counters);
 }
