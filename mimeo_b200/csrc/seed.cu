@@ -69,10 +69,14 @@ __device__ __forceinline__ int sub_lut(uint32_t idx) {
 
 // ---- first-stage x-drop, three columns per table lookup -------------------------------------------------------
 // Entry for target bases t0 t1 t2 / query bases q0 q1 q2 (index = t6 << 6 | q6, first column in the low bits):
-// bits 18.. = 375 + s0+s1+s2, bits 9..17 = 125 + max prefix sum, bits 0..8 = 375 + min prefix sum.
+// bits 18..31 = s0+s1+s2 (signed), bits 9..17 = 125 + max prefix sum, bits 0..8 = 375 + min prefix sum.
 // Exactness of the chunked rule: prefix sums inside a chunk differ by at most 2*125 < xdrop, so a column can only
 // terminate the extension against the maximum reached BEFORE the chunk; hence "terminates in this chunk" is
 // run + min_prefix < best - X (and then no column of the chunk has raised best), otherwise best = max(best, run + max_prefix).
+// The lane state is kept as (best, D) with D = (best - run) + 375 - X, the deficit to the running maximum in the bias of
+// the table's min-prefix field, so a chunk is: terminate iff min_field < D; DM = max(D, max_field + 250 - X);
+// best += DM - D; D = DM - sum. A finished lane parks at D = S1_DONE, where every later chunk is a no-op on best.
+constexpr int S1_DONE = 1 << 24;
 __device__ __forceinline__ uint32_t s1_entry(uint32_t idx) {
     const uint32_t t6 = idx >> 6, q6 = idx & 63;
     int sum = 0, mx = INT_MIN, mn = INT_MAX;
@@ -80,43 +84,50 @@ __device__ __forceinline__ uint32_t s1_entry(uint32_t idx) {
         sum += sub_lut((((t6 >> (2 * c)) & 3u) << 2) | ((q6 >> (2 * c)) & 3u));
         mx = max(mx, sum); mn = min(mn, sum);
     }
-    return ((uint32_t)(sum + 375) << 18) | ((uint32_t)(mx + 125) << 9) | (uint32_t)(mn + 375);
+    return ((uint32_t)sum << 18) | ((uint32_t)(mx + 125) << 9) | (uint32_t)(mn + 375);
 }
 // reverse the order of the 32 two-bit groups of a word
 __device__ __forceinline__ uint64_t rev2groups(uint64_t x) {
     x = __brevll(x);
     return ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
 }
-// 30 columns (first column in the low bits of wt / wq / an); updates (run, best, term) of the lane exactly as the
+// 30 columns (first column in the low bits of wt / wq / an); updates (best, D) of the lane exactly as the
 // column-by-column rule would. Lanes whose window holds a non-ACGT column take the per-column path.
 __device__ __forceinline__ void xdrop_window30(const uint32_t* __restrict__ tab, uint64_t wt, uint64_t wq, uint32_t an, int X,
-                                               int& run, int& best, bool& term, unsigned long long& ncells) {
-    bool fast = !term;
-    if (fast && an) {
-        fast = false;
+                                               int& best, int& D, uint32_t& nchunks) {
+    int d_keep = 0;
+    bool slow = false;
+    if (D < S1_DONE / 2 && an) {
+        int run = best - (D - 375 + X);
+        bool term = false;
         for (int c = 0; c < S1_WINDOW && !term; c++) {
             const int sc = (an & 1u) ? SCORE_N : sub_lut((uint32_t)((wt & 3) << 2 | (wq & 3)));
             wt >>= 2; wq >>= 2; an >>= 1;
-            run += sc; ncells++;
+            run += sc;
             if (run > best) best = run; else if (run < best - X) term = true;
         }
+        nchunks += S1_WINDOW / 3;
+        d_keep = term ? S1_DONE : (best - run) + 375 - X;
+        slow = true; D = S1_DONE;              // the window is consumed: the table loop below is a no-op for this lane
     }
     const uint32_t tl = (uint32_t)wt, th = (uint32_t)(wt >> 32), ql = (uint32_t)wq, qh = (uint32_t)(wq >> 32);
+    const int c2 = 250 - X;
 #pragma unroll
     for (int k = 0; k < S1_WINDOW / 3; k++) {
-        if (k == 3 || k == 6 || k == 8) { if (__all_sync(0xffffffffu, !fast)) break; }
+        if (k == 3 || k == 6 || k == 8) { if (__all_sync(0xffffffffu, D >= S1_DONE / 2)) break; }
         const int sh = 6 * k;
         uint32_t t6, q6;
         if (sh + 6 <= 32) { t6 = (tl >> sh) & 63u; q6 = (ql >> sh) & 63u; }
         else if (sh >= 32) { t6 = (th >> (sh - 32)) & 63u; q6 = (qh >> (sh - 32)) & 63u; }
         else { t6 = __funnelshift_r(tl, th, sh) & 63u; q6 = __funnelshift_r(ql, qh, sh) & 63u; }
         const uint32_t e = tab[(t6 << 6) | q6];
-        if (fast) {
-            ncells += 3;
-            if (run + (int)(e & 511u) - 375 < best - X) { term = true; fast = false; }
-            else { best = max(best, run + (int)((e >> 9) & 511u) - 125); run += (int)(e >> 18) - 375; }
-        }
+        nchunks += D < S1_DONE / 2 ? 1u : 0u;
+        const bool term = (int)(e & 511u) < D;
+        const int dm = max(D, (int)((e >> 9) & 511u) + c2);
+        best += dm - D;
+        D = term ? S1_DONE : dm - ((int)e >> 18);
     }
+    if (slow) D = d_keep;
 }
 
 // ---- load-balanced scan --------------------------------------------------------------------------------------
@@ -235,36 +246,36 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
             if (ln == 0 && seed_match(lt, lq, transition != 0)) live = false; else n_lead++;
         }
         // right of the seed: up to S1_RIGHT_WINDOWS windows of 30 columns; a warp stops as soon as all its lanes are done
-        int runv = 0, best_r = 0;
-        bool term_r = !live;
+        const int d_start = live ? 375 - X : S1_DONE;      // run = best = 0
+        int best_r = 0, dr = d_start;
+        uint32_t nchunks = 0;
 #pragma unroll 1
         for (int b = 0; b < S1_RIGHT_WINDOWS; b++) {
-            if (__all_sync(0xffffffffu, term_r)) break;
+            if (__all_sync(0xffffffffu, dr >= S1_DONE / 2)) break;
             uint64_t wt = rt, wq = rq; uint32_t an = rn;
-            if (b > 0 && !term_r) {
+            if (b > 0 && dr < S1_DONE / 2) {
                 const uint32_t ct = hi + SEED_SPAN + S1_WINDOW * b, cq = hj + SEED_SPAN + S1_WINDOW * b;
                 wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
                 an = (nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            xdrop_window30(s1tab, wt, wq, an, X, runv, best_r, term_r, n_cells);
+            xdrop_window30(s1tab, wt, wq, an, X, best_r, dr, nchunks);
         }
-        const bool open_r = live && !term_r;
+        const bool open_r = dr < S1_DONE / 2;
         // left, from the last seed column downwards: windows are reversed so that the same forward-order table applies
-        int best_l = 0;
-        runv = 0;
-        bool term_l = !live;
+        int best_l = 0, dl = d_start;
 #pragma unroll 1
         for (int b = 0; b < S1_LEFT_WINDOWS; b++) {
-            if (__all_sync(0xffffffffu, term_l)) break;
+            if (__all_sync(0xffffffffu, dl >= S1_DONE / 2)) break;
             uint64_t wt = ft, wq = fq; uint32_t an = fn;
-            if (b > 0 && !term_l) {
+            if (b > 0 && dl < S1_DONE / 2) {
                 const uint32_t ct = hi + SEED_SPAN - S1_WINDOW * b - 32, cq = hj + SEED_SPAN - S1_WINDOW * b - 32;
                 wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
                 an = __brev(nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            xdrop_window30(s1tab, rev2groups(wt), rev2groups(wq), an, X, runv, best_l, term_l, n_cells);
+            xdrop_window30(s1tab, rev2groups(wt), rev2groups(wq), an, X, best_l, dl, nchunks);
         }
-        const bool open_l = live && !term_l;
+        const bool open_l = dl < S1_DONE / 2;
+        n_cells += 3ull * nchunks;
         // dead iff both sides terminated inside their bounds with a total below K (spec D2: failed extensions leave no trace)
         const bool survivor = live && (open_r || open_l || (best_r + best_l >= K));
         const uint32_t smask = __ballot_sync(0xffffffffu, survivor);
