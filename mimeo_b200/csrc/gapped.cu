@@ -371,9 +371,9 @@ anchor_points_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ ti
         if (tid == 0) { a1[x] = hs1[g] + len / 2; a2[x] = hs2[g] + len / 2; }
         return;
     }
-    auto col = [&](int c) -> int {
-        const uint32_t an = isn_at(T.nm, ts + c) | isn_at(Q.nm, qs + c);
-        return an ? SCORE_N : sub_lut3((base_at(T.pk, ts + c) << 2) | base_at(Q.pk, qs + c));
+    // 32 column scores at a time from registers: words of 32 bases / 32 N flags starting at column c
+    auto score_at = [](uint64_t wt, uint64_t wq, uint32_t an, int t) -> int {
+        return ((an >> t) & 1u) ? SCORE_N : sub_lut3((uint32_t)(((wt >> (2 * t)) & 3) << 2) | (uint32_t)((wq >> (2 * t)) & 3));
     };
     const int nwin = len - 30;                       // window w covers columns [w, w + 30]
     const int chunk = (nwin + AP_NT - 1) / AP_NT;
@@ -381,11 +381,24 @@ anchor_points_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ ti
     int best = INT_MIN, bw = INT_MAX;
     if (w0 < w1) {
         int sum = 0;
-        for (int c = 0; c < 31; c++) sum += col(w0 + c);
+        {
+            const uint64_t wt = window32(T.pk, ts + w0), wq = window32(Q.pk, qs + w0);
+            const uint32_t an = nwindow32(T.nm, ts + w0) | nwindow32(Q.nm, qs + w0);
+#pragma unroll
+            for (int t = 0; t < 31; t++) sum += score_at(wt, wq, an, t);
+        }
         best = sum; bw = w0;
-        for (int w = w0 + 1; w < w1; w++) {
-            sum += col(w + 30) - col(w - 1);
-            if (sum > best) { best = sum; bw = w; }
+        // window w = w0 + 1 + 32 b + t: column w + 30 enters, column w - 1 leaves
+        for (int wb = w0 + 1; wb < w1; wb += 32) {
+            const uint64_t et = window32(T.pk, ts + wb + 30), eq = window32(Q.pk, qs + wb + 30);
+            const uint32_t en = nwindow32(T.nm, ts + wb + 30) | nwindow32(Q.nm, qs + wb + 30);
+            const uint64_t lt = window32(T.pk, ts + wb - 1), lq = window32(Q.pk, qs + wb - 1);
+            const uint32_t ln = nwindow32(T.nm, ts + wb - 1) | nwindow32(Q.nm, qs + wb - 1);
+#pragma unroll
+            for (int t = 0; t < 32; t++) {
+                sum += score_at(et, eq, en, t) - score_at(lt, lq, ln, t);
+                if (wb + t < w1 && sum > best) { best = sum; bw = wb + t; }
+            }
         }
     }
     // first maximum over the CTA: highest sum, then lowest window

@@ -137,3 +137,21 @@ def test_query_chunking_is_invisible(M, monkeypatch):
     assert gpu_rows(one) == gpu_rows(many) and len(one['t_id']) > 10
     for k in ('seed_hits', 'leaders', 'survivors', 'hsps', 'alignments'):
         assert s1[k] == s2[k], k
+
+
+def test_long_alignment_takes_the_exact_wide_payload_path(M):
+    """One alignment of > 65536 columns (a scaffold with a single N against itself: no closed form) must leave the
+    16+16-bit payload kernel, be redone with 32+32-bit payloads and still equal the oracle bit for bit."""
+    A, G = M
+    rng = np.random.default_rng(48)
+    n = 150_000
+    seq = np.frombuffer(b'ACGT', dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+    seq[100_000] = ord('N')
+    g = {'s': seq}
+    T = G.Genome.from_dict(g)
+    hits, stats = A.align(T, T, G.align_params(3000), strands=1)
+    p = lo.default_params(3000)
+    tix = lo.TargetIndex(lo.encode(seq))
+    want = {(0, 0, 0, s1 + 1, e1, s2 + 1, e2, sc, nm, nc) for (s1, e1, s2, e2, sc, nm, nc, _a, _b) in lo.align_tile(tix, lo.encode(seq), p).tolist()}
+    assert gpu_rows(hits) == want
+    assert max(r[4] - r[3] for r in want) > 140_000
