@@ -141,17 +141,19 @@ template <typename P, typename S> struct GpShared {
     EdgeBuf<P, S::NT> left;             // slot 0 of every thread: {h, i, hp, ip}
     EdgeBuf<P, S::NT> up;               // last slot of every thread: {h, d, hp, dp}
     int4 rng[2][S::WARPS];              // per parity, per warp: {warp max, alive diagonal lo, hi, -}
-    int4 top[2][S::WARPS];              // per parity, per warp: {row i of the warp max, payload lo, payload hi, -}
+    int4 fin[S::WARPS]; int2 finp[S::WARPS];   // end of the extension: per warp {score, k, i, -} and payload of its first maximum
     int2 lut[25];                       // {substitution score, is-match} for codes 0..4 x 0..4
     int red[S::WARPS];
 };
 
 // One DP cell (i,j) of anti-diagonal k on diagonal delta = i - j.  self = this diagonal's cell two anti-diagonals ago
 // (updated in place), (uh, ud) = H and D of cell (i-1,j), (lh, li) = H and I of cell (i,j-1), both of the previous anti-diagonal.
-// ok = cell lies inside both sequences (always true away from the sequence ends).
+// ok = cell lies inside both sequences (always true away from the sequence ends). Every thread remembers the first cell
+// (anti-diagonal, then row) that reached its own maximum; the alignment end is picked among those records once, at the end
+// of the extension, so an anti-diagonal only has to share ONE number (its maximum score) for the y-drop threshold.
 template <typename P>
 __device__ __forceinline__ void gp_cell(Cell<P>& self, int uh, int ud, P uhp, P udp, int lh, int li, P lhp, P lip, int2 sc, bool ok,
-                                        int OE, int E, int thr, int c, int& tmax, int& tc, P& tp, int& hmax) {
+                                        int OE, int E, int thr, int k, int i, int& tbest, int& tk, int& ti, P& tp, int& hmax) {
     // D: vertical gap state, I: horizontal gap state (ties prefer opening from H, as in the oracle)
     const int dopen = uh - OE, dext = ud - E;
     const bool dsel = dopen >= dext;
@@ -168,7 +170,7 @@ __device__ __forceinline__ void gp_cell(Cell<P>& self, int uh, int ud, P uhp, P 
     const bool alive = ok && nh >= thr;
     self.h = alive ? nh : NEG_INF; self.d = alive ? nd : NEG_INF; self.i = alive ? ni : NEG_INF;
     self.hp = nhp; self.dp = ndp; self.ip = nip;
-    if (self.h > tmax) { tmax = self.h; tc = c; tp = nhp; }     // tmax starts at best: only a new maximum registers
+    if (self.h > tbest) { tbest = self.h; tk = k; ti = i; tp = nhp; }   // the thread's own first maximum (strict >: earliest k, then smallest i)
     hmax = max(hmax, self.h);
 }
 
@@ -199,7 +201,8 @@ __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint3
     __syncthreads();
     int best = 0, dead_steps = 0;
     int lo1 = 0, hi1 = 0, lo2 = 1, hi2 = 0;     // alive diagonal ranges of anti-diagonals k-1 and k-2 (empty when lo > hi)
-    P bestp = 0;
+    int tbest = 0, tk = 0, ti = 0;              // this thread's first maximum; (0, 0, 0) = the anchor cell itself
+    P tp = 0;
     bool narrow_ok = true;
     const uint32_t kmax = (uint32_t)tn + (uint32_t)qn;
     for (uint32_t k = 1; k <= kmax; k++) {
@@ -213,8 +216,7 @@ __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint3
         const int d0 = base + ((GP_SLOTS * tid - base) & GP_DMASK);  // diagonal of slot 0; slot s holds d0 + s
         const int thr = best - Y;
         const int par = (int)(k & 1);
-        int tmax = best, tc = 0, hmax = NEG_INF;
-        P tp = 0;
+        int hmax = NEG_INF;
         const bool active = d0 + GP_SLOTS - 1 >= clo && d0 <= chi;
         const int i0 = ((int)k + d0 + par) >> 1, j0 = ((int)k - d0 - par) >> 1;   // cell c of this thread: (i0 + c, j0 - c)
         if (active) {
@@ -249,9 +251,9 @@ __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint3
                     const int s = 2 * c + 1;
                     if (s + 1 < GP_SLOTS) {
                         const Cell<P>& L = st[s + 1 < GP_SLOTS ? s + 1 : s];
-                        gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, L.h, L.i, L.hp, L.ip, sc[c], ok[c], OE, E, thr, c, tmax, tc, tp, hmax);
+                        gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, L.h, L.i, L.hp, L.ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
                     } else {
-                        gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, fl.h, fl.x, fl.hp, fl.xp, sc[c], ok[c], OE, E, thr, c, tmax, tc, tp, hmax);
+                        gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, fl.h, fl.x, fl.hp, fl.xp, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
                     }
                 }
                 const Cell<P>& e = st[GP_SLOTS - 1];
@@ -264,9 +266,9 @@ __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint3
                     const int s = 2 * c;
                     if (s > 0) {
                         const Cell<P>& U = st[s > 0 ? s - 1 : 0];
-                        gp_cell<P>(st[s], U.h, U.d, U.hp, U.dp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, c, tmax, tc, tp, hmax);
+                        gp_cell<P>(st[s], U.h, U.d, U.hp, U.dp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
                     } else {
-                        gp_cell<P>(st[s], fu.h, fu.x, fu.hp, fu.xp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, c, tmax, tc, tp, hmax);
+                        gp_cell<P>(st[s], fu.h, fu.x, fu.hp, fu.xp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
                     }
                 }
                 const Cell<P>& e = st[0];
@@ -276,20 +278,9 @@ __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint3
         }
         if (__any_sync(0xffffffffu, active)) {
             const bool any_alive = hmax > NEG_INF;
-            const int wmax = __reduce_max_sync(0xffffffffu, tmax);
+            const int wmax = __reduce_max_sync(0xffffffffu, hmax);
             const int wlo = __reduce_min_sync(0xffffffffu, any_alive ? d0 : INT_MAX);
             const int whi = __reduce_max_sync(0xffffffffu, any_alive ? d0 + GP_SLOTS - 1 : INT_MIN);
-            if (wmax > best) {
-                // first maximum in DIAGONAL order (= smallest row i): lanes at or after the window's wrap point come first
-                const uint32_t m = __ballot_sync(0xffffffffu, tmax == wmax);
-                const int wrap_t = (base / GP_SLOTS) & (GP_NT - 1);          // thread whose slot 0 holds diagonal `base`
-                uint32_t mh = m;
-                if ((wrap_t >> 5) == warp) { const uint32_t hi = m & (0xffffffffu << (wrap_t & 31)); if (hi) mh = hi; }
-                if (lane == __ffs(mh) - 1) {
-                    const uint64_t p64 = (uint64_t)tp;
-                    sm.top[par][warp] = make_int4(i0 + tc, (int)(uint32_t)p64, (int)(uint32_t)(p64 >> 32), 0);
-                }
-            }
             if (lane == 0) sm.rng[par][warp] = make_int4(wmax, wlo, whi, 0);
         } else if (lane == 0) {
             sm.rng[par][warp] = make_int4(INT_MIN, INT_MAX, INT_MIN, 0);
@@ -299,23 +290,37 @@ __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint3
         int4 q[GP_WARPS];
 #pragma unroll
         for (int w = 0; w < GP_WARPS; w++) { q[w] = sm.rng[par][w]; bmax = max(bmax, q[w].x); alo = min(alo, q[w].y); ahi = max(ahi, q[w].z); }
-        if (bmax > best) {
-            int bi = INT_MAX; uint64_t bp = 0;
-#pragma unroll
-            for (int w = 0; w < GP_WARPS; w++) {
-                if (q[w].x == bmax) {
-                    const int4 t4 = sm.top[par][w];
-                    if (t4.x < bi) { bi = t4.x; bp = (uint64_t)(uint32_t)t4.y | ((uint64_t)(uint32_t)t4.z << 32); }
-                }
-            }
-            best = bmax; r.score = bmax; r.di = bi; r.dj = (int)k - bi; bestp = (P)bp;
-        }
+        best = max(best, bmax);
         lo2 = lo1; hi2 = hi1; lo1 = alo; hi1 = ahi;          // empty ranges arrive as (INT_MAX, INT_MIN)
         if (hi1 < lo1) { lo1 = 1; hi1 = 0; }
         dead_steps = (hi1 < lo1) ? dead_steps + 1 : 0;
         if (dead_steps >= 2) break;         // two dead anti-diagonals in a row: nothing can revive
     }
-    r.nmatch = Pay<P>::nm(bestp); r.ncols = Pay<P>::nc(bestp);
+    // the alignment end: among the threads whose own maximum equals the global one, the earliest anti-diagonal, then the
+    // smallest row (each thread's record already is its first such cell)
+    {
+        const bool cand = tbest == best;
+        const int wk = __reduce_min_sync(0xffffffffu, cand ? tk : INT_MAX);
+        const int wi = __reduce_min_sync(0xffffffffu, (cand && tk == wk) ? ti : INT_MAX);
+        if (cand && tk == wk && ti == wi) {
+            const uint64_t p64 = (uint64_t)tp;
+            sm.fin[warp] = make_int4(best, wk, wi, 0); sm.finp[warp] = make_int2((int)(uint32_t)p64, (int)(uint32_t)(p64 >> 32));
+        }
+        if (wk == INT_MAX && lane == 0) sm.fin[warp] = make_int4(INT_MIN, INT_MAX, INT_MAX, 0);
+        __syncthreads();
+        int bk = INT_MAX, bi = INT_MAX; uint64_t bp = 0;
+#pragma unroll
+        for (int w = 0; w < GP_WARPS; w++) {
+            const int4 f = sm.fin[w];
+            if (f.x == best && (f.y < bk || (f.y == bk && f.z < bi))) {
+                bk = f.y; bi = f.z; const int2 q = sm.finp[w];
+                bp = (uint64_t)(uint32_t)q.x | ((uint64_t)(uint32_t)q.y << 32);
+            }
+        }
+        r.score = best; r.di = bi; r.dj = bk - bi;
+        r.nmatch = Pay<P>::nm((P)bp); r.ncols = Pay<P>::nc((P)bp);
+        __syncthreads();
+    }
     // 16-bit columns are exact iff the optimal path has fewer than 65536 columns, which min(di, dj) bounds from above
     if (sizeof(P) == 4 && min(r.di, r.dj) >= 65536) narrow_ok = false;
     return narrow_ok;
