@@ -41,6 +41,18 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` on this workload, from the committed
+    `ncu --set full` capture (profiles/roofline_traffic.json; a number measured under the profiler, so it is only ever
+    reported as traffic, never timed). None when no capture of this (workload, kernel) pair is committed."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
+            rec = json.load(f)[workload][kernel]
+        return rec['dram_bytes_per_launch'], rec['source']
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
@@ -416,8 +428,9 @@ def run_b200(args):
     dms, dcnt = prof[dom]
     per_launch_ms = dms / max(dcnt, 1)
     achieved = kb[dom] / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic(args.workload, dom)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'ms_per_launch': per_launch_ms, 'algorithmic_bytes_per_launch': kb[dom],
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'ms_per_launch': per_launch_ms, 'algorithmic_bytes_per_launch': kb[dom],
                 'kernels_ms_per_step': {t: prof[t][0] / args.steps for t in all_tags if prof[t][1]}}
     if '_stage_survey' in kb:
         roofline['stage_survey_model'] = {'bytes': kb['_stage_survey'], 'achieved': kb['_stage_survey'] / (ms_step / 1e3) / 1e9,
