@@ -697,7 +697,7 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
                 if (h_counts[0]) {
                     if (shape == 1) go(gp_extend_kernel<uint32_t, S1, 6>, h_counts[0], S1::NT, items_n.get());
                     else if (shape == 2) go(gp_extend_kernel<uint32_t, S2, 3>, h_counts[0], S2::NT, items_n.get());
-                    else go(gp_extend_kernel<uint32_t, S0, 4>, h_counts[0], S0::NT, items_n.get());
+                    else go(gp_extend_kernel<uint32_t, S0, 5>, h_counts[0], S0::NT, items_n.get());
                 }
                 if (h_counts[1]) {
                     if (shape == 1) go(gp_extend_kernel<uint64_t, S1, 4>, h_counts[1], S1::NT, items_w.get());

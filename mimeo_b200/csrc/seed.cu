@@ -10,7 +10,7 @@
 //   bucket_offsets_kernel  key -> [begin,end) in the sorted position list (2^24+1 offsets)
 //   seed_scan_kernel     per query position: 13 probes (exact + 12 single-transition variants);
 //                        per candidate target position: run-leader test (spec D1), then an exact
-//                        x-drop extension bounded to 64 columns right / 96 left. Hits whose
+//                        x-drop extension bounded to 60 columns right / 90 left. Hits whose
 //                        extension terminated inside the bounds with score < K are dead (they can
 //                        never become an HSP and, by spec D2, leave no trace); everything else is
 //                        a survivor and is appended as (diagonal, query position) for stage 2.
@@ -133,7 +133,7 @@ __device__ __forceinline__ void xdrop_window30(const uint32_t* __restrict__ tab,
 // ---- load-balanced scan --------------------------------------------------------------------------------------
 // Every WARP works on its own: no CTA barrier after the table build. A warp takes 32 consecutive query positions per
 // round (lane = position). Phase A: the 13 bucket ranges of each position are looked up, the non-empty ones are
-// compacted (warp scans) into the warp's ring of descriptors {first hit number, first index in pos[], query position};
+// compacted (warp scans, three probes at a time) into the warp's ring of descriptors {first hit number, first index in pos[], query position};
 // hit numbers are cumulative over the warp's whole life. Phase B: whenever 32 hits are pending, lane l takes hit
 // `consumed + l`, finds its descriptor by binary search in the ring, and runs the leader test and the bounded x-drop
 // (30-column windows, 3 columns per table lookup). Leftover hits (< 32) wait for the next round, so batches are always
@@ -142,8 +142,10 @@ __device__ __forceinline__ void xdrop_window30(const uint32_t* __restrict__ tab,
 constexpr int SC_NT = 256;                 // threads per CTA
 constexpr int SC_WARPS = SC_NT / 32;
 constexpr int SC_NPROBE = 13;
-constexpr int SC_HALF = 7;                 // probes appended per step: at most 7 * 32 = 224 descriptors
-constexpr int SC_RING = 256;               // descriptors per warp: < 32 pending (every descriptor holds >= 1 hit) + 224 new
+constexpr int SC_HALF = 3;                 // probes appended per step: at most 3 * 32 = 96 descriptors
+constexpr int SC_STEPS = (SC_NPROBE + SC_HALF - 1) / SC_HALF;   // steps per round
+constexpr int SC_RING = 128;               // descriptors per warp: < 32 pending (every descriptor holds >= 1 hit) + 96 new
+                                           // (a small ring keeps shared memory low, which leaves the SM more L1 for the gathers)
 
 __global__ void __launch_bounds__(SC_NT)
 seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, const uint32_t* __restrict__ pos,
@@ -162,9 +164,9 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
     const int nprobe = transition ? SC_NPROBE : 1;
     const uint32_t nrounds = (q_n + 31) / 32;
     const uint32_t nwarps = gridDim.x * SC_WARPS, gw = blockIdx.x * SC_WARPS + warp;
-    // a warp's step = (round, half): probes [0,7) then [7,13) of the round's 32 positions
+    // a warp's step = (round, part): SC_HALF probes of the round's 32 positions at a time
     const uint32_t my_rounds = gw < nrounds ? (nrounds - gw + nwarps - 1) / nwarps : 0;
-    const uint32_t nsteps = my_rounds * 2;
+    const uint32_t nsteps = my_rounds * SC_STEPS;
     uint32_t step = 0;
     uint32_t head = 0, tail = 0;            // ring positions (monotone, used modulo SC_RING)
     uint32_t cum_tail = 0, consumed = 0;    // hits appended / processed so far (wrapping arithmetic)
@@ -172,8 +174,8 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
     for (;;) {
         // ---------------- phase A: append half rounds until a full batch is pending
         while (cum_tail - consumed < 32u && step < nsteps) {
-            const uint32_t round = gw + (step >> 1) * nwarps;
-            const int p0 = (step & 1) ? SC_HALF : 0, p1 = (step & 1) ? SC_NPROBE : SC_HALF;
+            const uint32_t round = gw + (step / SC_STEPS) * nwarps;
+            const int p0 = (int)(step % SC_STEPS) * SC_HALF, p1 = min(SC_NPROBE, p0 + SC_HALF);
             step++;
             const uint32_t jrel = round * 32 + lane;
             const uint32_t j = q_lo + jrel;
@@ -310,7 +312,12 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
     if (n == 0) return;
     ProfScope ps("seed_scan");
     static int ctas_per_sm = 0;
-    if (!ctas_per_sm) MB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, seed_scan_kernel, SC_NT, 0));
+    if (!ctas_per_sm) {
+        if (getenv("MB2_SCAN_CARVEOUT"))
+            MB2_CUDA(cudaFuncSetAttribute(seed_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MB2_SCAN_CARVEOUT"))));
+        MB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, seed_scan_kernel, SC_NT, 0));
+        if (getenv("MB2_SCAN_CTAS")) ctas_per_sm = atoi(getenv("MB2_SCAN_CTAS"));
+    }
     const unsigned nrounds = cdiv(n, 32);
     // persistent: exactly one resident wave of CTAs; every warp strides over the 32-position rounds
     const unsigned grid = std::min<unsigned>(cdiv(nrounds, SC_WARPS), (unsigned)ctx().sm_count * (unsigned)std::max(1, ctas_per_sm));
