@@ -56,18 +56,24 @@ def tab_blocks(hits: Dict[str, np.ndarray], tnames: List[str], qnames: List[str]
     """Filtered, sorted 10-column rows (with newline) per (t_id, q_id) pair."""
     out: Dict[Tuple[int, int], List[str]] = {}
     n = len(hits['t_id'])
-    for k in range(n):
-        s1, e1 = int(hits['start1'][k]), int(hits['end1'][k])
-        if e1 - s1 + 1 < minLen:                               # awk '0+$5 >= minLen' on length1
+    if n == 0:
+        return out
+    s1, e1 = hits['start1'], hits['end1']
+    nm, nc = hits['nmatch'].astype(np.float64), hits['ncols'].astype(np.float64)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        ratio = np.where(nc > 0, 100.0 * nm / nc, 0.0)            # same double arithmetic as pct_text
+    long_enough = (e1.astype(np.int64) - s1 + 1) >= minLen          # awk '0+$5 >= minLen' on length1
+    idx = np.flatnonzero(long_enough)
+    pct = ['%.1f' % v for v in ratio[idx].tolist()]
+    lim = float(minIdt)
+    rows = []
+    cols = [hits[f][idx].tolist() for f in ('t_id', 'q_id', 'strand', 'start1', 'end1', 'start2', 'end2', 'score')]
+    for t, q, st, a, b, c, d, sc, p in zip(*cols, pct):
+        if float(p) < lim:                                         # awk '0+$13 >= minIdt' on the printed percentage
             continue
-        pct = pct_text(int(hits['nmatch'][k]), int(hits['ncols'][k]))
-        if float(pct) < float(minIdt):                         # awk '0+$13 >= minIdt' on the printed percentage
-            continue
-        t, q = int(hits['t_id'][k]), int(hits['q_id'][k])
-        row = '\t'.join((tnames[t], '+', str(s1), str(e1), qnames[q], '-' if hits['strand'][k] else '+',
-                         str(int(hits['start2'][k])), str(int(hits['end2'][k])), str(int(hits['score'][k])), pct))
+        row = f"{tnames[t]}\t+\t{a}\t{b}\t{qnames[q]}\t{'-' if st else '+'}\t{c}\t{d}\t{sc}\t{p}\n"
+        rows.append((t, q, a, row.encode(), row))
+    rows.sort()                 # per pair: sort -k 3n,4n then whole line (name1 equal inside a pair; the newline sorts below every field byte)
+    for t, q, _a, _b, row in rows:
         out.setdefault((t, q), []).append(row)
-    for key, rows in out.items():
-        rows.sort(key=lambda r: (float(r.split('\t')[2]), r.encode()))   # sort -k 3n,4n then whole line (name1 equal inside a pair)
-        out[key] = [r + '\n' for r in rows]
     return out
