@@ -150,6 +150,35 @@ MB2_API int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome
                       const int32_t* t_same_q, mb2_hits* out);
 MB2_API void mb2_free_hits(mb2_hits* h);
 
+/* ---- native text ingest (host side, no GPU needed) --------------------------------------------- */
+/* The BED projection of a LASTZ-style .tab file, i.e. what `awk '!/^#/ {print $1,$3,$4;}'` hands to
+ * sort | bedtools genomecov (wrappers.py:1120-1128, x: 827-835, self intra: 1201-1220): one (name, start1, end1)
+ * triple per line that does not start with '#', fields split on blanks/tabs. Names are dictionary-encoded in order of
+ * first appearance. The file is mmapped and parsed by `nthreads` threads (0 = all cores). Arrays owned by the library. */
+typedef struct mb2_tab_hits {
+    int32_t* chrom;      /* index into names */
+    int64_t* start;
+    int64_t* end;
+    uint64_t n;
+    char** names;        /* nnames NUL-terminated strings */
+    int32_t nnames;
+} mb2_tab_hits;
+MB2_API int mb2_tab_project(const char* path, int nthreads, mb2_tab_hits* out);
+MB2_API void mb2_free_tab_hits(mb2_tab_hits* h);
+
+/* Every record of a FASTA file: id = first word of the header, header = the whole '>' line, sequence with line breaks
+ * and blanks removed. Replaces Biopython's SeqIO.parse in chromlens / splitFasta (utils.py:301-309, 530-546).
+ * seq holds all sequences back to back; record r is seq[off[r] .. off[r+1]). Arrays owned by the library. */
+typedef struct mb2_fasta {
+    int32_t n;
+    char** ids;
+    char** headers;
+    uint64_t* off;       /* n + 1 entries */
+    uint8_t* seq;
+} mb2_fasta;
+MB2_API int mb2_fasta_read(const char* path, int nthreads, mb2_fasta* out);
+MB2_API void mb2_free_fasta(mb2_fasta* f);
+
 /* ---- device primitives exposed for parity tests ------------------------------------------- */
 /* Stable LSD radix sort of HOST arrays on bits [begin_bit, end_bit) (vals may be NULL). */
 MB2_API int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);

@@ -32,6 +32,16 @@ class Hits(C.Structure):
                [('n', C.c_uint64), ('stats', C.c_uint64 * 16)]
 
 
+class TabHits(C.Structure):
+    _fields_ = [('chrom', c_i32p), ('start', c_i64p), ('end', c_i64p), ('n', C.c_uint64), ('names', C.POINTER(C.c_char_p)),
+                ('nnames', C.c_int32)]
+
+
+class Fasta(C.Structure):
+    _fields_ = [('n', C.c_int32), ('ids', C.POINTER(C.c_char_p)), ('headers', C.POINTER(C.c_char_p)), ('off', c_u64p),
+                ('seq', C.POINTER(C.c_uint8))]
+
+
 class Segments(C.Structure):
     _fields_ = [('chrom', c_i32p), ('start', c_i32p), ('end', c_i32p), ('n', C.c_uint64), ('on_device', C.c_int)]
 
@@ -63,6 +73,10 @@ SIGNATURES = {
     'mb2_test_hsps': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(AlignParams), C.POINTER(Hsps), C.c_void_p]),
     'mb2_align': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AlignParams), C.c_int, C.c_void_p, C.POINTER(Hits)]),
     'mb2_free_hits': (None, [C.POINTER(Hits)]),
+    'mb2_tab_project': (C.c_int, [C.c_char_p, C.c_int, C.POINTER(TabHits)]),
+    'mb2_free_tab_hits': (None, [C.POINTER(TabHits)]),
+    'mb2_fasta_read': (C.c_int, [C.c_char_p, C.c_int, C.POINTER(Fasta)]),
+    'mb2_free_fasta': (None, [C.POINTER(Fasta)]),
     'mb2_test_sort_u32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     'mb2_test_sort_u64': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     'mb2_test_scan_u32': (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),

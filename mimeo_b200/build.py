@@ -46,7 +46,7 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError('nvcc compilation failed')
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
+    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart', '-lpthread']
     subprocess.check_call(cmd)
     return LIB
 

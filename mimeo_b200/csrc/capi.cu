@@ -369,4 +369,69 @@ int mb2_test_scan_u32(uint32_t* data, uint64_t n, uint32_t* total) {
     });
 }
 
+
+static char** dup_strings(const std::vector<std::string>& v) {
+    char** a = (char**)malloc(sizeof(char*) * (v.size() + 1));
+    for (size_t k = 0; k < v.size(); k++) {
+        a[k] = (char*)malloc(v[k].size() + 1);
+        memcpy(a[k], v[k].data(), v[k].size());
+        a[k][v[k].size()] = 0;
+    }
+    a[v.size()] = nullptr;
+    return a;
+}
+static void free_strings(char** a, size_t n) {
+    if (!a) return;
+    for (size_t k = 0; k < n; k++) free(a[k]);
+    free(a);
+}
+
+int mb2_tab_project(const char* path, int nthreads, mb2_tab_hits* out) {
+    return guarded([&] {
+        MB2_REQUIRE(path && out, MB2_ERR_INVALID_ARG, "mb2_tab_project: null argument");
+        memset(out, 0, sizeof(*out));
+        TabHits t;
+        tab_project_file(path, nthreads, t);
+        const size_t n = t.chrom.size();
+        out->n = n;
+        out->nnames = (int32_t)t.names.size();
+        out->names = dup_strings(t.names);
+        if (n) {
+            out->chrom = (int32_t*)malloc(n * sizeof(int32_t)); out->start = (int64_t*)malloc(n * sizeof(int64_t)); out->end = (int64_t*)malloc(n * sizeof(int64_t));
+            MB2_REQUIRE(out->chrom && out->start && out->end, MB2_ERR_INTERNAL, "mb2_tab_project: out of memory");
+            memcpy(out->chrom, t.chrom.data(), n * sizeof(int32_t));
+            memcpy(out->start, t.start.data(), n * sizeof(int64_t));
+            memcpy(out->end, t.end.data(), n * sizeof(int64_t));
+        }
+    });
+}
+void mb2_free_tab_hits(mb2_tab_hits* h) {
+    if (!h) return;
+    free(h->chrom); free(h->start); free(h->end);
+    free_strings(h->names, (size_t)h->nnames);
+    memset(h, 0, sizeof(*h));
+}
+
+int mb2_fasta_read(const char* path, int nthreads, mb2_fasta* out) {
+    return guarded([&] {
+        MB2_REQUIRE(path && out, MB2_ERR_INVALID_ARG, "mb2_fasta_read: null argument");
+        memset(out, 0, sizeof(*out));
+        FastaData f;
+        fasta_read_file(path, nthreads, f);
+        out->n = (int32_t)f.ids.size();
+        out->ids = dup_strings(f.ids);
+        out->headers = dup_strings(f.headers);
+        out->off = (uint64_t*)malloc((f.off.size() + 1) * sizeof(uint64_t));
+        if (f.off.empty()) out->off[0] = 0; else memcpy(out->off, f.off.data(), f.off.size() * sizeof(uint64_t));
+        out->seq = (uint8_t*)malloc(f.seq.size() + 1);
+        MB2_REQUIRE(out->off && out->seq, MB2_ERR_INTERNAL, "mb2_fasta_read: out of memory");
+        if (!f.seq.empty()) memcpy(out->seq, f.seq.data(), f.seq.size());
+    });
+}
+void mb2_free_fasta(mb2_fasta* f) {
+    if (!f) return;
+    free_strings(f->ids, (size_t)f->n); free_strings(f->headers, (size_t)f->n);
+    free(f->off); free(f->seq);
+    memset(f, 0, sizeof(*f));
+}
 }  // extern "C"

@@ -1,0 +1,270 @@
+// hostio.cu -- native host-side text ingest of the hot path; no device code.
+//
+//   tab_project_file   the BED projection of a LASTZ-style .tab file: what `awk '!/^#/ {print $1,$3,$4;}'` feeds into
+//                      sort | bedtools genomecov (wrappers.py:1120-1128, 827-835, 1201-1220), as dictionary-encoded
+//                      scaffold ids + integer columns, parsed from an mmap by several threads;
+//   fasta_read_file    every record of a FASTA file with line breaks removed -- the loader behind chromlens / splitFasta
+//                      (utils.py:274-309, 502-557; the reference uses Biopython's SeqIO.parse), two parallel passes
+//                      (count, compact) over the mmap.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstring>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+
+#include "internal.cuh"
+
+namespace mb2 {
+
+namespace {
+
+struct MappedFile {
+    const char* p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    explicit MappedFile(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        MB2_REQUIRE(fd >= 0, -2, std::string("cannot open ") + path);
+        struct stat st;
+        MB2_REQUIRE(::fstat(fd, &st) == 0, -2, std::string("cannot stat ") + path);
+        n = (size_t)st.st_size;
+        if (n) {
+            void* m = ::mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            MB2_REQUIRE(m != MAP_FAILED, -2, std::string("cannot map ") + path);
+            p = (const char*)m;
+            ::madvise(m, n, MADV_SEQUENTIAL);
+        }
+    }
+    ~MappedFile() {
+        if (p) ::munmap((void*)p, n);
+        if (fd >= 0) ::close(fd);
+    }
+    MappedFile(const MappedFile&) = delete;
+    MappedFile& operator=(const MappedFile&) = delete;
+};
+
+int pick_threads(int requested, size_t bytes) {
+    int t = requested > 0 ? requested : (int)std::thread::hardware_concurrency();
+    t = std::max(1, std::min(t, 64));
+    const size_t by_size = std::max<size_t>(1, bytes / (1u << 20));   // at least 1 MiB per thread
+    return (int)std::min<size_t>((size_t)t, by_size);
+}
+
+template <typename F>
+void run_threads(int nt, F&& f) {
+    if (nt <= 1) { f(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    for (int t = 0; t < nt; t++) th.emplace_back([&f, t] { f(t); });
+    for (auto& x : th) x.join();
+}
+
+inline bool is_blank(char c) { return c == ' ' || c == '\t'; }
+
+struct TabChunk {
+    std::vector<int32_t> chrom;                    // chunk-local name ids
+    std::vector<int64_t> start, end;
+    std::vector<std::string_view> names;           // chunk-local dictionary, first-appearance order (views into the mmap)
+    std::string err;
+    size_t err_off = 0;
+};
+
+// [+-]digits -> int64; false if anything else. '%' characters are ignored: the reference strips them from the projected
+// columns with sed 's/%//g' before bedtools reads them (wrappers.py:1125).
+inline bool parse_int(const char* b, const char* e, int64_t& v) {
+    while (b < e && *b == '%') b++;
+    while (e > b && e[-1] == '%') e--;
+    if (b == e) return false;
+    bool neg = false;
+    if (*b == '-' || *b == '+') { neg = *b == '-'; b++; if (b == e) return false; }
+    if (e - b > 18) return false;
+    int64_t x = 0;
+    for (; b < e; b++) {
+        const unsigned d = (unsigned)(*b - '0');
+        if (d > 9) return false;
+        x = x * 10 + (int64_t)d;
+    }
+    v = neg ? -x : x;
+    return true;
+}
+
+void parse_tab_range(const char* base, size_t lo, size_t hi, TabChunk& c) {
+    std::unordered_map<std::string_view, int32_t> dict;
+    const char* p = base + lo;
+    const char* const end = base + hi;
+    const size_t guess = (hi - lo) / 48 + 16;
+    c.chrom.reserve(guess); c.start.reserve(guess); c.end.reserve(guess);
+    std::string_view last_name;
+    int32_t last_id = -1;
+    while (p < end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = nl ? nl : end;
+        const char* next = nl ? nl + 1 : end;
+        const char* q = p;
+        if (le > q && le[-1] == '\r') le--;
+        if (q < le && *q != '#') {                 // awk '!/^#/': only a '#' in column one makes a comment line
+            const char* fb[4]; const char* fe[4];
+            int nf = 0;
+            while (nf < 4) {
+                while (q < le && is_blank(*q)) q++;
+                if (q >= le) break;
+                fb[nf] = q;
+                while (q < le && !is_blank(*q)) q++;
+                fe[nf] = q;
+                nf++;
+            }
+            if (nf > 0) {                          // a line of blanks only is skipped
+                int64_t s = 0, e = 0;
+                if (nf < 4 || !parse_int(fb[2], fe[2], s) || !parse_int(fb[3], fe[3], e)) {
+                    if (c.err.empty()) { c.err = nf < 4 ? "fewer than 4 fields" : "columns 3 and 4 must be integers"; c.err_off = (size_t)(p - base); }
+                    return;
+                }
+                const std::string_view name(fb[0], (size_t)(fe[0] - fb[0]));
+                int32_t id;
+                if (last_id >= 0 && name == last_name) id = last_id;       // rows of one scaffold come in runs
+                else {
+                    auto it = dict.find(name);
+                    if (it == dict.end()) { id = (int32_t)c.names.size(); dict.emplace(name, id); c.names.push_back(name); }
+                    else id = it->second;
+                    last_name = name; last_id = id;
+                }
+                c.chrom.push_back(id); c.start.push_back(s); c.end.push_back(e);
+            }
+        }
+        p = next;
+    }
+}
+
+}  // namespace
+
+void tab_project_file(const char* path, int nthreads, TabHits& out) {
+    out = TabHits();
+    MappedFile mf(path);
+    if (mf.n == 0) return;
+    const int nt = pick_threads(nthreads, mf.n);
+    // chunk boundaries at line starts
+    std::vector<size_t> cut(nt + 1, 0);
+    cut[nt] = mf.n;
+    for (int t = 1; t < nt; t++) {
+        size_t pos = mf.n / nt * t;
+        const char* nl = (const char*)memchr(mf.p + pos, '\n', mf.n - pos);
+        cut[t] = nl ? (size_t)(nl - mf.p) + 1 : mf.n;
+    }
+    for (int t = 1; t <= nt; t++) cut[t] = std::max(cut[t], cut[t - 1]);
+    std::vector<TabChunk> chunks(nt);
+    run_threads(nt, [&](int t) { parse_tab_range(mf.p, cut[t], cut[t + 1], chunks[t]); });
+    for (int t = 0; t < nt; t++) {
+        if (!chunks[t].err.empty()) {
+            size_t line = 1;
+            for (size_t k = 0; k < chunks[t].err_off; k++) line += mf.p[k] == '\n';
+            throw Error(-4, std::string(path) + ": line " + std::to_string(line) + ": " + chunks[t].err);
+        }
+    }
+    // merge the dictionaries in file order (global ids = order of first appearance)
+    std::unordered_map<std::string_view, int32_t> dict;
+    std::vector<std::vector<int32_t>> remap(nt);
+    size_t total = 0;
+    for (int t = 0; t < nt; t++) {
+        remap[t].resize(chunks[t].names.size());
+        for (size_t k = 0; k < chunks[t].names.size(); k++) {
+            auto it = dict.find(chunks[t].names[k]);
+            if (it == dict.end()) {
+                const int32_t id = (int32_t)out.names.size();
+                dict.emplace(chunks[t].names[k], id);
+                out.names.emplace_back(chunks[t].names[k]);
+                remap[t][k] = id;
+            } else remap[t][k] = it->second;
+        }
+        total += chunks[t].chrom.size();
+    }
+    out.chrom.resize(total); out.start.resize(total); out.end.resize(total);
+    std::vector<size_t> off(nt + 1, 0);
+    for (int t = 0; t < nt; t++) off[t + 1] = off[t] + chunks[t].chrom.size();
+    run_threads(nt, [&](int t) {
+        const TabChunk& c = chunks[t];
+        const size_t o = off[t];
+        for (size_t k = 0; k < c.chrom.size(); k++) out.chrom[o + k] = remap[t][c.chrom[k]];
+        if (!c.start.empty()) {
+            memcpy(out.start.data() + o, c.start.data(), c.start.size() * sizeof(int64_t));
+            memcpy(out.end.data() + o, c.end.data(), c.end.size() * sizeof(int64_t));
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- FASTA
+namespace {
+inline bool seq_byte(unsigned char c) { return c != '\n' && c != '\r' && c != ' '; }
+struct Piece { size_t lo, hi; int rec; uint64_t kept, dst; };
+}  // namespace
+
+void fasta_read_file(const char* path, int nthreads, FastaData& out) {
+    out = FastaData();
+    MappedFile mf(path);
+    if (mf.n == 0) return;
+    // record starts: '>' at the start of the file or right after a newline
+    std::vector<size_t> starts;
+    for (const char* p = mf.p; p < mf.p + mf.n;) {
+        const char* g = (const char*)memchr(p, '>', (size_t)(mf.p + mf.n - p));
+        if (!g) break;
+        if (g == mf.p || g[-1] == '\n') starts.push_back((size_t)(g - mf.p));
+        p = g + 1;
+    }
+    const int nrec = (int)starts.size();
+    out.ids.resize(nrec); out.headers.resize(nrec); out.off.assign(nrec + 1, 0);
+    std::vector<Piece> pieces;
+    constexpr size_t PIECE = 4u << 20;
+    for (int r = 0; r < nrec; r++) {
+        const size_t s = starts[r], e = r + 1 < nrec ? starts[r + 1] : mf.n;
+        const char* nl = (const char*)memchr(mf.p + s, '\n', e - s);
+        size_t he = nl ? (size_t)(nl - mf.p) : e;
+        const size_t body = nl ? he + 1 : e;
+        while (he > s + 1 && mf.p[he - 1] == '\r') he--;
+        out.headers[r].assign(mf.p + s + 1, he - (s + 1));
+        const std::string& h = out.headers[r];
+        size_t a = 0;
+        while (a < h.size() && isspace((unsigned char)h[a])) a++;
+        size_t b = a;
+        while (b < h.size() && !isspace((unsigned char)h[b])) b++;
+        out.ids[r] = h.substr(a, b - a);
+        for (size_t lo = body; lo < e; lo += PIECE) pieces.push_back(Piece{lo, std::min(e, lo + PIECE), r, 0, 0});
+    }
+    const int nt = pick_threads(nthreads, mf.n);
+    const size_t np = pieces.size();
+    // pass 1: bytes kept per piece
+    run_threads(nt, [&](int t) {
+        for (size_t k = (size_t)t; k < np; k += (size_t)nt) {
+            const unsigned char* p = (const unsigned char*)mf.p + pieces[k].lo;
+            const size_t n = pieces[k].hi - pieces[k].lo;
+            uint64_t cnt = 0;
+            for (size_t i = 0; i < n; i++) cnt += seq_byte(p[i]) ? 1u : 0u;
+            pieces[k].kept = cnt;
+        }
+    });
+    uint64_t total = 0;
+    for (size_t k = 0; k < np; k++) { pieces[k].dst = total; total += pieces[k].kept; out.off[pieces[k].rec + 1] += pieces[k].kept; }
+    for (int r = 0; r < nrec; r++) out.off[r + 1] += out.off[r];
+    out.seq.resize(total);
+    // pass 2: compact
+    run_threads(nt, [&](int t) {
+        for (size_t k = (size_t)t; k < np; k += (size_t)nt) {
+            const unsigned char* p = (const unsigned char*)mf.p + pieces[k].lo;
+            const unsigned char* const e = (const unsigned char*)mf.p + pieces[k].hi;
+            uint8_t* d = out.seq.data() + pieces[k].dst;
+            while (p < e) {                                   // whole lines by memcpy when they hold nothing to drop
+                const unsigned char* nl = (const unsigned char*)memchr(p, '\n', (size_t)(e - p));
+                const unsigned char* le = nl ? nl : e;
+                const size_t n = (size_t)(le - p);
+                if (n && !memchr(p, '\r', n) && !memchr(p, ' ', n)) { memcpy(d, p, n); d += n; }
+                else for (size_t i = 0; i < n; i++) if (seq_byte(p[i])) *d++ = p[i];
+                p = nl ? nl + 1 : e;
+            }
+        }
+    });
+}
+
+}  // namespace mb2

@@ -64,6 +64,20 @@ void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& 
 struct HostAlns { std::vector<uint32_t> tile; std::vector<int32_t> s1, e1, s2, e2, score, nmatch, ncols; };
 void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, HostAlns& alns, unsigned long long* h_counters);
 
+// hostio.cu : native text ingest (no device work)
+struct TabHits {                       // BED projection of a .tab file: columns 1, 3, 4 of every non-'#' line
+    std::vector<int32_t> chrom;        // index into names
+    std::vector<int64_t> start, end;
+    std::vector<std::string> names;    // distinct column-1 values in order of first appearance
+};
+void tab_project_file(const char* path, int nthreads, TabHits& out);
+struct FastaData {
+    std::vector<std::string> ids, headers;
+    std::vector<uint64_t> off;         // record r = seq[off[r], off[r+1])
+    std::vector<uint8_t> seq;          // all sequences, line breaks and blanks removed
+};
+void fasta_read_file(const char* path, int nthreads, FastaData& out);
+
 // counters layout (device, unsigned long long[16])
 enum { CNT_SURV = 0, CNT_SEED_HITS = 1, CNT_LEADERS = 2, CNT_S1_CELLS = 3, CNT_HSPS = 4, CNT_EXTENDED = 5, CNT_S2_CELLS = 6,
        CNT_GAPPED_CELLS = 7, CNT_ALNS = 8, CNT_ANCHORS = 9, CNT_ERR = 10, CNT_WORK = 11, CNT_N = 16 };

@@ -128,25 +128,36 @@ def read_lens(path: str) -> Dict[str, int]:
     return sizes
 
 
-def parse_tab_hits(path: str):
-    """Columns 1,3,4 of every non-'#' line (what awk '!/^#/ {print $1,$3,$4;}' projects, wrappers.py:1121)."""
-    import pandas as pd
+def parse_tab_hits(path: str, nthreads: int = 0):
+    """Columns 1,3,4 of every non-'#' line (what awk '!/^#/ {print $1,$3,$4;}' projects, wrappers.py:1121), parsed natively
+    (libmimeo_b200 `mb2_tab_project`: mmap + threads). Returns (distinct names in order of first appearance, int32 name
+    index per row, start int64, end int64)."""
+    import ctypes as C
+    from . import _lib
+    t = _lib.TabHits()
     try:
-        df = pd.read_csv(path, sep='\t', comment='#', header=None, usecols=[0, 2, 3], dtype={0: str, 2: np.int64, 3: np.int64},
-                         skip_blank_lines=True, engine='c')
-    except pd.errors.EmptyDataError:
-        return [], np.zeros(0, np.int64), np.zeros(0, np.int64)
-    except (ValueError, pd.errors.ParserError):
-        df = pd.read_csv(path, sep=r'\s+', comment='#', header=None, usecols=[0, 2, 3], dtype={0: str, 2: np.int64, 3: np.int64},
-                         skip_blank_lines=True, engine='python')
-    return df[0].tolist(), df[2].to_numpy(), df[3].to_numpy()
+        _lib.check(_lib.lib().mb2_tab_project(os.fsencode(path), int(nthreads), C.byref(t)))
+    except _lib.Mb2Error as e:
+        raise RuntimeError(f'malformed alignment table: {e}') from None
+    try:
+        n = int(t.n)
+        names = [t.names[k].decode('utf-8', 'replace') for k in range(int(t.nnames))]
+        if n == 0:
+            return names, np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64)
+        ids = np.ctypeslib.as_array(t.chrom, shape=(n,)).copy()
+        start = np.ctypeslib.as_array(t.start, shape=(n,)).copy()
+        end = np.ctypeslib.as_array(t.end, shape=(n,)).copy()
+    finally:
+        _lib.lib().mb2_free_tab_hits(C.byref(t))
+    return names, ids, start, end
 
 
 def coverage_rows(tab_path: str, sizes: Dict[str, int], cov, minLen, source: str, label: str, prefix) -> List[str]:
     """GFF3 feature rows of one coverage block."""
-    names, start, end = parse_tab_hits(tab_path)
-    if not len(names):
+    names, ids, start, end = parse_tab_hits(tab_path)
+    if not len(ids):
         return []
+    names = [n.replace('%', '') for n in names]          # sed 's/%//g' on the projected columns (wrappers.py:1125)
     order = c_sorted(set(names))
     missing = [n for n in order if n not in sizes]
     if missing:
@@ -154,7 +165,7 @@ def coverage_rows(tab_path: str, sizes: Dict[str, int], cov, minLen, source: str
     if (start < 0).any() or (start > end).any() or (end > 0x7fffffff).any():
         raise RuntimeError(f'malformed hit in {tab_path}: start must be >= 0 and <= end')
     idx = {n: i for i, n in enumerate(order)}
-    chrom = np.fromiter((idx[n] for n in names), dtype=np.int32, count=len(names))
+    chrom = np.asarray([idx[n] for n in names], dtype=np.int32)[ids]
     c, s, e = _coverage.coverage_segments(chrom, start.astype(np.int32), end.astype(np.int32), [sizes[n] for n in order],
                                           int(cov), int(minLen))
     return [f'{order[int(c[k])]}\t{source}\t{label}\t{int(s[k])}\t{int(e[k])}\t.\t+\t.\tID={prefix}_{k + 1:05d}\n' for k in range(len(c))]

@@ -1,0 +1,122 @@
+"""CPU tests of the native text ingest: the C++ FASTA reader and the .tab BED projection behind the
+C ABI (`mb2_fasta_read`, `mb2_tab_project`) against plain-Python statements of the same rules and the oracle's awk
+projection, single- and multi-threaded, on ragged and empty inputs. No GPU needed: these entry points are host code."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import annot_oracle as ao
+from tests.helpers import read_golden
+
+
+def py_read_fasta(data: bytes):
+    """Reference statement: a record starts at '>' in column one; id = first word; body minus \\n, \\r and blanks."""
+    out = []
+    starts = [i for i in range(len(data)) if data[i:i + 1] == b'>' and (i == 0 or data[i - 1:i] == b'\n')]
+    for k, s in enumerate(starts):
+        e = starts[k + 1] if k + 1 < len(starts) else len(data)
+        nl = data.find(b'\n', s, e)
+        if nl < 0:
+            nl = e
+        header = data[s + 1:nl].decode().rstrip('\r')
+        body = data[nl + 1:e]
+        seq = bytes(c for c in body if c not in (10, 13, 32))
+        out.append((header.split()[0] if header.split() else '', header, seq))
+    return out
+
+
+def rand_fasta(rng, nrec, maxlen, width, crlf=False):
+    eol = b'\r\n' if crlf else b'\n'
+    chunks = []
+    for r in range(nrec):
+        n = int(rng.integers(0, maxlen))
+        seq = bytes(rng.choice(np.frombuffer(b'ACGTNacgtn', dtype=np.uint8), n).tolist())
+        chunks.append(b'>rec%d some description %d' % (r, n) + eol)
+        for i in range(0, n, width):
+            chunks.append(seq[i:i + width] + eol)
+        if rng.random() < 0.3:
+            chunks.append(eol)
+    return b''.join(chunks)
+
+
+@pytest.mark.parametrize('threads', [1, 4])
+def test_fasta_reader_matches_plain_statement(tmp_path, threads):
+    from mimeo_b200 import fasta
+    rng = np.random.default_rng(11)
+    cases = [b'', b'>only_header', b'>a\nACGT', b'>a b c\r\nAC GT\r\n\r\n>b\nNN\n>\nAA\n', b'no header line\nACGT\n>x\nAC\n',
+             rand_fasta(rng, 7, 5000, 60), rand_fasta(rng, 3, 3_000_000, 70, crlf=True), rand_fasta(rng, 40, 200, 13)]
+    for k, data in enumerate(cases):
+        p = tmp_path / f'c{k}.fa'
+        p.write_bytes(data)
+        got = [(i, h, bytes(s)) for i, h, s in fasta.read_fasta(str(p), nthreads=threads)]
+        assert got == py_read_fasta(data), k
+
+
+def test_fasta_reader_missing_file_raises(tmp_path):
+    from mimeo_b200 import fasta, _lib
+    with pytest.raises(_lib.Mb2Error):
+        fasta.read_fasta(str(tmp_path / 'nope.fa'))
+
+
+def py_project(lines):
+    """awk '!/^#/ {print $1,$3,$4;}' for well-formed lines, blank lines dropped."""
+    rows = []
+    for ln in lines:
+        if ln.startswith('#'):
+            continue
+        f = ln.split()
+        if f:
+            rows.append((f[0], int(f[2]), int(f[3])))
+    return rows
+
+
+@pytest.mark.parametrize('threads', [1, 3, 16])
+def test_tab_projection_matches_awk_statement(tmp_path, threads):
+    from mimeo_b200 import engine
+    rng = np.random.default_rng(12)
+    names = ['s10', 'S3', 's2', 'chr_long_name.1']
+    lines = ['#name1\tstrand1\tstart1\tend1\tname2\tstrand2\tstart2+\tend2+\tscore\tidentity']
+    for _ in range(200_000):
+        s = int(rng.integers(0, 10**6))
+        lines.append('%s\t+\t%d\t%d\tq\t-\t1\t2\t3000\t%.1f' % (names[int(rng.integers(0, 4))], s, s + int(rng.integers(0, 5000)), rng.uniform(60, 100)))
+        if rng.random() < 0.001:
+            lines.append('' if rng.random() < 0.5 else '# lastz end-of-file')
+    lines.append('  s2   +  7   9')                      # awk splits on runs of blanks
+    p = tmp_path / 'big.tab'
+    p.write_text('\n'.join(lines))                        # no trailing newline on purpose
+    got_names, ids, start, end = engine.parse_tab_hits(str(p), nthreads=threads)
+    want = py_project(lines)
+    assert len(ids) == len(want)
+    assert [got_names[i] for i in ids[:2000].tolist()] == [w[0] for w in want[:2000]]
+    assert np.array_equal(np.asarray([got_names[i] for i in ids.tolist()]), np.asarray([w[0] for w in want]))
+    assert start.tolist() == [w[1] for w in want] and end.tolist() == [w[2] for w in want]
+    # names come out in order of first appearance
+    seen = list(dict.fromkeys(w[0] for w in want))
+    assert got_names == seen
+
+
+@pytest.mark.parametrize('case', ['cov_dense', 'cov_order', 'cov_nointra'])
+def test_tab_projection_of_goldens_equals_oracle_projection(tmp_path, case):
+    """Same triples as the oracle's restatement of the reference's awk projection on the reference-generated goldens."""
+    from mimeo_b200 import engine
+    txt = read_golden(f'{case}.tab')
+    p = tmp_path / 'g.tab'
+    p.write_text(txt)
+    names, ids, start, end = engine.parse_tab_hits(str(p))
+    got = ['%s\t%d\t%d' % (names[i], s, e) for i, s, e in zip(ids.tolist(), start.tolist(), end.tolist())]
+    want = [r.rstrip('\n') for r in ao.project_bed(txt.splitlines())]
+    assert [g.split('\t') for g in got] == [w.split() for w in want]
+
+
+def test_tab_projection_errors(tmp_path):
+    from mimeo_b200 import engine
+    for bad in ('a\t+\t5\n', 'a\t+\tx\t9\n', 'a\t+\t5\t9.5\n'):
+        p = tmp_path / 'bad.tab'
+        p.write_text('#h\n' + bad)
+        with pytest.raises(RuntimeError, match='line 2'):
+            engine.parse_tab_hits(str(p))
+    p = tmp_path / 'empty.tab'
+    p.write_text('#only a header\n')
+    names, ids, start, end = engine.parse_tab_hits(str(p))
+    assert names == [] and len(ids) == 0
