@@ -423,9 +423,9 @@ int mb2_fasta_read(const char* path, int nthreads, mb2_fasta* out) {
         out->headers = dup_strings(f.headers);
         out->off = (uint64_t*)malloc((f.off.size() + 1) * sizeof(uint64_t));
         if (f.off.empty()) out->off[0] = 0; else memcpy(out->off, f.off.data(), f.off.size() * sizeof(uint64_t));
-        out->seq = (uint8_t*)malloc(f.seq.size() + 1);
-        MB2_REQUIRE(out->off && out->seq, MB2_ERR_INTERNAL, "mb2_fasta_read: out of memory");
-        if (!f.seq.empty()) memcpy(out->seq, f.seq.data(), f.seq.size());
+        MB2_REQUIRE(out->off, MB2_ERR_INTERNAL, "mb2_fasta_read: out of memory");
+        out->seq = f.seq ? f.seq : (uint8_t*)malloc(1);      // ownership moves to the caller-visible struct
+        f.seq = nullptr;
     });
 }
 void mb2_free_fasta(mb2_fasta* f) {

@@ -203,7 +203,6 @@ struct Piece { size_t lo, hi; int rec; uint64_t kept, dst; };
 }  // namespace
 
 void fasta_read_file(const char* path, int nthreads, FastaData& out) {
-    out = FastaData();
     MappedFile mf(path);
     if (mf.n == 0) return;
     // record starts: '>' at the start of the file or right after a newline
@@ -248,13 +247,15 @@ void fasta_read_file(const char* path, int nthreads, FastaData& out) {
     uint64_t total = 0;
     for (size_t k = 0; k < np; k++) { pieces[k].dst = total; total += pieces[k].kept; out.off[pieces[k].rec + 1] += pieces[k].kept; }
     for (int r = 0; r < nrec; r++) out.off[r + 1] += out.off[r];
-    out.seq.resize(total);
+    out.total = total;
+    out.seq = (uint8_t*)malloc(total + 1);           // pages are first touched by the compacting threads
+    MB2_REQUIRE(out.seq != nullptr, -5, "fasta_read_file: out of memory");
     // pass 2: compact
     run_threads(nt, [&](int t) {
         for (size_t k = (size_t)t; k < np; k += (size_t)nt) {
             const unsigned char* p = (const unsigned char*)mf.p + pieces[k].lo;
             const unsigned char* const e = (const unsigned char*)mf.p + pieces[k].hi;
-            uint8_t* d = out.seq.data() + pieces[k].dst;
+            uint8_t* d = out.seq + pieces[k].dst;
             while (p < e) {                                   // whole lines by memcpy when they hold nothing to drop
                 const unsigned char* nl = (const unsigned char*)memchr(p, '\n', (size_t)(e - p));
                 const unsigned char* le = nl ? nl : e;

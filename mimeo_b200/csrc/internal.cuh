@@ -74,7 +74,12 @@ void tab_project_file(const char* path, int nthreads, TabHits& out);
 struct FastaData {
     std::vector<std::string> ids, headers;
     std::vector<uint64_t> off;         // record r = seq[off[r], off[r+1])
-    std::vector<uint8_t> seq;          // all sequences, line breaks and blanks removed
+    uint8_t* seq = nullptr;            // all sequences, line breaks and blanks removed (malloc; the caller takes it or it is freed)
+    uint64_t total = 0;
+    FastaData() = default;
+    FastaData(const FastaData&) = delete;
+    FastaData& operator=(const FastaData&) = delete;
+    ~FastaData() { free(seq); }
 };
 void fasta_read_file(const char* path, int nthreads, FastaData& out);
 
