@@ -63,6 +63,15 @@ static bool scan_chunk(const Genome& T, const Genome& Q, const SeedTable& tab, u
     return false;
 }
 
+std::vector<int32_t> same_scaffold_map(const Genome& T, const Genome& Q, const int32_t* h_same_q) {
+    std::vector<int32_t> same(T.nscaf, -1);
+    for (int t = 0; t < T.nscaf; t++) {
+        if (h_same_q) same[t] = h_same_q[t];
+        else if (Q.fwd_src_id != 0 && Q.fwd_src_id == T.id && t < Q.nfwd) same[t] = t;
+    }
+    return same;
+}
+
 // Test hook (stage a+b only): kept HSPs of every tile of T x Q in canonical order, single chunk.
 void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& hsps, unsigned long long* h_counters) {
     Ctx& cx = ctx();
@@ -77,7 +86,11 @@ void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& 
     const bool ok = scan_chunk(T, Q, tab, GENOME_END_PAD, (uint32_t)Q.G - GENOME_END_PAD, p, s0, cap, counters.get(), nsurv, acc);
     MB2_REQUIRE(ok, -3, "align: too many surviving seed hits for one pass");
     s1.alloc(nsurv ? nsurv : 1);
-    find_hsps(T, Q, s0.get(), s1.get(), (uint32_t)nsurv, p, hsps, counters.get());
+    const std::vector<int32_t> same = same_scaffold_map(T, Q, nullptr);
+    DevBuf<int32_t> d_same(T.nscaf);
+    MB2_CUDA(cudaMemcpyAsync(d_same.get(), same.data(), T.nscaf * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
+    MB2_CUDA(cudaStreamSynchronize(cx.stream));
+    find_hsps(T, Q, s0.get(), s1.get(), (uint32_t)nsurv, p, hsps, counters.get(), d_same.get());
     if (h_counters) {
         MB2_CUDA(cudaMemcpyAsync(h_counters, counters.get(), CNT_N * sizeof(unsigned long long), cudaMemcpyDeviceToHost, cx.stream));
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
@@ -116,6 +129,10 @@ void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const 
     build_seed_table(T, 0, (uint32_t)T.G, tab);
     DevBuf<unsigned long long> counters(CNT_N);
     DevBuf<uint64_t> s0, s1;
+    const std::vector<int32_t> same = same_scaffold_map(T, Q, h_same_q);
+    DevBuf<int32_t> d_same(T.nscaf);
+    MB2_CUDA(cudaMemcpyAsync(d_same.get(), same.data(), T.nscaf * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
+    MB2_CUDA(cudaStreamSynchronize(cx.stream));
 
     std::vector<QChunk> todo = make_chunks(Q);
     std::reverse(todo.begin(), todo.end());          // used as a stack; chunks are processed in scaffold order
@@ -137,7 +154,7 @@ void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const 
         if (nsurv == 0) continue;
         if (s1.n < nsurv) s1.alloc(nsurv);
         HspSet hsps;
-        find_hsps(T, Q, s0.get(), s1.get(), (uint32_t)nsurv, p, hsps, counters.get());
+        find_hsps(T, Q, s0.get(), s1.get(), (uint32_t)nsurv, p, hsps, counters.get(), d_same.get());
         DevBuf<uint8_t> in_chain;
         if (p.chain) chain_hsps(hsps, lb, tb, in_chain);
         else {

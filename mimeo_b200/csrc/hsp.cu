@@ -11,7 +11,10 @@
 //   3. HSPs with score >= K are entropy-adjusted in integer fixed point and kept if still >= K.
 #include "primitives.cuh"
 #include "seq.cuh"
+#include <cooperative_groups.h>
+
 #include "internal.cuh"
+#include "xdrop_table.cuh"
 
 namespace mb2 {
 
@@ -175,32 +178,58 @@ diag_starts_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict
     if (flag[k]) seg_start[flag_off[k]] = k;
 }
 
+constexpr uint32_t HSP_CLOSED_ITEM = 0xFFFFFFFFu;   // = HSP_CLOSED below
+// Warp-per-diagonal walk (1024 columns per warp step): takes the diagonals the thread-per-diagonal kernel handed over
+// because one of their extensions outgrew a single thread. Item k = {segment, first survivor to process, covered}.
 __global__ void __launch_bounds__(128)
 hsp_extend_kernel(GenomeView T, GenomeView Q, const uint64_t* __restrict__ surv, uint32_t nsurv,
-                  const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p, uint32_t diag_bias,
+                  const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
+                  const uint32_t* __restrict__ items, const uint32_t* __restrict__ nitems_p, uint32_t diag_bias,
                   int X, int K, int entropy, uint32_t cap,
                   uint32_t* __restrict__ o_tile, int32_t* __restrict__ o_s1, int32_t* __restrict__ o_s2,
                   int32_t* __restrict__ o_len, int32_t* __restrict__ o_score, unsigned long long* __restrict__ counters) {
     const int lane = threadIdx.x & 31;
-    const uint32_t nseg = *nseg_p;
+    const uint32_t nseg = *nseg_p, nitems = *nitems_p;
     unsigned long long cells = 0, extended = 0;
     for (;;) {
-        uint32_t seg = 0;
-        if (lane == 0) seg = (uint32_t)atomicAdd(&counters[CNT_WORK], 1ull);
-        seg = __shfl_sync(0xffffffffu, seg, 0);
-        if (seg >= nseg) break;
+        uint32_t it = 0;
+        if (lane == 0) it = (uint32_t)atomicAdd(&counters[CNT_WORK], 1ull);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= nitems) break;
+        const uint32_t seg = items[3 * it];
         const uint32_t a = seg_start[seg];
         const uint32_t b = (seg + 1 < nseg) ? seg_start[seg + 1] : nsurv;
         const uint32_t dg = (uint32_t)(surv[a] >> 32);          // i - j + bias
-        uint32_t covered = 0;                                     // exclusive end (target coords) of the last kept HSP
-        for (uint32_t x = a; x < b; x++) {
+        // Trivial self-diagonal (an N-free scaffold against itself, flagged by the thread kernel): every column is a match
+        // scoring s(b,b) > 0, so the extension from any seed covers the whole scaffold and stops in the pads:
+        // score = 91 * #(A,T) + 100 * #(C,G), no walk needed.
+        const bool closed = items[3 * it + 2] == HSP_CLOSED_ITEM;
+        uint32_t covered = closed ? 0u : items[3 * it + 2];      // exclusive end (target coords) of the last kept HSP
+        for (uint32_t x = items[3 * it + 1]; x < b; x++) {
             const uint32_t j = (uint32_t)surv[x];
             const uint32_t i = j + dg - diag_bias;
             if (i + SEED_SPAN <= covered) continue;               // spec D2
             extended++;
-            int best_r, best_l; uint32_t be, bs;
-            xdrop_side<+1>(T, Q, i + SEED_SPAN, j + SEED_SPAN, X, lane, best_r, be, cells);
-            xdrop_side<-1>(T, Q, i + SEED_SPAN - 1, j + SEED_SPAN - 1, X, lane, best_l, bs, cells);
+            int best_r = 0, best_l = 0; uint32_t be, bs;
+            if (closed) {
+                const int ts = scaf_of(T.off, T.nscaf, i);
+                bs = T.off[ts]; be = bs + T.len[ts];
+                int cgn = 0;
+                const uint32_t w0 = bs >> 5, w1 = (be - 1) >> 5;
+                for (uint32_t w = w0 + lane; w <= w1; w += 32) {
+                    const uint64_t xw = T.pk[w];
+                    uint64_t m = (xw ^ (xw >> 1)) & 0x5555555555555555ull;       // one bit per C or G base
+                    if (w == w0 && (bs & 31)) m &= ~0ull << (2 * (bs & 31));
+                    if (w == w1 && (be & 31)) m &= ~0ull >> (64 - 2 * (be & 31));
+                    cgn += __popcll(m);
+                }
+                cgn = __reduce_add_sync(0xffffffffu, cgn);
+                best_r = 91 * (int)(be - bs - (uint32_t)cgn) + 100 * cgn;
+                cells += be - bs;
+            } else {
+                xdrop_side<+1>(T, Q, i + SEED_SPAN, j + SEED_SPAN, X, lane, best_r, be, cells);
+                xdrop_side<-1>(T, Q, i + SEED_SPAN - 1, j + SEED_SPAN - 1, X, lane, best_l, bs, cells);
+            }
             int score = best_r + best_l;
             if (score < K) continue;
             const uint32_t qs = bs - (i - j);
@@ -250,6 +279,156 @@ hsp_extend_kernel(GenomeView T, GenomeView Q, const uint64_t* __restrict__ surv,
     }
 }
 
+
+// ---- thread-per-diagonal walk ---------------------------------------------------------------------------------
+// Most extensions are a few hundred columns long, far too short to feed a whole warp. Here every THREAD walks one
+// diagonal segment with the exact x-drop at three columns per table lookup (xdrop_table.cuh). An extension that is
+// still alive after HT_LIMIT windows of 30 columns on one side hands the rest of its diagonal (from that survivor on,
+// with the current `covered`) to the warp kernel above.
+constexpr int HT_LIMIT = 16;
+constexpr uint32_t HSP_CLOSED = 0xFFFFFFFFu;     // `covered` value of a handed-over item that is a trivial self-diagonal
+
+// one side, one thread. DIR=+1: columns ct0, ct0+1, ...; DIR=-1: ct0, ct0-1, ... Returns false if the limit was reached.
+// bcol = number of columns of the best prefix (0 = empty prefix).
+template <int DIR>
+__device__ __forceinline__ bool xdrop_thread(const uint32_t* __restrict__ tab, const GenomeView& T, const GenomeView& Q, uint32_t ct0, uint32_t cq0,
+                                             int X, int& best, uint32_t& bcol, unsigned long long& cells) {
+    best = 0; bcol = 0;
+    int D = 375 - X;
+    const int c2 = 250 - X;
+    for (int w = 0; w < HT_LIMIT; w++) {
+        const uint32_t ct = DIR > 0 ? ct0 + 30u * w : ct0 - 30u * w - 31u;
+        const uint32_t cq = DIR > 0 ? cq0 + 30u * w : cq0 - 30u * w - 31u;
+        uint64_t wt = window32(T.pk, ct), wq = window32(Q.pk, cq);
+        uint32_t an = nwindow32(T.nm, ct) | nwindow32(Q.nm, cq);
+        if (DIR < 0) { wt = rev2groups(wt); wq = rev2groups(wq); an = __brev(an); }
+        an &= (1u << 30) - 1u;
+        if (an) {                                             // a non-ACGT column in the window: column by column
+            int run = best - (D - 375 + X);
+            for (int c = 0; c < 30; c++) {
+                const int sc = (an & 1u) ? SCORE_N : sub_lut((uint32_t)((wt & 3) << 2 | (wq & 3)));
+                wt >>= 2; wq >>= 2; an >>= 1;
+                run += sc; cells++;
+                if (run > best) { best = run; bcol = 30u * w + c + 1; }
+                else if (run < best - X) return true;
+            }
+            D = (best - run) + 375 - X;
+            continue;
+        }
+        const uint32_t tl = (uint32_t)wt, th = (uint32_t)(wt >> 32), ql = (uint32_t)wq, qh = (uint32_t)(wq >> 32);
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            const uint32_t e = tab[xt_index(tl, th, ql, qh, k)];
+            cells += 3;
+            if (xt_minf(e) < D) return true;
+            const int dm = max(D, xt_maxf(e) + c2);
+            if (dm > D) { best += dm - D; bcol = 30u * w + 3u * k + (uint32_t)xt_argmax(e) + 1u; }
+            D = dm - xt_sum(e);
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(128)
+hsp_extend_thread_kernel(GenomeView T, GenomeView Q, const uint64_t* __restrict__ surv, uint32_t nsurv,
+                         const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p, uint32_t diag_bias,
+                         int X, int K, int entropy, uint32_t cap,
+                         uint32_t* __restrict__ o_tile, int32_t* __restrict__ o_s1, int32_t* __restrict__ o_s2,
+                         int32_t* __restrict__ o_len, int32_t* __restrict__ o_score,
+                         uint32_t* __restrict__ items, uint32_t* __restrict__ nitems_p, const int32_t* __restrict__ same_q,
+                         unsigned long long* __restrict__ counters) {
+    namespace cg = cooperative_groups;
+    __shared__ uint32_t tab[XT_SIZE];
+    for (int e = threadIdx.x; e < XT_SIZE; e += blockDim.x) tab[e] = xt_entry((uint32_t)e);
+    __syncthreads();
+    const uint32_t nseg = *nseg_p;
+    unsigned long long cells = 0, extended = 0;
+    for (;;) {
+        uint32_t seg;
+        {   // the threads that need work right now fetch it with one atomic
+            cg::coalesced_group g = cg::coalesced_threads();
+            unsigned long long base = 0;
+            if (g.thread_rank() == 0) base = atomicAdd(&counters[CNT_WORK], (unsigned long long)g.size());
+            seg = (uint32_t)g.shfl(base, 0) + g.thread_rank();
+        }
+        if (seg >= nseg) break;
+        const uint32_t a = seg_start[seg];
+        const uint32_t b = (seg + 1 < nseg) ? seg_start[seg + 1] : nsurv;
+        const uint32_t dg = (uint32_t)(surv[a] >> 32);          // i - j + bias
+        uint32_t covered = 0;                                     // exclusive end (target coords) of the last kept HSP
+        if (same_q) {
+            // main diagonal of an N-free scaffold against itself: the whole scaffold is one HSP (closed form in the warp kernel)
+            const uint32_t j0 = (uint32_t)surv[a], i0 = j0 + dg - diag_bias;
+            const int ts = scaf_of(T.off, T.nscaf, i0), qs = scaf_of(Q.off, Q.nscaf, j0);
+            if (same_q[ts] == qs && i0 - T.off[ts] == j0 - Q.off[qs] && T.nfree[ts]) {
+                const uint32_t slot = atomicAdd(nitems_p, 1u);
+                items[3 * slot] = seg; items[3 * slot + 1] = a; items[3 * slot + 2] = HSP_CLOSED;
+                continue;
+            }
+        }
+        for (uint32_t x = a; x < b; x++) {
+            const uint32_t j = (uint32_t)surv[x];
+            const uint32_t i = j + dg - diag_bias;
+            if (i + SEED_SPAN <= covered) continue;               // spec D2
+            int best_r, best_l; uint32_t cr, cl;
+            const unsigned long long cells0 = cells;
+            const bool done = xdrop_thread<+1>(tab, T, Q, i + SEED_SPAN, j + SEED_SPAN, X, best_r, cr, cells) &&
+                              xdrop_thread<-1>(tab, T, Q, i + SEED_SPAN - 1, j + SEED_SPAN - 1, X, best_l, cl, cells);
+            if (!done) {                                          // too long for one thread: the warp kernel redoes it and finishes the diagonal
+                cells = cells0;
+                const uint32_t slot = atomicAdd(nitems_p, 1u);
+                items[3 * slot] = seg; items[3 * slot + 1] = x; items[3 * slot + 2] = covered;
+                break;
+            }
+            extended++;
+            int score = best_r + best_l;
+            if (score < K) continue;
+            const uint32_t be = i + SEED_SPAN + cr, bs = i + SEED_SPAN - cl;     // [bs, be) in target coordinates
+            const uint32_t qs = bs - (i - j);
+            if (entropy) {
+                uint32_t cnt[4] = {0, 0, 0, 0};
+                for (uint32_t c = bs; c < be; c += 32u) {
+                    const uint64_t wt = window32(T.pk, c), wq = window32(Q.pk, qs + (c - bs));
+                    const uint32_t an = nwindow32(T.nm, c) | nwindow32(Q.nm, qs + (c - bs));
+                    const uint64_t xr = wt ^ wq;
+                    uint64_t m = ~(xr | (xr >> 1)) & 0x5555555555555555ull;      // bit 2k set iff column k matches
+                    if (an) {
+                        uint64_t nsp = 0;
+                        for (int k = 0; k < 32; k++) nsp |= (uint64_t)((an >> k) & 1u) << (2 * k);
+                        m &= ~nsp;
+                    }
+                    const uint32_t left = be - c;
+                    if (left < 32) m &= (~0ull) >> (64 - 2 * left);
+                    const uint64_t lo = wt & 0x5555555555555555ull, hi = (wt >> 1) & 0x5555555555555555ull;
+                    cnt[0] += __popcll(m & ~lo & ~hi); cnt[1] += __popcll(m & lo & ~hi);
+                    cnt[2] += __popcll(m & ~lo & hi);  cnt[3] += __popcll(m & lo & hi);
+                }
+                const uint32_t h = entropy_q24(cnt);
+                score = (int)(((long long)score * (long long)h) >> 24);
+                if (score < K) continue;
+            }
+            covered = be;
+            unsigned long long slot;
+            {
+                cg::coalesced_group g = cg::coalesced_threads();
+                unsigned long long base = 0;
+                if (g.thread_rank() == 0) base = atomicAdd(&counters[CNT_HSPS], (unsigned long long)g.size());
+                slot = g.shfl(base, 0) + g.thread_rank();
+            }
+            if (slot < cap) {
+                const int ts = scaf_of(T.off, T.nscaf, bs), qsf = scaf_of(Q.off, Q.nscaf, qs);
+                o_tile[slot] = (uint32_t)ts * (uint32_t)Q.nscaf + (uint32_t)qsf;
+                o_s1[slot] = (int32_t)(bs - T.off[ts]);
+                o_s2[slot] = (int32_t)(qs - Q.off[qsf]);
+                o_len[slot] = (int32_t)(be - bs);
+                o_score[slot] = score;
+            }
+        }
+    }
+    if (cells) atomicAdd(&counters[CNT_S2_CELLS], cells);
+    if (extended) atomicAdd(&counters[CNT_EXTENDED], extended);
+}
+
 // ---- canonical ordering (tile, s1, s2, len) by two stable radix sorts on packed keys
 __global__ void __launch_bounds__(256)
 hsp_key1_kernel(const int32_t* __restrict__ s2, const int32_t* __restrict__ len, uint32_t n, int lb, uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
@@ -279,7 +458,7 @@ hsp_gather_kernel(const uint32_t* __restrict__ perm, uint32_t n, const uint32_t*
 static int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) b++; return b; }
 
 void find_hsps(const Genome& T, const Genome& Q, uint64_t* surv0, uint64_t* surv1, uint32_t nsurv, const AlignParams& p,
-               HspSet& out, unsigned long long* counters) {
+               HspSet& out, unsigned long long* counters, const int32_t* d_same_q) {
     out.n = 0;
     if (nsurv == 0) return;
     Ctx& cx = ctx();
@@ -303,6 +482,10 @@ void find_hsps(const Genome& T, const Genome& Q, uint64_t* surv0, uint64_t* surv
     DevBuf<uint32_t> r_tile;
     DevBuf<int32_t> r_s1, r_s2, r_len, r_score;
     unsigned long long h_n = 0;
+    uint32_t h_nseg = 0;
+    MB2_CUDA(cudaMemcpyAsync(&h_nseg, d_nseg.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+    MB2_CUDA(cudaStreamSynchronize(cx.stream));
+    DevBuf<uint32_t> items(3 * (size_t)std::max<uint32_t>(h_nseg, 1u)), d_nitems(1);   // at most one hand-over per diagonal segment
     for (int attempt = 0; attempt < 2; attempt++) {
         r_tile.alloc(hcap); r_s1.alloc(hcap); r_s2.alloc(hcap); r_len.alloc(hcap); r_score.alloc(hcap);
         MB2_CUDA(cudaMemsetAsync(counters + CNT_WORK, 0, sizeof(unsigned long long), cx.stream));
@@ -313,8 +496,15 @@ void find_hsps(const Genome& T, const Genome& Q, uint64_t* surv0, uint64_t* surv
         }
         {
             ProfScope ps("hsp_extend");
+            MB2_REQUIRE(p.xdrop >= XT_MIN_XDROP, -2, "x-drop below 251 is not supported by the three-column extension table");
+            MB2_CUDA(cudaMemsetAsync(d_nitems.get(), 0, sizeof(uint32_t), cx.stream));
             const unsigned grid = (unsigned)cx.sm_count * 8;
-            launch(hsp_extend_kernel, grid, 128, 0, view(T), view(Q), sorted, nsurv, seg_start.get(), d_nseg.get(), (uint32_t)Q.G,
+            launch(hsp_extend_thread_kernel, grid, 128, 0, view(T), view(Q), sorted, nsurv, seg_start.get(), d_nseg.get(), (uint32_t)Q.G,
+                   p.xdrop, p.hspthresh, p.entropy, hcap, r_tile.get(), r_s1.get(), r_s2.get(), r_len.get(), r_score.get(),
+                   items.get(), d_nitems.get(), d_same_q, counters);
+            MB2_CUDA(cudaMemsetAsync(counters + CNT_WORK, 0, sizeof(unsigned long long), cx.stream));
+            launch(hsp_extend_kernel, grid, 128, 0, view(T), view(Q), sorted, nsurv, seg_start.get(), d_nseg.get(),
+                   (const uint32_t*)items.get(), (const uint32_t*)d_nitems.get(), (uint32_t)Q.G,
                    p.xdrop, p.hspthresh, p.entropy, hcap, r_tile.get(), r_s1.get(), r_s2.get(), r_len.get(), r_score.get(), counters);
         }
         MB2_CUDA(cudaMemcpyAsync(&h_n, counters + CNT_HSPS, sizeof(h_n), cudaMemcpyDeviceToHost, cx.stream));

@@ -43,8 +43,12 @@ struct HspSet {
     DevBuf<int32_t> s1, s2, len, score;
     uint32_t n = 0;
 };
+// d_same_q (device, may be null): per target scaffold the query scaffold holding the identical sequence, or -1; enables
+// the closed form of the trivial self-diagonal HSP (results do not depend on it)
 void find_hsps(const Genome& T, const Genome& Q, uint64_t* surv0, uint64_t* surv1, uint32_t nsurv, const AlignParams& p,
-               HspSet& out, unsigned long long* counters);
+               HspSet& out, unsigned long long* counters, const int32_t* d_same_q = nullptr);
+// host map target scaffold -> identical query scaffold (-1 if none): explicit hint, or inferred when Q was built from T
+std::vector<int32_t> same_scaffold_map(const Genome& T, const Genome& Q, const int32_t* h_same_q);
 
 // chain.cu : flags the members of the best collinear chain of every tile
 void chain_hsps(const HspSet& h, int len_bits, int tile_bits, DevBuf<uint8_t>& in_chain);

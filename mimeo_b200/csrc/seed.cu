@@ -17,6 +17,7 @@
 #include "primitives.cuh"
 #include "seq.cuh"
 #include "internal.cuh"
+#include "xdrop_table.cuh"
 
 namespace mb2 {
 
@@ -25,7 +26,7 @@ constexpr int S1_WINDOW = 30;        // columns per first-stage window = 10 tabl
 constexpr uint32_t S1_WINDOW_MASK = (1u << S1_WINDOW) - 1u;
 constexpr int S1_RIGHT_WINDOWS = 2;  // 60 columns
 constexpr int S1_LEFT_WINDOWS = 3;   // 90 columns (19 of them are the seed itself)
-constexpr int S1_TAB = 4096;         // (3 target bases, 3 query bases) -> packed {sum, max prefix, min prefix}
+constexpr int S1_TAB = XT_SIZE;      // (3 target bases, 3 query bases) -> packed {sum, first argmax, max prefix, min prefix}
 
 __global__ void __launch_bounds__(256)
 seed_keys_kernel(GenomeView T, uint32_t p_lo, uint32_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ pos) {
@@ -59,38 +60,9 @@ void build_seed_table(const Genome& T, uint32_t p_lo, uint32_t p_hi, SeedTable& 
     tab.p_lo = p_lo; tab.p_hi = p_hi;
 }
 
-// 16 HOXD70 scores as int8 in two 64-bit registers, index t*4+q
-__device__ __forceinline__ int sub_lut(uint32_t idx) {
-    // {91,-114,-31,-123, -114,100,-125,-31} , {-31,-125,100,-114, -123,-31,-114,91}
-    const uint64_t lo = 0xE183648E85E18E5Bull, hi = 0x5B8EE1858E6483E1ull;
-    const uint64_t v = (idx & 8) ? hi : lo;
-    return (int)(int8_t)(v >> ((idx & 7) * 8));
-}
-
-// ---- first-stage x-drop, three columns per table lookup -------------------------------------------------------
-// Entry for target bases t0 t1 t2 / query bases q0 q1 q2 (index = t6 << 6 | q6, first column in the low bits):
-// bits 18..31 = s0+s1+s2 (signed), bits 9..17 = 125 + max prefix sum, bits 0..8 = 375 + min prefix sum.
-// Exactness of the chunked rule: prefix sums inside a chunk differ by at most 2*125 < xdrop, so a column can only
-// terminate the extension against the maximum reached BEFORE the chunk; hence "terminates in this chunk" is
-// run + min_prefix < best - X (and then no column of the chunk has raised best), otherwise best = max(best, run + max_prefix).
-// The lane state is kept as (best, D) with D = (best - run) + 375 - X, the deficit to the running maximum in the bias of
-// the table's min-prefix field, so a chunk is: terminate iff min_field < D; DM = max(D, max_field + 250 - X);
-// best += DM - D; D = DM - sum. A finished lane parks at D = S1_DONE, where every later chunk is a no-op on best.
+// A finished lane of the first-stage x-drop parks at D = S1_DONE, where every later chunk is a no-op on best
+// (state (best, D) and table layout: xdrop_table.cuh).
 constexpr int S1_DONE = 1 << 24;
-__device__ __forceinline__ uint32_t s1_entry(uint32_t idx) {
-    const uint32_t t6 = idx >> 6, q6 = idx & 63;
-    int sum = 0, mx = INT_MIN, mn = INT_MAX;
-    for (int c = 0; c < 3; c++) {
-        sum += sub_lut((((t6 >> (2 * c)) & 3u) << 2) | ((q6 >> (2 * c)) & 3u));
-        mx = max(mx, sum); mn = min(mn, sum);
-    }
-    return ((uint32_t)sum << 18) | ((uint32_t)(mx + 125) << 9) | (uint32_t)(mn + 375);
-}
-// reverse the order of the 32 two-bit groups of a word
-__device__ __forceinline__ uint64_t rev2groups(uint64_t x) {
-    x = __brevll(x);
-    return ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
-}
 // 30 columns (first column in the low bits of wt / wq / an); updates (best, D) of the lane exactly as the
 // column-by-column rule would. Lanes whose window holds a non-ACGT column take the per-column path.
 __device__ __forceinline__ void xdrop_window30(const uint32_t* __restrict__ tab, uint64_t wt, uint64_t wq, uint32_t an, int X,
@@ -115,17 +87,12 @@ __device__ __forceinline__ void xdrop_window30(const uint32_t* __restrict__ tab,
 #pragma unroll
     for (int k = 0; k < S1_WINDOW / 3; k++) {
         if (k == 3 || k == 6 || k == 8) { if (__all_sync(0xffffffffu, D >= S1_DONE / 2)) break; }
-        const int sh = 6 * k;
-        uint32_t t6, q6;
-        if (sh + 6 <= 32) { t6 = (tl >> sh) & 63u; q6 = (ql >> sh) & 63u; }
-        else if (sh >= 32) { t6 = (th >> (sh - 32)) & 63u; q6 = (qh >> (sh - 32)) & 63u; }
-        else { t6 = __funnelshift_r(tl, th, sh) & 63u; q6 = __funnelshift_r(ql, qh, sh) & 63u; }
-        const uint32_t e = tab[(t6 << 6) | q6];
+        const uint32_t e = tab[xt_index(tl, th, ql, qh, k)];
         nchunks += D < S1_DONE / 2 ? 1u : 0u;
-        const bool term = (int)(e & 511u) < D;
-        const int dm = max(D, (int)((e >> 9) & 511u) + c2);
+        const bool term = xt_minf(e) < D;
+        const int dm = max(D, xt_maxf(e) + c2);
         best += dm - D;
-        D = term ? S1_DONE : dm - ((int)e >> 18);
+        D = term ? S1_DONE : dm - xt_sum(e);
     }
     if (slow) D = d_keep;
 }
@@ -155,7 +122,7 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
     __shared__ uint32_t r_cum[SC_WARPS][SC_RING], r_b0[SC_WARPS][SC_RING], r_j[SC_WARPS][SC_RING];
     __shared__ unsigned long long sh_stat[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < S1_TAB; e += SC_NT) s1tab[e] = s1_entry((uint32_t)e);
+    for (int e = tid; e < S1_TAB; e += SC_NT) s1tab[e] = xt_entry((uint32_t)e);
     if (tid < 3) sh_stat[tid] = 0;
     __syncthreads();
     uint32_t* __restrict__ rc = r_cum[warp];
