@@ -140,7 +140,8 @@ template <int NT> struct EdgeBuf<uint64_t, NT> {
 template <typename P, typename S> struct GpShared {
     EdgeBuf<P, S::NT> left;             // slot 0 of every thread: {h, i, hp, ip}
     EdgeBuf<P, S::NT> up;               // last slot of every thread: {h, d, hp, dp}
-    int4 rng[2][S::WARPS];              // per parity, per warp: {warp max, alive diagonal lo, hi, -}
+    int smax[2][S::WARPS];              // per parity, per warp: maximum score of the anti-diagonal (NEG_INF = nothing alive)
+    int2 rng[S::WARPS];                 // end of an epoch: per warp {lowest, highest} alive diagonal
     int4 fin[S::WARPS]; int2 finp[S::WARPS];   // end of the extension: per warp {score, k, i, -} and payload of its first maximum
     int2 lut[25];                       // {substitution score, is-match} for codes 0..4 x 0..4
     int red[S::WARPS];
@@ -175,13 +176,22 @@ __device__ __forceinline__ void gp_cell(Cell<P>& self, int uh, int ud, P uhp, P 
 }
 
 // One-sided y-drop extension by the whole CTA in diagonal-major coordinates. DIR=+1: cell (i,j) consumes T[ta+i-1],
-// Q[qa+j-1]; DIR=-1: T[ta-i], Q[qa-j]. Diagonals delta = i-j live in a circular window of GP_ND slots, slot = delta mod
-// GP_ND; thread t owns GP_SLOTS consecutive slots for the whole extension, so every cell and all but one of its neighbours
-// stay in registers. Per anti-diagonal a thread computes its four cells of the right parity (independent of each other),
-// reads ONE cell of a neighbouring thread from shared memory and publishes one; one __syncthreads per anti-diagonal. Dead
-// cells are -inf by value, so the window follows the alignment without bookkeeping: a slot that re-enters the band on
-// another diagonal is already dead. Alive ranges are tracked per thread (8 diagonals), a superset of the exact range.
+// Q[qa+j-1]; DIR=-1: T[ta-i], Q[qa-j]. Diagonals delta = i-j live in a circular window of ND slots, slot = delta mod ND;
+// thread t owns SLOTS consecutive slots for the whole extension, so every cell and all but one of its neighbours stay in
+// registers. Per anti-diagonal a thread computes its cells of the right parity (independent of each other), reads ONE
+// cell of a neighbouring thread from shared memory and publishes one; one __syncthreads per anti-diagonal, which shares
+// a single number per warp (the anti-diagonal's maximum, for the y-drop threshold and the "all dead" test). Dead cells
+// are -inf by value, so the window follows the alignment without bookkeeping: a slot that re-enters the band on another
+// diagonal is already dead.
+//
+// The band is re-measured only every GP_EPOCH anti-diagonals: the exact range [lo, hi] of alive diagonals is taken at the
+// end of an epoch, and because an alive cell needs an alive neighbour one anti-diagonal earlier (or itself two earlier),
+// the alive range grows by at most one diagonal per side and step, so computing [lo - GP_EPOCH, hi + GP_EPOCH] for the
+// whole next epoch covers every cell that can be alive (the extra cells evaluate to dead). Which threads and warps work,
+// the window base and the sequence-end test are therefore constants of an epoch; warps outside the range only keep
+// the barrier company.
 // Returns false if the payload type cannot represent the result (16-bit columns overflowed): rerun with P = uint64_t.
+constexpr int GP_EPOCH = 8;
 template <typename P, typename S, int DIR>
 __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E, int Y,
                                  GpShared<P, S>& sm, Ext& r, unsigned& ncell, int& err) {
@@ -200,105 +210,118 @@ __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint3
     sm.up.put(tid, Edge<P>{NEG_INF, NEG_INF, 0, 0});
     __syncthreads();
     int best = 0, dead_steps = 0;
-    int lo1 = 0, hi1 = 0, lo2 = 1, hi2 = 0;     // alive diagonal ranges of anti-diagonals k-1 and k-2 (empty when lo > hi)
+    int lo_e = 0, hi_e = 0;                     // exact alive diagonal range over the last two anti-diagonals
     int tbest = 0, tk = 0, ti = 0;              // this thread's first maximum; (0, 0, 0) = the anchor cell itself
     P tp = 0;
-    bool narrow_ok = true;
+    bool narrow_ok = true, finished = false;
     const uint32_t kmax = (uint32_t)tn + (uint32_t)qn;
-    for (uint32_t k = 1; k <= kmax; k++) {
+    uint32_t k = 1;
+    while (!finished && k <= kmax) {
         if (sizeof(P) == 4 && k >= (uint32_t)GP_NARROW_ABORT_K) { narrow_ok = false; break; }
-        // candidate diagonals of this anti-diagonal; the window base is a multiple of GP_SLOTS so a thread's slots stay consecutive
-        int clo = INT_MAX, chi = INT_MIN;
-        if (hi1 >= lo1) { clo = lo1 - 1; chi = hi1 + 1; }
-        if (hi2 >= lo2) { clo = min(clo, lo2); chi = max(chi, hi2); }
-        if (chi - clo > GP_MAXBAND) { err = 1; break; }
-        const int base = (clo - 16) & ~(GP_SLOTS - 1);
+        if (hi_e - lo_e + 2 * GP_EPOCH > GP_MAXBAND) { err = 1; break; }
+        // ---------------- constants of the epoch
+        const int rlo = lo_e - GP_EPOCH, rhi = hi_e + GP_EPOCH;
+        const int base = (rlo - 16) & ~(GP_SLOTS - 1);     // window base: a multiple of SLOTS so a thread's slots stay consecutive
         const int d0 = base + ((GP_SLOTS * tid - base) & GP_DMASK);  // diagonal of slot 0; slot s holds d0 + s
-        const int thr = best - Y;
-        const int par = (int)(k & 1);
-        int hmax = NEG_INF;
-        const bool active = d0 + GP_SLOTS - 1 >= clo && d0 <= chi;
-        const int i0 = ((int)k + d0 + par) >> 1, j0 = ((int)k - d0 - par) >> 1;   // cell c of this thread: (i0 + c, j0 - c)
+        const bool active = d0 + GP_SLOTS - 1 >= rlo && d0 <= rhi;
+        const bool wactive = __any_sync(0xffffffffu, active);
+        const uint32_t kend = min(kmax, k + (uint32_t)GP_EPOCH - 1u);
+        // can any cell of the epoch lie beyond the end of a sequence? (uniform over the CTA)
+        const bool edge = (((int)kend + rhi + GP_SLOTS + 1) >> 1) > tn || (((int)kend - rlo + GP_SLOTS + 1) >> 1) > qn;
+        if (!wactive && lane == 0) { sm.smax[0][warp] = NEG_INF; sm.smax[1][warp] = NEG_INF; }
+        for (; k <= kend; k++) {
+            const int thr = best - Y;
+            const int par = (int)(k & 1);
+            int hmax = NEG_INF;
+            if (active) {
+                const int i0 = ((int)k + d0 + par) >> 1, j0 = ((int)k - d0 - par) >> 1;   // cell c of this thread: (i0 + c, j0 - c)
+                int2 sc[GP_SLOTS / 2];
+                bool ok[GP_SLOTS / 2];
+                if (!edge) {
+                    const uint8_t* tp_ = DIR > 0 ? tcodes + ta + i0 - 1 : tcodes + ta - i0;
+                    const uint8_t* qp_ = DIR > 0 ? qcodes + qa + j0 - 1 : qcodes + qa - j0;
+#pragma unroll
+                    for (int c = 0; c < GP_SLOTS / 2; c++) {
+                        const uint32_t tb = DIR > 0 ? tp_[c] : tp_[-c], qb = DIR > 0 ? qp_[-c] : qp_[c];
+                        sc[c] = sm.lut[tb * 5 + qb]; ok[c] = true;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < GP_SLOTS / 2; c++) {
+                        const int i = i0 + c, j = j0 - c;
+                        ok[c] = i >= 0 && j >= 0 && i <= tn && j <= qn;
+                        const int ic_ = min(max(i, 1), max(tn, 1)), jc_ = min(max(j, 1), max(qn, 1));
+                        const uint32_t tb = tcodes[DIR > 0 ? ta + (uint32_t)ic_ - 1u : ta - (uint32_t)ic_];
+                        const uint32_t qb = qcodes[DIR > 0 ? qa + (uint32_t)jc_ - 1u : qa - (uint32_t)jc_];
+                        sc[c] = sm.lut[tb * 5 + qb];
+                    }
+                }
+                if (par) {
+                    // odd anti-diagonal: odd slots; up = slot s-1 (own), left = slot s+1 (own, or slot 0 of thread t+1 for the last slot)
+                    const Edge<P> fl = sm.left.get((tid + 1) & (GP_NT - 1));
+#pragma unroll
+                    for (int c = 0; c < GP_SLOTS / 2; c++) {
+                        const int s = 2 * c + 1;
+                        if (s + 1 < GP_SLOTS) {
+                            const Cell<P>& L = st[s + 1 < GP_SLOTS ? s + 1 : s];
+                            gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, L.h, L.i, L.hp, L.ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
+                        } else {
+                            gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, fl.h, fl.x, fl.hp, fl.xp, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
+                        }
+                    }
+                    const Cell<P>& e = st[GP_SLOTS - 1];
+                    sm.up.put(tid, Edge<P>{e.h, e.d, e.hp, e.dp});
+                } else {
+                    // even anti-diagonal: even slots; up = slot s-1 (own, or the last slot of thread t-1 for slot 0), left = slot s+1 (own)
+                    const Edge<P> fu = sm.up.get((tid - 1) & (GP_NT - 1));
+#pragma unroll
+                    for (int c = 0; c < GP_SLOTS / 2; c++) {
+                        const int s = 2 * c;
+                        if (s > 0) {
+                            const Cell<P>& U = st[s > 0 ? s - 1 : 0];
+                            gp_cell<P>(st[s], U.h, U.d, U.hp, U.dp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
+                        } else {
+                            gp_cell<P>(st[s], fu.h, fu.x, fu.hp, fu.xp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
+                        }
+                    }
+                    const Cell<P>& e = st[0];
+                    sm.left.put(tid, Edge<P>{e.h, e.i, e.hp, e.ip});
+                }
+                ncell += GP_SLOTS / 2;
+            }
+            if (wactive) {
+                const int wmax = __reduce_max_sync(0xffffffffu, hmax);
+                if (lane == 0) sm.smax[par][warp] = wmax;
+            }
+            __syncthreads();                    // the one barrier of this anti-diagonal
+            int bmax = NEG_INF;
+#pragma unroll
+            for (int w = 0; w < GP_WARPS; w++) bmax = max(bmax, sm.smax[par][w]);
+            best = max(best, bmax);
+            dead_steps = bmax > NEG_INF ? 0 : dead_steps + 1;
+            if (dead_steps >= 2) { finished = true; break; }   // two dead anti-diagonals in a row: nothing can revive
+        }
+        if (finished) break;
+        // ---------------- end of the epoch: exact range of alive diagonals (every slot holds its diagonal's latest cell)
+        int dlo = INT_MAX, dhi = INT_MIN;
         if (active) {
-            // is any cell of this anti-diagonal near the end of a sequence? (uniform over the CTA)
-            const bool edge = (((int)k + chi + GP_SLOTS + 1) >> 1) > tn || (((int)k - clo + GP_SLOTS + 1) >> 1) > qn;
-            int2 sc[GP_SLOTS / 2];
-            bool ok[GP_SLOTS / 2];
-            if (!edge) {
-                const uint8_t* tp_ = DIR > 0 ? tcodes + ta + i0 - 1 : tcodes + ta - i0;
-                const uint8_t* qp_ = DIR > 0 ? qcodes + qa + j0 - 1 : qcodes + qa - j0;
 #pragma unroll
-                for (int c = 0; c < GP_SLOTS / 2; c++) {
-                    const uint32_t tb = DIR > 0 ? tp_[c] : tp_[-c], qb = DIR > 0 ? qp_[-c] : qp_[c];
-                    sc[c] = sm.lut[tb * 5 + qb]; ok[c] = true;
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < GP_SLOTS / 2; c++) {
-                    const int i = i0 + c, j = j0 - c;
-                    ok[c] = i >= 0 && j >= 0 && i <= tn && j <= qn;
-                    const int ic_ = min(max(i, 1), max(tn, 1)), jc_ = min(max(j, 1), max(qn, 1));
-                    const uint32_t tb = tcodes[DIR > 0 ? ta + (uint32_t)ic_ - 1u : ta - (uint32_t)ic_];
-                    const uint32_t qb = qcodes[DIR > 0 ? qa + (uint32_t)jc_ - 1u : qa - (uint32_t)jc_];
-                    sc[c] = sm.lut[tb * 5 + qb];
-                }
-            }
-            if (par) {
-                // odd anti-diagonal: odd slots; up = slot s-1 (own), left = slot s+1 (own, or slot 0 of thread t+1 for the last slot)
-                const Edge<P> fl = sm.left.get((tid + 1) & (GP_NT - 1));
-#pragma unroll
-                for (int c = 0; c < GP_SLOTS / 2; c++) {
-                    const int s = 2 * c + 1;
-                    if (s + 1 < GP_SLOTS) {
-                        const Cell<P>& L = st[s + 1 < GP_SLOTS ? s + 1 : s];
-                        gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, L.h, L.i, L.hp, L.ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
-                    } else {
-                        gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, fl.h, fl.x, fl.hp, fl.xp, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
-                    }
-                }
-                const Cell<P>& e = st[GP_SLOTS - 1];
-                sm.up.put(tid, Edge<P>{e.h, e.d, e.hp, e.dp});
-            } else {
-                // even anti-diagonal: even slots; up = slot s-1 (own, or the last slot of thread t-1 for slot 0), left = slot s+1 (own)
-                const Edge<P> fu = sm.up.get((tid - 1) & (GP_NT - 1));
-#pragma unroll
-                for (int c = 0; c < GP_SLOTS / 2; c++) {
-                    const int s = 2 * c;
-                    if (s > 0) {
-                        const Cell<P>& U = st[s > 0 ? s - 1 : 0];
-                        gp_cell<P>(st[s], U.h, U.d, U.hp, U.dp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
-                    } else {
-                        gp_cell<P>(st[s], fu.h, fu.x, fu.hp, fu.xp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
-                    }
-                }
-                const Cell<P>& e = st[0];
-                sm.left.put(tid, Edge<P>{e.h, e.i, e.hp, e.ip});
-            }
-            ncell += GP_SLOTS / 2;
+            for (int s = 0; s < GP_SLOTS; s++)
+                if (st[s].h > NEG_INF) { dlo = min(dlo, d0 + s); dhi = max(dhi, d0 + s); }
         }
-        if (__any_sync(0xffffffffu, active)) {
-            const bool any_alive = hmax > NEG_INF;
-            const int wmax = __reduce_max_sync(0xffffffffu, hmax);
-            const int wlo = __reduce_min_sync(0xffffffffu, any_alive ? d0 : INT_MAX);
-            const int whi = __reduce_max_sync(0xffffffffu, any_alive ? d0 + GP_SLOTS - 1 : INT_MIN);
-            if (lane == 0) sm.rng[par][warp] = make_int4(wmax, wlo, whi, 0);
-        } else if (lane == 0) {
-            sm.rng[par][warp] = make_int4(INT_MIN, INT_MAX, INT_MIN, 0);
-        }
-        __syncthreads();                    // the one barrier of this anti-diagonal
-        int bmax = INT_MIN, alo = INT_MAX, ahi = INT_MIN;
-        int4 q[GP_WARPS];
+        const int wlo = __reduce_min_sync(0xffffffffu, dlo), whi = __reduce_max_sync(0xffffffffu, dhi);
+        if (lane == 0) sm.rng[warp] = make_int2(wlo, whi);
+        __syncthreads();
+        int alo = INT_MAX, ahi = INT_MIN;
 #pragma unroll
-        for (int w = 0; w < GP_WARPS; w++) { q[w] = sm.rng[par][w]; bmax = max(bmax, q[w].x); alo = min(alo, q[w].y); ahi = max(ahi, q[w].z); }
-        best = max(best, bmax);
-        lo2 = lo1; hi2 = hi1; lo1 = alo; hi1 = ahi;          // empty ranges arrive as (INT_MAX, INT_MIN)
-        if (hi1 < lo1) { lo1 = 1; hi1 = 0; }
-        dead_steps = (hi1 < lo1) ? dead_steps + 1 : 0;
-        if (dead_steps >= 2) break;         // two dead anti-diagonals in a row: nothing can revive
+        for (int w = 0; w < GP_WARPS; w++) { const int2 q = sm.rng[w]; alo = min(alo, q.x); ahi = max(ahi, q.y); }
+        if (ahi < alo) break;                   // nothing alive (the dead-step test catches this first)
+        lo_e = alo; hi_e = ahi;
     }
     // the alignment end: among the threads whose own maximum equals the global one, the earliest anti-diagonal, then the
     // smallest row (each thread's record already is its first such cell)
     {
+        __syncthreads();
         const bool cand = tbest == best;
         const int wk = __reduce_min_sync(0xffffffffu, cand ? tk : INT_MAX);
         const int wi = __reduce_min_sync(0xffffffffu, (cand && tk == wk) ? ti : INT_MAX);
