@@ -149,12 +149,13 @@ template <typename P, typename S> struct GpShared {
 
 // One DP cell (i,j) of anti-diagonal k on diagonal delta = i - j.  self = this diagonal's cell two anti-diagonals ago
 // (updated in place), (uh, ud) = H and D of cell (i-1,j), (lh, li) = H and I of cell (i,j-1), both of the previous anti-diagonal.
-// ok = cell lies inside both sequences (always true away from the sequence ends). Every thread remembers the first cell
-// (anti-diagonal, then row) that reached its own maximum; the alignment end is picked among those records once, at the end
-// of the extension, so an anti-diagonal only has to share ONE number (its maximum score) for the y-drop threshold.
+// ok = cell lies inside both sequences (always true away from the sequence ends). hmax collects the maximum of the
+// thread's cells on this anti-diagonal: every thread remembers the first cell (anti-diagonal, then row) that reached its own
+// maximum, and the alignment end is picked among those records once, at the end of the extension, so an anti-diagonal only
+// has to share ONE number (its maximum score) for the y-drop threshold.
 template <typename P>
 __device__ __forceinline__ void gp_cell(Cell<P>& self, int uh, int ud, P uhp, P udp, int lh, int li, P lhp, P lip, int2 sc, bool ok,
-                                        int OE, int E, int thr, int k, int i, int& tbest, int& tk, int& ti, P& tp, int& hmax) {
+                                        int OE, int E, int thr, int& hmax) {
     // D: vertical gap state, I: horizontal gap state (ties prefer opening from H, as in the oracle)
     const int dopen = uh - OE, dext = ud - E;
     const bool dsel = dopen >= dext;
@@ -171,7 +172,6 @@ __device__ __forceinline__ void gp_cell(Cell<P>& self, int uh, int ud, P uhp, P 
     const bool alive = ok && nh >= thr;
     self.h = alive ? nh : NEG_INF; self.d = alive ? nd : NEG_INF; self.i = alive ? ni : NEG_INF;
     self.hp = nhp; self.dp = ndp; self.ip = nip;
-    if (self.h > tbest) { tbest = self.h; tk = k; ti = i; tp = nhp; }   // the thread's own first maximum (strict >: earliest k, then smallest i)
     hmax = max(hmax, self.h);
 }
 
@@ -264,9 +264,9 @@ __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint3
                         const int s = 2 * c + 1;
                         if (s + 1 < GP_SLOTS) {
                             const Cell<P>& L = st[s + 1 < GP_SLOTS ? s + 1 : s];
-                            gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, L.h, L.i, L.hp, L.ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
+                            gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, L.h, L.i, L.hp, L.ip, sc[c], ok[c], OE, E, thr, hmax);
                         } else {
-                            gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, fl.h, fl.x, fl.hp, fl.xp, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
+                            gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, fl.h, fl.x, fl.hp, fl.xp, sc[c], ok[c], OE, E, thr, hmax);
                         }
                     }
                     const Cell<P>& e = st[GP_SLOTS - 1];
@@ -279,15 +279,26 @@ __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint3
                         const int s = 2 * c;
                         if (s > 0) {
                             const Cell<P>& U = st[s > 0 ? s - 1 : 0];
-                            gp_cell<P>(st[s], U.h, U.d, U.hp, U.dp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
+                            gp_cell<P>(st[s], U.h, U.d, U.hp, U.dp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, hmax);
                         } else {
-                            gp_cell<P>(st[s], fu.h, fu.x, fu.hp, fu.xp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, (int)k, i0 + c, tbest, tk, ti, tp, hmax);
+                            gp_cell<P>(st[s], fu.h, fu.x, fu.hp, fu.xp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, hmax);
                         }
                     }
                     const Cell<P>& e = st[0];
                     sm.left.put(tid, Edge<P>{e.h, e.i, e.hp, e.ip});
                 }
                 ncell += GP_SLOTS / 2;
+                if (hmax > tbest) {
+                    // a new maximum of this thread (rare): its first cell in row order on this anti-diagonal. Strict > across
+                    // anti-diagonals keeps the earliest one.
+                    tbest = hmax; tk = (int)k;
+                    bool found = false;
+#pragma unroll
+                    for (int c = 0; c < GP_SLOTS / 2; c++) {
+                        const int hv = par ? st[2 * c + 1].h : st[2 * c].h;
+                        if (!found && hv == hmax) { found = true; ti = i0 + c; tp = par ? st[2 * c + 1].hp : st[2 * c].hp; }
+                    }
+                }
             }
             if (wactive) {
                 const int wmax = __reduce_max_sync(0xffffffffu, hmax);
