@@ -155,3 +155,18 @@ def test_long_alignment_takes_the_exact_wide_payload_path(M):
     want = {(0, 0, 0, s1 + 1, e1, s2 + 1, e2, sc, nm, nc) for (s1, e1, s2, e2, sc, nm, nc, _a, _b) in lo.align_tile(tix, lo.encode(seq), p).tolist()}
     assert gpu_rows(hits) == want
     assert max(r[4] - r[3] for r in want) > 140_000
+
+
+def test_chain_batched_and_sequential_walks_agree(M, monkeypatch):
+    """The batched chain DP (dense tiles) and the one-HSP-at-a-time walk (sparse tiles) are the same dynamic programme:
+    forcing either on every tile must give identical alignments, equal to the oracle."""
+    A, G = M
+    g = synth_genome(49, 2, 60_000, 4, copies=(10, 16), fam_len=(400, 2500), sub=0.06, indel=0.004)
+    T = G.Genome.from_dict(g)
+    rows = {}
+    for mode in ('1', '2', '0'):
+        monkeypatch.setenv('MB2_CHAIN_MODE', mode)
+        hits, _ = A.align(T, T, G.align_params(3000))
+        rows[mode] = gpu_rows(hits)
+    assert rows['1'] == rows['2'] == rows['0'] and len(rows['0']) > 50
+    assert rows['0'] == oracle_rows(g, g, lo.default_params(3000))
