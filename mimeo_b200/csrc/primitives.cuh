@@ -79,6 +79,35 @@ scan_add_kernel(uint32_t* __restrict__ out, size_t n, const uint32_t* __restrict
         if (base + i < n) out[base + i] += off;
 }
 
+// Whole scan in ONE launch for small inputs (the histograms of the radix passes on a few hundred thousand keys): one CTA
+// walks the tiles and carries the running total, instead of block scan + scan of block sums + add (three launches whose
+// fixed cost dominates at these sizes).
+constexpr size_t SCAN_SINGLE_MAX = 8 * 1024;
+static __global__ void __launch_bounds__(SCAN_THREADS)
+scan_single_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t sh[SCAN_THREADS / 32 + 1];
+    uint32_t carry = 0;
+    for (size_t tile = 0; tile < n; tile += SCAN_TILE) {
+        const size_t base = tile + (size_t)threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            v[i] = (base + i < n) ? in[base + i] : 0u;
+            sum += v[i];
+        }
+        uint32_t total;
+        uint32_t run = block_excl_scan<SCAN_THREADS>(sum, sh, total) + carry;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            if (base + i < n) out[base + i] = run;
+            run += v[i];
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
 static __global__ void scan_total_kernel(const uint32_t* __restrict__ last_excl, const uint32_t* __restrict__ last_in, uint32_t* __restrict__ total) {
     *total = *last_excl + *last_in;
 }
@@ -86,6 +115,10 @@ static __global__ void scan_total_kernel(const uint32_t* __restrict__ last_excl,
 inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total = nullptr) {
     if (n == 0) {
         if (total) MB2_CUDA(cudaMemsetAsync(total, 0, sizeof(uint32_t), ctx().stream));
+        return;
+    }
+    if (n <= SCAN_SINGLE_MAX) {
+        launch(scan_single_kernel, 1, SCAN_THREADS, 0, in, out, n, total);
         return;
     }
     // total must be derived before `in` is overwritten when aliasing: keep the last input element.
