@@ -396,12 +396,65 @@ __device__ Ext selfdiag_extend_cta(const GenomeView& T, uint32_t p0, uint32_t p1
 // 31-column window of the HSP (first maximum), the whole HSP if it is shorter. One CTA per member; every thread slides a
 // window over its own contiguous share of the window positions, then the CTA keeps the first maximum.
 constexpr int AP_NT = 128;
+constexpr int AP_LONG = 16384;       // HSPs with more windows than this are split over AP_PARTS CTAs (second kernel)
+constexpr int AP_PARTS = 32;
+constexpr int AP_LONG_SLOTS = 64;
+
+// windows [w0, w1) of one HSP by one thread: best window sum and its first position (strict > keeps the first)
+__device__ __forceinline__ void ap_scan(const GenomeView& T, const GenomeView& Q, uint32_t ts, uint32_t qs, int w0, int w1, int& best, int& bw) {
+    // 32 column scores at a time from registers: words of 32 bases / 32 N flags starting at column c
+    auto score_at = [](uint64_t wt, uint64_t wq, uint32_t an, int t) -> int {
+        return ((an >> t) & 1u) ? SCORE_N : sub_lut3((uint32_t)(((wt >> (2 * t)) & 3) << 2) | (uint32_t)((wq >> (2 * t)) & 3));
+    };
+    best = INT_MIN; bw = INT_MAX;
+    if (w0 >= w1) return;
+    int sum = 0;
+    {
+        const uint64_t wt = window32(T.pk, ts + w0), wq = window32(Q.pk, qs + w0);
+        const uint32_t an = nwindow32(T.nm, ts + w0) | nwindow32(Q.nm, qs + w0);
+#pragma unroll
+        for (int t = 0; t < 31; t++) sum += score_at(wt, wq, an, t);
+    }
+    best = sum; bw = w0;
+    // window w = w0 + 1 + 32 b + t: column w + 30 enters, column w - 1 leaves
+    for (int wb = w0 + 1; wb < w1; wb += 32) {
+        const uint64_t et = window32(T.pk, ts + wb + 30), eq = window32(Q.pk, qs + wb + 30);
+        const uint32_t en = nwindow32(T.nm, ts + wb + 30) | nwindow32(Q.nm, qs + wb + 30);
+        const uint64_t lt = window32(T.pk, ts + wb - 1), lq = window32(Q.pk, qs + wb - 1);
+        const uint32_t ln = nwindow32(T.nm, ts + wb - 1) | nwindow32(Q.nm, qs + wb - 1);
+#pragma unroll
+        for (int t = 0; t < 32; t++) {
+            sum += score_at(et, eq, en, t) - score_at(lt, lq, ln, t);
+            if (wb + t < w1 && sum > best) { best = sum; bw = wb + t; }
+        }
+    }
+}
+// first maximum over the CTA (highest sum, then lowest window); valid in thread 0
+__device__ __forceinline__ void ap_reduce(int& best, int& bw, int* sh_best, int* sh_w) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wbest = __reduce_max_sync(0xffffffffu, best);
+    const int wbw = __reduce_min_sync(0xffffffffu, best == wbest ? bw : INT_MAX);
+    if (lane == 0) { sh_best[warp] = wbest; sh_w[warp] = wbw; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int b = sh_best[0], w = sh_w[0];
+        for (int k = 1; k < AP_NT / 32; k++)
+            if (sh_best[k] > b || (sh_best[k] == b && sh_w[k] < w)) { b = sh_best[k]; w = sh_w[k]; }
+        best = b; bw = w;
+    }
+}
+// (sum, window) packed so that "higher sum, then lower window" is plain unsigned max
+__device__ __forceinline__ unsigned long long ap_pack(int sum, int w) {
+    return ((unsigned long long)((uint32_t)sum ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)w);
+}
+
 __global__ void __launch_bounds__(AP_NT)
 anchor_points_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, const int32_t* __restrict__ hs1, const int32_t* __restrict__ hs2,
                      const int32_t* __restrict__ hlen, const uint32_t* __restrict__ order, uint32_t nmember,
-                     int32_t* __restrict__ a1, int32_t* __restrict__ a2) {
+                     int32_t* __restrict__ a1, int32_t* __restrict__ a2, uint32_t* __restrict__ long_list, uint32_t* __restrict__ nlong,
+                     unsigned long long* __restrict__ long_key) {
     __shared__ int sh_best[AP_NT / 32], sh_w[AP_NT / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const uint32_t x = blockIdx.x;
     const uint32_t g = order[x], tl = tile[g];
     const uint32_t ts = T.off[tl / (uint32_t)Q.nscaf] + (uint32_t)hs1[g], qs = Q.off[tl % (uint32_t)Q.nscaf] + (uint32_t)hs2[g];
@@ -410,45 +463,48 @@ anchor_points_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ ti
         if (tid == 0) { a1[x] = hs1[g] + len / 2; a2[x] = hs2[g] + len / 2; }
         return;
     }
-    // 32 column scores at a time from registers: words of 32 bases / 32 N flags starting at column c
-    auto score_at = [](uint64_t wt, uint64_t wq, uint32_t an, int t) -> int {
-        return ((an >> t) & 1u) ? SCORE_N : sub_lut3((uint32_t)(((wt >> (2 * t)) & 3) << 2) | (uint32_t)((wq >> (2 * t)) & 3));
-    };
     const int nwin = len - 30;                       // window w covers columns [w, w + 30]
-    const int chunk = (nwin + AP_NT - 1) / AP_NT;
-    const int w0 = tid * chunk, w1 = min(nwin, w0 + chunk);
-    int best = INT_MIN, bw = INT_MAX;
-    if (w0 < w1) {
-        int sum = 0;
-        {
-            const uint64_t wt = window32(T.pk, ts + w0), wq = window32(Q.pk, qs + w0);
-            const uint32_t an = nwindow32(T.nm, ts + w0) | nwindow32(Q.nm, qs + w0);
-#pragma unroll
-            for (int t = 0; t < 31; t++) sum += score_at(wt, wq, an, t);
-        }
-        best = sum; bw = w0;
-        // window w = w0 + 1 + 32 b + t: column w + 30 enters, column w - 1 leaves
-        for (int wb = w0 + 1; wb < w1; wb += 32) {
-            const uint64_t et = window32(T.pk, ts + wb + 30), eq = window32(Q.pk, qs + wb + 30);
-            const uint32_t en = nwindow32(T.nm, ts + wb + 30) | nwindow32(Q.nm, qs + wb + 30);
-            const uint64_t lt = window32(T.pk, ts + wb - 1), lq = window32(Q.pk, qs + wb - 1);
-            const uint32_t ln = nwindow32(T.nm, ts + wb - 1) | nwindow32(Q.nm, qs + wb - 1);
-#pragma unroll
-            for (int t = 0; t < 32; t++) {
-                sum += score_at(et, eq, en, t) - score_at(lt, lq, ln, t);
-                if (wb + t < w1 && sum > best) { best = sum; bw = wb + t; }
-            }
-        }
+    if (nwin > AP_LONG) {                            // split over several CTAs by anchor_points_long_kernel
+        if (tid == 0) { const uint32_t k = atomicAdd(nlong, 1u); long_list[k] = x; long_key[k] = 0ull; }
+        return;
     }
-    // first maximum over the CTA: highest sum, then lowest window
-    const int wbest = __reduce_max_sync(0xffffffffu, best);
-    const int wbw = __reduce_min_sync(0xffffffffu, best == wbest ? bw : INT_MAX);
-    if (lane == 0) { sh_best[warp] = wbest; sh_w[warp] = wbw; }
-    __syncthreads();
-    if (tid == 0) {
-        int b = sh_best[0], w = sh_w[0];
-        for (int k = 1; k < AP_NT / 32; k++)
-            if (sh_best[k] > b || (sh_best[k] == b && sh_w[k] < w)) { b = sh_best[k]; w = sh_w[k]; }
+    const int chunk = (nwin + AP_NT - 1) / AP_NT;
+    int best, bw;
+    ap_scan(T, Q, ts, qs, tid * chunk, min(nwin, tid * chunk + chunk), best, bw);
+    ap_reduce(best, bw, sh_best, sh_w);
+    if (tid == 0) { a1[x] = hs1[g] + bw + 15; a2[x] = hs2[g] + bw + 15; }
+}
+// grid (AP_PARTS, AP_LONG_SLOTS): CTA (p, s) scans part p of the long HSPs s, s + AP_LONG_SLOTS, ...
+__global__ void __launch_bounds__(AP_NT)
+anchor_points_long_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ tile, const int32_t* __restrict__ hs1, const int32_t* __restrict__ hs2,
+                          const int32_t* __restrict__ hlen, const uint32_t* __restrict__ order, const uint32_t* __restrict__ long_list,
+                          const uint32_t* __restrict__ nlong, unsigned long long* __restrict__ long_key) {
+    __shared__ int sh_best[AP_NT / 32], sh_w[AP_NT / 32];
+    const int tid = threadIdx.x;
+    const uint32_t n = *nlong;
+    for (uint32_t k = blockIdx.y; k < n; k += gridDim.y) {
+        const uint32_t x = long_list[k];
+        const uint32_t g = order[x], tl = tile[g];
+        const uint32_t ts = T.off[tl / (uint32_t)Q.nscaf] + (uint32_t)hs1[g], qs = Q.off[tl % (uint32_t)Q.nscaf] + (uint32_t)hs2[g];
+        const int nwin = hlen[g] - 30;
+        const int part = (nwin + AP_PARTS - 1) / AP_PARTS;
+        const int p0 = (int)blockIdx.x * part, p1 = min(nwin, p0 + part);
+        const int chunk = (max(p1 - p0, 0) + AP_NT - 1) / AP_NT;
+        int best, bw;
+        ap_scan(T, Q, ts, qs, p0 + tid * chunk, min(p1, p0 + tid * chunk + chunk), best, bw);
+        ap_reduce(best, bw, sh_best, sh_w);
+        if (tid == 0 && best != INT_MIN) atomicMax(&long_key[k], ap_pack(best, bw));
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(64)
+anchor_points_finish_kernel(const int32_t* __restrict__ hs1, const int32_t* __restrict__ hs2, const uint32_t* __restrict__ order,
+                            const uint32_t* __restrict__ long_list, const uint32_t* __restrict__ nlong,
+                            const unsigned long long* __restrict__ long_key, int32_t* __restrict__ a1, int32_t* __restrict__ a2) {
+    const uint32_t n = *nlong;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t x = long_list[k], g = order[x];
+        const int w = (int)(0xFFFFFFFFu - (uint32_t)(long_key[k] & 0xFFFFFFFFull));
         a1[x] = hs1[g] + w + 15; a2[x] = hs2[g] + w + 15;
     }
 }
@@ -698,8 +754,15 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
             MB2_CUDA(cudaMemsetAsync(resume.get(), 0, (size_t)h_nseg * sizeof(uint32_t), cx.stream));
             MB2_CUDA(cudaMemsetAsync(nkept.get(), 0, (size_t)h_nseg * sizeof(uint32_t), cx.stream));
             const GenomeView tv = view(T), qv = view(Q);
+            DevBuf<uint32_t> long_list(nm), d_nlong(1);
+            DevBuf<unsigned long long> long_key(nm);
+            MB2_CUDA(cudaMemsetAsync(d_nlong.get(), 0, sizeof(uint32_t), cx.stream));
             launch(anchor_points_kernel, nm, AP_NT, 0, tv, qv, h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(), order, nm,
-                   a1.get(), a2.get());
+                   a1.get(), a2.get(), long_list.get(), d_nlong.get(), long_key.get());
+            launch(anchor_points_long_kernel, dim3(AP_PARTS, AP_LONG_SLOTS), AP_NT, 0, tv, qv, h.tile.get(), h.s1.get(), h.s2.get(), h.len.get(),
+                   order, (const uint32_t*)long_list.get(), (const uint32_t*)d_nlong.get(), long_key.get());
+            launch(anchor_points_finish_kernel, 4, 64, 0, h.s1.get(), h.s2.get(), order, (const uint32_t*)long_list.get(),
+                   (const uint32_t*)d_nlong.get(), (const unsigned long long*)long_key.get(), a1.get(), a2.get());
             GpWork W;
             W.order = order; W.a1 = a1.get(); W.a2 = a2.get(); W.cluster_of = cluster_of.get(); W.status = status.get();
             W.e_score = e_score.get(); W.e_di = e_di.get(); W.e_dj = e_dj.get(); W.e_nm = e_nm.get(); W.e_nc = e_nc.get();
