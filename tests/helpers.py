@@ -154,3 +154,38 @@ def synth_c5(seed, total_bp=1_000_000_000, nscaf=500, repeat_frac=0.40, fam_len=
             if planted >= target:
                 break
     return {f'scaf{i:04d}': scafs[i] for i in range(nscaf)}
+
+
+def odd_genome(rng, k):
+    """Small genomes of awkward shapes for parity stress (kind = k % 6): ordinary / tiny scaffolds / tandem array and low
+    complexity / N-rich / one dense family / two long near-identical scaffolds."""
+    kind = k % 6
+    if kind == 0:      # ordinary
+        return synth_genome(1000 + k, int(rng.integers(1, 5)), int(rng.integers(3000, 40000)), int(rng.integers(1, 5)), copies=(2, 8),
+                            fam_len=(200, 2500), sub=float(rng.uniform(0.02, 0.14)), indel=float(rng.uniform(0, 0.01)), n_runs=int(rng.integers(0, 4)))
+    g = {}
+    acgt = np.frombuffer(b'ACGT', dtype=np.uint8)
+    if kind == 1:      # tiny scaffolds next to a normal one
+        g['big'] = acgt[rng.integers(0, 4, 20000)].copy()
+        for i, n in enumerate((1, 5, 18, 19, 20, 40, 63, 64, 65)):
+            g['t%02d' % i] = g['big'][100 * i:100 * i + n].copy()
+    elif kind == 2:    # tandem array + low complexity
+        unit = acgt[rng.integers(0, 4, int(rng.integers(150, 400)))]
+        arr = np.concatenate([mutate(rng, unit, 0.05, 0.003) for _ in range(int(rng.integers(5, 25)))])
+        g['tandem'] = np.concatenate([acgt[rng.integers(0, 4, 3000)], arr, acgt[rng.integers(0, 4, 3000)], np.tile(np.frombuffer(b'AC', dtype=np.uint8), 400)])
+        g['other'] = np.concatenate([acgt[rng.integers(0, 4, 2000)], mutate(rng, arr[:3000], 0.1, 0.005), acgt[rng.integers(0, 4, 2000)]])
+    elif kind == 3:    # N-rich
+        s = acgt[rng.integers(0, 4, 30000)].copy()
+        rep = s[2000:4500].copy()
+        s[10000:12500] = mutate(rng, rep, 0.08, 0.0)[:2500]
+        for _ in range(12):
+            p0 = int(rng.integers(0, 29000)); s[p0:p0 + int(rng.integers(1, 300))] = ord('N')
+        g['nrich'] = s
+        g['nother'] = np.concatenate([mutate(rng, rep, 0.06, 0.004), np.full(500, ord('N'), np.uint8), mutate(rng, rep, 0.12, 0.004)])
+    elif kind == 4:    # one dense family: many HSPs per tile (batched chain, long rings)
+        return synth_genome(2000 + k, 2, 60000, 2, copies=(20, 35), fam_len=(300, 1200), sub=0.05, indel=0.004)
+    else:              # near-identical long scaffolds (long gapped extensions, wide payload when > 65536 columns)
+        a = acgt[rng.integers(0, 4, int(rng.integers(70000, 90000)))].copy()
+        g['a'] = a
+        g['b'] = mutate(rng, a, 0.01, 0.0005)
+    return g

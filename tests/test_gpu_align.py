@@ -170,3 +170,16 @@ def test_chain_batched_and_sequential_walks_agree(M, monkeypatch):
         rows[mode] = gpu_rows(hits)
     assert rows['1'] == rows['2'] == rows['0'] and len(rows['0']) > 50
     assert rows['0'] == oracle_rows(g, g, lo.default_params(3000))
+
+
+@pytest.mark.parametrize('kind', range(6))
+def test_awkward_genomes_bit_exact_vs_oracle(M, kind):
+    """Tiny scaffolds (shorter than a seed), tandem arrays and low complexity, N-rich sequence, one dense family (batched chain
+    walk, long descriptor rings) and long near-identical scaffolds (alignments of more than 65536 columns)."""
+    A, G = M
+    from tests.helpers import odd_genome
+    g = odd_genome(np.random.default_rng(100 + kind), kind)
+    T = G.Genome.from_dict(g)
+    hits, _ = A.align(T, T, G.align_params(3000))
+    want = oracle_rows(g, g, lo.default_params(3000))
+    assert gpu_rows(hits) == want and len(want) >= 2
