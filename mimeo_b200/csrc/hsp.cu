@@ -216,7 +216,8 @@ hsp_extend_kernel(GenomeView T, GenomeView Q, const uint64_t* __restrict__ surv,
                 bs = T.off[ts]; be = bs + T.len[ts];
                 int cgn = 0;
                 const uint32_t w0 = bs >> 5, w1 = (be - 1) >> 5;
-                for (uint32_t w = w0 + lane; w <= w1; w += 32) {
+#pragma unroll 8
+                for (uint32_t w = w0 + lane; w <= w1; w += 32) {       // independent loads: unrolled so that several are in flight
                     const uint64_t xw = T.pk[w];
                     uint64_t m = (xw ^ (xw >> 1)) & 0x5555555555555555ull;       // one bit per C or G base
                     if (w == w0 && (bs & 31)) m &= ~0ull << (2 * (bs & 31));
@@ -235,6 +236,7 @@ hsp_extend_kernel(GenomeView T, GenomeView Q, const uint64_t* __restrict__ surv,
             const uint32_t qs = bs - (i - j);
             if (entropy) {
                 uint32_t cnt[4] = {0, 0, 0, 0};
+#pragma unroll 4
                 for (uint32_t c = bs + 32u * lane; c < be; c += 1024u) {      // each lane owns 32-column words
                     const uint64_t wt = window32(T.pk, c), wq = window32(Q.pk, qs + (c - bs));
                     const uint32_t an = nwindow32(T.nm, c) | nwindow32(Q.nm, qs + (c - bs));
