@@ -18,17 +18,17 @@ static const uint64_t MAX_SURVIVORS = 1500000000ull;   // 12 GB of keys (x2 for 
 
 struct QChunk { int s_lo, s_hi; };   // query scaffolds [s_lo, s_hi)
 
-static std::vector<QChunk> make_chunks(const Genome& Q) {
+static uint64_t default_chunk_bases() {
     uint64_t chunk_bases = 128ull << 20;
     if (const char* e = getenv("MB2_CHUNK_MBP")) { const double v = atof(e); if (v > 0) chunk_bases = (uint64_t)(v * 1e6); }
-    std::vector<QChunk> out;
-    int lo = 0; uint64_t acc = 0;
-    for (int s = 0; s < Q.nscaf; s++) {
-        if (s > lo && acc + Q.len[s] > chunk_bases) { out.push_back({lo, s}); lo = s; acc = 0; }
-        acc += Q.len[s];
-    }
-    out.push_back({lo, Q.nscaf});
-    return out;
+    return chunk_bases;
+}
+// the next chunk: whole scaffolds from s_lo on, at most `limit` bases (but at least one scaffold)
+static QChunk next_chunk(const Genome& Q, int s_lo, uint64_t limit) {
+    uint64_t acc = 0;
+    int s = s_lo;
+    while (s < Q.nscaf && (s == s_lo || acc + Q.len[s] <= limit)) { acc += Q.len[s]; s++; }
+    return {s_lo, s};
 }
 
 // query position range of scaffolds [s_lo, s_hi): from the first base of s_lo to the last base of s_hi-1 (windows that
@@ -134,23 +134,29 @@ void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const 
     MB2_CUDA(cudaMemcpyAsync(d_same.get(), same.data(), T.nscaf * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
     MB2_CUDA(cudaStreamSynchronize(cx.stream));
 
-    std::vector<QChunk> todo = make_chunks(Q);
-    std::reverse(todo.begin(), todo.end());          // used as a stack; chunks are processed in scaffold order
-    while (!todo.empty()) {
-        const QChunk c = todo.back(); todo.pop_back();
+    // Chunks are formed on the fly: the survivor density (survivors per query base) seen so far sizes the next chunk and
+    // its buffer, so that a repeat-rich genome costs at most one scan that overflows (the first), not one per chunk.
+    const uint64_t chunk_default = default_chunk_bases();
+    double dens = 0.0;                               // highest survivors-per-query-base observed so far
+    int s_next = 0;
+    while (s_next < Q.nscaf) {
+        uint64_t limit = chunk_default;
+        if (dens > 0.0) limit = std::min<uint64_t>(limit, std::max<uint64_t>(1, (uint64_t)(0.7 * (double)MAX_SURVIVORS / dens)));
+        const QChunk c = next_chunk(Q, s_next, limit);
         uint32_t q_lo, q_hi;
         chunk_range(Q, c, q_lo, q_hi);
         uint64_t cbases = 0;
         for (int s = c.s_lo; s < c.s_hi; s++) cbases += Q.len[s];
-        uint64_t cap = std::max<uint64_t>(1u << 20, std::min<uint64_t>(MAX_SURVIVORS, (T.nbases + cbases) / 2));
+        uint64_t cap = std::max<uint64_t>(1u << 20, std::min<uint64_t>(MAX_SURVIVORS, std::max<uint64_t>((T.nbases + cbases) / 2, (uint64_t)(1.3 * dens * (double)cbases))));
         unsigned long long nsurv = 0;
         MB2_CUDA(cudaMemsetAsync(counters.get(), 0, CNT_N * sizeof(unsigned long long), cx.stream));
-        if (!scan_chunk(T, Q, tab, q_lo, q_hi, p, s0, cap, counters.get(), nsurv, acc)) {
+        const bool ok = scan_chunk(T, Q, tab, q_lo, q_hi, p, s0, cap, counters.get(), nsurv, acc);
+        if (cbases) dens = std::max(dens, (double)nsurv / (double)cbases);
+        if (!ok) {
             MB2_REQUIRE(c.s_hi - c.s_lo > 1, -3, "align: one query scaffold alone produces more surviving seed hits than fit in memory");
-            const int mid = (c.s_lo + c.s_hi) / 2;
-            todo.push_back({mid, c.s_hi}); todo.push_back({c.s_lo, mid});      // split and retry (lower half first)
-            continue;
+            continue;                                // the same scaffolds again, in a smaller chunk sized by the density just measured
         }
+        s_next = c.s_hi;
         if (nsurv == 0) continue;
         if (s1.n < nsurv) s1.alloc(nsurv);
         HspSet hsps;
