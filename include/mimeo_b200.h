@@ -179,6 +179,25 @@ typedef struct mb2_fasta {
 MB2_API int mb2_fasta_read(const char* path, int nthreads, mb2_fasta* out);
 MB2_API void mb2_free_fasta(mb2_fasta* f);
 
+/* The filter + projection + sort that follows every LASTZ call in the reference's script (wrappers.py:1044-1056):
+ * rows with length1 >= min_len and printed identity ('%.1f' of 100*nmatch/ncols) >= min_idt, as 10 tab-separated columns,
+ * grouped by (t_id, q_id) block (ascending), each block sorted by start1 and then by the whole line's bytes
+ * (`sort -k 1,1 -k 3n,4n`). Input: the columns of mb2_hits as HOST arrays. Block b is text[off[b] .. off[b+1]). */
+typedef struct mb2_tab_text {
+    char* text;
+    uint64_t nbytes;
+    int32_t* t_id;
+    int32_t* q_id;
+    uint64_t* off;       /* nblocks + 1 entries */
+    uint32_t* nrows;
+    uint64_t nblocks;
+} mb2_tab_text;
+MB2_API int mb2_format_tab(const int32_t* t_id, const int32_t* q_id, const int32_t* strand, const int32_t* start1, const int32_t* end1,
+                           const int32_t* start2, const int32_t* end2, const int32_t* score, const int32_t* nmatch, const int32_t* ncols,
+                           uint64_t n, const char* const* tnames, int nt, const char* const* qnames, int nq, double min_len, double min_idt,
+                           mb2_tab_text* out);
+MB2_API void mb2_free_tab_text(mb2_tab_text* t);
+
 /* ---- device primitives exposed for parity tests ------------------------------------------- */
 /* Stable LSD radix sort of HOST arrays on bits [begin_bit, end_bit) (vals may be NULL). */
 MB2_API int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);

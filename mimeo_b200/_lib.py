@@ -42,6 +42,11 @@ class Fasta(C.Structure):
                 ('seq', C.POINTER(C.c_uint8))]
 
 
+class TabText(C.Structure):
+    _fields_ = [('text', C.POINTER(C.c_char)), ('nbytes', C.c_uint64), ('t_id', c_i32p), ('q_id', c_i32p), ('off', c_u64p),
+                ('nrows', c_u32p), ('nblocks', C.c_uint64)]
+
+
 class Segments(C.Structure):
     _fields_ = [('chrom', c_i32p), ('start', c_i32p), ('end', c_i32p), ('n', C.c_uint64), ('on_device', C.c_int)]
 
@@ -77,6 +82,9 @@ SIGNATURES = {
     'mb2_free_tab_hits': (None, [C.POINTER(TabHits)]),
     'mb2_fasta_read': (C.c_int, [C.c_char_p, C.c_int, C.POINTER(Fasta)]),
     'mb2_free_fasta': (None, [C.POINTER(Fasta)]),
+    'mb2_format_tab': (C.c_int, [C.c_void_p] * 10 + [C.c_uint64, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int,
+                                 C.c_double, C.c_double, C.POINTER(TabText)]),
+    'mb2_free_tab_text': (None, [C.POINTER(TabText)]),
     'mb2_test_sort_u32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     'mb2_test_sort_u64': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     'mb2_test_scan_u32': (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),

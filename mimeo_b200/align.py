@@ -53,27 +53,31 @@ def _sort_n(s: str) -> float:
 
 
 def tab_blocks(hits: Dict[str, np.ndarray], tnames: List[str], qnames: List[str], minLen, minIdt) -> Dict[Tuple[int, int], List[str]]:
-    """Filtered, sorted 10-column rows (with newline) per (t_id, q_id) pair."""
+    """Filtered, sorted 10-column rows (with newline) per (t_id, q_id) pair, formatted natively (`mb2_format_tab`)."""
     out: Dict[Tuple[int, int], List[str]] = {}
     n = len(hits['t_id'])
     if n == 0:
         return out
-    s1, e1 = hits['start1'], hits['end1']
-    nm, nc = hits['nmatch'].astype(np.float64), hits['ncols'].astype(np.float64)
-    with np.errstate(divide='ignore', invalid='ignore'):
-        ratio = np.where(nc > 0, 100.0 * nm / nc, 0.0)            # same double arithmetic as pct_text
-    long_enough = (e1.astype(np.int64) - s1 + 1) >= minLen          # awk '0+$5 >= minLen' on length1
-    idx = np.flatnonzero(long_enough)
-    pct = ['%.1f' % v for v in ratio[idx].tolist()]
-    lim = float(minIdt)
-    rows = []
-    cols = [hits[f][idx].tolist() for f in ('t_id', 'q_id', 'strand', 'start1', 'end1', 'start2', 'end2', 'score')]
-    for t, q, st, a, b, c, d, sc, p in zip(*cols, pct):
-        if float(p) < lim:                                         # awk '0+$13 >= minIdt' on the printed percentage
-            continue
-        row = f"{tnames[t]}\t+\t{a}\t{b}\t{qnames[q]}\t{'-' if st else '+'}\t{c}\t{d}\t{sc}\t{p}\n"
-        rows.append((t, q, a, row.encode(), row))
-    rows.sort()                 # per pair: sort -k 3n,4n then whole line (name1 equal inside a pair; the newline sorts below every field byte)
-    for t, q, _a, _b, row in rows:
-        out.setdefault((t, q), []).append(row)
+    cols = [np.ascontiguousarray(hits[f], dtype=np.int32) for f in HIT_FIELDS]
+    tn = (C.c_char_p * len(tnames))(*[s.encode() for s in tnames])
+    qn = tn if qnames is tnames else (C.c_char_p * len(qnames))(*[s.encode() for s in qnames])
+    t = _lib.TabText()
+    _lib.check(_lib.lib().mb2_format_tab(*[c.ctypes.data for c in cols], n, tn, len(tnames), qn, len(qnames),
+                                         float(minLen), float(minIdt), C.byref(t)))
+    try:
+        nb = int(t.nblocks)
+        if nb:
+            text = C.string_at(t.text, int(t.nbytes)).decode()
+            off = np.ctypeslib.as_array(t.off, shape=(nb + 1,)).tolist()
+            tid = np.ctypeslib.as_array(t.t_id, shape=(nb,)).tolist()
+            qid = np.ctypeslib.as_array(t.q_id, shape=(nb,)).tolist()
+            if len(text) == int(t.nbytes):                      # pure ASCII: byte offsets are character offsets
+                for b in range(nb):
+                    out[(tid[b], qid[b])] = text[off[b]:off[b + 1]].splitlines(keepends=True)
+            else:
+                raw = C.string_at(t.text, int(t.nbytes))
+                for b in range(nb):
+                    out[(tid[b], qid[b])] = raw[off[b]:off[b + 1]].decode().splitlines(keepends=True)
+    finally:
+        _lib.lib().mb2_free_tab_text(C.byref(t))
     return out

@@ -434,4 +434,33 @@ void mb2_free_fasta(mb2_fasta* f) {
     free(f->off); free(f->seq);
     memset(f, 0, sizeof(*f));
 }
+
+int mb2_format_tab(const int32_t* t_id, const int32_t* q_id, const int32_t* strand, const int32_t* start1, const int32_t* end1,
+                   const int32_t* start2, const int32_t* end2, const int32_t* score, const int32_t* nmatch, const int32_t* ncols,
+                   uint64_t n, const char* const* tnames, int nt, const char* const* qnames, int nq, double min_len, double min_idt,
+                   mb2_tab_text* out) {
+    return guarded([&] {
+        MB2_REQUIRE(out && tnames && qnames, MB2_ERR_INVALID_ARG, "mb2_format_tab: null argument");
+        memset(out, 0, sizeof(*out));
+        TabText t;
+        format_tab_blocks(t_id, q_id, strand, start1, end1, start2, end2, score, nmatch, ncols, n, tnames, nt, qnames, nq, min_len, min_idt, t);
+        const size_t nb = t.t_id.size();
+        out->nblocks = nb; out->nbytes = t.text.size();
+        out->text = (char*)malloc(t.text.size() + 1);
+        out->t_id = (int32_t*)malloc((nb + 1) * sizeof(int32_t)); out->q_id = (int32_t*)malloc((nb + 1) * sizeof(int32_t));
+        out->off = (uint64_t*)malloc((nb + 1) * sizeof(uint64_t)); out->nrows = (uint32_t*)malloc((nb + 1) * sizeof(uint32_t));
+        MB2_REQUIRE(out->text && out->t_id && out->q_id && out->off && out->nrows, MB2_ERR_INTERNAL, "mb2_format_tab: out of memory");
+        memcpy(out->text, t.text.data(), t.text.size()); out->text[t.text.size()] = 0;
+        if (nb) {
+            memcpy(out->t_id, t.t_id.data(), nb * sizeof(int32_t)); memcpy(out->q_id, t.q_id.data(), nb * sizeof(int32_t));
+            memcpy(out->nrows, t.nrows.data(), nb * sizeof(uint32_t));
+        }
+        memcpy(out->off, t.off.data(), t.off.size() * sizeof(uint64_t));
+    });
+}
+void mb2_free_tab_text(mb2_tab_text* t) {
+    if (!t) return;
+    free(t->text); free(t->t_id); free(t->q_id); free(t->off); free(t->nrows);
+    memset(t, 0, sizeof(*t));
+}
 }  // extern "C"

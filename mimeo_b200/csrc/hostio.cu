@@ -12,6 +12,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string_view>
 #include <thread>
@@ -266,6 +269,95 @@ void fasta_read_file(const char* path, int nthreads, FastaData& out) {
             }
         }
     });
+}
+
+
+// ---------------------------------------------------------------------------------------------- .tab formatter
+// The awk/sed/sort filter that follows every LASTZ call of the reference (wrappers.py:1044-1056): keep length1 >= minLen and
+// printed identity ('%.1f') >= minIdt, print the 10 columns, sort each (target, query) block by start1 numerically and then by
+// the whole line's bytes. Blocks come out ordered by (t_id, q_id).
+namespace {
+inline char* put_int(char* p, long long v) {
+    char tmp[24];
+    int k = 0;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) *p++ = '-';
+    while (k) *p++ = tmp[--k];
+    return p;
+}
+// '%.1f' of 100*nm/nc exactly as printf rounds the double; the integer fast path is taken unless the value sits within 1e-6 of
+// a rounding tie, where the C library decides
+inline char* put_pct(char* p, int nm, int nc, double& printed) {
+    const double ratio = nc > 0 ? 100.0 * (double)nm / (double)nc : 0.0;
+    const double t = ratio * 10.0 + 0.5;
+    const double fl = floor(t);
+    if (ratio >= 0.0 && ratio < 1e7 && t - fl > 1e-6 && (fl + 1.0) - t > 1e-6) {
+        const long long tenths = (long long)fl;
+        p = put_int(p, tenths / 10); *p++ = '.'; *p++ = (char)('0' + tenths % 10);
+        printed = (double)tenths / 10.0;
+        return p;
+    }
+    char buf[40];
+    const int n = snprintf(buf, sizeof(buf), "%.1f", ratio);
+    memcpy(p, buf, (size_t)n);
+    printed = strtod(buf, nullptr);
+    return p + n;
+}
+}  // namespace
+
+void format_tab_blocks(const int32_t* t_id, const int32_t* q_id, const int32_t* strand, const int32_t* start1, const int32_t* end1,
+                       const int32_t* start2, const int32_t* end2, const int32_t* score, const int32_t* nmatch, const int32_t* ncols,
+                       uint64_t n, const char* const* tnames, int nt, const char* const* qnames, int nq, double min_len, double min_idt,
+                       TabText& out) {
+    out = TabText();
+    struct Row { int32_t t, q, s1; uint32_t len; size_t off; };
+    std::vector<Row> rows;
+    rows.reserve(n);
+    std::vector<size_t> tlen(nt), qlen(nq);
+    size_t maxname = 0;
+    for (int k = 0; k < nt; k++) { tlen[k] = strlen(tnames[k]); maxname = std::max(maxname, tlen[k]); }
+    for (int k = 0; k < nq; k++) { qlen[k] = strlen(qnames[k]); maxname = std::max(maxname, qlen[k]); }
+    std::vector<char> pool;
+    pool.resize((size_t)n * (2 * maxname + 96) + 16);
+    char* w = pool.data();
+    for (uint64_t k = 0; k < n; k++) {
+        const long long len1 = (long long)end1[k] - (long long)start1[k] + 1;
+        if ((double)len1 < min_len) continue;                                    // awk '0+$5 >= minLen'
+        MB2_REQUIRE(t_id[k] >= 0 && t_id[k] < nt && q_id[k] >= 0 && q_id[k] < nq, -2, "format_tab: scaffold index out of range");
+        char* const r0 = w;
+        memcpy(w, tnames[t_id[k]], tlen[t_id[k]]); w += tlen[t_id[k]];
+        *w++ = '\t'; *w++ = '+'; *w++ = '\t';
+        w = put_int(w, start1[k]); *w++ = '\t';
+        w = put_int(w, end1[k]); *w++ = '\t';
+        memcpy(w, qnames[q_id[k]], qlen[q_id[k]]); w += qlen[q_id[k]];
+        *w++ = '\t'; *w++ = strand[k] ? '-' : '+'; *w++ = '\t';
+        w = put_int(w, start2[k]); *w++ = '\t';
+        w = put_int(w, end2[k]); *w++ = '\t';
+        w = put_int(w, score[k]); *w++ = '\t';
+        double printed;
+        w = put_pct(w, nmatch[k], ncols[k], printed);                            // what LASTZ prints, and what awk then compares
+        *w++ = '\n';
+        if (printed < min_idt) { w = r0; continue; }                             // awk '0+$13 >= minIdt'
+        rows.push_back(Row{t_id[k], q_id[k], start1[k], (uint32_t)(w - r0), (size_t)(r0 - pool.data())});
+    }
+    const char* base = pool.data();
+    std::sort(rows.begin(), rows.end(), [base](const Row& a, const Row& b) {
+        if (a.t != b.t) return a.t < b.t;
+        if (a.q != b.q) return a.q < b.q;
+        if (a.s1 != b.s1) return a.s1 < b.s1;
+        const int c = memcmp(base + a.off, base + b.off, std::min(a.len, b.len));   // bytes, shorter prefix first
+        return c != 0 ? c < 0 : a.len < b.len;
+    });
+    out.text.reserve((size_t)(w - pool.data()));
+    for (size_t k = 0; k < rows.size(); k++) {
+        if (k == 0 || rows[k].t != rows[k - 1].t || rows[k].q != rows[k - 1].q) {
+            out.t_id.push_back(rows[k].t); out.q_id.push_back(rows[k].q); out.off.push_back(out.text.size()); out.nrows.push_back(0);
+        }
+        out.nrows.back()++;
+        out.text.append(base + rows[k].off, rows[k].len);
+    }
+    out.off.push_back(out.text.size());
 }
 
 }  // namespace mb2

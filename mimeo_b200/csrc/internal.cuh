@@ -87,6 +87,17 @@ struct FastaData {
 };
 void fasta_read_file(const char* path, int nthreads, FastaData& out);
 
+struct TabText {                       // filtered, sorted .tab rows grouped by (t_id, q_id) block
+    std::string text;                  // all rows, blocks back to back
+    std::vector<int32_t> t_id, q_id;   // per block
+    std::vector<uint64_t> off;         // nblocks + 1 byte offsets into text
+    std::vector<uint32_t> nrows;       // per block
+};
+void format_tab_blocks(const int32_t* t_id, const int32_t* q_id, const int32_t* strand, const int32_t* start1, const int32_t* end1,
+                       const int32_t* start2, const int32_t* end2, const int32_t* score, const int32_t* nmatch, const int32_t* ncols,
+                       uint64_t n, const char* const* tnames, int nt, const char* const* qnames, int nq, double min_len, double min_idt,
+                       TabText& out);
+
 // counters layout (device, unsigned long long[16])
 enum { CNT_SURV = 0, CNT_SEED_HITS = 1, CNT_LEADERS = 2, CNT_S1_CELLS = 3, CNT_HSPS = 4, CNT_EXTENDED = 5, CNT_S2_CELLS = 6,
        CNT_GAPPED_CELLS = 7, CNT_ALNS = 8, CNT_ANCHORS = 9, CNT_ERR = 10, CNT_WORK = 11, CNT_N = 16 };

@@ -189,3 +189,26 @@ def odd_genome(rng, k):
         g['a'] = a
         g['b'] = mutate(rng, a, 0.01, 0.0005)
     return g
+
+
+def py_tab_blocks(hits, tnames, qnames, minLen, minIdt):
+    """Plain-Python statement of the filter that follows every LASTZ call (wrappers.py:1044-1056), the checker of the
+    native formatter: keep length1 >= minLen and printed identity >= minIdt, 10 columns, per (t, q) block sorted by
+    start1 numerically, then by the whole line."""
+    out = {}
+    for k in range(len(hits['t_id'])):
+        s1, e1 = int(hits['start1'][k]), int(hits['end1'][k])
+        if e1 - s1 + 1 < minLen:
+            continue
+        nm, nc = int(hits['nmatch'][k]), int(hits['ncols'][k])
+        pct = '%.1f' % (100.0 * nm / nc) if nc else '0.0'
+        if float(pct) < float(minIdt):
+            continue
+        t, q = int(hits['t_id'][k]), int(hits['q_id'][k])
+        row = '\t'.join((tnames[t], '+', str(s1), str(e1), qnames[q], '-' if hits['strand'][k] else '+',
+                         str(int(hits['start2'][k])), str(int(hits['end2'][k])), str(int(hits['score'][k])), pct))
+        out.setdefault((t, q), []).append(row)
+    for key, rows in out.items():
+        rows.sort(key=lambda r: (float(r.split('\t')[2]), r.encode()))
+        out[key] = [r + '\n' for r in rows]
+    return out

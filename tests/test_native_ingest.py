@@ -120,3 +120,48 @@ def test_tab_projection_errors(tmp_path):
     p.write_text('#only a header\n')
     names, ids, start, end = engine.parse_tab_hits(str(p))
     assert names == [] and len(ids) == 0
+
+
+def test_native_tab_formatter_matches_plain_statement():
+    """mb2_format_tab against the plain-Python statement of the awk/sed/sort filter: ties, rounding of the printed identity at
+    the threshold, zero columns, duplicated rows, names that are prefixes of each other."""
+    from mimeo_b200 import align as A
+    from tests.helpers import py_tab_blocks
+    rng = np.random.default_rng(3)
+    names = ['s10', 'S3', 's2', 's', 'zz_long.name']
+    for trial in range(25):
+        n = int(rng.integers(0, 3000))
+        nc = rng.integers(0, 5000, n)
+        nm = (nc * rng.uniform(0.5, 1, n)).astype(np.int64)
+        s1 = rng.integers(1, 2000, n)
+        hits = {'t_id': rng.integers(0, 5, n).astype(np.int32), 'q_id': rng.integers(0, 5, n).astype(np.int32),
+                'strand': rng.integers(0, 2, n).astype(np.int32), 'start1': s1.astype(np.int32),
+                'end1': (s1 + rng.integers(0, 300, n)).astype(np.int32), 'start2': rng.integers(1, 9999, n).astype(np.int32),
+                'end2': rng.integers(1, 99999, n).astype(np.int32), 'score': rng.integers(3000, 10**6, n).astype(np.int32),
+                'nmatch': nm.astype(np.int32), 'ncols': nc.astype(np.int32)}
+        if n > 20:
+            for k in range(5):                               # exact duplicates and near-duplicates
+                for f in hits:
+                    hits[f][k + 5] = hits[f][k]
+            hits['score'][7] = hits['score'][2] + 1
+            hits['nmatch'][11], hits['ncols'][11] = 7995, 10000      # 79.95 -> '80.0' (binary rounding decides)
+            hits['nmatch'][12], hits['ncols'][12] = 1599, 2000       # 79.95 again with another denominator
+            hits['end1'][11] = hits['start1'][11] + 99               # length1 = 100 exactly
+            hits['end1'][12] = hits['start1'][12] + 98               # length1 = 99
+        got = A.tab_blocks(hits, names, names, 100, 80)
+        assert got == py_tab_blocks(hits, names, names, 100, 80), trial
+
+
+def test_native_tab_formatter_rounds_the_identity_like_printf():
+    """Every ratio nm/nc with nc < 200: the printed '%.1f' (integer fast path or C library at ties) must equal Python's."""
+    from mimeo_b200 import align as A
+    from tests.helpers import py_tab_blocks
+    for nc in range(1, 200):
+        nm = np.arange(0, nc + 1)
+        n = len(nm)
+        pos = np.arange(1, n + 1).astype(np.int32)
+        hits = {'t_id': np.zeros(n, np.int32), 'q_id': np.zeros(n, np.int32), 'strand': np.zeros(n, np.int32), 'start1': pos,
+                'end1': pos + 200, 'start2': np.ones(n, np.int32), 'end2': np.ones(n, np.int32), 'score': np.full(n, 3000, np.int32),
+                'nmatch': nm.astype(np.int32), 'ncols': np.full(n, nc, np.int32)}
+        for min_idt in (0, 80):
+            assert A.tab_blocks(hits, ['a'], ['a'], 100, min_idt) == py_tab_blocks(hits, ['a'], ['a'], 100, min_idt), (nc, min_idt)
