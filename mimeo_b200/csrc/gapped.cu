@@ -191,7 +191,7 @@ __device__ __forceinline__ void gp_cell(Cell<P>& self, int uh, int ud, P uhp, P 
 // the window base and the sequence-end test are therefore constants of an epoch; warps outside the range only keep
 // the barrier company.
 // Returns false if the payload type cannot represent the result (16-bit columns overflowed): rerun with P = uint64_t.
-constexpr int GP_EPOCH = 8;
+constexpr int GP_EPOCH = 16;
 template <typename P, typename S, int DIR>
 __device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E, int Y,
                                  GpShared<P, S>& sm, Ext& r, unsigned& ncell, int& err) {
