@@ -768,7 +768,6 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
             W.e_score = e_score.get(); W.e_di = e_di.get(); W.e_dj = e_dj.get(); W.e_nm = e_nm.get(); W.e_nc = e_nc.get();
             W.stamp = stamp.get(); W.items_narrow = items_n.get(); W.items_wide = items_w.get(); W.counts = counts.get();
             static const bool dbg = getenv("MB2_GP_DEBUG") != nullptr;
-            static const int shape = getenv("MB2_GP_SHAPE") ? atoi(getenv("MB2_GP_SHAPE")) : 0;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (dbg) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); }
             for (uint32_t round = 1;; round++) {
@@ -790,17 +789,10 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
                 auto go = [&](auto kern, uint32_t count, int nt, const uint32_t* items) {
                     launch(kern, count, nt, 0, tv, qv, W, items, h.tile.get(), p.gap_open, p.gap_extend, p.ydrop, d_same.get(), counters);
                 };
-                using S0 = GpShape<128, 8>; using S1 = GpShape<64, 16>; using S2 = GpShape<256, 4>;
-                if (h_counts[0]) {
-                    if (shape == 1) go(gp_extend_kernel<uint32_t, S1, 6>, h_counts[0], S1::NT, items_n.get());
-                    else if (shape == 2) go(gp_extend_kernel<uint32_t, S2, 3>, h_counts[0], S2::NT, items_n.get());
-                    else go(gp_extend_kernel<uint32_t, S0, 5>, h_counts[0], S0::NT, items_n.get());
-                }
-                if (h_counts[1]) {
-                    if (shape == 1) go(gp_extend_kernel<uint64_t, S1, 4>, h_counts[1], S1::NT, items_w.get());
-                    else if (shape == 2) go(gp_extend_kernel<uint64_t, S2, 2>, h_counts[1], S2::NT, items_w.get());
-                    else go(gp_extend_kernel<uint64_t, S0, 3>, h_counts[1], S0::NT, items_w.get());
-                }
+                // 128 threads x 8 diagonals (window of 1024): measured best against 64 x 16 and 256 x 4; 5 CTAs per SM
+                using S0 = GpShape<128, 8>;
+                if (h_counts[0]) go(gp_extend_kernel<uint32_t, S0, 5>, h_counts[0], S0::NT, items_n.get());
+                if (h_counts[1]) go(gp_extend_kernel<uint64_t, S0, 3>, h_counts[1], S0::NT, items_w.get());
                 if (dbg) cudaEventRecord(ev1, cx.stream);
             }
             if (dbg) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
