@@ -91,7 +91,6 @@ int mb2_init(int device) {
 void mb2_shutdown(void) {
     if (g_ctx.ready) {
         cudaStreamSynchronize(g_ctx.stream);
-        if (g_ctx.pinned) { cudaFreeHost(g_ctx.pinned); g_ctx.pinned = nullptr; g_ctx.pinned_bytes = 0; }
         cudaStreamDestroy(g_ctx.stream);
         g_ctx.stream = nullptr;
         g_ctx.ready = false;

@@ -39,10 +39,6 @@ struct Ctx {
     unsigned long long launches = 0;   // kernels of THIS library launched so far
     // optional per-kernel timing with CUDA events on the library stream (bench.py's roofline leg)
     bool debug_sync = false;
-    // grow-only pinned staging buffer for host->device genome uploads (cudaMallocHost/cudaFreeHost per call cost
-    // milliseconds and occasionally tens of milliseconds)
-    uint8_t* pinned = nullptr;
-    size_t pinned_bytes = 0;
     bool prof = false;
     struct ProfRec { std::string tag; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;

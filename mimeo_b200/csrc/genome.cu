@@ -118,19 +118,14 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
     try {
         layout(*g, lens, n);
         Ctx& cx = ctx();
-        // stage ASCII with 'N' padding in pinned host memory, one H2D copy, pack on the device
+        // ASCII image of the padded coordinate space on the device: pads are 'N' (device memset), every scaffold is copied
+        // straight from the caller's buffer to its offset (DMA when that buffer is pinned; the driver stages pageable
+        // memory itself), then packed on the device
         const size_t nbytes = g->G + 64;   // = (G/32 + 2) * 32
-        if (cx.pinned_bytes < nbytes) {
-            if (cx.pinned) cudaFreeHost(cx.pinned);
-            cx.pinned = nullptr; cx.pinned_bytes = 0;
-            MB2_CUDA(cudaMallocHost((void**)&cx.pinned, nbytes + (nbytes >> 2)));
-            cx.pinned_bytes = nbytes + (nbytes >> 2);
-        }
-        uint8_t* h = cx.pinned;
-        memset(h, 'N', nbytes);
-        for (int s = 0; s < n; s++) memcpy(h + g->off[s], seqs[s], lens[s]);
         DevBuf<uint8_t> d_ascii(nbytes);
-        MB2_CUDA(cudaMemcpyAsync(d_ascii.get(), h, nbytes, cudaMemcpyHostToDevice, cx.stream));
+        MB2_CUDA(cudaMemsetAsync(d_ascii.get(), 'N', nbytes, cx.stream));
+        for (int s = 0; s < n; s++)
+            if (lens[s]) MB2_CUDA(cudaMemcpyAsync(d_ascii.get() + g->off[s], seqs[s], lens[s], cudaMemcpyHostToDevice, cx.stream));
         const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
         g->pk.alloc(nwords); g->nm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
         g->d_off.alloc(n); g->d_len.alloc(n);
@@ -139,7 +134,7 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get(), g->codes.get());
         g->d_nfree.alloc(n);
         launch(nfree_kernel, n, 256, 0, g->nm.get(), g->d_off.get(), g->d_len.get(), g->d_nfree.get());
-        MB2_CUDA(cudaStreamSynchronize(cx.stream));      // the staging buffer is reusable after this
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));      // the caller's buffers are free again after this
         g->id = next_genome_id(); g->fwd_src_id = g->id; g->nfwd = n;
     } catch (...) { delete g; throw; }
     return g;
