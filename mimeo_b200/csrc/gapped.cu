@@ -35,7 +35,7 @@ template <int NT_, int SLOTS_> struct GpShape {
     static constexpr int MAXBAND = ND - 64;   // widest alive diagonal range the circular window can hold
 };
 constexpr int NEG_INF = INT_MIN / 4;
-constexpr int GP_CLUSTER_GAP = 300;      // chain members further apart than this (either axis) start a new speculation cluster
+constexpr int GP_CLUSTER_GAP = 1000;     // chain members further apart than this (either axis) start a new speculation cluster
 constexpr int GP_NARROW_ABORT_K = 140000;  // 16-bit payload run: beyond this anti-diagonal every cell has >= 65536 columns behind it
 
 __device__ __forceinline__ int sub_lut3(uint32_t idx) {
