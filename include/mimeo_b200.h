@@ -198,6 +198,21 @@ MB2_API int mb2_format_tab(const int32_t* t_id, const int32_t* q_id, const int32
                            mb2_tab_text* out);
 MB2_API void mb2_free_tab_text(mb2_tab_text* t);
 
+/* `mimeo map` post-processing: import_Align + writeGFFlines of the reference (wrappers.py:33-117, 443-522) in one pass over
+ * the .tab file. Keeps rows with int(end1) - int(start1) >= min_len and float(identity) >= min_idt, sorts them (stable) by the
+ * STRING values of (name1, start1, end1, strand1), numbers them prefix_0001.. (zero-filled to the width of the row count;
+ * prefix NULL or "" = "BHit") and returns one GFF3 feature line per row:
+ * name1, mimeo-map, ftype, start1, end1, score, strand1, ., ID=..;identity=..;B_locus=name2_strand2_start2_end2.
+ * The header lines (##gff-version, ##sequence-region, ##seqid) are the caller's. Text owned by the library. */
+typedef struct mb2_text {
+    char* text;
+    uint64_t nbytes;
+    uint64_t nrows;
+} mb2_text;
+MB2_API int mb2_map_gff(const char* tab_path, const char* prefix, double min_len, double min_idt, const char* ftype, int nthreads,
+                        mb2_text* out);
+MB2_API void mb2_free_text(mb2_text* t);
+
 /* ---- device primitives exposed for parity tests ------------------------------------------- */
 /* Stable LSD radix sort of HOST arrays on bits [begin_bit, end_bit) (vals may be NULL). */
 MB2_API int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);

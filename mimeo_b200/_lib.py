@@ -47,6 +47,10 @@ class TabText(C.Structure):
                 ('nrows', c_u32p), ('nblocks', C.c_uint64)]
 
 
+class Text(C.Structure):
+    _fields_ = [('text', C.POINTER(C.c_char)), ('nbytes', C.c_uint64), ('nrows', C.c_uint64)]
+
+
 class Segments(C.Structure):
     _fields_ = [('chrom', c_i32p), ('start', c_i32p), ('end', c_i32p), ('n', C.c_uint64), ('on_device', C.c_int)]
 
@@ -85,6 +89,8 @@ SIGNATURES = {
     'mb2_format_tab': (C.c_int, [C.c_void_p] * 10 + [C.c_uint64, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int,
                                  C.c_double, C.c_double, C.POINTER(TabText)]),
     'mb2_free_tab_text': (None, [C.POINTER(TabText)]),
+    'mb2_map_gff': (C.c_int, [C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_char_p, C.c_int, C.POINTER(Text)]),
+    'mb2_free_text': (None, [C.POINTER(Text)]),
     'mb2_test_sort_u32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     'mb2_test_sort_u64': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     'mb2_test_scan_u32': (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),

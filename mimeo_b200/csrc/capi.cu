@@ -462,4 +462,22 @@ void mb2_free_tab_text(mb2_tab_text* t) {
     free(t->text); free(t->t_id); free(t->q_id); free(t->off); free(t->nrows);
     memset(t, 0, sizeof(*t));
 }
+
+int mb2_map_gff(const char* tab_path, const char* prefix, double min_len, double min_idt, const char* ftype, int nthreads, mb2_text* out) {
+    return guarded([&] {
+        MB2_REQUIRE(tab_path && out, MB2_ERR_INVALID_ARG, "mb2_map_gff: null argument");
+        memset(out, 0, sizeof(*out));
+        std::string text;
+        out->nrows = map_gff_rows(tab_path, prefix, min_len, min_idt, ftype, nthreads, text);
+        out->nbytes = text.size();
+        out->text = (char*)malloc(text.size() + 1);
+        MB2_REQUIRE(out->text, MB2_ERR_INTERNAL, "mb2_map_gff: out of memory");
+        memcpy(out->text, text.data(), text.size()); out->text[text.size()] = 0;
+    });
+}
+void mb2_free_text(mb2_text* t) {
+    if (!t) return;
+    free(t->text);
+    memset(t, 0, sizeof(*t));
+}
 }  // extern "C"

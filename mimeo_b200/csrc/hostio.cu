@@ -360,4 +360,108 @@ void format_tab_blocks(const int32_t* t_id, const int32_t* q_id, const int32_t* 
     out.off.push_back(out.text.size());
 }
 
+
+// ---------------------------------------------------------------------------------------------- mimeo map: .tab -> GFF3 rows
+// import_Align + writeGFFlines of the reference (wrappers.py:33-117, 443-522) without the DataFrame: rows whose first
+// non-blank character is not '#', split on white space; keep int(end1) - int(start1) >= minLen and float(identity) >= minIdt;
+// stable sort by the STRING values of (tName, tStart, tEnd, tStrand); UID = prefix_<row number zero-filled to the width of
+// the row count>; one GFF3 line per row with every field printed exactly as it stands in the file.
+namespace {
+struct MapRow { uint64_t off; uint16_t fo[10], fl[10]; };
+struct MapChunk { std::vector<MapRow> rows; std::string err; size_t err_off = 0; };
+inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+void parse_map_range(const char* base, size_t lo, size_t hi, double min_len, double min_idt, MapChunk& c) {
+    const char* p = base + lo;
+    const char* const end = base + hi;
+    while (p < end) {
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* le = nl ? nl : end;
+        const char* q = p;
+        while (q < le && is_space(*q)) q++;
+        if (!(q < le && *q == '#')) {
+            MapRow r; r.off = (uint64_t)(p - base);
+            int nf = 0;
+            while (nf < 10) {
+                while (q < le && is_space(*q)) q++;
+                if (q >= le) break;
+                const char* b = q;
+                while (q < le && !is_space(*q)) q++;
+                if (b - p > 65535 || q - b > 65535) { nf = -1; break; }
+                r.fo[nf] = (uint16_t)(b - p); r.fl[nf] = (uint16_t)(q - b);
+                nf++;
+            }
+            int64_t s1 = 0, e1 = 0;
+            double idt = 0;
+            bool ok = nf == 10 && parse_int(p + r.fo[2], p + r.fo[2] + r.fl[2], s1) && parse_int(p + r.fo[3], p + r.fo[3] + r.fl[3], e1);
+            if (ok) {
+                char tmp[64];
+                const size_t L = r.fl[9];
+                ok = L > 0 && L < sizeof(tmp);
+                if (ok) { memcpy(tmp, p + r.fo[9], L); tmp[L] = 0; char* endp = nullptr; idt = strtod(tmp, &endp); ok = endp == tmp + L; }
+            }
+            if (!ok) {
+                if (c.err.empty()) { c.err = nf != 10 ? "fewer than 10 fields" : "start1/end1 must be integers and identity a number"; c.err_off = (size_t)(p - base); }
+                return;
+            }
+            if ((double)(e1 - s1) >= min_len && idt >= min_idt) c.rows.push_back(r);
+        }
+        p = nl ? nl + 1 : end;
+    }
+}
+}  // namespace
+
+uint64_t map_gff_rows(const char* path, const char* prefix, double min_len, double min_idt, const char* ftype, int nthreads, std::string& out) {
+    out.clear();
+    MappedFile mf(path);
+    if (mf.n == 0) return 0;
+    const int nt = pick_threads(nthreads, mf.n);
+    std::vector<size_t> cut(nt + 1, 0);
+    cut[nt] = mf.n;
+    for (int t = 1; t < nt; t++) {
+        const size_t pos = mf.n / nt * t;
+        const char* nl = (const char*)memchr(mf.p + pos, '\n', mf.n - pos);
+        cut[t] = nl ? (size_t)(nl - mf.p) + 1 : mf.n;
+    }
+    for (int t = 1; t <= nt; t++) cut[t] = std::max(cut[t], cut[t - 1]);
+    std::vector<MapChunk> chunks(nt);
+    run_threads(nt, [&](int t) { parse_map_range(mf.p, cut[t], cut[t + 1], min_len, min_idt, chunks[t]); });
+    size_t total = 0;
+    for (int t = 0; t < nt; t++) {
+        if (!chunks[t].err.empty()) {
+            size_t line = 1;
+            for (size_t k = 0; k < chunks[t].err_off; k++) line += mf.p[k] == '\n';
+            throw Error(-4, std::string(path) + ": line " + std::to_string(line) + ": " + chunks[t].err);
+        }
+        total += chunks[t].rows.size();
+    }
+    std::vector<MapRow> rows;
+    rows.reserve(total);
+    for (int t = 0; t < nt; t++) rows.insert(rows.end(), chunks[t].rows.begin(), chunks[t].rows.end());   // file order
+    const char* base = mf.p;
+    auto field = [base](const MapRow& r, int f) { return std::string_view(base + r.off + r.fo[f], r.fl[f]); };
+    std::stable_sort(rows.begin(), rows.end(), [&](const MapRow& a, const MapRow& b) {
+        for (int f : {0, 2, 3, 1}) {                                   // tName, tStart, tEnd, tStrand as strings
+            const int c = field(a, f).compare(field(b, f));
+            if (c) return c < 0;
+        }
+        return false;
+    });
+    const std::string stem = (prefix && *prefix) ? prefix : "BHit";
+    const int width = (int)std::to_string(total).size();
+    const std::string ft = ftype ? ftype : "BHit";
+    out.reserve(total * 160);
+    char num[32];
+    for (size_t k = 0; k < rows.size(); k++) {
+        const MapRow& r = rows[k];
+        auto add = [&](int f) { out.append(base + r.off + r.fo[f], r.fl[f]); };
+        add(0); out += "\tmimeo-map\t"; out += ft; out += '\t'; add(2); out += '\t'; add(3); out += '\t'; add(8); out += '\t'; add(1);
+        out += "\t.\tID="; out += stem; out += '_';
+        snprintf(num, sizeof(num), "%0*llu", width, (unsigned long long)(k + 1));
+        out += num;
+        out += ";identity="; add(9); out += ";B_locus="; add(4); out += '_'; add(5); out += '_'; add(6); out += '_'; add(7); out += '\n';
+    }
+    return total;
+}
+
 }  // namespace mb2

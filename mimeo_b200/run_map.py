@@ -10,7 +10,7 @@ from typing import List
 from ._cli_common import add_loglevel, add_version
 from .logs import init_logging
 from .utils import chromlens, get_all_pairs, run_cmd, set_paths
-from .wrappers import import_Align, map_LZ_cmds, writeGFFlines
+from .wrappers import import_Align, map_LZ_cmds, write_map_gff, writeGFFlines  # noqa: F401  (the pandas pair stays importable)
 
 
 def mainArgs() -> argparse.Namespace:
@@ -66,11 +66,9 @@ def main() -> None:
                                       hspthresh=args.hspthresh, outfile=outtab, verbose=args.verbose)
         logging.info('Running alignments...')
         run_cmd(cmds, verbose=args.verbose, keeptemp=args.keeptemp)
-    alignments = import_Align(infile=outtab, prefix=args.prefix, minLen=args.minLen, minIdt=args.minIdt)
-    if gffout:
-        with open(gffout, 'w') as f:
-            for line in writeGFFlines(alnDF=alignments, chrlens=chrLens, ftype=args.label):
-                f.write(line)
+    # import_Align + writeGFFlines (still importable from .wrappers) in one native pass over the .tab file
+    write_map_gff(infile=outtab, gffout=gffout, chrlens=chrLens, prefix=args.prefix, minLen=args.minLen, minIdt=args.minIdt,
+                  ftype=args.label)
     if tempdir and os.path.isdir(tempdir) and not args.keeptemp:
         shutil.rmtree(tempdir)
     logging.info('Finished!')

@@ -60,6 +60,41 @@ def writeGFFlines(alnDF: pd.DataFrame = None, chrlens: List[Tuple[str, str]] = N
         yield '\t'.join([r.tName, 'mimeo-map', ftype, str(r.tStart), str(r.tEnd), str(r.score), r.tStrand, '.', attrs]) + '\n'
 
 
+def map_gff_text(infile: str, prefix: str = None, minLen: int = 100, minIdt: float = 95, ftype: str = 'BHit', nthreads: int = 0):
+    """(number of rows, GFF3 feature rows) of `mimeo map` straight from the .tab file: the native equivalent of
+    import_Align + writeGFFlines (same filter, same string sort, same UIDs, same bytes) without building a DataFrame."""
+    import ctypes as C
+    from . import _lib
+    t = _lib.Text()
+    try:
+        _lib.check(_lib.lib().mb2_map_gff(os.fsencode(infile), (str(prefix) if prefix else '').encode(), float(minLen), float(minIdt),
+                                          str(ftype).encode(), int(nthreads), C.byref(t)))
+    except _lib.Mb2Error as e:
+        raise RuntimeError(f'malformed alignment table: {e}') from None
+    try:
+        return int(t.nrows), C.string_at(t.text, int(t.nbytes)).decode('utf-8', 'surrogateescape')
+    finally:
+        _lib.lib().mb2_free_text(C.byref(t))
+
+
+def write_map_gff(infile: str, gffout: str = None, chrlens: List[Tuple[str, str]] = None, prefix: str = None, minLen: int = 100,
+                  minIdt: float = 95, ftype: str = 'BHit') -> int:
+    """What run_map.main does with import_Align + writeGFFlines (run_map.py:272-290), on the native path: exit 1 if no
+    alignment passes the filters, else write the GFF3 (if a path is given). Returns the number of features."""
+    n, body = map_gff_text(infile, prefix, minLen, minIdt, ftype)
+    if n == 0:
+        logging.warning('No alignments found in %s' % infile)
+        sys.exit(1)
+    if gffout:
+        with open(gffout, 'w', encoding='utf-8', errors='surrogateescape') as f:
+            f.write('##gff-version 3\n')
+            for name, maxlen in (chrlens or []):
+                f.write(f'##sequence-region {name} 1 {maxlen}\n')
+            f.write('##seqid\tsource\ttype\tstart\tend\tscore\tstrand\tphase\tattributes\n')
+            f.write(body)
+    return n
+
+
 def map_LZ_cmds(lzpath: str = 'lastz', pairs: List[Tuple[str, str]] = None, minIdt: float = 95, minLen: int = 100,
                 hspthresh: int = 3000, outfile: str = None, verbose: bool = False,
                 lastz_format: str = 'general:name1,strand1,start1,end1,length1,name2,strand2,start2+,end2+,length2,score,identity',

@@ -165,3 +165,60 @@ def test_native_tab_formatter_rounds_the_identity_like_printf():
                 'nmatch': nm.astype(np.int32), 'ncols': np.full(n, nc, np.int32)}
         for min_idt in (0, 80):
             assert A.tab_blocks(hits, ['a'], ['a'], 100, min_idt) == py_tab_blocks(hits, ['a'], ['a'], 100, min_idt), (nc, min_idt)
+
+
+def _pandas_map_gff(tab_path, prefix, minLen, minIdt, ftype, chrlens):
+    from mimeo_b200 import wrappers as W
+    return ''.join(W.writeGFFlines(W.import_Align(infile=tab_path, prefix=prefix, minLen=minLen, minIdt=minIdt), chrlens, ftype))
+
+
+def test_native_map_gff_equals_pandas_path_and_goldens(tmp_path):
+    """mb2_map_gff (one native pass) against import_Align + writeGFFlines (the pandas pair that mirrors the reference) and the
+    reference-generated goldens: string-order sort of coordinates, stability on full ties, UID width, filter edge (end-start)."""
+    from mimeo_b200 import wrappers as W
+    rng = np.random.default_rng(21)
+    names = ['chr1', 'chr10', 'chr2', 'Scaf_9', 's']
+    lines = ['#name1\tstrand1\tstart1\tend1\tname2\tstrand2\tstart2+\tend2+\tscore\tidentity']
+    for _ in range(5000):
+        s = int(rng.integers(1, 20000))
+        lines.append('%s\t+\t%d\t%d\t%s\t%s\t%d\t%d\t%d\t%.1f' % (names[int(rng.integers(0, 5))], s, s + int(rng.integers(90, 400)),
+                                                                  names[int(rng.integers(0, 5))], '+-'[int(rng.integers(0, 2))],
+                                                                  int(rng.integers(1, 9999)), int(rng.integers(1, 9999)),
+                                                                  int(rng.integers(3000, 99999)), rng.uniform(85, 100)))
+    lines += [lines[5], lines[5], lines[17]]                    # full ties: stability decides
+    lines.append('  # indented comment lines are skipped too')
+    tab = tmp_path / 'm.tab'
+    tab.write_text('\n'.join(lines) + '\n')
+    chrlens = [('chr1', '20000'), ('chr2', '30000')]
+    for prefix, minLen, minIdt in (('BHit', 100, 90), (None, 100, 95), ('X', 0, 0), ('p', 250, 99)):
+        n, body = W.map_gff_text(str(tab), prefix, minLen, minIdt, 'BHit')
+        want = _pandas_map_gff(str(tab), prefix, minLen, minIdt, 'BHit', None)
+        header = '##gff-version 3\n##seqid\tsource\ttype\tstart\tend\tscore\tstrand\tphase\tattributes\n'
+        assert header + body == want and n == body.count('\n') > 0
+    out = tmp_path / 'o.gff3'
+    W.write_map_gff(str(tab), str(out), chrlens, 'BHit', 100, 90, 'BHit')
+    assert out.read_text() == _pandas_map_gff(str(tab), 'BHit', 100, 90, 'BHit', chrlens)
+    # reference-generated goldens (made by running the reference's own import_Align + writeGFFlines)
+    import json
+    m = json.loads(read_golden('manifest.json'))['map']
+    g = tmp_path / 'gold_map.tab'
+    g.write_text(read_golden('map.tab'))
+    o = tmp_path / 'gold_map.gff3'
+    W.write_map_gff(str(g), str(o), [tuple(x) for x in m['chrlens']], m['prefix'], m['minLen'], m['minIdt'], m['ftype'])
+    assert o.read_text() == read_golden('map.gff3')
+    g7 = tmp_path / 'gold_kat7.tab'
+    g7.write_text(read_golden('map_kat7.tab'))
+    W.write_map_gff(str(g7), str(o), None, None, 100, 95, 'HGT')
+    assert o.read_text() == read_golden('map_kat7.gff3')
+
+
+def test_native_map_gff_empty_and_malformed(tmp_path):
+    from mimeo_b200 import wrappers as W
+    p = tmp_path / 'e.tab'
+    p.write_text('#h\nchr1\t+\t5\t50\tq\t+\t1\t2\t3000\t99.0\n')
+    assert W.map_gff_text(str(p), 'BHit', 100, 90)[0] == 0
+    with pytest.raises(SystemExit):
+        W.write_map_gff(str(p), None, None, 'BHit', 100, 90)
+    p.write_text('#h\nchr1\t+\t5\n')
+    with pytest.raises(RuntimeError, match='line 2'):
+        W.map_gff_text(str(p), 'BHit', 100, 90)
