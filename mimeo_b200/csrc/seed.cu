@@ -277,6 +277,7 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
                uint64_t* surv, uint32_t surv_cap, unsigned long long* counters) {
     const uint32_t n = q_hi - q_lo;
     if (n == 0) return;
+    MB2_REQUIRE(p.xdrop >= XT_MIN_XDROP, -2, "x-drop below 251 is not supported by the three-column extension table");
     ProfScope ps("seed_scan");
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
