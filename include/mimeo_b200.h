@@ -217,6 +217,9 @@ MB2_API void mb2_free_text(mb2_text* t);
 /* Stable LSD radix sort of HOST arrays on bits [begin_bit, end_bit) (vals may be NULL). */
 MB2_API int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);
 MB2_API int mb2_test_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);
+/* Two independent key arrays of the same length sorted by the same launches (how the coverage stage bins its +1 and -1
+   event arrays). */
+MB2_API int mb2_test_sort_u32_pair(uint32_t* keys_a, uint32_t* keys_b, uint64_t n, int begin_bit, int end_bit);
 /* Exclusive prefix sum of a HOST array, in place; *total receives the grand total. */
 MB2_API int mb2_test_scan_u32(uint32_t* data, uint64_t n, uint32_t* total);
 

@@ -356,6 +356,21 @@ int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit,
 int mb2_test_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit) {
     return guarded([&] { test_sort<uint64_t>(keys, vals, n, begin_bit, end_bit); });
 }
+int mb2_test_sort_u32_pair(uint32_t* keys_a, uint32_t* keys_b, uint64_t n, int begin_bit, int end_bit) {
+    return guarded([&] {
+        ensure_init();
+        if (n == 0) return;
+        MB2_REQUIRE(keys_a && keys_b, MB2_ERR_INVALID_ARG, "sort pair: null argument");
+        DevBuf<uint32_t> a0(n), a1(n), b0(n), b1(n);
+        MB2_CUDA(cudaMemcpyAsync(a0.get(), keys_a, n * sizeof(uint32_t), cudaMemcpyHostToDevice, g_ctx.stream));
+        MB2_CUDA(cudaMemcpyAsync(b0.get(), keys_b, n * sizeof(uint32_t), cudaMemcpyHostToDevice, g_ctx.stream));
+        NoVal* nv = nullptr;
+        const int w = radix_sort_bits<uint32_t, NoVal>(a0.get(), a1.get(), nv, nv, n, begin_bit, end_bit, b0.get(), b1.get());
+        MB2_CUDA(cudaMemcpyAsync(keys_a, w ? a1.get() : a0.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+        MB2_CUDA(cudaMemcpyAsync(keys_b, w ? b1.get() : b0.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+        MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    });
+}
 int mb2_test_scan_u32(uint32_t* data, uint64_t n, uint32_t* total) {
     return guarded([&] {
         ensure_init();

@@ -69,90 +69,72 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__
 
 __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
 
-__global__ void __launch_bounds__(COV_THREADS)
+constexpr int COV_MAX_TILES_PER_CTA = 32;
+
+__global__ void __launch_bounds__(COV_THREADS, 3)
 cov_tile_kernel(const uint32_t* __restrict__ ev_start, const uint32_t* __restrict__ ev_stop, uint32_t nev,
                 uint32_t num_tiles, uint32_t tiles_per_cta, int cov,
                 uint32_t* __restrict__ flips_staging, uint32_t* __restrict__ cta_count, uint32_t* __restrict__ cta_base,
                 int* __restrict__ err) {
     __shared__ int diff[COV_PAD_TILE];
     __shared__ uint32_t sh_scan[COV_THREADS / 32 + 1];
-    __shared__ uint32_t sh_idx[2];
+    __shared__ uint32_t s_off[COV_MAX_TILES_PER_CTA + 1], e_off[COV_MAX_TILES_PER_CTA + 1];
     const int tid = threadIdx.x;
     const uint32_t t0 = blockIdx.x * tiles_per_cta;
     const uint32_t t1 = min(t0 + tiles_per_cta, num_tiles);
-    if (tid == 0) sh_idx[0] = lower_bound_u32(ev_start, nev, t0 << COV_TILE_BITS);
-    if (tid == 32) sh_idx[1] = lower_bound_u32(ev_stop, nev, t0 << COV_TILE_BITS);
+    const uint32_t nt = t1 - t0;
+    // event ranges of all the CTA's tiles at once: 2 (nt + 1) independent binary searches, one latency chain in total
+    if (tid <= (int)nt) s_off[tid] = lower_bound_u32(ev_start, nev, (t0 + tid) << COV_TILE_BITS);
+    if (tid >= 64 && tid - 64 <= (int)nt) e_off[tid - 64] = lower_bound_u32(ev_stop, nev, (t0 + tid - 64) << COV_TILE_BITS);
     __syncthreads();
-    uint32_t is = sh_idx[0], ie = sh_idx[1];      // block-uniform running cursors into the two event arrays
-    const uint32_t out_base = is + ie;            // #flips in this CTA's range <= #events in it: disjoint staging regions
+    const uint32_t out_base = s_off[0] + e_off[0];   // #flips in this CTA's range <= #events in it: disjoint staging regions
     uint32_t out_n = 0;
 
-    uint32_t tile = t0;
-    while (tile < t1) {
-        // skip runs of tiles without events: depth is constant there, so no flip can occur
-        const uint32_t ns = (is < nev) ? ev_start[is] : COV_SENTINEL;
-        const uint32_t ne = (ie < nev) ? ev_stop[ie] : COV_SENTINEL;
-        const uint32_t nxt = min(ns, ne);
-        if (nxt == COV_SENTINEL) break;
-        const uint32_t nxt_tile = nxt >> COV_TILE_BITS;
-        if (nxt_tile >= t1) break;
-        tile = max(tile, nxt_tile);
-        const uint32_t lo = tile << COV_TILE_BITS;
-        const uint64_t hi64 = (uint64_t)lo + COV_TILE;
-        const uint32_t hi = hi64 > 0xfffffffeull ? 0xfffffffeu : (uint32_t)hi64;
-
+    for (uint32_t j = 0; j < nt; j++) {
+        const uint32_t s0 = s_off[j], s1 = s_off[j + 1], e0 = e_off[j], e1 = e_off[j + 1];
+        if (s0 == s1 && e0 == e1) continue;         // no event: depth is constant across the tile, so no flip can occur
+        const uint32_t lo = (t0 + j) << COV_TILE_BITS;
         for (int i = tid; i < COV_PAD_TILE; i += COV_THREADS) diff[i] = 0;
         __syncthreads();
-        const int base_depth = (int)is - (int)ie;   // depth at position lo-1
-        for (;;) {   // +1 events of this tile
-            const uint32_t idx = is + tid;
-            const uint32_t k = (idx < nev) ? ev_start[idx] : COV_SENTINEL;
-            const bool in = k < hi;
-            if (in && k < lo) atomicOr(err, 2);         // invariant: events of earlier tiles were consumed (never expected)
-            if (in && k >= lo) atomicAdd(&diff[pad_idx((int)(k - lo))], 1);
-            const int cnt = __syncthreads_count(in);
-            is += cnt;
-            if (cnt < COV_THREADS) break;
+        for (uint32_t i = s0 + tid; i < s1; i += COV_THREADS) {   // +1 events of this tile (independent loads)
+            const uint32_t r = ev_start[i] - lo;
+            if (r < (uint32_t)COV_TILE) atomicAdd(&diff[pad_idx((int)r)], 1); else atomicOr(err, 2);   // binning invariant
         }
-        for (;;) {   // -1 events of this tile
-            const uint32_t idx = ie + tid;
-            const uint32_t k = (idx < nev) ? ev_stop[idx] : COV_SENTINEL;
-            const bool in = k < hi;
-            if (in && k < lo) atomicOr(err, 2);
-            if (in && k >= lo) atomicAdd(&diff[pad_idx((int)(k - lo))], -1);
-            const int cnt = __syncthreads_count(in);
-            ie += cnt;
-            if (cnt < COV_THREADS) break;
+        for (uint32_t i = e0 + tid; i < e1; i += COV_THREADS) {   // -1 events
+            const uint32_t r = ev_stop[i] - lo;
+            if (r < (uint32_t)COV_TILE) atomicAdd(&diff[pad_idx((int)r)], -1); else atomicOr(err, 2);
         }
+        __syncthreads();
+        const int base_depth = (int)s0 - (int)e0;   // depth at position lo-1 = (#starts before) - (#stops before)
         // each thread owns 16 consecutive positions
         int d[COV_PER_THREAD];
         int tsum = 0;
 #pragma unroll
-        for (int j = 0; j < COV_PER_THREAD; j++) { d[j] = diff[tid * (COV_PER_THREAD + 1) + j]; tsum += d[j]; }
+        for (int k = 0; k < COV_PER_THREAD; k++) { d[k] = diff[tid * (COV_PER_THREAD + 1) + k]; tsum += d[k]; }
         uint32_t total;
         const uint32_t excl = block_excl_scan<COV_THREADS>((uint32_t)tsum, sh_scan, total);
         int depth = base_depth + (int)excl;
         bool prev = depth >= cov;
         uint32_t mask = 0;
 #pragma unroll
-        for (int j = 0; j < COV_PER_THREAD; j++) {
-            depth += d[j];
+        for (int k = 0; k < COV_PER_THREAD; k++) {
+            depth += d[k];
             const bool f = depth >= cov;
-            if (f != prev) mask |= 1u << j;
+            if (f != prev) mask |= 1u << k;
             prev = f;
         }
+        if (!__syncthreads_or(mask != 0)) continue;   // most tiles of a deep pile-up hold no flip at all
         uint32_t ftotal;
         uint32_t off = block_excl_scan<COV_THREADS>((uint32_t)__popc(mask), sh_scan, ftotal);
         uint32_t widx = out_base + out_n + off;
         while (mask) {
-            const int j = __ffs(mask) - 1;
+            const int k = __ffs(mask) - 1;
             mask &= mask - 1;
-            if (widx < 2u * nev) flips_staging[widx] = lo + tid * COV_PER_THREAD + j; else atomicOr(err, 4);   // #flips <= #events
+            if (widx < 2u * nev) flips_staging[widx] = lo + tid * COV_PER_THREAD + k; else atomicOr(err, 4);   // #flips <= #events
             widx++;
         }
         out_n += ftotal;
-        tile++;
-        // block_excl_scan ends with a barrier, so diff[] can be zeroed again
+        // every path to the next tile ends with a block barrier after the last read of diff[], so it can be zeroed again
     }
     if (tid == 0) { cta_count[blockIdx.x] = out_n; cta_base[blockIdx.x] = out_base; }
 }
@@ -196,6 +178,14 @@ cov_runs_write_kernel(const uint32_t* __restrict__ flips, const uint32_t* __rest
     seg_end[o] = (int32_t)(e - chrom_off[lo]);
 }
 
+// pinned landing zone for the few counters the host reads back (pageable targets would stage every 4-byte copy)
+struct HostInfo { int err; uint32_t nflips, nseg; };   // err and nflips mirror d_info[0..1]
+static HostInfo* host_info() {
+    static HostInfo* p = nullptr;
+    if (!p) MB2_CUDA(cudaMallocHost((void**)&p, sizeof(HostInfo)));
+    return p;
+}
+
 // -------------------------------------------------------------------------------------------------
 // Host driver. All pointers are device pointers; everything is enqueued on the library stream.
 // Returns the number of segments (device->host read of two counters is the only sync).
@@ -229,53 +219,59 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
 
     const uint32_t H = (uint32_t)nhits;
     DevBuf<uint32_t> evs0(H), evs1(H), eve0(H), eve1(H);
-    DevBuf<int> d_err(1);
-    MB2_CUDA(cudaMemsetAsync(d_err.get(), 0, sizeof(int), cx.stream));
+    DevBuf<uint32_t> d_info(2);   // [0] error bits, [1] flip count: one read-back
+    MB2_CUDA(cudaMemsetAsync(d_info.get(), 0, 2 * sizeof(uint32_t), cx.stream));
+    int* const d_err_p = (int*)d_info.get();
+    uint32_t* const d_nflips_p = d_info.get() + 1;
     { ProfScope ps("cov_events");
     launch(cov_events_kernel, cdiv(H, 256), 256, 0, d_chrom, d_start, d_end, H, d_off.get(), d_size.get(), nchrom,
-           evs0.get(), eve0.get(), d_err.get()); }
+           evs0.get(), eve0.get(), d_err_p); }
 
     int top = COV_TILE_BITS;
     while (top < 32 && ((G + COV_TILE) >> top) != 0) top++;       // sentinel (all ones) must stay the largest tile id
     NoVal* nv = nullptr;
-    int ws, we;
-    { ProfScope ps("cov_bin_events");
-      ws = radix_sort_bits<uint32_t, NoVal>(evs0.get(), evs1.get(), nv, nv, H, COV_TILE_BITS, top);
-      we = radix_sort_bits<uint32_t, NoVal>(eve0.get(), eve1.get(), nv, nv, H, COV_TILE_BITS, top); }
-    const uint32_t* s_sorted = ws ? evs1.get() : evs0.get();
-    const uint32_t* e_sorted = we ? eve1.get() : eve0.get();
+    int w;
+    { ProfScope ps("cov_bin_events");   // both event arrays through the same launches
+      w = radix_sort_bits<uint32_t, NoVal>(evs0.get(), evs1.get(), nv, nv, H, COV_TILE_BITS, top, eve0.get(), eve1.get()); }
+    const uint32_t* s_sorted = w ? evs1.get() : evs0.get();
+    const uint32_t* e_sorted = w ? eve1.get() : eve0.get();
 
     const uint32_t num_tiles = (uint32_t)((G + COV_TILE - 1) >> COV_TILE_BITS);
     const uint32_t max_ctas = (uint32_t)cx.sm_count * 4;
-    const uint32_t tiles_per_cta = (num_tiles + max_ctas - 1) / max_ctas;
+    const uint32_t tiles_per_cta = std::min<uint32_t>((num_tiles + max_ctas - 1) / max_ctas, COV_MAX_TILES_PER_CTA);
     const uint32_t nctas = (num_tiles + tiles_per_cta - 1) / tiles_per_cta;
-    DevBuf<uint32_t> staging((size_t)2 * H), cta_count(nctas), cta_base(nctas), cta_out(nctas), d_nflips(1);
+    DevBuf<uint32_t> staging((size_t)2 * H), cta_count(nctas), cta_base(nctas), cta_out(nctas);
     { ProfScope ps("cov_tile");
     launch(cov_tile_kernel, nctas, COV_THREADS, 0, s_sorted, e_sorted, H, num_tiles, tiles_per_cta,
-           min_cov < 1 ? 1 : min_cov, staging.get(), cta_count.get(), cta_base.get(), d_err.get()); }
-    exclusive_scan_u32(cta_count.get(), cta_out.get(), nctas, d_nflips.get());
+           min_cov < 1 ? 1 : min_cov, staging.get(), cta_count.get(), cta_base.get(), d_err_p); }
+    exclusive_scan_u32(cta_count.get(), cta_out.get(), nctas, d_nflips_p);
     DevBuf<uint32_t> flips((size_t)2 * H);
-    launch(cov_gather_kernel, nctas, 256, 0, staging.get(), cta_count.get(), cta_base.get(), cta_out.get(), flips.get(), 2u * H, d_err.get());
+    launch(cov_gather_kernel, nctas, 256, 0, staging.get(), cta_count.get(), cta_base.get(), cta_out.get(), flips.get(), 2u * H, d_err_p);
 
-    // runs: at most H of them (every run needs at least one start event)
-    DevBuf<uint32_t> keep(H), keep_off(H), d_nseg(1);
-    MB2_CUDA(cudaMemsetAsync(keep.get(), 0, (size_t)H * sizeof(uint32_t), cx.stream));
-    launch(cov_runs_flag_kernel, cdiv(H, 256), 256, 0, flips.get(), d_nflips.get(), min_len, keep.get(), H);
-    exclusive_scan_u32(keep.get(), keep_off.get(), H, d_nseg.get());
-
-    uint32_t h_nseg = 0; int h_err = 0; uint32_t h_nflips = 0;
-    MB2_CUDA(cudaMemcpyAsync(&h_nseg, d_nseg.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
-    MB2_CUDA(cudaMemcpyAsync(&h_err, d_err.get(), sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
-    MB2_CUDA(cudaMemcpyAsync(&h_nflips, d_nflips.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+    // first (and usually only large) host round trip: the flip count sizes everything downstream, so the run stage
+    // costs O(runs), not O(hits)
+    HostInfo* hi = host_info();
+    MB2_CUDA(cudaMemcpyAsync(hi, d_info.get(), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
     MB2_CUDA(cudaStreamSynchronize(cx.stream));
+    const int h_err = hi->err;
+    const uint32_t h_nflips = hi->nflips;
     MB2_REQUIRE((h_err & 1) == 0, -4, "coverage: invalid hit (scaffold index out of range, negative start, or start > end)");
     MB2_REQUIRE(h_err == 0, -5, std::string("coverage: internal invariant violated, code ") + std::to_string(h_err));
     MB2_REQUIRE((h_nflips & 1u) == 0 && h_nflips <= 2ull * H, -5, std::string("coverage: internal error, inconsistent flip count ") + std::to_string(h_nflips));
+    const uint32_t nruns = h_nflips >> 1;   // consecutive (rise, fall) flips
+    if (nruns == 0) return;
+    DevBuf<uint32_t> keep(nruns), keep_off(nruns), d_nseg(1);
+    launch(cov_runs_flag_kernel, cdiv(nruns, 256), 256, 0, flips.get(), d_nflips_p, min_len, keep.get(), nruns);
+    exclusive_scan_u32(keep.get(), keep_off.get(), nruns, d_nseg.get());
+    MB2_CUDA(cudaMemcpyAsync(&hi->nseg, d_nseg.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+    MB2_CUDA(cudaStreamSynchronize(cx.stream));
+    const uint32_t h_nseg = hi->nseg;
+    MB2_REQUIRE(h_nseg <= nruns, -5, "coverage: internal error, more segments than runs");
     res.chrom.alloc(h_nseg); res.start.alloc(h_nseg); res.end.alloc(h_nseg);
     res.n = h_nseg;
     if (h_nseg)
-        launch(cov_runs_write_kernel, cdiv(H, 256), 256, 0, flips.get(), d_nflips.get(), min_len, keep_off.get(),
-               d_off.get(), nchrom, res.chrom.get(), res.start.get(), res.end.get(), H, h_nseg);
+        launch(cov_runs_write_kernel, cdiv(nruns, 256), 256, 0, flips.get(), d_nflips_p, min_len, keep_off.get(),
+               d_off.get(), nchrom, res.chrom.get(), res.start.get(), res.end.get(), nruns, h_nseg);
 }
 
 }  // namespace mb2

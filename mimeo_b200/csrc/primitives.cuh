@@ -150,38 +150,73 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 keys per CTA, 512 contiguous keys per warp
 
+// One launch serves up to two independent key arrays of the same length (blockIdx.y picks the array): the coverage stage
+// bins its +1 and -1 event arrays together, which halves the launches and doubles the CTAs in flight per launch.
+// hist layout: [array][digit][CTA].
 template <typename K>
 __global__ void __launch_bounds__(RS_THREADS)
-radix_hist_kernel(const K* __restrict__ keys, uint32_t n, int shift, int bits, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t sh[256];
+radix_hist_kernel(const K* __restrict__ in0, const K* __restrict__ in1, uint32_t n, int shift, int bits, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[RS_WARPS][256];   // per-warp counters: no contention between warps
+    const K* __restrict__ keys = blockIdx.y ? in1 : in0;
     const int nbins = 1 << bits;
-    for (int i = threadIdx.x; i < nbins; i += RS_THREADS) sh[i] = 0;
+    const uint32_t mask = nbins - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&sh[0][0])[i] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * RS_TILE;
-    const uint32_t mask = nbins - 1;
-#pragma unroll 4
-    for (int i = 0; i < RS_ITEMS; i++) {
-        uint32_t idx = base + i * RS_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&sh[(uint32_t)(keys[idx] >> shift) & mask], 1u);
+    uint32_t* my = sh[warp];
+    if (n - base >= (uint32_t)RS_TILE) {
+        K key[RS_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) key[i] = keys[base + i * RS_THREADS + threadIdx.x];   // all loads in flight at once
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+            int same;
+            __match_all_sync(0xffffffffu, d, &same);
+            if (same) {                       // (nearly) sorted input: one update per warp instead of 32 colliding ones
+                if (lane == 0) atomicAdd(&my[d], 32u);
+            } else {
+                atomicAdd(&my[d], 1u);
+            }
+        }
+    } else {
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const uint32_t idx = base + i * RS_THREADS + threadIdx.x;
+            if (idx < n) atomicAdd(&my[(uint32_t)(keys[idx] >> shift) & mask], 1u);
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < nbins; i += RS_THREADS) hist[(size_t)i * gridDim.x + blockIdx.x] = sh[i];
+    for (int d = threadIdx.x; d < nbins; d += RS_THREADS) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) c += sh[w][d];
+        hist[((size_t)blockIdx.y * nbins + d) * gridDim.x + blockIdx.x] = c;
+    }
 }
 
 template <typename K, typename V, bool HAS_V>
 __global__ void __launch_bounds__(RS_THREADS)
-radix_scatter_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, const V* __restrict__ vals_in,
-                     V* __restrict__ vals_out, uint32_t n, int shift, int bits, const uint32_t* __restrict__ hist_scanned) {
+radix_scatter_kernel(const K* __restrict__ in0, const K* __restrict__ in1, K* __restrict__ out0, K* __restrict__ out1,
+                     const V* __restrict__ vals_in, V* __restrict__ vals_out, uint32_t n, int shift, int bits,
+                     const uint32_t* __restrict__ hist_scanned) {
     __shared__ uint32_t wcount[RS_WARPS][256];   // per-warp running digit counters, then warp prefixes
     __shared__ uint32_t gbase[256];
+    const K* __restrict__ keys_in = blockIdx.y ? in1 : in0;
+    K* __restrict__ keys_out = blockIdx.y ? out1 : out0;
     const int nbins = 1 << bits;
     const uint32_t mask = nbins - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
-    __syncthreads();
 
     const uint32_t wbase = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
     K key[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {   // every load of the thread in flight before the ranking rounds (their warp
+        const uint32_t idx = wbase + r * 32 + lane;   // barriers would otherwise serialise 16 global-memory latencies)
+        key[r] = idx < n ? keys_in[idx] : (K)0;
+    }
+    __syncthreads();
     uint16_t rank[RS_ITEMS];
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
@@ -191,7 +226,6 @@ radix_scatter_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, co
         const uint32_t act = __ballot_sync(0xffffffffu, valid);
         uint32_t rk = 0;
         if (valid) {
-            key[r] = keys_in[idx];
             const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
             const uint32_t peers = __match_any_sync(act, d);
             const uint32_t prev = wcount[warp][d];
@@ -203,12 +237,13 @@ radix_scatter_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, co
         rank[r] = (uint16_t)rk;
     }
     __syncthreads();
-    // per digit: exclusive prefix over warps, plus the block's global base
+    // per digit: exclusive prefix over warps, plus the block's global base (the scan ran over both arrays back to back,
+    // so the second array's offsets carry the first array's n keys)
     for (int d = threadIdx.x; d < nbins; d += RS_THREADS) {
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) { uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
-        gbase[d] = hist_scanned[(size_t)d * gridDim.x + blockIdx.x];
+        gbase[d] = hist_scanned[((size_t)blockIdx.y * nbins + d) * gridDim.x + blockIdx.x] - blockIdx.y * n;
     }
     __syncthreads();
 #pragma unroll
@@ -224,25 +259,30 @@ radix_scatter_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, co
 }
 
 // Sort keys (and payload) on bits [begin_bit, end_bit). Ping-pongs between (k0,v0) and (k1,v1);
-// returns 0 if the result is in (k0,v0), 1 if in (k1,v1).
+// returns 0 if the result is in (k0,v0), 1 if in (k1,v1). With a second key array (j0, j1; keys only, same n) both
+// arrays are sorted by the same launches and end up on the same side.
 template <typename K, typename V>
-inline int radix_sort_bits(K* k0, K* k1, V* v0, V* v1, size_t n, int begin_bit, int end_bit) {
+inline int radix_sort_bits(K* k0, K* k1, V* v0, V* v1, size_t n, int begin_bit, int end_bit, K* j0 = nullptr, K* j1 = nullptr) {
     constexpr bool HAS_V = !std::is_same<V, NoVal>::value;
     if (n == 0 || end_bit <= begin_bit) return 0;
     MB2_REQUIRE(n < 0xffffffffull, -3, "radix sort: n must be < 2^32");
+    const unsigned narr = j0 ? 2 : 1;
+    MB2_REQUIRE(narr == 1 || (!HAS_V && j1 && 2 * n < 0xffffffffull), -3, "radix sort: a second array is keys-only and needs 2n < 2^32");
     const int total_bits = end_bit - begin_bit;
     const int passes = (total_bits + 7) / 8;
     const unsigned nb = cdiv(n, RS_TILE);
-    DevBuf<uint32_t> hist((size_t)256 * nb);
+    DevBuf<uint32_t> hist((size_t)256 * nb * narr);
     int cur = 0;
     int bit = begin_bit;
     for (int p = 0; p < passes; p++) {
         const int bits = (total_bits - (bit - begin_bit) + (passes - p) - 1) / (passes - p);   // spread evenly
         K* kin = cur ? k1 : k0; K* kout = cur ? k0 : k1;
+        K* jin = cur ? j1 : j0; K* jout = cur ? j0 : j1;
         V* vin = cur ? v1 : v0; V* vout = cur ? v0 : v1;
-        launch(radix_hist_kernel<K>, nb, RS_THREADS, 0, kin, (uint32_t)n, bit, bits, hist.get());
-        exclusive_scan_u32(hist.get(), hist.get(), (size_t)(1 << bits) * nb);
-        launch(radix_scatter_kernel<K, V, HAS_V>, nb, RS_THREADS, 0, kin, kout, vin, vout, (uint32_t)n, bit, bits, hist.get());
+        launch(radix_hist_kernel<K>, dim3(nb, narr), RS_THREADS, 0, kin, jin, (uint32_t)n, bit, bits, hist.get());
+        exclusive_scan_u32(hist.get(), hist.get(), (size_t)(1 << bits) * nb * narr);
+        launch(radix_scatter_kernel<K, V, HAS_V>, dim3(nb, narr), RS_THREADS, 0, kin, jin, kout, jout, vin, vout, (uint32_t)n, bit,
+               bits, hist.get());
         cur ^= 1;
         bit += bits;
     }

@@ -40,6 +40,24 @@ def test_sort_u32_stable_bit_range(L, n, b0, b1):
     assert (kk == k[order]).all()
 
 
+@pytest.mark.parametrize('n,b0,b1,presorted', [(1, 0, 32, False), (4096, 13, 27, True), (4097, 13, 27, False), (777777, 13, 28, True),
+                                               (2_000_001, 13, 31, False), (50001, 3, 9, False)])
+def test_sort_u32_pair_one_launch_set(L, n, b0, b1, presorted):
+    """Two key arrays through the same launches: each must come out as its own stable sort (the sorted-input fast path of
+    the histogram is exercised by the presorted cases)."""
+    rng = np.random.default_rng(n + b1)
+    a = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    if presorted:
+        a.sort()
+        b[: n // 2] = np.uint32(12345 << b0)       # one digit for half of the keys
+    mask = np.uint32(((1 << (b1 - b0)) - 1) << b0)
+    wa, wb = a[np.argsort(a & mask, kind='stable')], b[np.argsort(b & mask, kind='stable')]
+    ga, gb = a.copy(), b.copy()
+    L.check(L.lib().mb2_test_sort_u32_pair(ga.ctypes.data, gb.ctypes.data, n, b0, b1))
+    assert (ga == wa).all() and (gb == wb).all()
+
+
 @pytest.mark.parametrize('n,b0,b1', [(5, 0, 64), (100001, 0, 64), (1_500_000, 0, 40), (300000, 20, 64)])
 def test_sort_u64(L, n, b0, b1):
     rng = np.random.default_rng(n)
