@@ -36,6 +36,7 @@ extern "C" {
 #define MB2_ERR_TOO_LARGE (-3)
 #define MB2_ERR_BAD_HIT (-4)
 #define MB2_ERR_INTERNAL (-5)
+#define MB2_ERR_CAPACITY (-6)   /* caller-provided output buffers too small; the needed size is reported */
 #define MB2_ERR_CUDA (-100)
 
 /* ---- library / device -------------------------------------------------------------------- */
@@ -86,6 +87,14 @@ MB2_API int mb2_coverage_segments(const int32_t* chrom, const int32_t* start, co
  * tensors' data_ptr()); the result arrays stay on the device (out->on_device = 1). */
 MB2_API int mb2_coverage_segments_dev(const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, uint64_t nhits,
                               const int64_t* chrom_sizes, int nchrom, int min_cov, int min_len, mb2_segments* out);
+
+/* Same again, writing straight into CALLER-OWNED device arrays of `capacity` elements each (a pipeline that keeps its
+ * tables in HBM, e.g. preallocated torch tensors): no allocation handed over, no copy. *n_out receives the number of
+ * segments; if that exceeds `capacity` nothing is written, the call returns MB2_ERR_CAPACITY and *n_out says how many
+ * elements a retry needs. */
+MB2_API int mb2_coverage_segments_into(const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, uint64_t nhits,
+                               const int64_t* chrom_sizes, int nchrom, int min_cov, int min_len, int32_t* d_out_chrom,
+                               int32_t* d_out_start, int32_t* d_out_end, uint64_t capacity, uint64_t* n_out);
 
 MB2_API void mb2_free_segments(mb2_segments* seg);
 

@@ -71,6 +71,8 @@ SIGNATURES = {
                                         C.c_int, C.POINTER(Segments)]),
     'mb2_coverage_segments_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int, C.POINTER(Segments)]),
+    'mb2_coverage_segments_into': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     'mb2_free_segments': (None, [C.POINTER(Segments)]),
     'mb2_genome_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     'mb2_genome_revcomp': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -120,6 +122,9 @@ def lib():
             fn.argtypes = args
         _lib = l
     return _lib
+
+
+ERR_CAPACITY = -6
 
 
 def check(rc):

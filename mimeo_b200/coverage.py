@@ -38,35 +38,28 @@ def coverage_segments(chrom, start, end, chrom_sizes, min_cov: int, min_len: int
     return out
 
 
-def coverage_segments_device(d_chrom, d_start, d_end, chrom_sizes, min_cov: int, min_len: int):
-    """torch CUDA int32 tensors in (used only as device buffers); returns torch CUDA int32 tensors."""
+def coverage_segments_device(d_chrom, d_start, d_end, chrom_sizes, min_cov: int, min_len: int, capacity: int = 0):
+    """torch CUDA int32 tensors in (used only as device buffers); returns torch CUDA int32 tensors.
+    The library writes straight into one (3, capacity) tensor allocated here (`mb2_coverage_segments_into`): nothing is
+    copied afterwards; a result larger than `capacity` (default min(#hits, 2^18)) costs one retry at the reported size."""
     import torch
     _lib.init()
     for t in (d_chrom, d_start, d_end):
         assert t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()
     sizes = np.ascontiguousarray(chrom_sizes, dtype=np.int64)
-    seg = _lib.Segments()
-    torch.cuda.current_stream().synchronize()
-    _lib.check(_lib.lib().mb2_coverage_segments_dev(d_chrom.data_ptr(), d_start.data_ptr(), d_end.data_ptr(),
-                                                    d_chrom.numel(), sizes.ctypes.data, len(sizes), int(min_cov),
-                                                    int(min_len), C.byref(seg)))
-    try:
-        n = int(seg.n)
-        outs = []
-        for p in (seg.chrom, seg.start, seg.end):
-            if n:
-                view = torch.as_tensor(_DevView(C.cast(p, C.c_void_p).value, n), device=d_chrom.device)
-                outs.append(view.clone())
-            else:
-                outs.append(torch.empty(0, dtype=torch.int32, device=d_chrom.device))
-        torch.cuda.current_stream().synchronize()
-    finally:
-        _lib.lib().mb2_free_segments(C.byref(seg))
-    return tuple(outs)
-
-
-class _DevView:
-    """Zero-copy view of a library-owned int32 device array for torch.as_tensor()."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<i4', 'data': (ptr, False), 'version': 2}
+    nhits = d_chrom.numel()
+    cap = int(capacity) if capacity > 0 else max(1, min(nhits, 1 << 18))
+    n = C.c_uint64(0)
+    while True:
+        out = torch.empty((3, cap), dtype=torch.int32, device=d_chrom.device)
+        torch.cuda.current_stream().synchronize()   # inputs (and the recycled output block) are quiescent before the library's stream touches them
+        p = out.data_ptr()
+        rc = _lib.lib().mb2_coverage_segments_into(d_chrom.data_ptr(), d_start.data_ptr(), d_end.data_ptr(), nhits, sizes.ctypes.data,
+                                                   len(sizes), int(min_cov), int(min_len), p, p + 4 * cap, p + 8 * cap, cap, C.byref(n))
+        if rc == _lib.ERR_CAPACITY and int(n.value) > cap:
+            cap = int(n.value)
+            continue
+        _lib.check(rc)
+        break
+    k = int(n.value)
+    return out[0, :k], out[1, :k], out[2, :k]

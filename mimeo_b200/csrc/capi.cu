@@ -184,6 +184,25 @@ int mb2_coverage_segments(const int32_t* chrom, const int32_t* start, const int3
     });
 }
 
+int mb2_coverage_segments_into(const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, uint64_t nhits,
+                               const int64_t* chrom_sizes, int nchrom, int min_cov, int min_len, int32_t* d_out_chrom,
+                               int32_t* d_out_start, int32_t* d_out_end, uint64_t capacity, uint64_t* n_out) {
+    CoverageResult res;
+    const int rc = guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(n_out != nullptr && chrom_sizes != nullptr, MB2_ERR_INVALID_ARG, "coverage: null argument");
+        *n_out = 0;
+        MB2_REQUIRE(nhits == 0 || (d_chrom && d_start && d_end), MB2_ERR_INVALID_ARG, "coverage: null hit arrays");
+        MB2_REQUIRE(capacity > 0 && d_out_chrom && d_out_start && d_out_end, MB2_ERR_INVALID_ARG, "coverage: null or empty output arrays");
+        res.ext_chrom = d_out_chrom; res.ext_start = d_out_start; res.ext_end = d_out_end; res.ext_cap = capacity;
+        coverage_segments_device(d_chrom, d_start, d_end, nhits, chrom_sizes, nchrom, min_cov, min_len, res);
+        MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        *n_out = res.n;
+    });
+    if (rc == MB2_ERR_CAPACITY && n_out) *n_out = res.n;
+    return rc;
+}
+
 void mb2_free_segments(mb2_segments* seg) {
     if (!seg) return;
     if (seg->on_device) {

@@ -70,6 +70,16 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__
 __device__ __forceinline__ int pad_idx(int i) { return i + (i >> 4); }
 
 constexpr int COV_MAX_TILES_PER_CTA = 32;
+constexpr int COV_PF = 2;   // events per thread and array fetched one tile ahead (covers tiles of up to 1024 + 1024 events)
+
+// Events [r0, r1) of one array for one tile: the first COV_PF * COV_THREADS of them into registers.
+__device__ __forceinline__ void cov_fetch(const uint32_t* __restrict__ ev, uint32_t r0, uint32_t r1, int tid, uint32_t (&q)[COV_PF]) {
+#pragma unroll
+    for (int k = 0; k < COV_PF; k++) {
+        const uint32_t i = r0 + tid + k * COV_THREADS;
+        q[k] = i < r1 ? ev[i] : COV_SENTINEL;
+    }
+}
 
 __global__ void __launch_bounds__(COV_THREADS, 3)
 cov_tile_kernel(const uint32_t* __restrict__ ev_start, const uint32_t* __restrict__ ev_stop, uint32_t nev,
@@ -78,7 +88,7 @@ cov_tile_kernel(const uint32_t* __restrict__ ev_start, const uint32_t* __restric
                 int* __restrict__ err) {
     __shared__ int diff[COV_PAD_TILE];
     __shared__ uint32_t sh_scan[COV_THREADS / 32 + 1];
-    __shared__ uint32_t s_off[COV_MAX_TILES_PER_CTA + 1], e_off[COV_MAX_TILES_PER_CTA + 1];
+    __shared__ uint32_t s_off[COV_MAX_TILES_PER_CTA + 2], e_off[COV_MAX_TILES_PER_CTA + 2];
     const int tid = threadIdx.x;
     const uint32_t t0 = blockIdx.x * tiles_per_cta;
     const uint32_t t1 = min(t0 + tiles_per_cta, num_tiles);
@@ -86,67 +96,133 @@ cov_tile_kernel(const uint32_t* __restrict__ ev_start, const uint32_t* __restric
     // event ranges of all the CTA's tiles at once: 2 (nt + 1) independent binary searches, one latency chain in total
     if (tid <= (int)nt) s_off[tid] = lower_bound_u32(ev_start, nev, (t0 + tid) << COV_TILE_BITS);
     if (tid >= 64 && tid - 64 <= (int)nt) e_off[tid - 64] = lower_bound_u32(ev_stop, nev, (t0 + tid - 64) << COV_TILE_BITS);
+    for (int i = tid; i < COV_PAD_TILE; i += COV_THREADS) diff[i] = 0;   // once: every tile re-zeroes what it read
+    __syncthreads();
+    if (tid == 0) { s_off[nt + 1] = s_off[nt]; e_off[nt + 1] = e_off[nt]; }   // "tile nt" is empty: the look-ahead of the last tile fetches nothing
     __syncthreads();
     const uint32_t out_base = s_off[0] + e_off[0];   // #flips in this CTA's range <= #events in it: disjoint staging regions
     uint32_t out_n = 0;
 
+    uint32_t ps[COV_PF], pe[COV_PF];   // first events of the tile about to be processed
+    cov_fetch(ev_start, s_off[0], s_off[1], tid, ps);
+    cov_fetch(ev_stop, e_off[0], e_off[1], tid, pe);
     for (uint32_t j = 0; j < nt; j++) {
         const uint32_t s0 = s_off[j], s1 = s_off[j + 1], e0 = e_off[j], e1 = e_off[j + 1];
-        if (s0 == s1 && e0 == e1) continue;         // no event: depth is constant across the tile, so no flip can occur
-        const uint32_t lo = (t0 + j) << COV_TILE_BITS;
-        for (int i = tid; i < COV_PAD_TILE; i += COV_THREADS) diff[i] = 0;
-        __syncthreads();
-        for (uint32_t i = s0 + tid; i < s1; i += COV_THREADS) {   // +1 events of this tile (independent loads)
-            const uint32_t r = ev_start[i] - lo;
-            if (r < (uint32_t)COV_TILE) atomicAdd(&diff[pad_idx((int)r)], 1); else atomicOr(err, 2);   // binning invariant
-        }
-        for (uint32_t i = e0 + tid; i < e1; i += COV_THREADS) {   // -1 events
-            const uint32_t r = ev_stop[i] - lo;
-            if (r < (uint32_t)COV_TILE) atomicAdd(&diff[pad_idx((int)r)], -1); else atomicOr(err, 2);
-        }
-        __syncthreads();
-        const int base_depth = (int)s0 - (int)e0;   // depth at position lo-1 = (#starts before) - (#stops before)
-        // each thread owns 16 consecutive positions
-        int d[COV_PER_THREAD];
-        int tsum = 0;
+        uint32_t ns[COV_PF], ne[COV_PF];   // the next tile's events stay in flight while this tile is scanned
+        cov_fetch(ev_start, s1, s_off[j + 2], tid, ns);
+        cov_fetch(ev_stop, e1, e_off[j + 2], tid, ne);
+        if (s0 != s1 || e0 != e1) {         // no event: depth is constant across the tile, so no flip can occur
+            const uint32_t lo = (t0 + j) << COV_TILE_BITS;
 #pragma unroll
-        for (int k = 0; k < COV_PER_THREAD; k++) { d[k] = diff[tid * (COV_PER_THREAD + 1) + k]; tsum += d[k]; }
-        uint32_t total;
-        const uint32_t excl = block_excl_scan<COV_THREADS>((uint32_t)tsum, sh_scan, total);
-        int depth = base_depth + (int)excl;
-        bool prev = depth >= cov;
-        uint32_t mask = 0;
+            for (int k = 0; k < COV_PF; k++) {
+                if (ps[k] != COV_SENTINEL) {
+                    const uint32_t r = ps[k] - lo;
+                    if (r < (uint32_t)COV_TILE) atomicAdd(&diff[pad_idx((int)r)], 1); else atomicOr(err, 2);   // binning invariant
+                }
+                if (pe[k] != COV_SENTINEL) {
+                    const uint32_t r = pe[k] - lo;
+                    if (r < (uint32_t)COV_TILE) atomicAdd(&diff[pad_idx((int)r)], -1); else atomicOr(err, 2);
+                }
+            }
+            for (uint32_t i = s0 + tid + COV_PF * COV_THREADS; i < s1; i += COV_THREADS) {   // crowded tiles: the rest
+                const uint32_t r = ev_start[i] - lo;
+                if (r < (uint32_t)COV_TILE) atomicAdd(&diff[pad_idx((int)r)], 1); else atomicOr(err, 2);
+            }
+            for (uint32_t i = e0 + tid + COV_PF * COV_THREADS; i < e1; i += COV_THREADS) {
+                const uint32_t r = ev_stop[i] - lo;
+                if (r < (uint32_t)COV_TILE) atomicAdd(&diff[pad_idx((int)r)], -1); else atomicOr(err, 2);
+            }
+            __syncthreads();
+            // each thread owns 16 consecutive positions
+            int* const mine = diff + tid * (COV_PER_THREAD + 1);
+            int tsum = 0;
 #pragma unroll
-        for (int k = 0; k < COV_PER_THREAD; k++) {
-            depth += d[k];
-            const bool f = depth >= cov;
-            if (f != prev) mask |= 1u << k;
-            prev = f;
+            for (int k = 0; k < COV_PER_THREAD; k++) tsum += mine[k];
+            uint32_t total;
+            const uint32_t excl = block_excl_scan_open<COV_THREADS>((uint32_t)tsum, sh_scan, total);
+            int depth = (int)s0 - (int)e0 + (int)excl;   // depth at lo-1 = (#starts before) - (#stops before), plus the threads before
+            bool prev = depth >= cov;
+            uint32_t mask = 0;
+#pragma unroll
+            for (int k = 0; k < COV_PER_THREAD; k++) {
+                depth += mine[k];
+                mine[k] = 0;                   // leave the difference array clean for the next tile
+                const bool f = depth >= cov;
+                if (f != prev) mask |= 1u << k;
+                prev = f;
+            }
+            if (__syncthreads_or(mask != 0)) {   // most tiles of a deep pile-up hold no flip at all
+                uint32_t ftotal;
+                uint32_t off = block_excl_scan<COV_THREADS>((uint32_t)__popc(mask), sh_scan, ftotal);
+                uint32_t widx = out_base + out_n + off;
+                while (mask) {
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (widx < 2u * nev) flips_staging[widx] = lo + tid * COV_PER_THREAD + k; else atomicOr(err, 4);   // #flips <= #events
+                    widx++;
+                }
+                out_n += ftotal;
+            }
+            // both paths end with a block barrier after the last access to diff[] and sh_scan[]
         }
-        if (!__syncthreads_or(mask != 0)) continue;   // most tiles of a deep pile-up hold no flip at all
-        uint32_t ftotal;
-        uint32_t off = block_excl_scan<COV_THREADS>((uint32_t)__popc(mask), sh_scan, ftotal);
-        uint32_t widx = out_base + out_n + off;
-        while (mask) {
-            const int k = __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (widx < 2u * nev) flips_staging[widx] = lo + tid * COV_PER_THREAD + k; else atomicOr(err, 4);   // #flips <= #events
-            widx++;
-        }
-        out_n += ftotal;
-        // every path to the next tile ends with a block barrier after the last read of diff[], so it can be zeroed again
+#pragma unroll
+        for (int k = 0; k < COV_PF; k++) { ps[k] = ns[k]; pe[k] = ne[k]; }
     }
     if (tid == 0) { cta_count[blockIdx.x] = out_n; cta_base[blockIdx.x] = out_base; }
 }
 
+// Per-CTA flip lists -> one dense, globally ordered flip list. Every CTA sums the counts of the CTAs before it (a few
+// thousand words at most), so no separate scan launch; the last CTA publishes the total.
 __global__ void __launch_bounds__(256)
 cov_gather_kernel(const uint32_t* __restrict__ flips_staging, const uint32_t* __restrict__ cta_count,
-                  const uint32_t* __restrict__ cta_base, const uint32_t* __restrict__ cta_out, uint32_t* __restrict__ flips,
-                  uint32_t cap, int* __restrict__ err) {
+                  const uint32_t* __restrict__ cta_base, uint32_t* __restrict__ flips, uint32_t cap,
+                  uint32_t* __restrict__ nflips_out, int* __restrict__ err) {
+    __shared__ uint32_t sh[256 / 32 + 1];
+    uint32_t part = 0;
+    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += 256) part += cta_count[i];
+    uint32_t o0;
+    block_excl_scan<256>(part, sh, o0);
     const uint32_t n = cta_count[blockIdx.x];
-    const uint32_t b0 = cta_base[blockIdx.x], o0 = cta_out[blockIdx.x];
+    const uint32_t b0 = cta_base[blockIdx.x];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *nflips_out = o0 + n;
     if ((uint64_t)b0 + n > cap || (uint64_t)o0 + n > cap) { if (threadIdx.x == 0) atomicOr(err, 8); return; }
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) flips[o0 + i] = flips_staging[b0 + i];
+    for (uint32_t i = threadIdx.x; i < n; i += 256) flips[o0 + i] = flips_staging[b0 + i];
+}
+
+// Runs -> segments in ONE launch when there are at most cap_seg runs (one CTA walks them with a running output offset):
+// minLen filter, ordered compaction, scaffold lookup. More runs than that: *nseg_out = 0xffffffff and the host takes the
+// flag / scan / write path below.
+constexpr uint32_t COV_RUNS_FUSED_MAX = 1u << 18;
+__global__ void __launch_bounds__(1024)
+cov_runs_fused_kernel(const uint32_t* __restrict__ flips, const uint32_t* __restrict__ nflips_p, int min_len,
+                      const uint32_t* __restrict__ chrom_off, int nchrom, int32_t* __restrict__ seg_chrom,
+                      int32_t* __restrict__ seg_start, int32_t* __restrict__ seg_end, uint32_t cap_seg, uint32_t* __restrict__ nseg_out) {
+    __shared__ uint32_t sh[1024 / 32 + 1];
+    const uint32_t nruns = *nflips_p >> 1;
+    if (nruns > cap_seg) { if (threadIdx.x == 0) *nseg_out = 0xffffffffu; return; }
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nruns; base += 1024) {
+        const uint32_t k = base + threadIdx.x;
+        uint32_t s = 0, e = 0;
+        bool keep = false;
+        if (k < nruns) {
+            const uint2 se = reinterpret_cast<const uint2*>(flips)[k];
+            s = se.x; e = se.y;
+            keep = (int64_t)e - (int64_t)s >= (int64_t)min_len;
+        }
+        uint32_t total;
+        const uint32_t off = block_excl_scan<1024>(keep ? 1u : 0u, sh, total);
+        if (keep) {
+            int lo = 0, hi = nchrom;            // last scaffold whose offset <= s
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (chrom_off[mid] <= s) lo = mid; else hi = mid; }
+            const uint32_t o = carry + off;
+            seg_chrom[o] = lo;
+            seg_start[o] = (int32_t)(s - chrom_off[lo]);
+            seg_end[o] = (int32_t)(e - chrom_off[lo]);
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) *nseg_out = carry;
 }
 
 // flips[2k], flips[2k+1] = rise/fall of run k in concatenated coordinates
@@ -178,29 +254,42 @@ cov_runs_write_kernel(const uint32_t* __restrict__ flips, const uint32_t* __rest
     seg_end[o] = (int32_t)(e - chrom_off[lo]);
 }
 
-// pinned landing zone for the few counters the host reads back (pageable targets would stage every 4-byte copy)
-struct HostInfo { int err; uint32_t nflips, nseg; };   // err and nflips mirror d_info[0..1]
-static HostInfo* host_info() {
-    static HostInfo* p = nullptr;
-    if (!p) MB2_CUDA(cudaMallocHost((void**)&p, sizeof(HostInfo)));
-    return p;
+// pinned landing / staging zone: the few counters the host reads back (pageable targets would stage every copy) and the
+// per-scaffold offsets and sizes it sends (no wait for a pageable upload). Reused by every call: each call ends with a
+// stream synchronisation, so the previous call's transfers are complete.
+struct HostInfo { int err; uint32_t nflips, nseg; };   // mirrors d_info[0..2]
+struct HostZone {
+    HostInfo* info = nullptr;
+    uint32_t* meta = nullptr;   // [nchrom] offsets, then [nchrom] sizes
+    size_t meta_cap = 0;
+};
+static HostZone& host_zone(size_t nchrom) {
+    static HostZone z;
+    if (!z.info) MB2_CUDA(cudaMallocHost((void**)&z.info, sizeof(HostInfo)));
+    if (2 * nchrom > z.meta_cap) {
+        if (z.meta) cudaFreeHost(z.meta);
+        z.meta = nullptr; z.meta_cap = 0;
+        const size_t cap = std::max<size_t>(2 * nchrom, 4096);
+        MB2_CUDA(cudaMallocHost((void**)&z.meta, cap * sizeof(uint32_t)));
+        z.meta_cap = cap;
+    }
+    return z;
 }
 
 // -------------------------------------------------------------------------------------------------
 // Host driver. All pointers are device pointers; everything is enqueued on the library stream.
-// Returns the number of segments (device->host read of two counters is the only sync).
+// One host round trip (error bits, flip count, segment count) unless there are more than COV_RUNS_FUSED_MAX runs.
 // -------------------------------------------------------------------------------------------------
 void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, uint64_t nhits,
                               const int64_t* h_sizes, int nchrom, int min_cov, int min_len, CoverageResult& res) {
     MB2_REQUIRE(nchrom > 0, -2, "coverage: need at least one scaffold");
     MB2_REQUIRE(nhits < 0x7fffffffull, -2, "coverage: more than 2^31-1 hits in one call");
-    std::vector<uint32_t> off(nchrom);
-    std::vector<int32_t> size32(nchrom);
+    HostZone& hz = host_zone((size_t)nchrom);
     uint64_t G = 0;
     for (int c = 0; c < nchrom; c++) {
         MB2_REQUIRE(h_sizes[c] > 0 && h_sizes[c] < 0x7fffffffll, -2, "coverage: scaffold size out of range");
-        off[c] = (uint32_t)G;
-        size32[c] = (int32_t)h_sizes[c];
+        hz.meta[c] = (uint32_t)G;
+        hz.meta[nchrom + c] = (uint32_t)h_sizes[c];
         G += (uint64_t)h_sizes[c] + 1;   // one pad base after every scaffold
         MB2_REQUIRE(G < 0xfff00000ull, -2, "coverage: concatenated genome exceeds 2^32 positions; split the call by scaffold groups");
     }
@@ -211,20 +300,20 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
         bool prev; DebugScope() : prev(ctx().debug_sync) { if (getenv("MB2_DEBUG_COV")) { cudaError_t e = cudaStreamSynchronize(ctx().stream); if (e != cudaSuccess) throw Error(-100, std::string("fault BEFORE the coverage stage: ") + cudaGetErrorString(e)); ctx().debug_sync = true; } }
         ~DebugScope() { ctx().debug_sync = prev; }
     } debug_scope;
-    DevBuf<uint32_t> d_off(nchrom);
-    DevBuf<int32_t> d_size(nchrom);
-    MB2_CUDA(cudaMemcpyAsync(d_off.get(), off.data(), nchrom * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
-    MB2_CUDA(cudaMemcpyAsync(d_size.get(), size32.data(), nchrom * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
-    MB2_CUDA(cudaStreamSynchronize(cx.stream));   // off/size32 are stack-lifetime host buffers
+    DevBuf<uint32_t> d_meta((size_t)2 * nchrom);
+    MB2_CUDA(cudaMemcpyAsync(d_meta.get(), hz.meta, (size_t)2 * nchrom * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
+    const uint32_t* const d_off = d_meta.get();
+    const int32_t* const d_size = (const int32_t*)(d_meta.get() + nchrom);
 
     const uint32_t H = (uint32_t)nhits;
     DevBuf<uint32_t> evs0(H), evs1(H), eve0(H), eve1(H);
-    DevBuf<uint32_t> d_info(2);   // [0] error bits, [1] flip count: one read-back
-    MB2_CUDA(cudaMemsetAsync(d_info.get(), 0, 2 * sizeof(uint32_t), cx.stream));
+    DevBuf<uint32_t> d_info(3);   // [0] error bits, [1] flip count, [2] segment count: one read-back
+    MB2_CUDA(cudaMemsetAsync(d_info.get(), 0, 3 * sizeof(uint32_t), cx.stream));
     int* const d_err_p = (int*)d_info.get();
     uint32_t* const d_nflips_p = d_info.get() + 1;
+    uint32_t* const d_nseg_p = d_info.get() + 2;
     { ProfScope ps("cov_events");
-    launch(cov_events_kernel, cdiv(H, 256), 256, 0, d_chrom, d_start, d_end, H, d_off.get(), d_size.get(), nchrom,
+    launch(cov_events_kernel, cdiv(H, 256), 256, 0, d_chrom, d_start, d_end, H, d_off, d_size, nchrom,
            evs0.get(), eve0.get(), d_err_p); }
 
     int top = COV_TILE_BITS;
@@ -236,42 +325,62 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
     const uint32_t* s_sorted = w ? evs1.get() : evs0.get();
     const uint32_t* e_sorted = w ? eve1.get() : eve0.get();
 
+    // one wave of CTAs (the kernel is a chain of short barrier-separated phases: a second, partial wave would idle most SMs),
+    // more only when a CTA would otherwise own more than COV_MAX_TILES_PER_CTA tiles
+    static int occ = 0;
+    if (occ == 0) {
+        MB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile_kernel, COV_THREADS, 0));
+        if (occ < 1) occ = 1;
+    }
     const uint32_t num_tiles = (uint32_t)((G + COV_TILE - 1) >> COV_TILE_BITS);
-    const uint32_t max_ctas = (uint32_t)cx.sm_count * 4;
+    const uint32_t max_ctas = (uint32_t)cx.sm_count * (uint32_t)occ;
     const uint32_t tiles_per_cta = std::min<uint32_t>((num_tiles + max_ctas - 1) / max_ctas, COV_MAX_TILES_PER_CTA);
     const uint32_t nctas = (num_tiles + tiles_per_cta - 1) / tiles_per_cta;
-    DevBuf<uint32_t> staging((size_t)2 * H), cta_count(nctas), cta_base(nctas), cta_out(nctas);
+    DevBuf<uint32_t> staging((size_t)2 * H), cta_count(nctas), cta_base(nctas);
     { ProfScope ps("cov_tile");
     launch(cov_tile_kernel, nctas, COV_THREADS, 0, s_sorted, e_sorted, H, num_tiles, tiles_per_cta,
            min_cov < 1 ? 1 : min_cov, staging.get(), cta_count.get(), cta_base.get(), d_err_p); }
-    exclusive_scan_u32(cta_count.get(), cta_out.get(), nctas, d_nflips_p);
     DevBuf<uint32_t> flips((size_t)2 * H);
-    launch(cov_gather_kernel, nctas, 256, 0, staging.get(), cta_count.get(), cta_base.get(), cta_out.get(), flips.get(), 2u * H, d_err_p);
+    launch(cov_gather_kernel, nctas, 256, 0, staging.get(), cta_count.get(), cta_base.get(), flips.get(), 2u * H, d_nflips_p, d_err_p);
 
-    // first (and usually only large) host round trip: the flip count sizes everything downstream, so the run stage
-    // costs O(runs), not O(hits)
-    HostInfo* hi = host_info();
-    MB2_CUDA(cudaMemcpyAsync(hi, d_info.get(), 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+    // runs: at most H of them (every run needs at least one start event)
+    const bool ext = res.ext_chrom != nullptr;
+    const uint32_t cap_fused = (uint32_t)std::min<uint64_t>(std::min<uint32_t>(H, COV_RUNS_FUSED_MAX), ext ? res.ext_cap : ~0ull);
+    if (!ext) { res.chrom.alloc(cap_fused); res.start.alloc(cap_fused); res.end.alloc(cap_fused); }
+    int32_t* o_chrom = ext ? res.ext_chrom : res.chrom.get();
+    int32_t* o_start = ext ? res.ext_start : res.start.get();
+    int32_t* o_end = ext ? res.ext_end : res.end.get();
+    launch(cov_runs_fused_kernel, 1, 1024, 0, flips.get(), d_nflips_p, min_len, d_off, nchrom, o_chrom, o_start, o_end, cap_fused, d_nseg_p);
+    MB2_CUDA(cudaMemcpyAsync(hz.info, d_info.get(), 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
     MB2_CUDA(cudaStreamSynchronize(cx.stream));
-    const int h_err = hi->err;
-    const uint32_t h_nflips = hi->nflips;
+    const int h_err = hz.info->err;
+    const uint32_t h_nflips = hz.info->nflips;
+    uint32_t h_nseg = hz.info->nseg;
     MB2_REQUIRE((h_err & 1) == 0, -4, "coverage: invalid hit (scaffold index out of range, negative start, or start > end)");
     MB2_REQUIRE(h_err == 0, -5, std::string("coverage: internal invariant violated, code ") + std::to_string(h_err));
     MB2_REQUIRE((h_nflips & 1u) == 0 && h_nflips <= 2ull * H, -5, std::string("coverage: internal error, inconsistent flip count ") + std::to_string(h_nflips));
     const uint32_t nruns = h_nflips >> 1;   // consecutive (rise, fall) flips
-    if (nruns == 0) return;
-    DevBuf<uint32_t> keep(nruns), keep_off(nruns), d_nseg(1);
-    launch(cov_runs_flag_kernel, cdiv(nruns, 256), 256, 0, flips.get(), d_nflips_p, min_len, keep.get(), nruns);
-    exclusive_scan_u32(keep.get(), keep_off.get(), nruns, d_nseg.get());
-    MB2_CUDA(cudaMemcpyAsync(&hi->nseg, d_nseg.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
-    MB2_CUDA(cudaStreamSynchronize(cx.stream));
-    const uint32_t h_nseg = hi->nseg;
+    if (nruns > cap_fused) {                // very many runs: flag, device-wide scan, write at the exact size
+        MB2_REQUIRE(h_nseg == 0xffffffffu, -5, "coverage: internal error, fused run stage ignored its capacity");
+        DevBuf<uint32_t> keep(nruns), keep_off(nruns);
+        launch(cov_runs_flag_kernel, cdiv(nruns, 256), 256, 0, flips.get(), d_nflips_p, min_len, keep.get(), nruns);
+        exclusive_scan_u32(keep.get(), keep_off.get(), nruns, d_nseg_p);
+        MB2_CUDA(cudaMemcpyAsync(&hz.info->nseg, d_nseg_p, sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));
+        h_nseg = hz.info->nseg;
+        MB2_REQUIRE(h_nseg <= nruns, -5, "coverage: internal error, more segments than runs");
+        if (ext) {
+            if (h_nseg > res.ext_cap) { res.n = h_nseg; throw Error(-6, "coverage: " + std::to_string(h_nseg) + " segments do not fit the caller's arrays of " + std::to_string(res.ext_cap)); }
+        } else {
+            res.chrom.alloc(h_nseg); res.start.alloc(h_nseg); res.end.alloc(h_nseg);
+            o_chrom = res.chrom.get(); o_start = res.start.get(); o_end = res.end.get();
+        }
+        if (h_nseg)
+            launch(cov_runs_write_kernel, cdiv(nruns, 256), 256, 0, flips.get(), d_nflips_p, min_len, keep_off.get(),
+                   d_off, nchrom, o_chrom, o_start, o_end, nruns, h_nseg);
+    }
     MB2_REQUIRE(h_nseg <= nruns, -5, "coverage: internal error, more segments than runs");
-    res.chrom.alloc(h_nseg); res.start.alloc(h_nseg); res.end.alloc(h_nseg);
     res.n = h_nseg;
-    if (h_nseg)
-        launch(cov_runs_write_kernel, cdiv(nruns, 256), 256, 0, flips.get(), d_nflips_p, min_len, keep_off.get(),
-               d_off.get(), nchrom, res.chrom.get(), res.start.get(), res.end.get(), nruns, h_nseg);
 }
 
 }  // namespace mb2

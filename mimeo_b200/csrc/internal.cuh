@@ -8,8 +8,12 @@ namespace mb2 {
 
 // ---- coverage.cu
 struct CoverageResult {
-    DevBuf<int32_t> chrom, start, end;
+    DevBuf<int32_t> chrom, start, end;   // library-owned result (unused when the caller supplies its own arrays)
     uint64_t n = 0;
+    // caller-owned device arrays of ext_cap elements each: the result is written there instead; more segments than that
+    // -> Error(-6) with n = the number needed and nothing written
+    int32_t *ext_chrom = nullptr, *ext_start = nullptr, *ext_end = nullptr;
+    uint64_t ext_cap = 0;
 };
 void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, uint64_t nhits,
                               const int64_t* h_sizes, int nchrom, int min_cov, int min_len, CoverageResult& res);

@@ -49,6 +49,24 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* sh, ui
     return res;
 }
 
+// Same, without the trailing barrier: the caller guarantees a block barrier before sh is written again.
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan_open(uint32_t v, uint32_t* sh, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = warp_incl_scan(v, lane);
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < NT / 32) ? sh[lane] : 0;
+        uint32_t wi = warp_incl_scan(w, lane);
+        if (lane < NT / 32) sh[lane] = wi - w;
+        if (lane == NT / 32 - 1) sh[NT / 32] = wi;
+    }
+    __syncthreads();
+    total = sh[NT / 32];
+    return incl - v + sh[warp];
+}
+
 static __global__ void __launch_bounds__(SCAN_THREADS)
 scan_block_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t* __restrict__ block_sums) {
     __shared__ uint32_t sh[SCAN_THREADS / 32 + 1];
@@ -195,8 +213,24 @@ radix_hist_kernel(const K* __restrict__ in0, const K* __restrict__ in1, uint32_t
     }
 }
 
+// Lanes of `act` holding the same (at most 8-bit) digit. Not __match_any_sync: MATCH.ANY issues on the ADU pipe, which ncu
+// showed 55-60 % busy and the limiter of the scatter kernel (profiles/r1_cov_v18_ncu_summary.txt); votes are cheap, and a
+// warp of (nearly) sorted keys takes the one-vote exit.
+__device__ __forceinline__ uint32_t match_digit(uint32_t act, uint32_t d) {
+    const uint32_t d0 = __shfl_sync(act, d, __ffs(act) - 1);
+    if (__all_sync(act, d == d0)) return act;
+    uint32_t peers = act;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(act, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 template <typename K, typename V, bool HAS_V>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, sizeof(K) == 4 ? 4 : 3)
 radix_scatter_kernel(const K* __restrict__ in0, const K* __restrict__ in1, K* __restrict__ out0, K* __restrict__ out1,
                      const V* __restrict__ vals_in, V* __restrict__ vals_out, uint32_t n, int shift, int bits,
                      const uint32_t* __restrict__ hist_scanned) {
@@ -227,7 +261,7 @@ radix_scatter_kernel(const K* __restrict__ in0, const K* __restrict__ in1, K* __
         uint32_t rk = 0;
         if (valid) {
             const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
-            const uint32_t peers = __match_any_sync(act, d);
+            const uint32_t peers = match_digit(act, d);
             const uint32_t prev = wcount[warp][d];
             __syncwarp(act);
             if ((peers & lt) == 0) wcount[warp][d] = prev + __popc(peers);

@@ -136,3 +136,35 @@ def test_full_size_properties(cov):
     # duplicating every hit doubles the depth: cov=42 on doubled input == cov=21 on the original
     cd, sd, ed = cov.coverage_segments(np.tile(chrom, 2), np.tile(start, 2), np.tile(end, 2), sizes, 42, 1)
     assert (cd == c3).all() and (sd == s3).all() and (ed == e3).all()
+
+
+def test_device_resident_entry_points(cov, oracle_build):
+    """Hits already in HBM (torch tensors as plain device buffers): `mb2_coverage_segments_into` writes into the caller's
+    arrays; too small a capacity is reported and retried; same segments as the host entry point."""
+    import ctypes as C
+    import torch
+    from mimeo_b200 import _lib
+    chrom, start, end, sizes = synth_hits(seed=7, nchrom=6, chrom_size=300_000, nhits=200_000, hotspots=40)
+    want = cov.coverage_segments(chrom, start, end, sizes, 9, 20)
+    assert len(want[0]) > 10
+    dev = [torch.from_numpy(a).cuda() for a in (chrom, start, end)]
+    for capacity in (0, 7, len(want[0])):
+        got = cov.coverage_segments_device(dev[0], dev[1], dev[2], sizes, 9, 20, capacity=capacity)
+        for g, w in zip(got, want):
+            assert g.is_cuda and (g.cpu().numpy() == w).all()
+    # the raw call reports the needed size and writes nothing when the arrays are too small
+    out = torch.full((3, 5), -7, dtype=torch.int32, device='cuda')
+    n = C.c_uint64(0)
+    s64 = np.ascontiguousarray(sizes, dtype=np.int64)
+    rc = _lib.lib().mb2_coverage_segments_into(dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), len(chrom), s64.ctypes.data,
+                                               len(s64), 9, 20, out.data_ptr(), out.data_ptr() + 20, out.data_ptr() + 40, 5, C.byref(n))
+    torch.cuda.synchronize()
+    assert rc == _lib.ERR_CAPACITY and int(n.value) == len(want[0]) and bool((out == -7).all())
+    # very many runs (more than the single-launch run stage handles): one short hit every 16 bases
+    m = 300_000
+    st = (np.arange(m, dtype=np.int32) * 16)
+    big = cov.coverage_segments(np.zeros(m, np.int32), st, st + 5, [16 * m + 100], 1, 1)
+    assert len(big[0]) == m and (big[1] == st).all() and (big[2] == st + 5).all()
+    gd = cov.coverage_segments_device(torch.zeros(m, dtype=torch.int32, device='cuda'), torch.from_numpy(st).cuda(),
+                                      torch.from_numpy(st + 5).cuda(), [16 * m + 100], 1, 1)
+    assert gd[0].numel() == m and (gd[1].cpu().numpy() == st).all() and (gd[2].cpu().numpy() == st + 5).all()
