@@ -67,6 +67,12 @@ class ClockSampler:
                                           '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi attaches to the driver while it starts up, which stalls this process's CUDA calls for a while: let
+            # it reach its steady 100 ms polling (first row printed) BEFORE the timed region begins, not inside it
+            t0 = time.perf_counter()
+            while not self.rows and self.proc.poll() is None and time.perf_counter() - t0 < 10.0:
+                time.sleep(0.01)
+            self.rows_before = len(self.rows)
         except Exception:
             self.proc = None
 
@@ -397,9 +403,9 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     _lib.prof_reset(); _lib.prof_enable(True)
     launches0 = _lib.launch_count()
-    barrier()
     if rank == 0:
         sampler.start()
+    barrier()
     total_ms = 0.0
     for _ in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (outside the timed interval)

@@ -333,7 +333,9 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
         if (occ < 1) occ = 1;
     }
     const uint32_t num_tiles = (uint32_t)((G + COV_TILE - 1) >> COV_TILE_BITS);
-    const uint32_t max_ctas = (uint32_t)cx.sm_count * (uint32_t)occ;
+    static int waves = 0;   // MB2_COV_WAVES: CTAs per resident slot (measurement knob; default 1)
+    if (waves == 0) { const char* e = getenv("MB2_COV_WAVES"); waves = e ? std::max(1, atoi(e)) : 1; }
+    const uint32_t max_ctas = (uint32_t)cx.sm_count * (uint32_t)occ * (uint32_t)waves;
     const uint32_t tiles_per_cta = std::min<uint32_t>((num_tiles + max_ctas - 1) / max_ctas, COV_MAX_TILES_PER_CTA);
     const uint32_t nctas = (num_tiles + tiles_per_cta - 1) / tiles_per_cta;
     DevBuf<uint32_t> staging((size_t)2 * H), cta_count(nctas), cta_base(nctas);

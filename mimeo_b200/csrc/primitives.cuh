@@ -234,14 +234,24 @@ __global__ void __launch_bounds__(RS_THREADS, sizeof(K) == 4 ? 4 : 3)
 radix_scatter_kernel(const K* __restrict__ in0, const K* __restrict__ in1, K* __restrict__ out0, K* __restrict__ out1,
                      const V* __restrict__ vals_in, V* __restrict__ vals_out, uint32_t n, int shift, int bits,
                      const uint32_t* __restrict__ hist_scanned) {
-    __shared__ uint32_t wcount[RS_WARPS][256];   // per-warp running digit counters, then warp prefixes
-    __shared__ uint32_t gbase[256];
+    // Keys-only sorts stage the tile in shared memory in digit order and write it out in runs of consecutive addresses
+    // (a warp's direct stores would hit 32 different sectors on unsorted input; ncu: same time with a third of the
+    // instructions, i.e. bound by scattered L2 writes). With a payload the keys and values go straight to their slots.
+    constexpr bool STAGE = !HAS_V;
+    constexpr int MATCH_BYTES = RS_WARPS * 256 * 4, STAGE_BYTES = STAGE ? RS_TILE * (int)sizeof(K) : 0;
+    __shared__ uint32_t wcount[RS_WARPS][256];   // per-warp running digit counters, then output bases
+    __shared__ __align__(16) unsigned char raw[MATCH_BYTES > STAGE_BYTES ? MATCH_BYTES : STAGE_BYTES];
+    uint32_t (*wmatch)[256] = reinterpret_cast<uint32_t (*)[256]>(raw);   // lane masks of the digit groups of the current round
+    K* const stage = reinterpret_cast<K*>(raw);                           // later: the tile in digit order
+    __shared__ uint32_t gofs[256];
+    __shared__ uint32_t sh_scan[RS_THREADS / 32 + 1];
     const K* __restrict__ keys_in = blockIdx.y ? in1 : in0;
     K* __restrict__ keys_out = blockIdx.y ? out1 : out0;
     const int nbins = 1 << bits;
     const uint32_t mask = nbins - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) { (&wcount[0][0])[i] = 0; (&wmatch[0][0])[i] = 0; }
+    static_assert(RS_THREADS >= 256, "one digit per thread in the staged write-out");
 
     const uint32_t wbase = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
     K key[RS_ITEMS];
@@ -253,41 +263,93 @@ radix_scatter_kernel(const K* __restrict__ in0, const K* __restrict__ in1, K* __
     __syncthreads();
     uint16_t rank[RS_ITEMS];
     const uint32_t lt = (1u << lane) - 1u;
+    if (n - blockIdx.x * (uint32_t)RS_TILE >= (uint32_t)RS_TILE) {
+        // Full tile (all but the last CTA): every lane holds a key, all warp primitives take the full mask.
+        // Lanes with the same digit find each other through a shared-memory OR of lane bits (one atomic, one load)
+        // instead of one vote per digit bit; a warp whose 32 keys share the digit (sorted input) skips even that.
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const uint32_t idx = wbase + r * 32 + lane;
-        const bool valid = idx < n;
-        const uint32_t act = __ballot_sync(0xffffffffu, valid);
-        uint32_t rk = 0;
-        if (valid) {
+        for (int r = 0; r < RS_ITEMS; r++) {
             const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
-            const uint32_t peers = match_digit(act, d);
+            const bool uniform = __all_sync(0xffffffffu, d == __shfl_sync(0xffffffffu, d, 0));
+            uint32_t peers = 0xffffffffu;
+            if (!uniform) {
+                atomicOr(&wmatch[warp][d], 1u << lane);
+                __syncwarp();
+                peers = wmatch[warp][d];
+            }
             const uint32_t prev = wcount[warp][d];
-            __syncwarp(act);
-            if ((peers & lt) == 0) wcount[warp][d] = prev + __popc(peers);
-            rk = prev + __popc(peers & lt);
+            __syncwarp();                          // every peer has read the mask and the count
+            if ((peers & lt) == 0) {               // lowest lane of the group
+                wcount[warp][d] = prev + __popc(peers);
+                if (!uniform) wmatch[warp][d] = 0;   // clean for the next round
+            }
+            __syncwarp();
+            rank[r] = (uint16_t)(prev + __popc(peers & lt));
         }
-        __syncwarp();
-        rank[r] = (uint16_t)rk;
+    } else {
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; r++) {
+            const uint32_t idx = wbase + r * 32 + lane;
+            const bool valid = idx < n;
+            const uint32_t act = __ballot_sync(0xffffffffu, valid);
+            uint32_t rk = 0;
+            if (valid) {
+                const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+                const uint32_t peers = match_digit(act, d);
+                const uint32_t prev = wcount[warp][d];
+                __syncwarp(act);
+                if ((peers & lt) == 0) wcount[warp][d] = prev + __popc(peers);
+                rk = prev + __popc(peers & lt);
+            }
+            __syncwarp();
+            rank[r] = (uint16_t)rk;
+        }
     }
     __syncthreads();
-    // per digit: exclusive prefix over warps, plus the block's global base (the scan ran over both arrays back to back,
-    // so the second array's offsets carry the first array's n keys)
-    for (int d = threadIdx.x; d < nbins; d += RS_THREADS) {
-        uint32_t run = 0;
+    // the scan ran over both arrays back to back, so the second array's offsets carry the first array's n keys
+    if (STAGE) {
+        const int d = threadIdx.x;   // RS_THREADS >= 256 bins: one digit per thread
+        uint32_t c[RS_WARPS], tot = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) { uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
-        gbase[d] = hist_scanned[((size_t)blockIdx.y * nbins + d) * gridDim.x + blockIdx.x] - blockIdx.y * n;
-    }
-    __syncthreads();
+        for (int w = 0; w < RS_WARPS; w++) { c[w] = d < nbins ? wcount[w][d] : 0u; tot += c[w]; }
+        uint32_t tile_total;
+        const uint32_t lstart = block_excl_scan<RS_THREADS>(tot, sh_scan, tile_total);   // where the digit starts inside the tile
+        if (d < nbins) {
+            uint32_t run = lstart;
 #pragma unroll
-    for (int r = 0; r < RS_ITEMS; r++) {
-        const uint32_t idx = wbase + r * 32 + lane;
-        if (idx < n) {
-            const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
-            const uint32_t pos = gbase[d] + wcount[warp][d] + rank[r];
-            keys_out[pos] = key[r];
-            if (HAS_V) vals_out[pos] = vals_in[idx];
+            for (int w = 0; w < RS_WARPS; w++) { wcount[w][d] = run; run += c[w]; }
+            gofs[d] = hist_scanned[((size_t)blockIdx.y * nbins + d) * gridDim.x + blockIdx.x] - blockIdx.y * n - lstart;
+        }
+        __syncthreads();   // also: nobody touches wmatch any more, raw[] becomes the staging tile
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; r++) {
+            const uint32_t idx = wbase + r * 32 + lane;
+            if (idx < n) stage[wcount[warp][(uint32_t)(key[r] >> shift) & mask] + rank[r]] = key[r];
+        }
+        __syncthreads();
+        const uint32_t ntile = min((uint32_t)RS_TILE, n - blockIdx.x * (uint32_t)RS_TILE);
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < ntile; i += RS_THREADS) {
+            const K k = stage[i];
+            keys_out[gofs[(uint32_t)(k >> shift) & mask] + i] = k;
+        }
+    } else {
+        // per digit: exclusive prefix over warps on top of the block's global base: wcount becomes the output base of (warp, digit)
+        for (int d = threadIdx.x; d < nbins; d += RS_THREADS) {
+            uint32_t run = hist_scanned[((size_t)blockIdx.y * nbins + d) * gridDim.x + blockIdx.x] - blockIdx.y * n;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) { uint32_t c = wcount[w][d]; wcount[w][d] = run; run += c; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; r++) {
+            const uint32_t idx = wbase + r * 32 + lane;
+            if (idx < n) {
+                const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+                const uint32_t pos = wcount[warp][d] + rank[r];
+                keys_out[pos] = key[r];
+                if (HAS_V) vals_out[pos] = vals_in[idx];
+            }
         }
     }
 }
