@@ -366,6 +366,25 @@ def run_reference(args):
     }))
 
 
+def quick_config2(steps=5, warmup=3):
+    """BASELINE config 2 (10 M hits / 100 Mbp) measured by this same script in a fresh process (`--workload cov`): same arms,
+    same timing rules as the headline; the parent holds the GPU idle meanwhile. Returns the child's line, trimmed."""
+    env = dict(os.environ, MB2_BENCH_NO_C2='1')
+    for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE'):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--workload', 'cov', '--steps', str(steps), '--warmup', str(warmup)],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    if out.returncode != 0:
+        raise RuntimeError(f'child exited {out.returncode}: {out.stderr[-200:]}')
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    r = d['roofline']
+    return {'workload': d['config']['workload'], 'steps': d['steps'], 'warmup': d['warmup'], 'ms_per_step': d['ms_per_step'],
+            'value': d['value'], 'unit': d['unit'], 'e2e': d['e2e'], 'gpu_launches': d['gpu_launches'], 'clocks': d['clocks'],
+            'cpu_baseline': d['cpu_baseline'],
+            'roofline': {k: r.get(k) for k in ('kernel', 'achieved', 'peak', 'frac', 'traffic', 'ms_per_launch',
+                                               'algorithmic_bytes_per_launch', 'kernels_ms_per_step', 'stage_survey_model')}}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -474,6 +493,14 @@ def run_b200(args):
     barrier()
     e2e = {'value': job_mbp / (e2e_ms / 1e3), 'unit': 'Mbp/s', 'ms_per_step': e2e_ms,
            'h2d_bytes_per_step': wl.h2d_bytes, 'd2h_bytes_per_step': wl.d2h_bytes}
+
+    # ---- BASELINE config 2 beside the headline (single GPU, default workload only): the coverage/threshold stage on its own
+    # 10 M-hit table, same timing rules, a few steps; reported as an extra key, never mixed into `value`
+    if rank == 0 and world == 1 and args.workload == 'self' and not os.environ.get('MB2_BENCH_NO_C2'):
+        try:
+            extra['config2_coverage_stage'] = quick_config2()
+        except Exception as e:      # the headline line must not depend on this leg
+            extra['config2_coverage_stage'] = {'error': f'{type(e).__name__}: {e}'[:300]}
 
     cpu = None
     if rank == 0 and world == 1:

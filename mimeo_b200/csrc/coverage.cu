@@ -276,6 +276,34 @@ static HostZone& host_zone(size_t nchrom) {
     return z;
 }
 
+// Grow-only device scratch of this stage, carved per call: a call makes no allocator traffic once the arena is large enough
+// (a dozen stream-ordered allocations and frees per call were a visible share of a 0.6 ms step). Safe to reuse: everything
+// runs on the one library stream and every call ends with a stream synchronisation.
+struct Arena {
+    uint8_t* p = nullptr;
+    size_t cap = 0, used = 0;
+    void reserve(size_t bytes) {
+        used = 0;
+        if (bytes <= cap) return;
+        if (p) { cudaFreeAsync(p, ctx().stream); p = nullptr; cap = 0; }
+        const size_t want = bytes + bytes / 8;
+        MB2_CUDA(cudaMallocAsync((void**)&p, want, ctx().stream));
+        cap = want;
+    }
+    template <typename T> T* take(size_t count) {
+        T* r = (T*)(p + used);
+        used += (count * sizeof(T) + 255) & ~(size_t)255;
+        MB2_REQUIRE(used <= cap, -5, "coverage: scratch arena overrun");
+        return r;
+    }
+};
+static Arena g_arena;
+void coverage_release_scratch() {   // mb2_shutdown
+    if (g_arena.p) cudaFreeAsync(g_arena.p, ctx().stream);
+    g_arena.p = nullptr; g_arena.cap = g_arena.used = 0;
+}
+static size_t arena_slot(size_t count, size_t elem) { return (count * elem + 255) & ~(size_t)255; }
+
 // -------------------------------------------------------------------------------------------------
 // Host driver. All pointers are device pointers; everything is enqueued on the library stream.
 // One host round trip (error bits, flip count, segment count) unless there are more than COV_RUNS_FUSED_MAX runs.
@@ -300,50 +328,58 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
         bool prev; DebugScope() : prev(ctx().debug_sync) { if (getenv("MB2_DEBUG_COV")) { cudaError_t e = cudaStreamSynchronize(ctx().stream); if (e != cudaSuccess) throw Error(-100, std::string("fault BEFORE the coverage stage: ") + cudaGetErrorString(e)); ctx().debug_sync = true; } }
         ~DebugScope() { ctx().debug_sync = prev; }
     } debug_scope;
-    DevBuf<uint32_t> d_meta((size_t)2 * nchrom);
-    MB2_CUDA(cudaMemcpyAsync(d_meta.get(), hz.meta, (size_t)2 * nchrom * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
-    const uint32_t* const d_off = d_meta.get();
-    const int32_t* const d_size = (const int32_t*)(d_meta.get() + nchrom);
-
     const uint32_t H = (uint32_t)nhits;
-    DevBuf<uint32_t> evs0(H), evs1(H), eve0(H), eve1(H);
-    DevBuf<uint32_t> d_info(3);   // [0] error bits, [1] flip count, [2] segment count: one read-back
-    MB2_CUDA(cudaMemsetAsync(d_info.get(), 0, 3 * sizeof(uint32_t), cx.stream));
-    int* const d_err_p = (int*)d_info.get();
-    uint32_t* const d_nflips_p = d_info.get() + 1;
-    uint32_t* const d_nseg_p = d_info.get() + 2;
+    static int occ = 0;
+    if (occ == 0) {
+        MB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile_kernel, COV_THREADS, 0));
+        if (occ < 1) occ = 1;
+    }
+    // one wave of CTAs (the kernel is a chain of short barrier-separated phases: a second, partial wave would idle most SMs),
+    // more only when a CTA would otherwise own more than COV_MAX_TILES_PER_CTA tiles
+    static int waves = 0;   // MB2_COV_WAVES: CTAs per resident slot (measurement knob; default 1)
+    if (waves == 0) { const char* e = getenv("MB2_COV_WAVES"); waves = e ? std::max(1, atoi(e)) : 1; }
+    const uint32_t num_tiles = (uint32_t)((G + COV_TILE - 1) >> COV_TILE_BITS);
+    const uint32_t max_ctas = (uint32_t)cx.sm_count * (uint32_t)occ * (uint32_t)waves;
+    const uint32_t tiles_per_cta = std::min<uint32_t>((num_tiles + max_ctas - 1) / max_ctas, COV_MAX_TILES_PER_CTA);
+    const uint32_t nctas = (num_tiles + tiles_per_cta - 1) / tiles_per_cta;
+    const size_t sort_words = radix_sort_scratch_words(H, 2);
+    g_arena.reserve(arena_slot((size_t)2 * nchrom, 4) + arena_slot(4, 4) + 4 * arena_slot(H, 4) + arena_slot(sort_words, 4) +
+                    2 * arena_slot((size_t)2 * H, 4) + 2 * arena_slot(nctas, 4));
+    uint32_t* const d_meta = g_arena.take<uint32_t>((size_t)2 * nchrom);
+    uint32_t* const d_info = g_arena.take<uint32_t>(4);   // [0] error bits, [1] flip count, [2] segment count: one read-back
+    uint32_t* const evs0 = g_arena.take<uint32_t>(H);
+    uint32_t* const evs1 = g_arena.take<uint32_t>(H);
+    uint32_t* const eve0 = g_arena.take<uint32_t>(H);
+    uint32_t* const eve1 = g_arena.take<uint32_t>(H);
+    uint32_t* const sort_scratch = g_arena.take<uint32_t>(sort_words);
+    uint32_t* const staging = g_arena.take<uint32_t>((size_t)2 * H);
+    uint32_t* const flips = g_arena.take<uint32_t>((size_t)2 * H);
+    uint32_t* const cta_count = g_arena.take<uint32_t>(nctas);
+    uint32_t* const cta_base = g_arena.take<uint32_t>(nctas);
+    MB2_CUDA(cudaMemcpyAsync(d_meta, hz.meta, (size_t)2 * nchrom * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
+    const uint32_t* const d_off = d_meta;
+    const int32_t* const d_size = (const int32_t*)(d_meta + nchrom);
+    MB2_CUDA(cudaMemsetAsync(d_info, 0, 3 * sizeof(uint32_t), cx.stream));
+    int* const d_err_p = (int*)d_info;
+    uint32_t* const d_nflips_p = d_info + 1;
+    uint32_t* const d_nseg_p = d_info + 2;
     { ProfScope ps("cov_events");
     launch(cov_events_kernel, cdiv(H, 256), 256, 0, d_chrom, d_start, d_end, H, d_off, d_size, nchrom,
-           evs0.get(), eve0.get(), d_err_p); }
+           evs0, eve0, d_err_p); }
 
     int top = COV_TILE_BITS;
     while (top < 32 && ((G + COV_TILE) >> top) != 0) top++;       // sentinel (all ones) must stay the largest tile id
     NoVal* nv = nullptr;
     int w;
     { ProfScope ps("cov_bin_events");   // both event arrays through the same launches
-      w = radix_sort_bits<uint32_t, NoVal>(evs0.get(), evs1.get(), nv, nv, H, COV_TILE_BITS, top, eve0.get(), eve1.get()); }
-    const uint32_t* s_sorted = w ? evs1.get() : evs0.get();
-    const uint32_t* e_sorted = w ? eve1.get() : eve0.get();
+      w = radix_sort_bits<uint32_t, NoVal>(evs0, evs1, nv, nv, H, COV_TILE_BITS, top, eve0, eve1, sort_scratch); }
+    const uint32_t* s_sorted = w ? evs1 : evs0;
+    const uint32_t* e_sorted = w ? eve1 : eve0;
 
-    // one wave of CTAs (the kernel is a chain of short barrier-separated phases: a second, partial wave would idle most SMs),
-    // more only when a CTA would otherwise own more than COV_MAX_TILES_PER_CTA tiles
-    static int occ = 0;
-    if (occ == 0) {
-        MB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cov_tile_kernel, COV_THREADS, 0));
-        if (occ < 1) occ = 1;
-    }
-    const uint32_t num_tiles = (uint32_t)((G + COV_TILE - 1) >> COV_TILE_BITS);
-    static int waves = 0;   // MB2_COV_WAVES: CTAs per resident slot (measurement knob; default 1)
-    if (waves == 0) { const char* e = getenv("MB2_COV_WAVES"); waves = e ? std::max(1, atoi(e)) : 1; }
-    const uint32_t max_ctas = (uint32_t)cx.sm_count * (uint32_t)occ * (uint32_t)waves;
-    const uint32_t tiles_per_cta = std::min<uint32_t>((num_tiles + max_ctas - 1) / max_ctas, COV_MAX_TILES_PER_CTA);
-    const uint32_t nctas = (num_tiles + tiles_per_cta - 1) / tiles_per_cta;
-    DevBuf<uint32_t> staging((size_t)2 * H), cta_count(nctas), cta_base(nctas);
     { ProfScope ps("cov_tile");
     launch(cov_tile_kernel, nctas, COV_THREADS, 0, s_sorted, e_sorted, H, num_tiles, tiles_per_cta,
-           min_cov < 1 ? 1 : min_cov, staging.get(), cta_count.get(), cta_base.get(), d_err_p); }
-    DevBuf<uint32_t> flips((size_t)2 * H);
-    launch(cov_gather_kernel, nctas, 256, 0, staging.get(), cta_count.get(), cta_base.get(), flips.get(), 2u * H, d_nflips_p, d_err_p);
+           min_cov < 1 ? 1 : min_cov, staging, cta_count, cta_base, d_err_p); }
+    launch(cov_gather_kernel, nctas, 256, 0, staging, cta_count, cta_base, flips, 2u * H, d_nflips_p, d_err_p);
 
     // runs: at most H of them (every run needs at least one start event)
     const bool ext = res.ext_chrom != nullptr;
@@ -352,8 +388,8 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
     int32_t* o_chrom = ext ? res.ext_chrom : res.chrom.get();
     int32_t* o_start = ext ? res.ext_start : res.start.get();
     int32_t* o_end = ext ? res.ext_end : res.end.get();
-    launch(cov_runs_fused_kernel, 1, 1024, 0, flips.get(), d_nflips_p, min_len, d_off, nchrom, o_chrom, o_start, o_end, cap_fused, d_nseg_p);
-    MB2_CUDA(cudaMemcpyAsync(hz.info, d_info.get(), 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
+    launch(cov_runs_fused_kernel, 1, 1024, 0, flips, d_nflips_p, min_len, d_off, nchrom, o_chrom, o_start, o_end, cap_fused, d_nseg_p);
+    MB2_CUDA(cudaMemcpyAsync(hz.info, d_info, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
     MB2_CUDA(cudaStreamSynchronize(cx.stream));
     const int h_err = hz.info->err;
     const uint32_t h_nflips = hz.info->nflips;
@@ -365,7 +401,7 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
     if (nruns > cap_fused) {                // very many runs: flag, device-wide scan, write at the exact size
         MB2_REQUIRE(h_nseg == 0xffffffffu, -5, "coverage: internal error, fused run stage ignored its capacity");
         DevBuf<uint32_t> keep(nruns), keep_off(nruns);
-        launch(cov_runs_flag_kernel, cdiv(nruns, 256), 256, 0, flips.get(), d_nflips_p, min_len, keep.get(), nruns);
+        launch(cov_runs_flag_kernel, cdiv(nruns, 256), 256, 0, flips, d_nflips_p, min_len, keep.get(), nruns);
         exclusive_scan_u32(keep.get(), keep_off.get(), nruns, d_nseg_p);
         MB2_CUDA(cudaMemcpyAsync(&hz.info->nseg, d_nseg_p, sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
@@ -378,7 +414,7 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
             o_chrom = res.chrom.get(); o_start = res.start.get(); o_end = res.end.get();
         }
         if (h_nseg)
-            launch(cov_runs_write_kernel, cdiv(nruns, 256), 256, 0, flips.get(), d_nflips_p, min_len, keep_off.get(),
+            launch(cov_runs_write_kernel, cdiv(nruns, 256), 256, 0, flips, d_nflips_p, min_len, keep_off.get(),
                    d_off, nchrom, o_chrom, o_start, o_end, nruns, h_nseg);
     }
     MB2_REQUIRE(h_nseg <= nruns, -5, "coverage: internal error, more segments than runs");

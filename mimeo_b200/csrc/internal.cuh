@@ -18,6 +18,8 @@ struct CoverageResult {
 void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, const int32_t* d_end, uint64_t nhits,
                               const int64_t* h_sizes, int nchrom, int min_cov, int min_len, CoverageResult& res);
 
+void coverage_release_scratch();   // frees the stage's grow-only device scratch (kept between calls)
+
 // ---- alignment half
 struct Genome;
 struct AlignParams {   // LASTZ defaults for mimeo's command line

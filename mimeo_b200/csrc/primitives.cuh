@@ -130,7 +130,8 @@ static __global__ void scan_total_kernel(const uint32_t* __restrict__ last_excl,
     *total = *last_excl + *last_in;
 }
 
-inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total = nullptr) {
+// sums_scratch (optional, cdiv(n, SCAN_TILE) words): block sums go there instead of a fresh allocation.
+inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* total = nullptr, uint32_t* sums_scratch = nullptr) {
     if (n == 0) {
         if (total) MB2_CUDA(cudaMemsetAsync(total, 0, sizeof(uint32_t), ctx().stream));
         return;
@@ -149,10 +150,12 @@ inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, uint
     if (nb == 1) {
         launch(scan_block_kernel, 1, SCAN_THREADS, 0, in, out, n, (uint32_t*)nullptr);
     } else {
-        DevBuf<uint32_t> sums(nb);
-        launch(scan_block_kernel, nb, SCAN_THREADS, 0, in, out, n, sums.get());
-        exclusive_scan_u32(sums.get(), sums.get(), nb, nullptr);
-        launch(scan_add_kernel, nb, SCAN_THREADS, 0, out, n, sums.get());
+        DevBuf<uint32_t> sums_own;
+        if (!sums_scratch) sums_own.alloc(nb);
+        uint32_t* const sums = sums_scratch ? sums_scratch : sums_own.get();
+        launch(scan_block_kernel, nb, SCAN_THREADS, 0, in, out, n, sums);
+        exclusive_scan_u32(sums, sums, nb, nullptr);
+        launch(scan_add_kernel, nb, SCAN_THREADS, 0, out, n, sums);
     }
     if (total) launch(scan_total_kernel, 1, 1, 0, out + (n - 1), last_in.get(), total);
 }
@@ -357,8 +360,14 @@ radix_scatter_kernel(const K* __restrict__ in0, const K* __restrict__ in1, K* __
 // Sort keys (and payload) on bits [begin_bit, end_bit). Ping-pongs between (k0,v0) and (k1,v1);
 // returns 0 if the result is in (k0,v0), 1 if in (k1,v1). With a second key array (j0, j1; keys only, same n) both
 // arrays are sorted by the same launches and end up on the same side.
+// radix_sort_scratch_words(n, narr) words at `scratch` (optional) replace the per-call allocations of the histogram and scan sums.
+inline size_t radix_sort_scratch_words(size_t n, unsigned narr) {
+    const size_t hist = (size_t)256 * cdiv(n, 4096) * narr;
+    return hist + cdiv(hist, SCAN_TILE) + 64;
+}
 template <typename K, typename V>
-inline int radix_sort_bits(K* k0, K* k1, V* v0, V* v1, size_t n, int begin_bit, int end_bit, K* j0 = nullptr, K* j1 = nullptr) {
+inline int radix_sort_bits(K* k0, K* k1, V* v0, V* v1, size_t n, int begin_bit, int end_bit, K* j0 = nullptr, K* j1 = nullptr,
+                           uint32_t* scratch = nullptr) {
     constexpr bool HAS_V = !std::is_same<V, NoVal>::value;
     if (n == 0 || end_bit <= begin_bit) return 0;
     MB2_REQUIRE(n < 0xffffffffull, -3, "radix sort: n must be < 2^32");
@@ -367,7 +376,11 @@ inline int radix_sort_bits(K* k0, K* k1, V* v0, V* v1, size_t n, int begin_bit, 
     const int total_bits = end_bit - begin_bit;
     const int passes = (total_bits + 7) / 8;
     const unsigned nb = cdiv(n, RS_TILE);
-    DevBuf<uint32_t> hist((size_t)256 * nb * narr);
+    static_assert(RS_TILE == 4096, "radix_sort_scratch_words assumes 4096 keys per CTA");
+    DevBuf<uint32_t> hist_own;
+    if (!scratch) hist_own.alloc((size_t)256 * nb * narr);
+    uint32_t* const hist = scratch ? scratch : hist_own.get();
+    uint32_t* const sums = scratch ? scratch + (size_t)256 * nb * narr : nullptr;
     int cur = 0;
     int bit = begin_bit;
     for (int p = 0; p < passes; p++) {
@@ -375,10 +388,10 @@ inline int radix_sort_bits(K* k0, K* k1, V* v0, V* v1, size_t n, int begin_bit, 
         K* kin = cur ? k1 : k0; K* kout = cur ? k0 : k1;
         K* jin = cur ? j1 : j0; K* jout = cur ? j0 : j1;
         V* vin = cur ? v1 : v0; V* vout = cur ? v0 : v1;
-        launch(radix_hist_kernel<K>, dim3(nb, narr), RS_THREADS, 0, kin, jin, (uint32_t)n, bit, bits, hist.get());
-        exclusive_scan_u32(hist.get(), hist.get(), (size_t)(1 << bits) * nb * narr);
+        launch(radix_hist_kernel<K>, dim3(nb, narr), RS_THREADS, 0, kin, jin, (uint32_t)n, bit, bits, hist);
+        exclusive_scan_u32(hist, hist, (size_t)(1 << bits) * nb * narr, nullptr, sums);
         launch(radix_scatter_kernel<K, V, HAS_V>, dim3(nb, narr), RS_THREADS, 0, kin, jin, kout, jout, vin, vout, (uint32_t)n, bit,
-               bits, hist.get());
+               bits, hist);
         cur ^= 1;
         bit += bits;
     }
