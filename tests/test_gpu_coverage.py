@@ -168,3 +168,20 @@ def test_device_resident_entry_points(cov, oracle_build):
     gd = cov.coverage_segments_device(torch.zeros(m, dtype=torch.int32, device='cuda'), torch.from_numpy(st).cuda(),
                                       torch.from_numpy(st + 5).cuda(), [16 * m + 100], 1, 1)
     assert gd[0].numel() == m and (gd[1].cpu().numpy() == st).all() and (gd[2].cpu().numpy() == st + 5).all()
+
+
+def test_large_sparse_genome_many_ctas_per_slot(cov, oracle_build):
+    """300 Mbp in 5 scaffolds: more 8192-base tiles than one wave of CTAs may own (32 each), so the tile kernel runs in
+    several waves and most tiles are empty; 400 k hits, bit-exact against the C oracle."""
+    import ctypes, os
+    chrom, start, end, sizes = synth_hits(seed=31, nchrom=5, chrom_size=60_000_000, nhits=400_000, hotspots=300)
+    got = cov.coverage_segments(chrom, start, end, sizes, 2, 50)
+    lib = ctypes.CDLL(os.path.join(oracle_build, 'libannot_oracle.so'))
+    lib.ora_coverage_segments.restype = ctypes.c_long
+    cap = len(chrom) + 8
+    oc, os_, oe = (np.zeros(cap, np.int32) for _ in range(3))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    k = lib.ora_coverage_segments(P(chrom), P(start), P(end), ctypes.c_long(len(chrom)), P(sizes), ctypes.c_int(len(sizes)),
+                                  ctypes.c_int(2), ctypes.c_int(50), P(oc), P(os_), P(oe), ctypes.c_long(cap))
+    assert k == len(got[0]) and k > 300
+    assert (got[0] == oc[:k]).all() and (got[1] == os_[:k]).all() and (got[2] == oe[:k]).all()
