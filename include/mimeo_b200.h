@@ -188,6 +188,13 @@ typedef struct mb2_fasta {
 MB2_API int mb2_fasta_read(const char* path, int nthreads, mb2_fasta* out);
 MB2_API void mb2_free_fasta(mb2_fasta* f);
 
+/* splitFasta (utils.py:274-309): one `<outdir>/<id>.fa` per record of a multi-FASTA file, header line kept whole, sequence
+ * wrapped at `width` columns (Biopython writes 60), files written by `nthreads` workers (0 = all cores). With `unique` a
+ * repeated id stops the split at that record, as the reference does: the call returns MB2_ERR_DUPLICATE_ID and
+ * mb2_last_error() is the id. *nfiles receives the number of files written. */
+#define MB2_ERR_DUPLICATE_ID (-7)
+MB2_API int mb2_fasta_split(const char* path, const char* outdir, int unique, int width, int nthreads, uint64_t* nfiles);
+
 /* The filter + projection + sort that follows every LASTZ call in the reference's script (wrappers.py:1044-1056):
  * rows with length1 >= min_len and printed identity ('%.1f' of 100*nmatch/ncols) >= min_idt, as 10 tab-separated columns,
  * grouped by (t_id, q_id) block (ascending), each block sorted by start1 and then by the whole line's bytes

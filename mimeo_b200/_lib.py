@@ -88,6 +88,7 @@ SIGNATURES = {
     'mb2_free_tab_hits': (None, [C.POINTER(TabHits)]),
     'mb2_fasta_read': (C.c_int, [C.c_char_p, C.c_int, C.POINTER(Fasta)]),
     'mb2_free_fasta': (None, [C.POINTER(Fasta)]),
+    'mb2_fasta_split': (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
     'mb2_format_tab': (C.c_int, [C.c_void_p] * 10 + [C.c_uint64, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int,
                                  C.c_double, C.c_double, C.POINTER(TabText)]),
     'mb2_free_tab_text': (None, [C.POINTER(TabText)]),
@@ -125,6 +126,7 @@ def lib():
 
 
 ERR_CAPACITY = -6
+ERR_DUPLICATE_ID = -7
 
 
 def check(rc):

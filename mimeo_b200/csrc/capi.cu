@@ -462,6 +462,14 @@ int mb2_fasta_read(const char* path, int nthreads, mb2_fasta* out) {
         f.seq = nullptr;
     });
 }
+int mb2_fasta_split(const char* path, const char* outdir, int unique, int width, int nthreads, uint64_t* nfiles) {
+    return guarded([&] {
+        MB2_REQUIRE(path && outdir, MB2_ERR_INVALID_ARG, "mb2_fasta_split: null argument");
+        if (nfiles) *nfiles = 0;
+        const uint64_t k = fasta_split_file(path, outdir, unique != 0, width, nthreads);
+        if (nfiles) *nfiles = k;
+    });
+}
 void mb2_free_fasta(mb2_fasta* f) {
     if (!f) return;
     free_strings(f->ids, (size_t)f->n); free_strings(f->headers, (size_t)f->n);

@@ -12,6 +12,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -462,6 +464,85 @@ uint64_t map_gff_rows(const char* path, const char* prefix, double min_len, doub
         out += ";identity="; add(9); out += ";B_locus="; add(4); out += '_'; add(5); out += '_'; add(6); out += '_'; add(7); out += '\n';
     }
     return total;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// fasta_split_file: one `<outdir>/<id>.fa` per record, header line kept whole, sequence wrapped at `width` columns -- what
+// splitFasta (utils.py:274-309: SeqIO.parse + SeqIO.write per record) leaves in --adir / --bdir. Records are written by
+// `nthreads` workers (one file each). With `unique`, the records before the first repeated id are written and the call then
+// fails with -7 naming the id (the reference exits at that record); without it a later record replaces an earlier file of
+// the same id, so only the last one of each id is written. Returns the number of files written.
+// ------------------------------------------------------------------------------------------------
+namespace {
+void write_all(int fd, const char* p, size_t n, const std::string& path) {
+    while (n) {
+        const ssize_t w = ::write(fd, p, n);
+        if (w < 0) throw Error(-5, "write " + path + ": " + strerror(errno));
+        p += w; n -= (size_t)w;
+    }
+}
+void write_record(const std::string& path, const std::string& header, const uint8_t* seq, uint64_t n, int width) {
+    const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) throw Error(-5, "open " + path + ": " + strerror(errno));
+    try {
+        std::string buf;
+        const size_t lines_per_block = std::max<size_t>(1, ((size_t)1 << 20) / (size_t)(width + 1));
+        buf.reserve(lines_per_block * (size_t)(width + 1) + header.size() + 2);
+        buf.push_back('>'); buf += header; buf.push_back('\n');
+        uint64_t i = 0;
+        while (i < n) {
+            for (size_t l = 0; l < lines_per_block && i < n; l++) {
+                const uint64_t m = std::min<uint64_t>((uint64_t)width, n - i);
+                buf.append((const char*)seq + i, (size_t)m);
+                buf.push_back('\n');
+                i += m;
+            }
+            write_all(fd, buf.data(), buf.size(), path);
+            buf.clear();
+        }
+        if (!buf.empty()) write_all(fd, buf.data(), buf.size(), path);
+    } catch (...) { ::close(fd); throw; }
+    if (::close(fd) != 0) throw Error(-5, "close " + path + ": " + strerror(errno));
+}
+}  // namespace
+
+uint64_t fasta_split_file(const char* path, const char* outdir, bool unique, int width, int nthreads) {
+    MB2_REQUIRE(width > 0, -2, "fasta_split_file: width must be positive");
+    FastaData f;
+    fasta_read_file(path, nthreads, f);
+    const size_t n = f.ids.size();
+    std::unordered_map<std::string_view, size_t> last;     // id -> index of its last record
+    size_t stop = n;                                        // first record whose id was seen before
+    for (size_t r = 0; r < n; r++) {
+        auto it = last.find(f.ids[r]);
+        if (it != last.end() && stop == n) stop = r;
+        last[f.ids[r]] = r;
+    }
+    const size_t upto = unique ? stop : n;
+    std::vector<size_t> todo;
+    for (size_t r = 0; r < upto; r++)
+        if (unique || last[f.ids[r]] == r) todo.push_back(r);
+    for (size_t r : todo)
+        MB2_REQUIRE(!f.ids[r].empty() && f.ids[r].find('/') == std::string::npos, -2,
+                    std::string(path) + ": record id '" + f.ids[r] + "' cannot name a file");
+    const int nt = std::max(1, std::min<int>(nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency(), (int)std::max<size_t>(todo.size(), 1)));
+    std::vector<std::string> errs(nt);
+    std::atomic<size_t> next{0};
+    const std::string dir(outdir);
+    run_threads(nt, [&](int t) {
+        try {
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= todo.size()) break;
+                const size_t r = todo[k];
+                write_record(dir + "/" + f.ids[r] + ".fa", f.headers[r], f.seq + f.off[r], f.off[r + 1] - f.off[r], width);
+            }
+        } catch (const std::exception& e) { errs[t] = e.what(); }
+    });
+    for (const auto& e : errs) if (!e.empty()) throw Error(-5, e);
+    if (unique && stop < n) throw Error(-7, f.ids[stop]);   // message = the repeated id
+    return todo.size();
 }
 
 }  // namespace mb2

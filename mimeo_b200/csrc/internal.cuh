@@ -92,6 +92,8 @@ struct FastaData {
     ~FastaData() { free(seq); }
 };
 void fasta_read_file(const char* path, int nthreads, FastaData& out);
+// one <outdir>/<id>.fa per record (splitFasta, utils.py:274-309); returns the number of files written; Error(-7, id) on a repeated id
+uint64_t fasta_split_file(const char* path, const char* outdir, bool unique, int width, int nthreads);
 
 struct TabText {                       // filtered, sorted .tab rows grouped by (t_id, q_id) block
     std::string text;                  // all rows, blocks back to back

@@ -97,14 +97,16 @@ def getTimestring() -> str:
 
 
 def splitFasta(infile: str, outdir: str, unique: bool = True) -> None:
-    """One `<id>.fa` per record (utils.py:274-309); exits on duplicate ids when unique."""
-    seen = set()
-    for rid, header, seq in fasta.read_fasta(infile):
-        if rid in seen and unique:
-            logging.error('Non-unique name in genome: %s. Quitting.' % rid)
-            sys.exit(1)
-        seen.add(rid)
-        fasta.write_fasta_record(os.path.join(outdir, rid + '.fa'), header, seq)
+    """One `<id>.fa` per record (utils.py:274-309); exits on duplicate ids when unique (the records before the repeated
+    one are written first, as in the reference). Read, wrapped at 60 columns and written natively (`mb2_fasta_split`)."""
+    import ctypes as C
+    from . import _lib
+    n = C.c_uint64(0)
+    rc = _lib.lib().mb2_fasta_split(os.fsencode(infile), os.fsencode(outdir), 1 if unique else 0, 60, 0, C.byref(n))
+    if rc == _lib.ERR_DUPLICATE_ID:
+        logging.error('Non-unique name in genome: %s. Quitting.' % _lib.lib().mb2_last_error().decode('utf-8', 'replace'))
+        sys.exit(1)
+    _lib.check(rc)
 
 
 def isfile(path: str) -> str:

@@ -222,3 +222,44 @@ def test_native_map_gff_empty_and_malformed(tmp_path):
     p.write_text('#h\nchr1\t+\t5\n')
     with pytest.raises(RuntimeError, match='line 2'):
         W.map_gff_text(str(p), 'BHit', 100, 90)
+
+
+def test_native_split_fasta_bytes_equal_the_plain_writer(tmp_path):
+    """mb2_fasta_split against the plain numpy statement of SeqIO.write's layout (fasta.write_fasta_record), record by
+    record: awkward lengths (0, 1, 59, 60, 61, multiples of 60), headers with descriptions, CRLF and blank-padded input."""
+    import ctypes as C
+    from mimeo_b200 import _lib, fasta, utils
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 59, 60, 61, 120, 121, 4097, 250_003]
+    recs = []
+    text = []
+    for k, n in enumerate(lens):
+        seq = rng.choice(np.frombuffer(b'ACGTNacgt', dtype=np.uint8), n)
+        hdr = f'rec{k} some description {k}' if k % 2 else f'rec{k}'
+        recs.append((f'rec{k}', hdr, seq))
+        w = [70, 60, 13][k % 3]
+        body = '\n'.join(seq[i:i + w].tobytes().decode() for i in range(0, n, w))
+        eol = '\r\n' if k == 3 else '\n'
+        text.append('>' + hdr + eol + body.replace('\n', eol) + (eol if n else ''))
+    fa = tmp_path / 'g.fa'
+    fa.write_bytes(''.join(text).encode())
+    out, ref = tmp_path / 'native', tmp_path / 'plain'
+    out.mkdir(); ref.mkdir()
+    utils.splitFasta(str(fa), str(out))
+    for rid, hdr, seq in recs:
+        fasta.write_fasta_record(str(ref / (rid + '.fa')), hdr, seq)
+    assert sorted(os.listdir(out)) == sorted(os.listdir(ref))
+    for fn in os.listdir(ref):
+        assert (out / fn).read_bytes() == (ref / fn).read_bytes(), fn
+    # not unique + unique=False: the last record of an id wins; unique=True: the files before the repeat exist, then exit 1
+    dup = tmp_path / 'dup.fa'
+    dup.write_text('>a first\nAC\n>b\nGG\n>a second\nTTT\n>c\nA\n')
+    d1, d2 = tmp_path / 'd1', tmp_path / 'd2'
+    d1.mkdir(); d2.mkdir()
+    utils.splitFasta(str(dup), str(d1), unique=False)
+    assert sorted(os.listdir(d1)) == ['a.fa', 'b.fa', 'c.fa'] and (d1 / 'a.fa').read_text() == '>a second\nTTT\n'
+    with pytest.raises(SystemExit) as e:
+        utils.splitFasta(str(dup), str(d2))
+    assert e.value.code == 1 and sorted(os.listdir(d2)) == ['a.fa', 'b.fa'] and (d2 / 'a.fa').read_text() == '>a first\nAC\n'
+    n = C.c_uint64(0)
+    assert _lib.lib().mb2_fasta_split(os.fsencode(str(dup)), os.fsencode(str(tmp_path / 'missing_dir')), 0, 60, 2, C.byref(n)) != 0
