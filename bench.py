@@ -458,7 +458,9 @@ def run_b200(args):
     traffic, traffic_src = ncu_traffic(args.workload, dom)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'ms_per_launch': per_launch_ms, 'algorithmic_bytes_per_launch': kb[dom],
-                'kernels_ms_per_step': {t: prof[t][0] / args.steps for t in all_tags if prof[t][1]}}
+                'kernels_ms_per_step': {t: prof[t][0] / args.steps for t in all_tags if prof[t][1]},
+                'note': 'the dominant HBM-bound launch group of this workload; kernels bound by the integer pipe (x-drop and y-drop '
+                        'extension, the largest share of a self-alignment step) are reported under gcups, not against HBM'}
     if '_stage_survey' in kb:
         roofline['stage_survey_model'] = {'bytes': kb['_stage_survey'], 'achieved': kb['_stage_survey'] / (ms_step / 1e3) / 1e9,
                                           'frac': kb['_stage_survey'] / (ms_step / 1e3) / 1e9 / peak}
