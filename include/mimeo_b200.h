@@ -229,6 +229,14 @@ MB2_API int mb2_map_gff(const char* tab_path, const char* prefix, double min_len
                         mb2_text* out);
 MB2_API void mb2_free_text(mb2_text* t);
 
+/* The awk that ends every coverage block of the reference's script (wrappers.py:1166-1173; x: 885-891; intra: 1257-1264):
+ * one GFF3 feature row per segment (HOST arrays, e.g. an mb2_segments result),
+ *   names[chrom] \t source \t label \t start \t end \t . \t + \t . \t ID=<prefix>_%05d \n
+ * numbered from first_id (the reference restarts at 1 in every block). Header lines are the caller's. */
+MB2_API int mb2_format_gff(const int32_t* chrom, const int32_t* start, const int32_t* end, uint64_t n, const char* const* names,
+                           int nnames, const char* source, const char* label, const char* prefix, uint64_t first_id, int nthreads,
+                           mb2_text* out);
+
 /* ---- device primitives exposed for parity tests ------------------------------------------- */
 /* Stable LSD radix sort of HOST arrays on bits [begin_bit, end_bit) (vals may be NULL). */
 MB2_API int mb2_test_sort_u32(uint32_t* keys, uint32_t* vals, uint64_t n, int begin_bit, int end_bit);

@@ -93,6 +93,8 @@ SIGNATURES = {
                                  C.c_double, C.c_double, C.POINTER(TabText)]),
     'mb2_free_tab_text': (None, [C.POINTER(TabText)]),
     'mb2_map_gff': (C.c_int, [C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_char_p, C.c_int, C.POINTER(Text)]),
+    'mb2_format_gff': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p,
+                                 C.c_char_p, C.c_uint64, C.c_int, C.POINTER(Text)]),
     'mb2_free_text': (None, [C.POINTER(Text)]),
     'mb2_test_sort_u32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
     'mb2_test_sort_u64': (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),

@@ -518,6 +518,20 @@ int mb2_map_gff(const char* tab_path, const char* prefix, double min_len, double
         memcpy(out->text, text.data(), text.size()); out->text[text.size()] = 0;
     });
 }
+int mb2_format_gff(const int32_t* chrom, const int32_t* start, const int32_t* end, uint64_t n, const char* const* names,
+                   int nnames, const char* source, const char* label, const char* prefix, uint64_t first_id, int nthreads, mb2_text* out) {
+    return guarded([&] {
+        MB2_REQUIRE(out && source && label && prefix && (nnames == 0 || names), MB2_ERR_INVALID_ARG, "mb2_format_gff: null argument");
+        MB2_REQUIRE(n == 0 || (chrom && start && end), MB2_ERR_INVALID_ARG, "mb2_format_gff: null segment arrays");
+        memset(out, 0, sizeof(*out));
+        std::string text;
+        out->nrows = format_segment_gff(chrom, start, end, n, names, nnames, source, label, prefix, first_id, nthreads, text);
+        out->nbytes = text.size();
+        out->text = (char*)malloc(text.size() + 1);
+        MB2_REQUIRE(out->text, MB2_ERR_INTERNAL, "mb2_format_gff: out of memory");
+        memcpy(out->text, text.data(), text.size()); out->text[text.size()] = 0;
+    });
+}
 void mb2_free_text(mb2_text* t) {
     if (!t) return;
     free(t->text);

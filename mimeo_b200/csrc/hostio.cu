@@ -545,4 +545,68 @@ uint64_t fasta_split_file(const char* path, const char* outdir, bool unique, int
     return todo.size();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// format_segment_gff: the awk that ends every coverage block of the reference's script (wrappers.py:1166-1173, 885-891,
+// 1257-1264): one GFF3 feature row per merged run,
+//   chrom \t source \t label \t start \t end \t . \t + \t . \t ID=<prefix>_%05d \n      counter from first_id within the block
+// ------------------------------------------------------------------------------------------------
+namespace {
+inline char* put_uint(char* p, uint64_t v, int min_width) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    for (int k = n; k < min_width; k++) *p++ = '0';
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+}  // namespace
+
+uint64_t format_segment_gff(const int32_t* chrom, const int32_t* start, const int32_t* end, uint64_t n, const char* const* names,
+                            int nnames, const char* source, const char* label, const char* prefix, uint64_t first_id, int nthreads,
+                            std::string& out) {
+    out.clear();
+    if (n == 0) return 0;
+    const std::string mid = std::string("\t") + source + "\t" + label + "\t";
+    const std::string pre = std::string("\t.\t+\t.\tID=") + prefix + "_";
+    std::vector<std::string_view> nm((size_t)nnames);
+    for (int k = 0; k < nnames; k++) nm[k] = names[k];
+    for (uint64_t i = 0; i < n; i++)
+        MB2_REQUIRE(chrom[i] >= 0 && chrom[i] < nnames, -2, "format_segment_gff: scaffold index out of range");
+    const int nt = (int)std::max<uint64_t>(1, std::min<uint64_t>(nthreads > 0 ? (uint64_t)nthreads : std::thread::hardware_concurrency(), n / 4096 + 1));
+    std::vector<uint64_t> cut(nt + 1), bytes(nt + 1, 0);
+    for (int t = 0; t <= nt; t++) cut[t] = n * (uint64_t)t / (uint64_t)nt;
+    const size_t fixed = mid.size() + pre.size() + 11 + 11 + 1 + 20 + 1;     // two ints, tab, id digits, newline
+    run_threads(nt, [&](int t) {
+        uint64_t b = 0;
+        for (uint64_t i = cut[t]; i < cut[t + 1]; i++) b += nm[chrom[i]].size() + fixed;
+        bytes[t + 1] = b;                                                        // upper bound of the thread's text
+    });
+    for (int t = 0; t < nt; t++) bytes[t + 1] += bytes[t];
+    std::string buf(bytes[nt], '\0');
+    std::vector<uint64_t> used(nt, 0);
+    run_threads(nt, [&](int t) {
+        char* const p0 = &buf[bytes[t]];
+        char* p = p0;
+        for (uint64_t i = cut[t]; i < cut[t + 1]; i++) {
+            const std::string_view& c = nm[chrom[i]];
+            memcpy(p, c.data(), c.size()); p += c.size();
+            memcpy(p, mid.data(), mid.size()); p += mid.size();
+            p = put_int(p, (long long)start[i]); *p++ = '\t';
+            p = put_int(p, (long long)end[i]);
+            memcpy(p, pre.data(), pre.size()); p += pre.size();
+            p = put_uint(p, first_id + i, 5); *p++ = '\n';
+        }
+        used[t] = (uint64_t)(p - p0);
+    });
+    uint64_t total = 0;                                                          // close the gaps between the threads' pieces
+    for (int t = 0; t < nt; t++) {
+        if (bytes[t] != total) memmove(&buf[total], &buf[bytes[t]], used[t]);
+        total += used[t];
+    }
+    buf.resize(total);
+    out.swap(buf);
+    return n;
+}
+
 }  // namespace mb2

@@ -109,6 +109,11 @@ void format_tab_blocks(const int32_t* t_id, const int32_t* q_id, const int32_t* 
 // GFF3 feature rows of `mimeo map` straight from the .tab file; returns the number of rows
 uint64_t map_gff_rows(const char* path, const char* prefix, double min_len, double min_idt, const char* ftype, int nthreads, std::string& out);
 
+// GFF3 feature rows of one coverage block (the awk formatter of wrappers.py:1166-1173); returns the number of rows
+uint64_t format_segment_gff(const int32_t* chrom, const int32_t* start, const int32_t* end, uint64_t n, const char* const* names,
+                            int nnames, const char* source, const char* label, const char* prefix, uint64_t first_id, int nthreads,
+                            std::string& out);
+
 // counters layout (device, unsigned long long[16])
 enum { CNT_SURV = 0, CNT_SEED_HITS = 1, CNT_LEADERS = 2, CNT_S1_CELLS = 3, CNT_HSPS = 4, CNT_EXTENDED = 5, CNT_S2_CELLS = 6,
        CNT_GAPPED_CELLS = 7, CNT_ALNS = 8, CNT_ANCHORS = 9, CNT_ERR = 10, CNT_WORK = 11, CNT_N = 16 };

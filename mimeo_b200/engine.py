@@ -168,7 +168,26 @@ def coverage_rows(tab_path: str, sizes: Dict[str, int], cov, minLen, source: str
     chrom = np.asarray([idx[n] for n in names], dtype=np.int32)[ids]
     c, s, e = _coverage.coverage_segments(chrom, start.astype(np.int32), end.astype(np.int32), [sizes[n] for n in order],
                                           int(cov), int(minLen))
-    return [f'{order[int(c[k])]}\t{source}\t{label}\t{int(s[k])}\t{int(e[k])}\t.\t+\t.\tID={prefix}_{k + 1:05d}\n' for k in range(len(c))]
+    return segment_gff_text(c, s, e, order, source, label, prefix).splitlines(keepends=True)
+
+
+def segment_gff_text(chrom, start, end, names: Sequence[str], source: str, label: str, prefix, first_id: int = 1) -> str:
+    """GFF3 feature rows of one coverage block as one string: the awk formatter that ends the block in the reference's script
+    (wrappers.py:1166-1173), `ID=<prefix>_%05d` counted from first_id. Formatted natively (`mb2_format_gff`)."""
+    import ctypes as C
+    from . import _lib
+    n = len(chrom)
+    if n == 0:
+        return ''
+    c, s, e = (np.ascontiguousarray(a, dtype=np.int32) for a in (chrom, start, end))
+    arr = (C.c_char_p * len(names))(*[x.encode() for x in names])
+    t = _lib.Text()
+    _lib.check(_lib.lib().mb2_format_gff(c.ctypes.data, s.ctypes.data, e.ctypes.data, n, arr, len(names), str(source).encode(),
+                                         str(label).encode(), str(prefix).encode(), int(first_id), 0, C.byref(t)))
+    try:
+        return C.string_at(t.text, int(t.nbytes)).decode('utf-8', 'replace')
+    finally:
+        _lib.lib().mb2_free_text(C.byref(t))
 
 
 def coverage_to_gff(tab_path: str, lens_path: str, outgff: str, cov, minLen, source: str, label: str, prefix,

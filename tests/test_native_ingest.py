@@ -263,3 +263,22 @@ def test_native_split_fasta_bytes_equal_the_plain_writer(tmp_path):
     assert e.value.code == 1 and sorted(os.listdir(d2)) == ['a.fa', 'b.fa'] and (d2 / 'a.fa').read_text() == '>a first\nAC\n'
     n = C.c_uint64(0)
     assert _lib.lib().mb2_fasta_split(os.fsencode(str(dup)), os.fsencode(str(tmp_path / 'missing_dir')), 0, 60, 2, C.byref(n)) != 0
+
+
+def test_native_gff_rows_equal_the_plain_statement():
+    """mb2_format_gff against the f-string statement of the reference's closing awk (wrappers.py:1166-1173): names with
+    odd bytes, ids beyond 99999 (the %05d field widens), prefix None as the reference would print it, thread seams."""
+    from mimeo_b200 import engine
+    rng = np.random.default_rng(11)
+    names = ['S3', 's10', 's2', 'chr_with.dots|and|bars', 'x' * 70]
+    for n, first in [(0, 1), (1, 1), (7, 1), (20_011, 1), (5000, 99_990)]:
+        c = np.sort(rng.integers(0, len(names), n)).astype(np.int32)
+        s = rng.integers(0, 2_000_000_000, n).astype(np.int32)
+        e = (s.astype(np.int64) + rng.integers(0, 100_000, n)).clip(0, 2**31 - 1).astype(np.int32)
+        for prefix in ('Self_Repeat', None):
+            want = ''.join(f'{names[int(c[k])]}\tmimeo-self\tSelf_Repeat_intra\t{int(s[k])}\t{int(e[k])}\t.\t+\t.\tID={prefix}_{first + k:05d}\n'
+                           for k in range(n))
+            got = engine.segment_gff_text(c, s, e, names, 'mimeo-self', 'Self_Repeat_intra', prefix, first)
+            assert got == want
+    with pytest.raises(Exception):
+        engine.segment_gff_text(np.array([5], np.int32), np.array([1], np.int32), np.array([2], np.int32), names, 'a', 'b', 'c')
