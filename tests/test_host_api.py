@@ -138,3 +138,50 @@ def test_cli_surfaces_match_reference_defaults(monkeypatch):
     monkeypatch.setattr(sys, 'argv', ['mimeo-map'])
     a = run_map.mainArgs()
     assert (a.gffout, a.label, a.prefix, a.maxtandem, a.tmaxperiod) == (None, 'BHit', 'BHit', None, 50)
+
+
+@pytest.mark.parametrize('case', ['cov_order', 'cov_dense', 'cov_nointra'])
+def test_recycle_cli_host_path_against_reference_goldens_with_the_device_stage_stubbed(tmp_path, monkeypatch, case):
+    """Everything AROUND the coverage kernel on the `mimeo self -r` / `mimeo x -r` path -- CLI, chromlens, native .tab
+    projection, scaffold ordering, native GFF3 rows, header and block order -- against the files the reference's own script
+    wrote (tests/golden), on CPU: the device stage alone is replaced by the oracle's array statement (the GPU test
+    test_gpu_cli.py::test_self_recycle_is_byte_identical_to_reference_script runs the same flow through the kernels)."""
+    import json
+    import shutil
+    import sys
+    from oracle import annot_oracle as ao
+    from tests.helpers import read_golden
+    from mimeo_b200 import app, coverage
+    golden = os.path.join(os.path.dirname(__file__), 'golden')
+    m = json.loads(read_golden('manifest.json'))[case]
+
+    def stub(chrom, start, end, sizes, cov, min_len):
+        out = ao.coverage_segments_arrays(np.asarray(chrom), np.asarray(start), np.asarray(end), sizes, max(int(cov), 1), int(min_len))
+        return tuple(np.asarray(a, dtype=np.int32) for a in out)
+    monkeypatch.setattr(coverage, 'coverage_segments', stub)
+    monkeypatch.chdir(tmp_path)
+    shutil.copy(os.path.join(golden, case + '.tab'), tmp_path / 'hits.tab')
+    if m['has_intra']:
+        shutil.copy(os.path.join(golden, case + '.tab_intra.tab'), tmp_path / 'hits.tab_intra.tab')
+    adir = tmp_path / 'A'
+    adir.mkdir()
+    for ln in read_golden(case + '.lens').splitlines():
+        n, size = ln.split('\t')
+        (adir / (n + '.fa')).write_text(f'>{n}\n' + 'A' * int(size) + '\n')
+
+    def run(argv):
+        monkeypatch.setattr(sys, 'argv', ['mimeo'] + argv)
+        try:
+            app.main()
+        except SystemExit as e:
+            assert e.code in (0, None)
+    argv = ['self', '--adir', str(adir), '-r', '--outfile', 'hits.tab', '--gffout', 'out.gff3', '--minCov', str(m['minCov']),
+            '--intraCov', str(m['intraCov']), '--minLen', str(m['minLen']), '--label', m['label'], '--prefix', m['prefix']]
+    if m['has_intra']:
+        argv.append('--strictSelf')
+    run(argv)
+    assert (tmp_path / 'out.gff3').read_text() == read_golden(case + '.gff3')
+    assert (tmp_path / 'A_gen_lens.txt').read_text() == read_golden(case + '.lens')
+    run(['x', '--adir', str(adir), '--bdir', str(adir), '-r', '--outfile', 'hits.tab', '--gffout', 'x.gff3',
+         '--minCov', str(m['minCov']), '--minLen', str(m['minLen'])])
+    assert (tmp_path / 'x.gff3').read_text() == read_golden(case + '.x.gff3')
