@@ -185,3 +185,98 @@ def test_recycle_cli_host_path_against_reference_goldens_with_the_device_stage_s
     run(['x', '--adir', str(adir), '--bdir', str(adir), '-r', '--outfile', 'hits.tab', '--gffout', 'x.gff3',
          '--minCov', str(m['minCov']), '--minLen', str(m['minLen'])])
     assert (tmp_path / 'x.gff3').read_text() == read_golden(case + '.x.gff3')
+
+
+def _oracle_device_stubs(monkeypatch):
+    """Replace the two device stages by their oracle statements (tests only): `engine.align_genomes` by the C
+    LASTZ-restatement, `coverage.coverage_segments` by the numpy sweep. Everything else on the path stays the product's."""
+    from oracle import annot_oracle as ao
+    from oracle import lastz_oracle as lo
+    from mimeo_b200 import align, coverage, engine
+
+    def align_stub(tnames, tseqs, qnames, qseqs, hspthresh=3000, same=False):
+        p = lo.default_params(hspthresh)
+        cols = {f: [] for f in align.HIT_FIELDS}
+        qenc = [lo.encode(np.asarray(s)) for s in qseqs]
+        for ti, ts in enumerate(tseqs):
+            t = lo.TargetIndex(lo.encode(np.asarray(ts)))
+            for qi, q in enumerate(qenc):
+                m = len(q)
+                for strand, qq in ((0, q), (1, lo.revcomp_codes(q))):
+                    for (s1, e1, s2, e2, score, nm, nc, _a1, _a2) in lo.align_tile(t, qq, p).tolist():
+                        qs, qe = (s2 + 1, e2) if strand == 0 else (m - e2 + 1, m - s2)
+                        for f, v in zip(align.HIT_FIELDS, (ti, qi, strand, s1 + 1, e1, qs, qe, score, nm, nc)):
+                            cols[f].append(v)
+        return {f: np.asarray(v, dtype=np.int32) for f, v in cols.items()}, {n: 0 for n in align.STAT_NAMES}
+
+    def cov_stub(chrom, start, end, sizes, cov, min_len):
+        out = ao.coverage_segments_arrays(np.asarray(chrom), np.asarray(start), np.asarray(end), sizes, max(int(cov), 1), int(min_len))
+        return tuple(np.asarray(a, dtype=np.int32) for a in out)
+    monkeypatch.setattr(engine, 'align_genomes', align_stub)
+    monkeypatch.setattr(coverage, 'coverage_segments', cov_stub)
+
+
+def _write_genome(path, g):
+    with open(path, 'w') as f:
+        for n, s in g.items():
+            f.write(f'>{n}\n')
+            t = s.tobytes().decode()
+            for k in range(0, len(t), 70):
+                f.write(t[k:k + 70] + '\n')
+
+
+def _cli(monkeypatch, argv):
+    from mimeo_b200 import app
+    monkeypatch.setattr(sys, 'argv', ['mimeo'] + argv)
+    try:
+        app.main()
+    except SystemExit as e:
+        assert e.code in (0, None)
+
+
+def test_self_cli_host_path_against_the_oracle_pipeline_with_device_stages_stubbed(tmp_path, monkeypatch):
+    """`mimeo self` from a FASTA file on CPU: split directory, per-pair .tab blocks, _intra.tab, GFF3 -- the product's host
+    code (native splitter, .tab and GFF formatters, block order) around stubbed device stages must reproduce the oracle's
+    statement of the reference script byte for byte (GPU twin: test_gpu_cli.py::test_self_from_fasta_matches_oracle_pipeline)."""
+    from oracle import lastz_oracle as lo
+    from tests.helpers import synth_genome
+    _oracle_device_stubs(monkeypatch)
+    g = synth_genome(51, 3, 12_000, 2, copies=(5, 7), fam_len=(300, 900), sub=0.08, indel=0.004)
+    monkeypatch.chdir(tmp_path)
+    _write_genome(tmp_path / 'g.fa', g)
+    _cli(monkeypatch, ['self', '--afasta', 'g.fa', '--adir', 'split', '--strictSelf', '--minIdt', '80', '--minCov', '2',
+                       '--intraCov', '2', '--outfile', 'o.tab', '--gffout', 'o.gff3'])
+    enc = {k: lo.encode(v) for k, v in g.items()}
+    tab, intra, gff = lo.mimeo_self(enc, minIdt=80, minLen=100, minCov=2, intraCov=2, strictSelf=True)
+    assert (tmp_path / 'o.tab').read_text() == tab and tab.count('\n') > 5
+    assert (tmp_path / 'o.tab_intra.tab').read_text() == intra
+    assert (tmp_path / 'o.gff3').read_text() == gff and gff.count('\n') > 3
+    assert sorted(os.listdir(tmp_path / 'split')) == [n + '.fa' for n in sorted(g)]
+
+
+def test_x_and_map_cli_host_path_against_the_oracle_pipeline_with_device_stages_stubbed(tmp_path, monkeypatch):
+    from oracle import lastz_oracle as lo
+    from tests.helpers import mutate, revcomp_ascii, synth_genome
+    _oracle_device_stubs(monkeypatch)
+    a = synth_genome(52, 2, 12_000, 0)
+    b = synth_genome(53, 3, 8_000, 0)
+    rng = np.random.default_rng(1)
+    fam = a['scaf000'][3000:3900].copy()
+    for k, (s, p) in enumerate([('scaf000', 100), ('scaf001', 1000), ('scaf001', 4000), ('scaf002', 300), ('scaf002', 3000), ('scaf002', 6000)]):
+        cp = mutate(rng, fam, 0.04, 0.003)
+        if k % 2:
+            cp = revcomp_ascii(cp)
+        b[s][p:p + len(cp)] = cp
+    monkeypatch.chdir(tmp_path)
+    _write_genome(tmp_path / 'a.fa', a)
+    _write_genome(tmp_path / 'b.fa', b)
+    _cli(monkeypatch, ['x', '--afasta', 'a.fa', '--bfasta', 'b.fa', '--minIdt', '80', '--minCov', '5', '--outfile', 'x.tab', '--gffout', 'x.gff3'])
+    ea = {k: lo.encode(v) for k, v in a.items()}
+    eb = {k: lo.encode(v) for k, v in b.items()}
+    tab, gff = lo.mimeo_x(ea, eb, minIdt=80, minLen=100, minCov=5)
+    assert (tmp_path / 'x.tab').read_text() == tab and (tmp_path / 'x.gff3').read_text() == gff
+    assert gff.count('B_Repeat_00001') == 1
+    _cli(monkeypatch, ['map', '--afasta', 'a.fa', '--bfasta', 'b.fa', '--minIdt', '90', '--outfile', 'm.tab', '--gffout', 'm.gff3'])
+    tabm, gffm = lo.mimeo_map(ea, eb, minIdt=90, minLen=100)
+    assert (tmp_path / 'm.tab').read_text() == tabm and (tmp_path / 'm.gff3').read_text() == gffm
+    assert gffm.count('mimeo-map') >= 3
