@@ -1,8 +1,8 @@
 // primitives.cuh -- device-wide exclusive scan and LSD radix sort, hand-written for sm_100a.
 //
 // Both are global-atomic-free: the radix pass is histogram -> scan -> stable scatter with
-// per-warp digit counters in shared memory (warp match/ballot ranking), so results are
-// deterministic. Used by the coverage stage (bin interval events by genome tile) and by the
+// per-warp digit counters in shared memory (lanes of a warp with the same digit find each other
+// through a shared-memory OR of lane bits, ranks follow lane order), so results are deterministic. Used by the coverage stage (bin interval events by genome tile) and by the
 // alignment stage (group seed hits by diagonal, HSPs by scaffold pair).
 #pragma once
 #include <type_traits>
@@ -218,7 +218,8 @@ radix_hist_kernel(const K* __restrict__ in0, const K* __restrict__ in1, uint32_t
 
 // Lanes of `act` holding the same (at most 8-bit) digit. Not __match_any_sync: MATCH.ANY issues on the ADU pipe, which ncu
 // showed 55-60 % busy and the limiter of the scatter kernel (profiles/r1_cov_v18_ncu_summary.txt); votes are cheap, and a
-// warp of (nearly) sorted keys takes the one-vote exit.
+// warp of (nearly) sorted keys takes the one-vote exit. Used for the one partial tile of a sort; full tiles use the
+// shared-memory OR in radix_scatter_kernel (an eighth of the instructions on unsorted keys).
 __device__ __forceinline__ uint32_t match_digit(uint32_t act, uint32_t d) {
     const uint32_t d0 = __shfl_sync(act, d, __ffs(act) - 1);
     if (__all_sync(act, d == d0)) return act;
