@@ -91,6 +91,7 @@ int mb2_init(int device) {
 void mb2_shutdown(void) {
     if (g_ctx.ready) {
         coverage_release_scratch();
+        gapped_release_scratch();
         cudaStreamSynchronize(g_ctx.stream);
         cudaStreamDestroy(g_ctx.stream);
         g_ctx.stream = nullptr;

@@ -22,21 +22,16 @@
 //   gp_extend_kernel   one CTA per (anchor, direction), all tiles in one launch.
 // Speculation changes which extensions are computed early, never the result: a speculative result is
 // only used when the sequential walk reaches its anchor and finds it uncovered.
+#include <algorithm>
+
 #include "primitives.cuh"
 #include "seq.cuh"
 #include "internal.cuh"
+#include "ydrop_warp.cuh"
 
 namespace mb2 {
 
-// CTA shape of the extension kernel: NT threads, each owning SLOTS consecutive diagonals of a circular window of
-// ND = NT * SLOTS diagonal slots, slot = (i - j) & (ND - 1); a thread computes SLOTS/2 independent cells per anti-diagonal.
-template <int NT_, int SLOTS_> struct GpShape {
-    static constexpr int NT = NT_, SLOTS = SLOTS_, WARPS = NT_ / 32, ND = NT_ * SLOTS_, DMASK = ND - 1;
-    static constexpr int MAXBAND = ND - 64;   // widest alive diagonal range the circular window can hold
-};
-constexpr int NEG_INF = INT_MIN / 4;
 constexpr int GP_CLUSTER_GAP = 1000;     // chain members further apart than this (either axis) start a new speculation cluster
-constexpr int GP_NARROW_ABORT_K = 140000;  // 16-bit payload run: beyond this anti-diagonal every cell has >= 65536 columns behind it
 
 __device__ __forceinline__ int sub_lut3(uint32_t idx) {
     const uint64_t lo = 0xE183648E85E18E5Bull, hi = 0x5B8EE1858E6483E1ull;
@@ -98,280 +93,18 @@ cluster_ids_kernel(const uint32_t* __restrict__ mlist, uint32_t nmember, const u
 
 struct Ext { int score, di, dj, nmatch, ncols; };
 
-// ---- payload (matches, aligned columns) of a DP state, packed in one register (16+16 bits) or two (32+32)
-template <typename P> struct Pay;
-template <> struct Pay<uint32_t> {
-    static __device__ __forceinline__ uint32_t step(uint32_t p, int match) { return p + 0x10000u + (uint32_t)match; }
-    static __device__ __forceinline__ int nm(uint32_t p) { return (int)(p & 0xffffu); }
-    static __device__ __forceinline__ int nc(uint32_t p) { return (int)(p >> 16); }
-};
-template <> struct Pay<uint64_t> {
-    static __device__ __forceinline__ uint64_t step(uint64_t p, int match) { return p + (1ull << 32) + (uint64_t)(uint32_t)match; }
-    static __device__ __forceinline__ int nm(uint64_t p) { return (int)(uint32_t)p; }
-    static __device__ __forceinline__ int nc(uint64_t p) { return (int)(p >> 32); }
-};
-
-template <typename P> struct Cell { int h, d, i; P hp, dp, ip; };
-// A dead cell holds NEG_INF in all three scores; arithmetic on it stays far below any threshold (thr >= -ydrop), so the
-// recurrence needs no "is this predecessor alive" branches: a cell whose predecessors are all dead evaluates to ~NEG_INF,
-// fails H >= thr and is reset to exactly NEG_INF.
-template <typename P> __device__ __forceinline__ void cell_dead(Cell<P>& c) { c.h = c.d = c.i = NEG_INF; c.hp = c.dp = c.ip = 0; }
-
-// what a thread publishes for its neighbours: slot 0 is read as the LEFT neighbour (h, i) of thread t-1's last slot,
-// the last slot as the UP neighbour (h, d) of thread t+1's slot 0
-template <typename P> struct Edge { int h, x; P hp, xp; };
-template <typename P, int NT> struct EdgeBuf;
-template <int NT> struct EdgeBuf<uint32_t, NT> {
-    int4 v[NT];
-    __device__ __forceinline__ void put(int t, const Edge<uint32_t>& e) { v[t] = make_int4(e.h, e.x, (int)e.hp, (int)e.xp); }
-    __device__ __forceinline__ Edge<uint32_t> get(int t) const { const int4 a = v[t]; return Edge<uint32_t>{a.x, a.y, (uint32_t)a.z, (uint32_t)a.w}; }
-};
-template <int NT> struct EdgeBuf<uint64_t, NT> {
-    int4 v[NT]; int2 w[NT];
-    __device__ __forceinline__ void put(int t, const Edge<uint64_t>& e) {
-        v[t] = make_int4(e.h, e.x, (int)(uint32_t)e.hp, (int)(uint32_t)(e.hp >> 32)); w[t] = make_int2((int)(uint32_t)e.xp, (int)(uint32_t)(e.xp >> 32));
-    }
-    __device__ __forceinline__ Edge<uint64_t> get(int t) const {
-        const int4 a = v[t]; const int2 b = w[t];
-        return Edge<uint64_t>{a.x, a.y, (uint64_t)(uint32_t)a.z | ((uint64_t)(uint32_t)a.w << 32), (uint64_t)(uint32_t)b.x | ((uint64_t)(uint32_t)b.y << 32)};
-    }
-};
-
-template <typename P, typename S> struct GpShared {
-    EdgeBuf<P, S::NT> left;             // slot 0 of every thread: {h, i, hp, ip}
-    EdgeBuf<P, S::NT> up;               // last slot of every thread: {h, d, hp, dp}
-    int smax[2][S::WARPS];              // per parity, per warp: maximum score of the anti-diagonal (NEG_INF = nothing alive)
-    int2 rng[S::WARPS];                 // end of an epoch: per warp {lowest, highest} alive diagonal
-    int4 fin[S::WARPS]; int2 finp[S::WARPS];   // end of the extension: per warp {score, k, i, -} and payload of its first maximum
-    int2 lut[25];                       // {substitution score, is-match} for codes 0..4 x 0..4
-    int red[S::WARPS];
-};
-
-// One DP cell (i,j) of anti-diagonal k on diagonal delta = i - j.  self = this diagonal's cell two anti-diagonals ago
-// (updated in place), (uh, ud) = H and D of cell (i-1,j), (lh, li) = H and I of cell (i,j-1), both of the previous anti-diagonal.
-// ok = cell lies inside both sequences (always true away from the sequence ends). hmax collects the maximum of the
-// thread's cells on this anti-diagonal: every thread remembers the first cell (anti-diagonal, then row) that reached its own
-// maximum, and the alignment end is picked among those records once, at the end of the extension, so an anti-diagonal only
-// has to share ONE number (its maximum score) for the y-drop threshold.
-template <typename P>
-__device__ __forceinline__ void gp_cell(Cell<P>& self, int uh, int ud, P uhp, P udp, int lh, int li, P lhp, P lip, int2 sc, bool ok,
-                                        int OE, int E, int thr, int& hmax) {
-    // D: vertical gap state, I: horizontal gap state (ties prefer opening from H, as in the oracle)
-    const int dopen = uh - OE, dext = ud - E;
-    const bool dsel = dopen >= dext;
-    const int nd = dsel ? dopen : dext; const P ndp = dsel ? uhp : udp;
-    const int iopen = lh - OE, iext = li - E;
-    const bool isel = iopen >= iext;
-    const int ni = isel ? iopen : iext; const P nip = isel ? lhp : lip;
-    const int mval = self.h + sc.x; const P mp = Pay<P>::step(self.hp, sc.y);
-    // H = max(M, D, I) with ties M > D > I
-    const bool pickm = mval >= nd && mval >= ni;
-    const bool pickd = nd >= ni;
-    const int nh = pickm ? mval : (pickd ? nd : ni);
-    const P nhp = pickm ? mp : (pickd ? ndp : nip);
-    const bool alive = ok && nh >= thr;
-    self.h = alive ? nh : NEG_INF; self.d = alive ? nd : NEG_INF; self.i = alive ? ni : NEG_INF;
-    self.hp = nhp; self.dp = ndp; self.ip = nip;
-    hmax = max(hmax, self.h);
-}
-
-// One-sided y-drop extension by the whole CTA in diagonal-major coordinates. DIR=+1: cell (i,j) consumes T[ta+i-1],
-// Q[qa+j-1]; DIR=-1: T[ta-i], Q[qa-j]. Diagonals delta = i-j live in a circular window of ND slots, slot = delta mod ND;
-// thread t owns SLOTS consecutive slots for the whole extension, so every cell and all but one of its neighbours stay in
-// registers. Per anti-diagonal a thread computes its cells of the right parity (independent of each other), reads ONE
-// cell of a neighbouring thread from shared memory and publishes one; one __syncthreads per anti-diagonal, which shares
-// a single number per warp (the anti-diagonal's maximum, for the y-drop threshold and the "all dead" test). Dead cells
-// are -inf by value, so the window follows the alignment without bookkeeping: a slot that re-enters the band on another
-// diagonal is already dead.
-//
-// The band is re-measured only every GP_EPOCH anti-diagonals: the exact range [lo, hi] of alive diagonals is taken at the
-// end of an epoch, and because an alive cell needs an alive neighbour one anti-diagonal earlier (or itself two earlier),
-// the alive range grows by at most one diagonal per side and step, so computing [lo - GP_EPOCH, hi + GP_EPOCH] for the
-// whole next epoch covers every cell that can be alive (the extra cells evaluate to dead). Which threads and warps work,
-// the window base and the sequence-end test are therefore constants of an epoch; warps outside the range only keep
-// the barrier company.
-// Returns false if the payload type cannot represent the result (16-bit columns overflowed): rerun with P = uint64_t.
-constexpr int GP_EPOCH = 16;
-template <typename P, typename S, int DIR>
-__device__ bool ydrop_extend_cta(const GenomeView& T, const GenomeView& Q, uint32_t ta, uint32_t qa, int tn, int qn, int O, int E, int Y,
-                                 GpShared<P, S>& sm, Ext& r, unsigned& ncell, int& err) {
-    constexpr int GP_NT = S::NT, GP_SLOTS = S::SLOTS, GP_WARPS = S::WARPS, GP_DMASK = S::DMASK, GP_MAXBAND = S::MAXBAND;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint8_t* __restrict__ tcodes = T.codes;
-    const uint8_t* __restrict__ qcodes = Q.codes;
-    const int OE = O + E;
-    r = Ext{0, 0, 0, 0, 0};
-    Cell<P> st[GP_SLOTS];
-#pragma unroll
-    for (int s = 0; s < GP_SLOTS; s++) cell_dead(st[s]);
-    if (tid == 0) st[0].h = 0;             // cell (0,0) on diagonal 0 = slot 0 of thread 0
-    __syncthreads();                        // previous users of the buffers are done
-    sm.left.put(tid, Edge<P>{st[0].h, NEG_INF, 0, 0});
-    sm.up.put(tid, Edge<P>{NEG_INF, NEG_INF, 0, 0});
-    __syncthreads();
-    int best = 0, dead_steps = 0;
-    int lo_e = 0, hi_e = 0;                     // exact alive diagonal range over the last two anti-diagonals
-    int tbest = 0, tk = 0, ti = 0;              // this thread's first maximum; (0, 0, 0) = the anchor cell itself
-    P tp = 0;
-    bool narrow_ok = true, finished = false;
-    const uint32_t kmax = (uint32_t)tn + (uint32_t)qn;
-    uint32_t k = 1;
-    while (!finished && k <= kmax) {
-        if (sizeof(P) == 4 && k >= (uint32_t)GP_NARROW_ABORT_K) { narrow_ok = false; break; }
-        if (hi_e - lo_e + 2 * GP_EPOCH > GP_MAXBAND) { err = 1; break; }
-        // ---------------- constants of the epoch
-        const int rlo = lo_e - GP_EPOCH, rhi = hi_e + GP_EPOCH;
-        const int base = (rlo - 16) & ~(GP_SLOTS - 1);     // window base: a multiple of SLOTS so a thread's slots stay consecutive
-        const int d0 = base + ((GP_SLOTS * tid - base) & GP_DMASK);  // diagonal of slot 0; slot s holds d0 + s
-        const bool active = d0 + GP_SLOTS - 1 >= rlo && d0 <= rhi;
-        const bool wactive = __any_sync(0xffffffffu, active);
-        const uint32_t kend = min(kmax, k + (uint32_t)GP_EPOCH - 1u);
-        // can any cell of the epoch lie beyond the end of a sequence? (uniform over the CTA)
-        const bool edge = (((int)kend + rhi + GP_SLOTS + 1) >> 1) > tn || (((int)kend - rlo + GP_SLOTS + 1) >> 1) > qn;
-        if (!wactive && lane == 0) { sm.smax[0][warp] = NEG_INF; sm.smax[1][warp] = NEG_INF; }
-        for (; k <= kend; k++) {
-            const int thr = best - Y;
-            const int par = (int)(k & 1);
-            int hmax = NEG_INF;
-            if (active) {
-                const int i0 = ((int)k + d0 + par) >> 1, j0 = ((int)k - d0 - par) >> 1;   // cell c of this thread: (i0 + c, j0 - c)
-                int2 sc[GP_SLOTS / 2];
-                bool ok[GP_SLOTS / 2];
-                if (!edge) {
-                    const uint8_t* tp_ = DIR > 0 ? tcodes + ta + i0 - 1 : tcodes + ta - i0;
-                    const uint8_t* qp_ = DIR > 0 ? qcodes + qa + j0 - 1 : qcodes + qa - j0;
-#pragma unroll
-                    for (int c = 0; c < GP_SLOTS / 2; c++) {
-                        const uint32_t tb = DIR > 0 ? tp_[c] : tp_[-c], qb = DIR > 0 ? qp_[-c] : qp_[c];
-                        sc[c] = sm.lut[tb * 5 + qb]; ok[c] = true;
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < GP_SLOTS / 2; c++) {
-                        const int i = i0 + c, j = j0 - c;
-                        ok[c] = i >= 0 && j >= 0 && i <= tn && j <= qn;
-                        const int ic_ = min(max(i, 1), max(tn, 1)), jc_ = min(max(j, 1), max(qn, 1));
-                        const uint32_t tb = tcodes[DIR > 0 ? ta + (uint32_t)ic_ - 1u : ta - (uint32_t)ic_];
-                        const uint32_t qb = qcodes[DIR > 0 ? qa + (uint32_t)jc_ - 1u : qa - (uint32_t)jc_];
-                        sc[c] = sm.lut[tb * 5 + qb];
-                    }
-                }
-                if (par) {
-                    // odd anti-diagonal: odd slots; up = slot s-1 (own), left = slot s+1 (own, or slot 0 of thread t+1 for the last slot)
-                    const Edge<P> fl = sm.left.get((tid + 1) & (GP_NT - 1));
-#pragma unroll
-                    for (int c = 0; c < GP_SLOTS / 2; c++) {
-                        const int s = 2 * c + 1;
-                        if (s + 1 < GP_SLOTS) {
-                            const Cell<P>& L = st[s + 1 < GP_SLOTS ? s + 1 : s];
-                            gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, L.h, L.i, L.hp, L.ip, sc[c], ok[c], OE, E, thr, hmax);
-                        } else {
-                            gp_cell<P>(st[s], st[s - 1].h, st[s - 1].d, st[s - 1].hp, st[s - 1].dp, fl.h, fl.x, fl.hp, fl.xp, sc[c], ok[c], OE, E, thr, hmax);
-                        }
-                    }
-                    const Cell<P>& e = st[GP_SLOTS - 1];
-                    sm.up.put(tid, Edge<P>{e.h, e.d, e.hp, e.dp});
-                } else {
-                    // even anti-diagonal: even slots; up = slot s-1 (own, or the last slot of thread t-1 for slot 0), left = slot s+1 (own)
-                    const Edge<P> fu = sm.up.get((tid - 1) & (GP_NT - 1));
-#pragma unroll
-                    for (int c = 0; c < GP_SLOTS / 2; c++) {
-                        const int s = 2 * c;
-                        if (s > 0) {
-                            const Cell<P>& U = st[s > 0 ? s - 1 : 0];
-                            gp_cell<P>(st[s], U.h, U.d, U.hp, U.dp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, hmax);
-                        } else {
-                            gp_cell<P>(st[s], fu.h, fu.x, fu.hp, fu.xp, st[s + 1].h, st[s + 1].i, st[s + 1].hp, st[s + 1].ip, sc[c], ok[c], OE, E, thr, hmax);
-                        }
-                    }
-                    const Cell<P>& e = st[0];
-                    sm.left.put(tid, Edge<P>{e.h, e.i, e.hp, e.ip});
-                }
-                ncell += GP_SLOTS / 2;
-                if (hmax > tbest) {
-                    // a new maximum of this thread (rare): its first cell in row order on this anti-diagonal. Strict > across
-                    // anti-diagonals keeps the earliest one.
-                    tbest = hmax; tk = (int)k;
-                    bool found = false;
-#pragma unroll
-                    for (int c = 0; c < GP_SLOTS / 2; c++) {
-                        const int hv = par ? st[2 * c + 1].h : st[2 * c].h;
-                        if (!found && hv == hmax) { found = true; ti = i0 + c; tp = par ? st[2 * c + 1].hp : st[2 * c].hp; }
-                    }
-                }
-            }
-            if (wactive) {
-                const int wmax = __reduce_max_sync(0xffffffffu, hmax);
-                if (lane == 0) sm.smax[par][warp] = wmax;
-            }
-            __syncthreads();                    // the one barrier of this anti-diagonal
-            int bmax = NEG_INF;
-#pragma unroll
-            for (int w = 0; w < GP_WARPS; w++) bmax = max(bmax, sm.smax[par][w]);
-            best = max(best, bmax);
-            dead_steps = bmax > NEG_INF ? 0 : dead_steps + 1;
-            if (dead_steps >= 2) { finished = true; break; }   // two dead anti-diagonals in a row: nothing can revive
-        }
-        if (finished) break;
-        // ---------------- end of the epoch: exact range of alive diagonals (every slot holds its diagonal's latest cell)
-        int dlo = INT_MAX, dhi = INT_MIN;
-        if (active) {
-#pragma unroll
-            for (int s = 0; s < GP_SLOTS; s++)
-                if (st[s].h > NEG_INF) { dlo = min(dlo, d0 + s); dhi = max(dhi, d0 + s); }
-        }
-        const int wlo = __reduce_min_sync(0xffffffffu, dlo), whi = __reduce_max_sync(0xffffffffu, dhi);
-        if (lane == 0) sm.rng[warp] = make_int2(wlo, whi);
-        __syncthreads();
-        int alo = INT_MAX, ahi = INT_MIN;
-#pragma unroll
-        for (int w = 0; w < GP_WARPS; w++) { const int2 q = sm.rng[w]; alo = min(alo, q.x); ahi = max(ahi, q.y); }
-        if (ahi < alo) break;                   // nothing alive (the dead-step test catches this first)
-        lo_e = alo; hi_e = ahi;
-    }
-    // the alignment end: among the threads whose own maximum equals the global one, the earliest anti-diagonal, then the
-    // smallest row (each thread's record already is its first such cell)
-    {
-        __syncthreads();
-        const bool cand = tbest == best;
-        const int wk = __reduce_min_sync(0xffffffffu, cand ? tk : INT_MAX);
-        const int wi = __reduce_min_sync(0xffffffffu, (cand && tk == wk) ? ti : INT_MAX);
-        if (cand && tk == wk && ti == wi) {
-            const uint64_t p64 = (uint64_t)tp;
-            sm.fin[warp] = make_int4(best, wk, wi, 0); sm.finp[warp] = make_int2((int)(uint32_t)p64, (int)(uint32_t)(p64 >> 32));
-        }
-        if (wk == INT_MAX && lane == 0) sm.fin[warp] = make_int4(INT_MIN, INT_MAX, INT_MAX, 0);
-        __syncthreads();
-        int bk = INT_MAX, bi = INT_MAX; uint64_t bp = 0;
-#pragma unroll
-        for (int w = 0; w < GP_WARPS; w++) {
-            const int4 f = sm.fin[w];
-            if (f.x == best && (f.y < bk || (f.y == bk && f.z < bi))) {
-                bk = f.y; bi = f.z; const int2 q = sm.finp[w];
-                bp = (uint64_t)(uint32_t)q.x | ((uint64_t)(uint32_t)q.y << 32);
-            }
-        }
-        r.score = best; r.di = bi; r.dj = bk - bi;
-        r.nmatch = Pay<P>::nm((P)bp); r.ncols = Pay<P>::nc((P)bp);
-        __syncthreads();
-    }
-    // 16-bit columns are exact iff the optimal path has fewer than 65536 columns, which min(di, dj) bounds from above
-    if (sizeof(P) == 4 && min(r.di, r.dj) >= 65536) narrow_ok = false;
-    return narrow_ok;
-}
-
 // Exact shortcut for the trivial alignment of a scaffold with itself. When target and query are the SAME N-free
 // sequence and the anchor lies on the main diagonal, the y-drop DP has a closed form: every column (x,x) is a match
 // scoring s(b,b) > 0, and any other path to an anti-diagonal k uses at most min(i,j) <= k/2 aligned columns, each
 // worth at most s(b,b) of its row base, minus gap costs -- so the main-diagonal cell is the strict maximum of every
 // even anti-diagonal, is never pruned, and the extension ends at the scaffold end with score = sum of s(b,b),
 // matches = columns = length. (Proof in DESIGN.md; sequences with any non-ACGT base take the general DP.)
-__device__ Ext selfdiag_extend_cta(const GenomeView& T, uint32_t p0, uint32_t p1, int* __restrict__ sm, int nwarps) {
+__device__ Ext selfdiag_extend_warp(const GenomeView& T, uint32_t p0, uint32_t p1) {
     // count C/G bases in padded-coordinate range [p0, p1): 2-bit code has exactly one bit set for C (01) and G (10)
     int cg = 0;
     if (p1 > p0) {
         const uint32_t w0 = p0 >> 5, w1 = (p1 - 1) >> 5;
-        for (uint32_t w = w0 + threadIdx.x; w <= w1; w += blockDim.x) {
+        for (uint32_t w = w0 + (threadIdx.x & 31); w <= w1; w += 32) {
             uint64_t x = T.pk[w];
             uint64_t m = (x ^ (x >> 1)) & 0x5555555555555555ull;
             if (w == w0 && (p0 & 31)) m &= ~0ull << (2 * (p0 & 31));
@@ -379,13 +112,7 @@ __device__ Ext selfdiag_extend_cta(const GenomeView& T, uint32_t p0, uint32_t p1
             cg += __popcll(m);
         }
     }
-    cg = __reduce_add_sync(0xffffffffu, cg);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cg;
-    __syncthreads();
-    int tot = 0;
-    for (int w = 0; w < nwarps; w++) tot += sm[w];
-    __syncthreads();
+    const int tot = __reduce_add_sync(0xffffffffu, cg);
     const int n = (int)(p1 - p0);
     Ext r;
     r.score = 91 * (n - tot) + 100 * tot; r.di = n; r.dj = n; r.nmatch = n; r.ncols = n;
@@ -621,43 +348,110 @@ gp_select_kernel(GpWork W, const uint32_t* __restrict__ tile, uint32_t nmember, 
     }
 }
 
-// One CTA per work item = (anchor, direction). P = uint32_t: 16+16-bit payload (fast path); uint64_t: always exact.
-template <typename P, typename S, int MINB>
-__global__ void __launch_bounds__(S::NT, MINB)
-gp_extend_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restrict__ items, const uint32_t* __restrict__ tile,
-                 int O, int E, int Y, const int32_t* __restrict__ same_q, unsigned long long* __restrict__ counters) {
-    __shared__ __align__(16) GpShared<P, S> sm;
-    const int tid = threadIdx.x;
-    if (tid < 25) {
-        const int a = tid / 5, b = tid % 5;
-        sm.lut[tid] = make_int2((a == 4 || b == 4) ? SCORE_N : c_sub[a * 4 + b], (a == b && a < 4) ? 1 : 0);
+// ---- y-drop extension (ydrop_warp.cuh): one warp per work item = (anchor, direction)
+constexpr int ST_CLOSED = 100;       // ExtResult.status of an item answered by the closed form (no trace to walk back)
+
+// Persistent grid of one-warp CTAs; items are handed out by an atomic counter. MAXS = 32: common kernel; 64: wide bands.
+template <int MAXS, int MINB>
+__global__ void __launch_bounds__(32, MINB)
+gp_forward_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restrict__ items, uint32_t nitems, uint32_t* __restrict__ next_item,
+                  const uint32_t* __restrict__ tile, yw::Params prm, const int32_t* __restrict__ same_q, yw::Pool pool,
+                  yw::ExtResult* __restrict__ res, unsigned long long* __restrict__ counters) {
+    const int lane = threadIdx.x;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(next_item, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nitems) break;
+        const uint32_t item = items[w];
+        const uint32_t x = item >> 1, dir = item & 1u;
+        const uint32_t tl = tile[W.order[x]];
+        const uint32_t tsc = tl / (uint32_t)Q.nscaf, qsc = tl % (uint32_t)Q.nscaf;
+        const uint32_t toff = T.off[tsc], qoff = Q.off[qsc];
+        const int tlen = (int)T.len[tsc];
+        const int a1 = W.a1[x], a2 = W.a2[x];
+        if (same_q[tsc] == (int)qsc && a1 == a2 && T.nfree[tsc]) {
+            const Ext r = dir == 0 ? selfdiag_extend_warp(T, toff + a1, toff + tlen) : selfdiag_extend_warp(T, toff, toff + a1);
+            if (lane == 0) {
+                W.e_score[item] = r.score; W.e_di[item] = r.di; W.e_dj[item] = r.dj; W.e_nm[item] = r.nmatch; W.e_nc[item] = r.ncols;
+                res[item].status = ST_CLOSED;
+            }
+            continue;
+        }
+        yw::ydrop_forward_warp<MAXS>(T.codes, Q.codes, (int64_t)toff + a1, (int64_t)qoff + a2, dir == 0 ? +1 : -1, prm, pool, item, blockIdx.x,
+                                     &res[item]);
+        __syncwarp();
+        if (lane == 0) {
+            const yw::ExtResult r = res[item];
+            atomicAdd(&counters[CNT_GAPPED_CELLS], (unsigned long long)r.cells);
+            if (r.status == yw::ST_NOMEM) { W.status[item] = GX_NONE; atomicAdd(&counters[CNT_WORK], 1ull); }       // scheduled again next round
+            else if (r.status == yw::ST_WIDE) W.status[item] = GX_NEED_WIDE;
+            else if (r.status != yw::ST_OK) atomicAdd(&counters[CNT_ERR], 1ull);
+        }
     }
-    const uint32_t item = items[blockIdx.x];
+}
+
+// walk-back of every traced item of the round: one warp per item
+__global__ void __launch_bounds__(128)
+gp_walk_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restrict__ items, uint32_t nitems, const uint32_t* __restrict__ tile,
+               yw::Params prm, yw::Pool pool, yw::ExtResult* __restrict__ res, unsigned long long* __restrict__ counters) {
+    __shared__ yw::WalkCache wc[4];
+    const uint32_t w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w >= nitems) return;
+    const uint32_t item = items[w];
+    if (res[item].status != yw::ST_OK) return;
     const uint32_t x = item >> 1, dir = item & 1u;
     const uint32_t tl = tile[W.order[x]];
     const uint32_t tsc = tl / (uint32_t)Q.nscaf, qsc = tl % (uint32_t)Q.nscaf;
-    const uint32_t toff = T.off[tsc], qoff = Q.off[qsc];
-    const int tlen = (int)T.len[tsc], qlen = (int)Q.len[qsc];
-    const int a1 = W.a1[x], a2 = W.a2[x];
-    const bool closed = same_q[tsc] == (int)qsc && a1 == a2 && T.nfree[tsc];
-    Ext r;
-    unsigned ncell = 0;
-    int err = 0;
-    bool ok = true;
-    if (closed) {
-        r = dir == 0 ? selfdiag_extend_cta(T, toff + a1, toff + tlen, sm.red, S::WARPS) : selfdiag_extend_cta(T, toff, toff + a1, sm.red, S::WARPS);
-    } else if (dir == 0) {
-        ok = ydrop_extend_cta<P, S, +1>(T, Q, toff + a1, qoff + a2, tlen - a1, qlen - a2, O, E, Y, sm, r, ncell, err);
-    } else {
-        ok = ydrop_extend_cta<P, S, -1>(T, Q, toff + a1, qoff + a2, a1, a2, O, E, Y, sm, r, ncell, err);
-    }
-    if (tid == 0) {
+    const int64_t ta = (int64_t)T.off[tsc] + W.a1[x], qa = (int64_t)Q.off[qsc] + W.a2[x];
+    yw::ydrop_walk_warp(T.codes, Q.codes, ta, qa, dir == 0 ? +1 : -1, prm, pool, &res[item], wc[threadIdx.x >> 5]);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        const yw::ExtResult r = res[item];
         W.e_score[item] = r.score; W.e_di[item] = r.di; W.e_dj[item] = r.dj; W.e_nm[item] = r.nmatch; W.e_nc[item] = r.ncols;
-        if (!ok) W.status[item] = GX_NEED_WIDE;
-        if (err) atomicAdd(&counters[CNT_ERR], 1ull);
+        if (r.status != yw::ST_OK) atomicAdd(&counters[CNT_ERR], 1ull);
     }
-    ncell = __reduce_add_sync(0xffffffffu, ncell);
-    if ((tid & 31) == 0 && ncell) atomicAdd(&counters[CNT_GAPPED_CELLS], (unsigned long long)ncell);
+}
+
+// Trace pool + re-layout scratch of the extension kernels: one device arena, grown on demand, kept between calls.
+struct TraceArena {
+    uint8_t* base = nullptr; yw::ChunkMeta* meta = nullptr; uint32_t* next = nullptr; int16_t* scratch = nullptr;
+    size_t nchunks = 0; int nslots = 0;
+};
+static TraceArena g_trace;
+void gapped_release_scratch() {
+    if (g_trace.base) cudaFree(g_trace.base);
+    if (g_trace.meta) cudaFree(g_trace.meta);
+    if (g_trace.next) cudaFree(g_trace.next);
+    if (g_trace.scratch) cudaFree(g_trace.scratch);
+    g_trace = TraceArena();
+}
+static yw::Pool trace_pool(int nslots) {
+    Ctx& cx = ctx();
+    if (!g_trace.base) {
+        size_t free_b = 0, total_b = 0;
+        MB2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        size_t want = (size_t)16 << 30;                                   // 2 bytes per evaluated DP cell of one round
+        if (const char* e = getenv("MB2_TRACE_POOL_MB")) { const double v = atof(e); if (v > 0) want = (size_t)(v * 1048576.0); }
+        want = std::min(want, free_b / 3);
+        size_t nchunks = want / yw::CHUNK_BYTES / yw::NSUB * yw::NSUB;
+        MB2_REQUIRE(nchunks >= (size_t)yw::NSUB, -3, "gapped stage: not enough device memory for the trace pool");
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));
+        MB2_CUDA(cudaMalloc((void**)&g_trace.base, nchunks * yw::CHUNK_BYTES));
+        MB2_CUDA(cudaMalloc((void**)&g_trace.meta, nchunks * sizeof(yw::ChunkMeta)));
+        MB2_CUDA(cudaMalloc((void**)&g_trace.next, yw::NSUB * sizeof(uint32_t)));
+        g_trace.nchunks = nchunks;
+    }
+    if (g_trace.nslots < nslots) {
+        MB2_CUDA(cudaStreamSynchronize(cx.stream));
+        if (g_trace.scratch) MB2_CUDA(cudaFree(g_trace.scratch));
+        MB2_CUDA(cudaMalloc((void**)&g_trace.scratch, (size_t)nslots * 3 * yw::WIN * sizeof(int16_t)));
+        g_trace.nslots = nslots;
+    }
+    yw::Pool p;
+    p.base = g_trace.base; p.meta = g_trace.meta; p.next = g_trace.next; p.per_sub = (uint32_t)(g_trace.nchunks / yw::NSUB);
+    p.scratch = g_trace.scratch;
+    return p;
 }
 
 __global__ void __launch_bounds__(256)
@@ -770,29 +564,48 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
             static const bool dbg = getenv("MB2_GP_DEBUG") != nullptr;
             cudaEvent_t ev0 = nullptr, ev1 = nullptr;
             if (dbg) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); }
+            MB2_REQUIRE(p.ydrop >= 1000 && p.ydrop <= 20000 && p.gap_open >= 0 && p.gap_open <= 2000 && p.gap_extend >= 10 && p.gap_extend <= 60,
+                        -2, "gapped stage: y-drop / gap penalties outside the range the 16-bit extension kernel supports");
+            const yw::Params prm{p.gap_open, p.gap_extend, p.ydrop};
+            const int nslots = cx.sm_count * 16;
+            const yw::Pool pool = trace_pool(nslots);
+            DevBuf<yw::ExtResult> res(2 * (size_t)nm);
+            DevBuf<uint32_t> next_item(2);
+            unsigned long long h_nomem_before = 0;
             for (uint32_t round = 1;; round++) {
                 MB2_CUDA(cudaMemsetAsync(counts.get(), 0, 2 * sizeof(uint32_t), cx.stream));
                 launch(gp_select_kernel, cdiv((size_t)h_nseg * 32, 128), 128, 0, W, h.tile.get(), nm, seg_start.get(), h_nseg, resume.get(), nkept.get(),
                        round, p.gappedthresh, r_s1.get(), r_e1.get(), r_s2.get(), r_e2.get(), r_score.get(), r_nm.get(), r_nc.get(), r_tile.get(),
                        keep.get(), counters);
                 uint32_t h_counts[2] = {0, 0};
+                unsigned long long h_nomem = 0;
                 MB2_CUDA(cudaMemcpyAsync(h_counts, counts.get(), sizeof(h_counts), cudaMemcpyDeviceToHost, cx.stream));
+                MB2_CUDA(cudaMemcpyAsync(&h_nomem, counters + CNT_WORK, sizeof(h_nomem), cudaMemcpyDeviceToHost, cx.stream));
                 MB2_CUDA(cudaStreamSynchronize(cx.stream));
                 if (dbg) {
                     float ms = 0;
                     if (round > 1) { cudaEventSynchronize(ev1); cudaEventElapsedTime(&ms, ev0, ev1); }
-                    fprintf(stderr, "[gapped] members %u tiles %u | extend of round %u took %.3f ms | round %u schedules narrow %u wide %u\n", nm, h_nseg,
-                            round - 1, ms, round, h_counts[0], h_counts[1]);
+                    fprintf(stderr, "[gapped] members %u tiles %u | extend of round %u took %.3f ms (%llu items deferred: trace pool full) | round %u schedules %u + wide %u\n",
+                            nm, h_nseg, round - 1, ms, h_nomem - h_nomem_before, round, h_counts[0], h_counts[1]);
                     cudaEventRecord(ev0, cx.stream);
                 }
                 if (h_counts[0] == 0 && h_counts[1] == 0) break;
-                auto go = [&](auto kern, uint32_t count, int nt, const uint32_t* items) {
-                    launch(kern, count, nt, 0, tv, qv, W, items, h.tile.get(), p.gap_open, p.gap_extend, p.ydrop, d_same.get(), counters);
-                };
-                // 128 threads x 8 diagonals (window of 1024): measured best against 64 x 16 and 256 x 4; 5 CTAs per SM
-                using S0 = GpShape<128, 8>;
-                if (h_counts[0]) go(gp_extend_kernel<uint32_t, S0, 5>, h_counts[0], S0::NT, items_n.get());
-                if (h_counts[1]) go(gp_extend_kernel<uint64_t, S0, 3>, h_counts[1], S0::NT, items_w.get());
+                // every item of the previous round deferred again: one extension alone does not fit the pool
+                MB2_REQUIRE(round == 1 || h_nomem - h_nomem_before < (unsigned long long)(h_counts[0] + h_counts[1]) || h_nomem == h_nomem_before, -3,
+                            "gapped stage: the trace pool is too small for a single extension (raise MB2_TRACE_POOL_MB)");
+                h_nomem_before = h_nomem;
+                MB2_CUDA(cudaMemsetAsync(pool.next, 0, yw::NSUB * sizeof(uint32_t), cx.stream));      // previous round's traces are consumed
+                MB2_CUDA(cudaMemsetAsync(next_item.get(), 0, 2 * sizeof(uint32_t), cx.stream));
+                if (h_counts[0]) {
+                    launch(gp_forward_kernel<32, 16>, std::min<uint32_t>(h_counts[0], (uint32_t)nslots), 32, 0, tv, qv, W, (const uint32_t*)items_n.get(), h_counts[0],
+                           next_item.get(), h.tile.get(), prm, d_same.get(), pool, res.get(), counters);
+                }
+                if (h_counts[1]) {
+                    launch(gp_forward_kernel<64, 4>, std::min<uint32_t>(h_counts[1], (uint32_t)nslots), 32, 0, tv, qv, W, (const uint32_t*)items_w.get(), h_counts[1],
+                           next_item.get() + 1, h.tile.get(), prm, d_same.get(), pool, res.get(), counters);
+                }
+                if (h_counts[0]) launch(gp_walk_kernel, cdiv(h_counts[0], 4), 128, 0, tv, qv, W, (const uint32_t*)items_n.get(), h_counts[0], h.tile.get(), prm, pool, res.get(), counters);
+                if (h_counts[1]) launch(gp_walk_kernel, cdiv(h_counts[1], 4), 128, 0, tv, qv, W, (const uint32_t*)items_w.get(), h_counts[1], h.tile.get(), prm, pool, res.get(), counters);
                 if (dbg) cudaEventRecord(ev1, cx.stream);
             }
             if (dbg) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
@@ -803,7 +616,7 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
     MB2_CUDA(cudaMemcpyAsync(&h_nout, d_nout.get(), sizeof(uint32_t), cudaMemcpyDeviceToHost, cx.stream));
     MB2_CUDA(cudaMemcpyAsync(&h_err, counters + CNT_ERR, sizeof(h_err), cudaMemcpyDeviceToHost, cx.stream));
     MB2_CUDA(cudaStreamSynchronize(cx.stream));
-    MB2_REQUIRE(h_err == 0, -3, "gapped stage: y-drop band exceeded the anti-diagonal buffer capacity");
+    MB2_REQUIRE(h_err == 0, -5, "gapped stage: an extension failed (band wider than 1900 diagonals, or an inconsistent trace)");
     out.n = h_nout;
     if (h_nout == 0) return;
     out.tile.alloc(h_nout); out.s1.alloc(h_nout); out.e1.alloc(h_nout); out.s2.alloc(h_nout); out.e2.alloc(h_nout);

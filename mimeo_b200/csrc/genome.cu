@@ -6,6 +6,12 @@
 
 namespace mb2 {
 
+// `codes` mirror (1 byte per base, read by the gapped DP, ydrop_warp.cuh): base | parity(base) << 2 for A,C,G,T (0,5,6,3);
+// 8 = any other character; 12 = pad (outside every scaffold): a DP cell that would consume it does not exist
+__device__ __forceinline__ uint32_t code_byte(uint32_t base, uint32_t bad, uint32_t pad) {
+    return pad ? 12u : (bad ? 8u : (base | (((base ^ (base >> 1)) & 1u) << 2)));
+}
+
 // one thread packs 32 bases -> one uint64 of 2-bit codes + one uint32 of N flags
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm,
@@ -14,7 +20,7 @@ pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __rest
     if (w >= nwords) return;
     const uint4* src = reinterpret_cast<const uint4*>(ascii + (size_t)w * 32);
     uint64_t bits = 0;
-    uint32_t nflag = 0;
+    uint32_t nflag = 0, padflag = 0;
 #pragma unroll
     for (int v = 0; v < 2; v++) {
         const uint4 x = src[v];
@@ -23,12 +29,14 @@ pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __rest
         for (int k = 0; k < 4; k++) {
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-                const uint32_t c = ((words[k] >> (8 * b)) & 0xFFu) & 0xDFu;   // fold to upper case (soft-masking ignored)
+                const uint32_t raw = (words[k] >> (8 * b)) & 0xFFu;
+                const uint32_t c = raw & 0xDFu;   // fold to upper case (soft-masking ignored)
                 uint32_t code = 0, bad = 0;
                 if (c == 'A') code = 0; else if (c == 'C') code = 1; else if (c == 'G') code = 2; else if (c == 'T') code = 3; else bad = 1;
                 const int idx = v * 16 + k * 4 + b;
                 bits |= (uint64_t)code << (2 * idx);
                 nflag |= bad << idx;
+                padflag |= (raw == 0u ? 1u : 0u) << idx;                      // pad positions of the ASCII image are NUL bytes
             }
         }
     }
@@ -41,8 +49,7 @@ pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __rest
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const int idx = k * 4 + b;
-            const uint32_t c = ((nflag >> idx) & 1u) ? 4u : (uint32_t)((bits >> (2 * idx)) & 3u);
-            v |= c << (8 * b);
+            v |= code_byte((uint32_t)((bits >> (2 * idx)) & 3u), (nflag >> idx) & 1u, (padflag >> idx) & 1u) << (8 * b);
         }
         out[k] = v;
     }
@@ -73,7 +80,7 @@ revcomp_kernel(GenomeView src, uint64_t* __restrict__ pk, uint32_t* __restrict__
         }
         bits |= (uint64_t)code << (2 * c);
         nflag |= bad << c;
-        codes[(size_t)p0 + c] = bad ? 4 : (uint8_t)code;
+        codes[(size_t)p0 + c] = (uint8_t)code_byte(code, bad, (p >= so && p < so + sl) ? 0u : 1u);
     }
     pk[w] = bits;
     nm[w] = nflag;
@@ -123,7 +130,7 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         // memory itself), then packed on the device
         const size_t nbytes = g->G + 64;   // = (G/32 + 2) * 32
         DevBuf<uint8_t> d_ascii(nbytes);
-        MB2_CUDA(cudaMemsetAsync(d_ascii.get(), 'N', nbytes, cx.stream));
+        MB2_CUDA(cudaMemsetAsync(d_ascii.get(), 0, nbytes, cx.stream));   // NUL = pad (pack_kernel flags it non-ACGT and codes it 12)
         for (int s = 0; s < n; s++)
             if (lens[s]) MB2_CUDA(cudaMemcpyAsync(d_ascii.get() + g->off[s], seqs[s], lens[s], cudaMemcpyHostToDevice, cx.stream));
         const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
@@ -185,7 +192,7 @@ both_strands_kernel(GenomeView src, const uint32_t* __restrict__ noff, const uin
         }
         bits |= (uint64_t)code << (2 * c);
         nflag |= bad << c;
-        cw[c >> 2] |= (bad ? 4u : code) << (8 * (c & 3));
+        cw[c >> 2] |= code_byte(code, bad, (p >= so && p < so + sl) ? 0u : 1u) << (8 * (c & 3));
     }
     pk[w] = bits; nm[w] = nflag;
     uint4* dst = reinterpret_cast<uint4*>(codes + (size_t)w * 32);

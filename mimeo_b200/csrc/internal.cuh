@@ -19,6 +19,7 @@ void coverage_segments_device(const int32_t* d_chrom, const int32_t* d_start, co
                               const int64_t* h_sizes, int nchrom, int min_cov, int min_len, CoverageResult& res);
 
 void coverage_release_scratch();   // frees the stage's grow-only device scratch (kept between calls)
+void gapped_release_scratch();     // frees the gapped stage's trace pool (kept between calls)
 
 // ---- alignment half
 struct Genome;

@@ -24,7 +24,7 @@ struct Genome {
     uint64_t nbases = 0;              // sum of scaffold lengths
     DevBuf<uint64_t> pk;              // G/32 + 2 words
     DevBuf<uint32_t> nm;              // G/32 + 2 words
-    DevBuf<uint8_t> codes;            // 1 byte/base: 0..3 = ACGT, 4 = other/pad (gapped DP reads single bases)
+    DevBuf<uint8_t> codes;            // 1 byte/base for the gapped DP: base | parity << 2, 8 = other, 12 = pad (genome.cu:code_byte)
     DevBuf<uint32_t> d_off, d_len;
     DevBuf<uint32_t> d_nfree;         // per scaffold: 1 = every base is A/C/G/T
     bool is_rc = false;

@@ -260,6 +260,29 @@ def coverage_segments_arrays(chrom: np.ndarray, start: np.ndarray, end: np.ndarr
     return (np.array(oc, dtype=np.int32), np.array(os_, dtype=np.int32), np.array(oe, dtype=np.int32))
 
 
+def coverage_segments_c(chrom: np.ndarray, start: np.ndarray, end: np.ndarray, sizes, cov: int, minLen: int):
+    """The same steps by the C restatement (oracle/bedtools_oracle.c: ora_coverage_segments), for inputs of millions of hits."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, '_build', 'libannot_oracle.so')
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(here, 'bedtools_oracle.c')):
+        subprocess.check_call(['make', '-C', here, '_build/libannot_oracle.so'], stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(so)
+    lib.ora_coverage_segments.restype = ctypes.c_long
+    chrom = np.ascontiguousarray(chrom, dtype=np.int32); start = np.ascontiguousarray(start, dtype=np.int32)
+    end = np.ascontiguousarray(end, dtype=np.int32); sizes = np.ascontiguousarray(sizes, dtype=np.int64)
+    cap = len(chrom) + 8
+    oc, os_, oe = (np.zeros(cap, np.int32) for _ in range(3))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    k = lib.ora_coverage_segments(P(chrom), P(start), P(end), ctypes.c_long(len(chrom)), P(sizes), ctypes.c_int(len(sizes)),
+                                  ctypes.c_int(cov), ctypes.c_int(minLen), P(oc), P(os_), P(oe), ctypes.c_long(cap))
+    if k < 0:
+        raise ValueError('invalid hit')
+    return oc[:k].copy(), os_[:k].copy(), oe[:k].copy()
+
+
 # --------------------------------------------------------------------------- a-7 / a-8 (map)
 def import_align_rows(tab_lines: Iterable[str], prefix, minLen=100, minIdt=95) -> List[Dict[str, str]]:
     """Restates import_Align (wrappers.py:66-115) without pandas: filter int(end)-int(start) >= minLen and

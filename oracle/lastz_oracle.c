@@ -449,6 +449,16 @@ static ext_t ydrop_extend(const uint8_t *t, long a1, long tn, const uint8_t *q, 
     return r;
 }
 
+/* Test hook: one one-sided extension. out = {score, di, dj, nmatch, ncols}; returns the number of DP cells. */
+long lzo_ydrop_extend(const uint8_t *t, long a1, long tn, const uint8_t *q, long a2, long qn, int dir, const lzo_params *p,
+                      int32_t *out)
+{
+    int64_t cells = 0;
+    ext_t r = ydrop_extend(t, a1, tn, q, a2, qn, dir, p, &cells);
+    out[0] = r.score; out[1] = r.di; out[2] = r.dj; out[3] = r.nmatch; out[4] = r.ncols;
+    return (long)cells;
+}
+
 /* Gapped stage for one tile-strand: chained HSPs in, alignments out. */
 long lzo_gapped(const uint8_t *t, long n, const uint8_t *q, long m, const lzo_hsp *h, long nh, const lzo_params *p,
                 lzo_aln *out, long cap, lzo_stats *st)

@@ -195,15 +195,44 @@ def _pairs(anames: Sequence[str], bnames: Optional[Sequence[str]]):
     return [(a, b) for a in sorted(anames) for b in sorted(bnames if bnames is not None else anames)]
 
 
+def _pair_job(args):
+    """One `lastz T Q ...` process of the reference's script (target table built per pair, both strands) -- pool worker."""
+    a, tcodes, b, qcodes, hspthresh, kw = args
+    st = Stats()
+    lines = lastz_general(a, TargetIndex(tcodes), b, qcodes, default_params(hspthresh, **kw), st)
+    return (a, b), lines, st.as_dict()
+
+
+def general_all_pairs(agenome: Dict[str, np.ndarray], bgenome: Optional[Dict[str, np.ndarray]], hspthresh=3000, workers: int = 1,
+                      stats: Optional[Stats] = None, **kw) -> Dict[Tuple[str, str], List[str]]:
+    """LASTZ's text for every ordered (target, query) scaffold pair, the pairs spread over `workers` processes (the oracle
+    itself stays single-threaded per pair, as LASTZ is)."""
+    qg = agenome if bgenome is None else bgenome
+    jobs = [(a, agenome[a], b, qg[b], hspthresh, kw) for a, b in _pairs(list(agenome), None if bgenome is None else list(bgenome))]
+    if workers > 1 and len(jobs) > 1:
+        from concurrent.futures import ProcessPoolExecutor
+        jobs.sort(key=lambda j: -(len(j[1]) * len(j[3])))
+        with ProcessPoolExecutor(max_workers=workers) as ex:
+            res = list(ex.map(_pair_job, jobs, chunksize=1))
+    else:
+        res = [_pair_job(j) for j in jobs]
+    out = {}
+    for key, lines, st in res:
+        out[key] = lines
+        if stats is not None:
+            for n, v in st.items():
+                setattr(stats, n, getattr(stats, n) + v)
+    return out
+
+
 def mimeo_self(genome: Dict[str, np.ndarray], minIdt=60, minLen=100, minCov=3, intraCov=5, hspthresh=3000, strictSelf=False,
-               label='Self_Repeat', prefix='Self_Repeat', stats: Optional[Stats] = None) -> Tuple[str, Optional[str], str]:
+               label='Self_Repeat', prefix='Self_Repeat', stats: Optional[Stats] = None, workers: int = 1) -> Tuple[str, Optional[str], str]:
     """Reference pipeline of `mimeo self` (run_self.py:169-255 + wrappers.py:899-1271) on encoded scaffolds.
     Returns (tab text, intra tab text or None, gff3 text)."""
-    p = default_params(hspthresh)
-    idx = {n: TargetIndex(c) for n, c in genome.items()}
+    general = general_all_pairs(genome, None, hspthresh, workers, stats)
     tab, intra = ao.TAB_HEADER, (ao.TAB_HEADER if strictSelf else None)
     for a, b in _pairs(list(genome), None):
-        rows = ''.join(ao.filter_lastz_general(lastz_general(a, idx[a], b, genome[b], p, stats), minLen, minIdt))
+        rows = ''.join(ao.filter_lastz_general(general[(a, b)], minLen, minIdt))
         if a == b and strictSelf:
             intra += rows
         else:
@@ -213,24 +242,38 @@ def mimeo_self(genome: Dict[str, np.ndarray], minIdt=60, minLen=100, minCov=3, i
     return tab, intra, gff
 
 
-def mimeo_x(agenome, bgenome, minIdt=60, minLen=100, minCov=5, label='B_Repeat', prefix='B_Repeat', stats=None):
+def mimeo_x(agenome, bgenome, minIdt=60, minLen=100, minCov=5, label='B_Repeat', prefix='B_Repeat', stats=None, workers: int = 1):
     """Reference pipeline of `mimeo x` (run_interspecies.py:173-258; hspthresh is always 3000 there)."""
-    p = default_params(3000)
-    idx = {n: TargetIndex(c) for n, c in agenome.items()}
+    general = general_all_pairs(agenome, bgenome, 3000, workers, stats)
     tab = ao.TAB_HEADER
     for a, b in _pairs(list(agenome), list(bgenome)):
-        tab += ''.join(ao.filter_lastz_general(lastz_general(a, idx[a], b, bgenome[b], p, stats), minLen, minIdt))
+        tab += ''.join(ao.filter_lastz_general(general[(a, b)], minLen, minIdt))
     sizes = {n: len(c) for n, c in agenome.items()}
     return tab, ao.x_gff3(tab.splitlines(True), sizes, minCov, minLen, label, prefix)
 
 
-def mimeo_map(agenome, bgenome, minIdt=90, minLen=100, hspthresh=3000, label='BHit', prefix='BHit', stats=None):
+def mimeo_map(agenome, bgenome, minIdt=90, minLen=100, hspthresh=3000, label='BHit', prefix='BHit', stats=None, workers: int = 1):
     """Reference pipeline of `mimeo map` without TRF (run_map.py:190-328)."""
-    p = default_params(hspthresh)
-    idx = {n: TargetIndex(c) for n, c in agenome.items()}
+    general = general_all_pairs(agenome, bgenome, hspthresh, workers, stats)
     tab = ao.TAB_HEADER
     for a, b in _pairs(list(agenome), list(bgenome)):
-        tab += ''.join(ao.filter_lastz_general(lastz_general(a, idx[a], b, bgenome[b], p, stats), minLen, minIdt))
+        tab += ''.join(ao.filter_lastz_general(general[(a, b)], minLen, minIdt))
     hits = ao.import_align_rows(tab.splitlines(True), prefix, minLen, minIdt)
     chrlens = sorted((n, str(len(c))) for n, c in agenome.items())
     return tab, ''.join(ao.write_gff_lines(hits, chrlens, label))
+
+
+def general_rows(general: Dict[Tuple[str, str], List[str]], anames: Sequence[str], bnames: Sequence[str]):
+    """The alignments of general_all_pairs() as the integer rows mb2_align reports:
+    (t_id, q_id, strand, start1, end1, start2+, end2+, score, nmatch, ncols), ids = positions in anames / bnames."""
+    ai = {n: k for k, n in enumerate(anames)}
+    bi = {n: k for k, n in enumerate(bnames)}
+    rows = set()
+    for (a, b), lines in general.items():
+        for ln in lines:
+            if ln.startswith('#'):
+                continue
+            f = ln.rstrip('\n').split('\t')
+            nm, nc = f[11].split('/')
+            rows.add((ai[a], bi[b], 0 if f[6] == '+' else 1, int(f[2]), int(f[3]), int(f[7]), int(f[8]), int(f[10]), int(nm), int(nc)))
+    return rows
