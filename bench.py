@@ -449,7 +449,7 @@ def run_b200(args):
     peak, peak_src = measured_peaks()
     kb = wl.kernel_bytes()
     tags = [t for t in kb if not t.startswith('_')]
-    all_tags = tags + [t for t in ('surv_sort', 'hsp_extend', 'hsp_sort', 'chain', 'gapped', 'cov_events', 'cov_bin_events', 'cov_tile') if t not in tags]
+    all_tags = tags + [t for t in ('surv_sort', 'hsp_extend', 'hsp_sort', 'chain', 'gapped', 'gp_forward', 'gp_walk', 'cov_events', 'cov_bin_events', 'cov_tile') if t not in tags]
     prof = {t: _lib.prof_get(t) for t in all_tags}
     dom = max(tags, key=lambda t: prof[t][0])
     dms, dcnt = prof[dom]

@@ -349,14 +349,16 @@ gp_select_kernel(GpWork W, const uint32_t* __restrict__ tile, uint32_t nmember, 
 }
 
 // ---- y-drop extension (ydrop_warp.cuh): one warp per work item = (anchor, direction)
+constexpr int GP_WARPS_PER_SM = 24;  // most resident one-warp CTAs per SM of any variant of the extension kernel (sizes the scratch slots)
 constexpr int ST_CLOSED = 100;       // ExtResult.status of an item answered by the closed form (no trace to walk back)
 
-// Persistent grid of one-warp CTAs; items are handed out by an atomic counter. MAXS = 32: common kernel; 64: wide bands.
+// Persistent grid of one-warp CTAs; items are handed out by an atomic counter. MAXS = 32: common kernel (bands up to 928
+// diagonals); 64: wide bands (rerun of the few items the common kernel hands back).
 template <int MAXS, int MINB>
 __global__ void __launch_bounds__(32, MINB)
 gp_forward_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restrict__ items, uint32_t nitems, uint32_t* __restrict__ next_item,
                   const uint32_t* __restrict__ tile, yw::Params prm, const int32_t* __restrict__ same_q, yw::Pool pool,
-                  yw::ExtResult* __restrict__ res, unsigned long long* __restrict__ counters) {
+                  yw::ExtResult* __restrict__ res, unsigned long long* __restrict__ counters, uint32_t lay_mask) {
     const int lane = threadIdx.x;
     for (;;) {
         uint32_t w = 0;
@@ -379,7 +381,7 @@ gp_forward_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restri
             continue;
         }
         yw::ydrop_forward_warp<MAXS>(T.codes, Q.codes, (int64_t)toff + a1, (int64_t)qoff + a2, dir == 0 ? +1 : -1, prm, pool, item, blockIdx.x,
-                                     &res[item]);
+                                     &res[item], lay_mask);
         __syncwarp();
         if (lane == 0) {
             const yw::ExtResult r = res[item];
@@ -389,6 +391,15 @@ gp_forward_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restri
             else if (r.status != yw::ST_OK) atomicAdd(&counters[CNT_ERR], 1ull);
         }
     }
+}
+
+// launch order of the round's items: the higher-scoring anchor first (long extensions start early, short ones fill the tail)
+__global__ void __launch_bounds__(256)
+gp_item_keys_kernel(GpWork W, const uint32_t* __restrict__ items, uint32_t nitems, const int32_t* __restrict__ hscore, uint32_t* __restrict__ key) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nitems) return;
+    const int sc = hscore[W.order[items[k] >> 1]];
+    key[k] = 0xffffffu - (uint32_t)min(sc, 0xffffff);
 }
 
 // walk-back of every traced item of the round: one warp per item
@@ -419,6 +430,21 @@ struct TraceArena {
     size_t nchunks = 0; int nslots = 0;
 };
 static TraceArena g_trace;
+// allowed layouts (diagonals per lane) as a bit mask, bit S/4
+static uint32_t layout_mask(const char* env, const char* dflt) {
+    const char* e = getenv(env);
+    std::string v = (e && *e) ? e : dflt;
+    uint32_t m = 0;
+    size_t pos = 0;
+    while (pos < v.size()) {
+        const size_t c = v.find(',', pos);
+        const int S = atoi(v.substr(pos, c == std::string::npos ? std::string::npos : c - pos).c_str());
+        if (S == 8 || S == 12 || S == 16 || S == 20 || S == 24 || S == 32) m |= 1u << (S >> 2);
+        if (c == std::string::npos) break;
+        pos = c + 1;
+    }
+    return m ? m : (1u << 4) | (1u << 6) | (1u << 8);
+}
 void gapped_release_scratch() {
     if (g_trace.base) cudaFree(g_trace.base);
     if (g_trace.meta) cudaFree(g_trace.meta);
@@ -567,7 +593,7 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
             MB2_REQUIRE(p.ydrop >= 1000 && p.ydrop <= 20000 && p.gap_open >= 0 && p.gap_open <= 2000 && p.gap_extend >= 10 && p.gap_extend <= 60,
                         -2, "gapped stage: y-drop / gap penalties outside the range the 16-bit extension kernel supports");
             const yw::Params prm{p.gap_open, p.gap_extend, p.ydrop};
-            const int nslots = cx.sm_count * 16;
+            const int nslots = cx.sm_count * GP_WARPS_PER_SM;
             const yw::Pool pool = trace_pool(nslots);
             DevBuf<yw::ExtResult> res(2 * (size_t)nm);
             DevBuf<uint32_t> next_item(2);
@@ -596,16 +622,37 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
                 h_nomem_before = h_nomem;
                 MB2_CUDA(cudaMemsetAsync(pool.next, 0, yw::NSUB * sizeof(uint32_t), cx.stream));      // previous round's traces are consumed
                 MB2_CUDA(cudaMemsetAsync(next_item.get(), 0, 2 * sizeof(uint32_t), cx.stream));
-                if (h_counts[0]) {
-                    launch(gp_forward_kernel<32, 16>, std::min<uint32_t>(h_counts[0], (uint32_t)nslots), 32, 0, tv, qv, W, (const uint32_t*)items_n.get(), h_counts[0],
-                           next_item.get(), h.tile.get(), prm, d_same.get(), pool, res.get(), counters);
+                static const uint32_t lay_narrow = layout_mask("MB2_GP_LAYOUTS", "16,24,32"), lay_wide = lay_narrow | (1u << 12) | (1u << 16);
+                static const bool sort_items = !getenv("MB2_GP_NOSORT");
+                static const int occ = getenv("MB2_GP_OCC") ? atoi(getenv("MB2_GP_OCC")) : 20;
+                const uint32_t* it_n = items_n.get();
+                DevBuf<uint32_t> sk0, sk1, si1;
+                if (sort_items && h_counts[0] > (uint32_t)nslots) {
+                    sk0.alloc(h_counts[0]); sk1.alloc(h_counts[0]); si1.alloc(h_counts[0]);
+                    launch(gp_item_keys_kernel, cdiv(h_counts[0], 256), 256, 0, W, (const uint32_t*)items_n.get(), h_counts[0], (const int32_t*)h.score.get(), sk0.get());
+                    const int w = radix_sort_bits<uint32_t, uint32_t>(sk0.get(), sk1.get(), items_n.get(), si1.get(), h_counts[0], 8, 24);
+                    it_n = w ? si1.get() : items_n.get();
                 }
-                if (h_counts[1]) {
-                    launch(gp_forward_kernel<64, 4>, std::min<uint32_t>(h_counts[1], (uint32_t)nslots), 32, 0, tv, qv, W, (const uint32_t*)items_w.get(), h_counts[1],
-                           next_item.get() + 1, h.tile.get(), prm, d_same.get(), pool, res.get(), counters);
+                {
+                    ProfScope pf("gp_forward");
+                    if (h_counts[0]) {
+                        auto go = [&](auto kern, int per_sm) {
+                            launch(kern, std::min<uint32_t>(h_counts[0], (uint32_t)(cx.sm_count * per_sm)), 32, 0, tv, qv, W, it_n, h_counts[0],
+                                   next_item.get(), h.tile.get(), prm, d_same.get(), pool, res.get(), counters, lay_narrow);
+                        };
+                        if (occ >= 20) go(gp_forward_kernel<32, 20>, 20);
+                        else go(gp_forward_kernel<32, 16>, 16);
+                    }
+                    if (h_counts[1]) {
+                        launch(gp_forward_kernel<64, 4>, std::min<uint32_t>(h_counts[1], (uint32_t)nslots), 32, 0, tv, qv, W, (const uint32_t*)items_w.get(), h_counts[1],
+                               next_item.get() + 1, h.tile.get(), prm, d_same.get(), pool, res.get(), counters, lay_wide);
+                    }
                 }
-                if (h_counts[0]) launch(gp_walk_kernel, cdiv(h_counts[0], 4), 128, 0, tv, qv, W, (const uint32_t*)items_n.get(), h_counts[0], h.tile.get(), prm, pool, res.get(), counters);
-                if (h_counts[1]) launch(gp_walk_kernel, cdiv(h_counts[1], 4), 128, 0, tv, qv, W, (const uint32_t*)items_w.get(), h_counts[1], h.tile.get(), prm, pool, res.get(), counters);
+                {
+                    ProfScope pw("gp_walk");
+                    if (h_counts[0]) launch(gp_walk_kernel, cdiv(h_counts[0], 4), 128, 0, tv, qv, W, it_n, h_counts[0], h.tile.get(), prm, pool, res.get(), counters);
+                    if (h_counts[1]) launch(gp_walk_kernel, cdiv(h_counts[1], 4), 128, 0, tv, qv, W, (const uint32_t*)items_w.get(), h_counts[1], h.tile.get(), prm, pool, res.get(), counters);
+                }
                 if (dbg) cudaEventRecord(ev1, cx.stream);
             }
             if (dbg) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }

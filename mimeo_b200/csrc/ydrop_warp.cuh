@@ -31,9 +31,11 @@
 #ifdef YW_EMU
 #include "ydrop_emu.h"
 #define YW_DEV inline
+#define YW_DEV_NOINLINE inline
 #else
 #include <cuda_runtime.h>
 #define YW_DEV __device__ __forceinline__
+#define YW_DEV_NOINLINE __device__ __noinline__
 #endif
 
 namespace yw {
@@ -113,6 +115,7 @@ YW_DEV uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
     return r;
 }
 YW_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+YW_DEV uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_rc(lo, hi, sh); }   // shift clamped to 32
 YW_DEV uint32_t ld32(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 YW_DEV uint32_t ld8(const uint8_t* p) { return (uint32_t)__ldg(p); }
 YW_DEV void fence() { __threadfence(); }
@@ -129,6 +132,11 @@ YW_DEV uint32_t bytes_at(const uint32_t (&w)[N], int off) {
 }
 template <int N>
 YW_DEV uint32_t byte_of(const uint32_t (&w)[N], int n) { return (w[n >> 2] >> ((n & 3) * 8)) & 0xffu; }
+// the same with a run-time part r (0..4 bytes) of the offset: word index and byte position stay compile-time constants
+template <int N>
+YW_DEV uint32_t bytes_at_rt(const uint32_t (&w)[N], int word, int r) { return funnel_rc(w[word], w[word + 1 < N ? word + 1 : word], (uint32_t)r * 8u); }
+template <int N>
+YW_DEV uint32_t byte_of_rt(const uint32_t (&w)[N], int n, int r) { return (bytes_at_rt(w, n >> 2, r) >> ((n & 3) * 8)) & 0xffu; }
 
 // ------------------------------------------------------------------------------------------ layout
 template <int S_> struct Lay {
@@ -160,6 +168,8 @@ struct Ctx {
     int best_real, kbest, bestv;
     int dead_steps;
     int lo_lane, hi_lane; // alive lanes after the last block
+    int alo, ahi;         // exact alive diagonal range when a layout ends
+    uint32_t lay_mask;    // allowed layouts: bit S/4
     uint32_t cells;
     int status;
     // trace
@@ -171,14 +181,14 @@ struct Ctx {
 };
 
 // ------------------------------------------------------------------------------------------ trace pool
-YW_DEV uint32_t pool_alloc(Ctx& c) {
+YW_DEV_NOINLINE uint32_t pool_alloc(uint32_t* next, uint32_t per_sub, uint32_t item) {
     uint32_t id = 0xffffffffu;
     if (lane_id() == 0) {
         for (uint32_t t = 0; t < NSUB; t++) {
-            const uint32_t sub = (c.item + t) % NSUB;
-            if (*(volatile uint32_t*)&c.pool.next[sub] >= c.pool.per_sub) continue;
-            const uint32_t idx = atomic_add(&c.pool.next[sub], 1u);
-            if (idx < c.pool.per_sub) { id = sub * c.pool.per_sub + idx; break; }
+            const uint32_t sub = (item + t) % NSUB;
+            if (*(volatile uint32_t*)&next[sub] >= per_sub) continue;
+            const uint32_t idx = atomic_add(&next[sub], 1u);
+            if (idx < per_sub) { id = sub * per_sub + idx; break; }
         }
     }
     return shfl(id, 0);
@@ -187,7 +197,7 @@ YW_DEV uint32_t pool_alloc(Ctx& c) {
 YW_DEV bool chunk_open(Ctx& c, int k_first, int rows_per_chunk) {
     const uint32_t prev = c.chunk;
     if (prev != 0xffffffffu && lane_id() == 0) c.pool.meta[prev].nrows = c.nrows;
-    const uint32_t id = pool_alloc(c);
+    const uint32_t id = pool_alloc(c.pool.next, c.pool.per_sub, c.item);
     if (id == 0xffffffffu) { c.status = ST_NOMEM; return false; }
     if (lane_id() == 0) {
         ChunkMeta m;
@@ -226,7 +236,9 @@ YW_DEV void load_stream(const uint8_t* codes, int64_t a0, bool asc, uint32_t (&o
 }
 
 // ------------------------------------------------------------------------------------------ one step
-// PAR = 1: odd step (odd slots), PAR = 0: even step. v = 0..3 = position inside the block (compile time after unrolling).
+// PAR = 1: odd step (odd slots), PAR = 0: even step. v = 0..3 = position inside the block: a RUN-TIME value (the block is
+// a rolled loop: the kernel is instruction-cache bound when every step of every layout is unrolled), so it only ever
+// enters as a funnel-shift amount.
 // XC / YC: combined streams (normal blocks), XR / YR: raw streams (special blocks: N or pad bases in sight).
 template <int S, bool SPECIAL, int PAR>
 YW_DEV void step(State<S>& st, const uint32_t (&XC)[Lay<S>::NWC], const uint32_t (&YC)[Lay<S>::NWC],
@@ -241,7 +253,7 @@ YW_DEV void step(State<S>& st, const uint32_t (&XC)[Lay<S>::NWC], const uint32_t
     if (!SPECIAL) {
 #pragma unroll
         for (int g = 0; g < NG; g++) {
-            const uint32_t sel = bytes_at(XC, xo + 4 * g) ^ bytes_at(YC, yo + 4 * g);
+            const uint32_t sel = bytes_at_rt(XC, g, xo) ^ bytes_at_rt(YC, g, yo);
             const uint32_t r0 = prmt(TAB_LO, TAB_HI, sel & 0xffffu);
             if (4 * g + 0 < CH) sc[4 * g + 0] = prmt(r0, 0, 0x4140);
             if (4 * g + 1 < CH) sc[4 * g + 1] = prmt(r0, 0, 0x4342);
@@ -257,7 +269,7 @@ YW_DEV void step(State<S>& st, const uint32_t (&XC)[Lay<S>::NWC], const uint32_t
             uint32_t u[2], kl[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const uint32_t t = byte_of(XR, xo + c + h * CH), q = byte_of(YR, yo + c + h * CH);
+                const uint32_t t = byte_of_rt(XR, c + h * CH, xo), q = byte_of_rt(YR, c + h * CH, yo);
                 const bool end = ((t & 12u) == 12u) || ((q & 12u) == 12u);
                 const bool n = ((t | q) & 8u) != 0;
                 const uint32_t idx = (t ^ (q & 3u)) & 7u;
@@ -302,7 +314,21 @@ YW_DEV void step(State<S>& st, const uint32_t (&XC)[Lay<S>::NWC], const uint32_t
         const uint32_t od = (nd & ~dead) | (SENT2 & dead);
         const uint32_t oi = (ni & ~dead) | (SENT2 & dead);
         if (PAR == 0) { st.He[c] = oh; st.De[c] = od; st.Ie[c] = oi; } else { st.Ho[c] = oh; st.Do[c] = od; st.Io[c] = oi; }
-        hmax2 = vmax2(hmax2, oh);
+    }
+    // maximum of the step's cells of this lane: a tree, not a chain (it sits on the critical path to the next threshold)
+    {
+        uint32_t m[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) m[c] = PAR == 0 ? st.He[c] : st.Ho[c];
+#pragma unroll
+        for (int n = CH; n > 1; n = (n + 2) / 3) {
+#pragma unroll
+            for (int x = 0; x < (n + 2) / 3; x++) {
+                const uint32_t a = m[3 * x], b = 3 * x + 1 < n ? m[3 * x + 1] : a, d = 3 * x + 2 < n ? m[3 * x + 2] : a;
+                m[x] = vmax3_2(a, b, d);
+            }
+        }
+        hmax2 = m[0];
     }
 }
 
@@ -310,40 +336,37 @@ template <int S>
 YW_DEV void store_row(uint8_t* row, const uint32_t (&h)[Lay<S>::CH]) {
     constexpr int CH = Lay<S>::CH;
     uint32_t* p = reinterpret_cast<uint32_t*>(row) + lane_id() * CH;
+#ifdef YW_EMU
+#pragma unroll
+    for (int c = 0; c < CH; c++) p[c] = h[c];
+#else
     if (CH % 4 == 0) {
 #pragma unroll
-        for (int c = 0; c < CH; c += 4) {
-#ifdef YW_EMU
-            p[c] = h[c]; p[c + 1] = h[c + 1]; p[c + 2] = h[c + 2]; p[c + 3] = h[c + 3];
-#else
-            *reinterpret_cast<uint4*>(p + c) = make_uint4(h[c], h[c + 1], h[c + 2], h[c + 3]);
-#endif
-        }
+        for (int c = 0; c + 3 < CH; c += 4) *reinterpret_cast<uint4*>(p + c) = make_uint4(h[c], h[c + 1], h[c + 2], h[c + 3]);
+    } else if (CH % 2 == 0) {
+#pragma unroll
+        for (int c = 0; c + 1 < CH; c += 2) *reinterpret_cast<uint2*>(p + c) = make_uint2(h[c], h[c + 1]);
     } else {
 #pragma unroll
-        for (int c = 0; c < CH; c += 2) {
-#ifdef YW_EMU
-            p[c] = h[c]; p[c + 1] = h[c + 1];
-#else
-            *reinterpret_cast<uint2*>(p + c) = make_uint2(h[c], h[c + 1]);
-#endif
-        }
+        for (int c = 0; c < CH; c++) p[c] = h[c];
     }
+#endif
 }
 
-// after a step: the step maximum (stored domain) -> running best, threshold of the next step, dead-step count
+// after a step: the step maximum (stored domain) -> running best, threshold of the next step, dead-step count.
+// Branch-free: the hot loop should not carry reconvergence points.
 YW_DEV void after_step(Ctx& c, uint32_t hmax2) {
     const uint32_t both = vmax2(hmax2, prmt(hmax2, hmax2, 0x1032));
     const int bmax = lo16((uint32_t)redmax((int)both));
     c.k++;
     const int stepmax = bmax + c.bias;                 // T domain
-    if (bmax > ALIVE_MIN) {
-        c.dead_steps = 0;
-        if (stepmax > c.bestT) { c.bestT = stepmax; c.kbest = c.k; c.bestv = bmax; c.best_real = stepmax + c.F - c.p.E * c.k; }
-    } else {
-        c.dead_steps++;
-    }
-    c.bestT += c.p.E;                                   // image of the best on the next anti-diagonal
+    const bool alive = bmax > ALIVE_MIN;
+    c.dead_steps = alive ? 0 : c.dead_steps + 1;
+    const bool better = alive && stepmax > c.bestT;
+    c.kbest = better ? c.k : c.kbest;
+    c.bestv = better ? bmax : c.bestv;
+    c.best_real = better ? stepmax + c.F - c.p.E * c.k : c.best_real;
+    c.bestT = (better ? stepmax : c.bestT) + c.p.E;    // image of the best on the next anti-diagonal
 }
 
 // ------------------------------------------------------------------------------------------ one layout
@@ -395,25 +418,43 @@ YW_DEV void run_block(Ctx& c, State<S>& st, const uint32_t (&XC)[Lay<S>::NWC], c
     const uint32_t kopen2 = pack2(c.bias - c.p.O, c.bias - c.p.O), negbias2 = pack2(-c.bias, -c.bias);
     const uint32_t SENT2 = pack2(SENT, SENT);
     alive2 = SENT2;
-#pragma unroll
+#pragma unroll 1
     for (int v = 0; v < BLOCK_STEPS / 2; v++) {
-        if (c.dead_steps < 2) {
+        if (c.dead_steps >= 2) break;
+        uint32_t hm1 = SENT2, hm0 = SENT2;
+        {
             const int thr = c.bestT - c.p.Y;
-            uint32_t hm = SENT2;
-            step<S, SPECIAL, 1>(st, XC, YC, XR, YR, v, kopen2, negbias2, pack2(-thr, -thr), hm);
+            step<S, SPECIAL, 1>(st, XC, YC, XR, YR, v, kopen2, negbias2, pack2(-thr, -thr), hm1);
             store_row<S>(rowp, st.Ho); rowp += Lay<S>::ROW_BYTES; c.nrows++;
-            after_step(c, hm);
-            if (v == BLOCK_STEPS / 2 - 1) alive2 = vmax2(alive2, hm);
+            after_step(c, hm1);
         }
         if (c.dead_steps < 2) {
             const int thr = c.bestT - c.p.Y;
-            uint32_t hm = SENT2;
-            step<S, SPECIAL, 0>(st, XC, YC, XR, YR, v, kopen2, negbias2, pack2(-thr, -thr), hm);
+            step<S, SPECIAL, 0>(st, XC, YC, XR, YR, v, kopen2, negbias2, pack2(-thr, -thr), hm0);
             store_row<S>(rowp, st.He); rowp += Lay<S>::ROW_BYTES; c.nrows++;
-            after_step(c, hm);
-            if (v == BLOCK_STEPS / 2 - 1) alive2 = vmax2(alive2, hm);
+            after_step(c, hm0);
         }
+        alive2 = vmax2(hm1, hm0);
     }
+}
+
+// diagonals a layout of S per lane can hold with one free lane and 16 diagonals of slack on both sides
+YW_DEV int usable(int S) { return 32 * S - 2 * (S + 16); }
+// smallest allowed layout that holds `need` diagonals (+ hysteresis), 0 if none
+YW_DEV int pick_layout(uint32_t mask, int need, int hyst, int max_S) {
+    for (int S = 8; S <= max_S; S += 4)
+        if (((mask >> (S >> 2)) & 1u) && need + hyst <= usable(S)) return S;     // mask bits exist only for instantiated layouts
+    return 0;
+}
+
+// raw code streams of the block that starts after step kb, for this lane
+template <int S>
+YW_DEV void load_windows(const Ctx& c, int kb, uint32_t (&XR)[Lay<S>::NWR], uint32_t (&YR)[Lay<S>::NWR]) {
+    constexpr int NWR = Lay<S>::NWR;
+    const int lane = lane_id();
+    const int64_t ib = ((int64_t)kb + c.rbase + (int64_t)S * lane) >> 1, jb = ((int64_t)kb - c.rbase - (int64_t)S * lane) >> 1;
+    if (c.dir > 0) { load_stream<NWR>(c.tc, c.ta + ib, true, XR); load_stream<NWR>(c.qc, c.qa + jb + 3, false, YR); }
+    else { load_stream<NWR>(c.tc, c.ta - ib - 1, false, XR); load_stream<NWR>(c.qc, c.qa - jb - 4, true, YR); }
 }
 
 // Runs blocks in layout (c.rbase, S) until the extension ends or the layout has to change. State comes from and goes
@@ -429,6 +470,8 @@ YW_DEV void run_layout(Ctx& c, bool first) {
         store_row<S>(c.pool.base + (size_t)c.chunk * CHUNK_BYTES, st.He);
         c.nrows = 1;
     }
+    uint32_t XN[NWR], YN[NWR];                 // raw streams of the coming block
+    load_windows<S>(c, c.k, XN, YN);
     for (;;) {
         // frame
         if (c.bestT > c.rebase_at) {
@@ -439,13 +482,13 @@ YW_DEV void run_layout(Ctx& c, bool first) {
         } else if (c.nrows + BLOCK_STEPS > c.cap) {
             if (!chunk_open(c, c.k + 1, Lay<S>::ROWS_PER_CHUNK)) break;
         }
-        // windows of this block: kb = c.k (even), cells of lane: i0 = ib + v + 1, j0 = jb + v (+1 on even steps)
-        const int kb = c.k;
-        const int64_t ib = ((int64_t)kb + c.rbase + (int64_t)S * lane) >> 1, jb = ((int64_t)kb - c.rbase - (int64_t)S * lane) >> 1;
+        // windows of this block: kb = c.k (even), cells of lane: i0 = ib + v + 1, j0 = jb + v (+1 on even steps).
+        // X[n] = t(ib + 1 + n), Y[n] = q(jb + 4 - n);  dir +1: t(i) = T[ta + i - 1], dir -1: t(i) = T[ta - i].
+        // The loads were issued one block ago (software pipeline); the ones for the next block (ib + 4, jb + 4) go out now.
         uint32_t XR[NWR], YR[NWR];
-        // X[n] = t(ib + 1 + n), Y[n] = q(jb + 4 - n);  dir +1: t(i) = T[ta + i - 1], dir -1: t(i) = T[ta - i]
-        if (c.dir > 0) { load_stream<NWR>(c.tc, c.ta + ib, true, XR); load_stream<NWR>(c.qc, c.qa + jb + 3, false, YR); }
-        else { load_stream<NWR>(c.tc, c.ta - ib - 1, false, XR); load_stream<NWR>(c.qc, c.qa - jb - 4, true, YR); }
+#pragma unroll
+        for (int w = 0; w < NWR; w++) { XR[w] = XN[w]; YR[w] = YN[w]; }
+        load_windows<S>(c, c.k + BLOCK_STEPS, XN, YN);
         uint32_t flags = 0;
 #pragma unroll
         for (int w = 0; w < NWR; w++) flags |= (XR[w] | YR[w]) & 0x08080808u;
@@ -478,10 +521,20 @@ YW_DEV void run_layout(Ctx& c, bool first) {
 #endif
         // the band may move one diagonal per step: a free lane on both sides covers the next block (S >= BLOCK_STEPS)
         if (c.lo_lane < 1 || c.hi_lane > 30) break;
-        // shrink when a much smaller layout would do
-        if (S > 16 && (c.hi_lane - c.lo_lane + 1) * S + 2 * (16 + 48) <= 32 * 16) break;
-        if (S > 24 && (c.hi_lane - c.lo_lane + 1) * S + 2 * (24 + 24) + 64 <= 32 * 24) break;
-        if (S > 32 && (c.hi_lane - c.lo_lane + 1) * S + 2 * (32 + 8) + 96 <= 32 * 32) break;
+        // shrink when a smaller layout would do (with hysteresis; lane granularity overestimates the need, which is safe)
+        { const int ps = pick_layout(c.lay_mask, (c.hi_lane - c.lo_lane + 1) * S, 64, S - 4); if (ps != 0) break; }
+    }
+    {   // exact range of alive diagonals (every slot holds its diagonal's latest cell)
+        int dlo = INT32_MAX, dhi = INT32_MIN;
+        const int d0 = c.rbase + S * lane;
+#pragma unroll
+        for (int x = 0; x < CH; x++) {
+            if (lo16(st.He[x]) > ALIVE_MIN) { dlo = dlo < d0 + 2 * x ? dlo : d0 + 2 * x; dhi = dhi > d0 + 2 * x ? dhi : d0 + 2 * x; }
+            if (hi16(st.He[x]) > ALIVE_MIN) { dlo = dlo < d0 + 2 * x + S / 2 ? dlo : d0 + 2 * x + S / 2; dhi = dhi > d0 + 2 * x + S / 2 ? dhi : d0 + 2 * x + S / 2; }
+            if (lo16(st.Ho[x]) > ALIVE_MIN) { dlo = dlo < d0 + 2 * x + 1 ? dlo : d0 + 2 * x + 1; dhi = dhi > d0 + 2 * x + 1 ? dhi : d0 + 2 * x + 1; }
+            if (hi16(st.Ho[x]) > ALIVE_MIN) { dlo = dlo < d0 + 2 * x + 1 + S / 2 ? dlo : d0 + 2 * x + 1 + S / 2; dhi = dhi > d0 + 2 * x + 1 + S / 2 ? dhi : d0 + 2 * x + 1 + S / 2; }
+        }
+        c.alo = redmin(dlo); c.ahi = redmax(dhi);
     }
     if (lane == 0 && c.chunk != 0xffffffffu) c.pool.meta[c.chunk].nrows = c.nrows;
     dump_state<S>(c, st);
@@ -492,12 +545,13 @@ YW_DEV void run_layout(Ctx& c, bool first) {
 // this instantiation may use (32: the common kernel; 64: the wide-band kernel, more registers).
 template <int MAXS>
 YW_DEV void ydrop_forward_warp(const uint8_t* tcodes, const uint8_t* qcodes, int64_t ta, int64_t qa, int dir, Params p,
-                               Pool pool, uint32_t item, uint32_t warp_slot, ExtResult* res) {
+                               Pool pool, uint32_t item, uint32_t warp_slot, ExtResult* res, uint32_t lay_mask) {
     constexpr int max_S = MAXS;
     Ctx c;
     c.tc = tcodes; c.qc = qcodes; c.ta = ta; c.qa = qa; c.dir = dir; c.p = p;
     c.bias = 125 - 2 * p.E;
-    c.k = 0; c.S = 16; c.rbase = -256;
+    c.lay_mask = lay_mask; c.alo = c.ahi = 0;
+    c.k = 0; c.S = pick_layout(lay_mask, 1, 0, max_S); c.rbase = -16 * c.S;
     c.init_best = INIT_THR + p.Y; c.rebase_at = REBASE_THR + p.Y;
     c.F = -c.bias - c.init_best;               // stored H(0,0) = 0 + 0 - bias - F = init_best
     c.bestT = c.init_best + c.bias + p.E;      // image of best = 0 on anti-diagonal 1
@@ -518,24 +572,31 @@ YW_DEV void ydrop_forward_warp(const uint8_t* tcodes, const uint8_t* qcodes, int
     int maxs = 0, nlay = 0;
     while (c.status == ST_OK) {
         maxs = c.S > maxs ? c.S : maxs; nlay++;
-        if (c.S == 16) run_layout<16>(c, first);
+        if (c.S == 8) run_layout<8>(c, first);
+        else if (c.S == 12) run_layout<12>(c, first);
+        else if (c.S == 16) run_layout<16>(c, first);
+        else if (c.S == 20) run_layout<20>(c, first);
         else if (c.S == 24) run_layout<24>(c, first);
-        else if (MAXS < 64 || c.S == 32) run_layout<32>(c, first);
-        else run_layout<(MAXS >= 64 ? 64 : 32)>(c, first);
+        else if (c.S == 32) run_layout<32>(c, first);
+        else {
+            if constexpr (MAXS >= 64) {
+                if (c.S == 48) run_layout<48>(c, first);
+                else if (c.S == 64) run_layout<64>(c, first);
+                else c.status = ST_FAIL;
+            } else {
+                c.status = ST_FAIL;
+            }
+        }
         first = false;
         if (c.status != ST_OK || c.dead_steps >= 2) break;
-        // next layout: alive diagonals are within [alo, ahi] (lane granularity)
-        const int alo = c.rbase + c.S * c.lo_lane, ahi = c.rbase + c.S * (c.hi_lane + 1) - 1;
-        const int need = ahi - alo + 1;
-        int ns = 0;
-        if (need + 2 * (16 + 48) <= 32 * 16) ns = 16;
-        else if (need + 2 * (24 + 24) <= 32 * 24) ns = 24;
-        else if (need + 2 * (32 + 8) <= 32 * 32) ns = 32;
-        else if (max_S >= 64 && need + 2 * (64 + 8) <= 32 * 64) ns = 64;
-        if (ns == 0 || ns > max_S) { c.status = ns == 0 && max_S >= 64 ? ST_FAIL : ST_WIDE; break; }
+        // next layout: the smallest allowed one that holds the alive diagonals [alo, ahi], centred on them
+        if (c.ahi < c.alo) break;                      // nothing alive (the dead-step test normally catches this first)
+        const int need = c.ahi - c.alo + 1;
+        int ns = pick_layout(c.lay_mask, need, 0, max_S);
+        if (ns == 0) { c.status = max_S >= 64 ? ST_FAIL : ST_WIDE; break; }    // ST_WIDE: the caller reruns the item with the wide kernel
         const int slack = (32 * ns - need) / 2;
         c.S = ns;
-        c.rbase = (alo - slack) & ~1;
+        c.rbase = (c.alo - slack) & ~1;
     }
     if (lane == 0) {
         ExtResult r;

@@ -68,6 +68,7 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {          // PTX prmt.
     return r;
 }
 inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32); return (uint32_t)(v >> (sh & 31u)); }
+inline uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t sh) { const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32); return sh >= 32 ? hi : (uint32_t)(v >> sh); }
 inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline uint32_t ld8(const uint8_t* p) { return *p; }
 inline void fence() {}

@@ -61,6 +61,6 @@ def test_c2_full_segments_equal_oracle():
     wl = CoverageWorkload(0)
     got = coverage.coverage_segments(wl.chrom, wl.start, wl.end, wl.sizes, wl.MIN_COV, wl.MIN_LEN)
     want = ao.coverage_segments_c(wl.chrom, wl.start, wl.end, wl.sizes, wl.MIN_COV, wl.MIN_LEN)
-    assert len(want[0]) > 1000
+    assert len(want[0]) >= 50          # 70x mean depth: every scaffold is one segment, clipped at its ends
     for g, w in zip(got, want):
         assert np.array_equal(np.asarray(g), np.asarray(w))

@@ -24,7 +24,7 @@ def emu_lib():
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-I', os.path.join(HERE, 'emu'), '-o', SO, srcs[0]])
     l = C.CDLL(SO)
     l.emu_extend.restype = C.c_int
-    l.emu_extend.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    l.emu_extend.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]
     return l
 
 
@@ -46,9 +46,12 @@ def oracle_ext(t, a1, q, a2, d, p):
     return out.tolist(), cells
 
 
-def emu_ext(l, tk, a1, qk, a2, d, p, max_s=32, nchunks=4096):
+ALL_LAYOUTS = sum(1 << (s // 4) for s in (8, 12, 16, 20, 24, 32, 48, 64))
+
+
+def emu_ext(l, tk, a1, qk, a2, d, p, max_s=32, nchunks=4096, layouts=ALL_LAYOUTS):
     out = np.zeros(11, np.int32)
-    l.emu_extend(tk.ctypes.data, qk.ctypes.data, PAD + a1, PAD + a2, d, p.gap_open, p.gap_extend, p.ydrop, max_s, nchunks, out.ctypes.data)
+    l.emu_extend(tk.ctypes.data, qk.ctypes.data, PAD + a1, PAD + a2, d, p.gap_open, p.gap_extend, p.ydrop, max_s, nchunks, layouts, out.ctypes.data)
     return out.tolist()
 
 
@@ -80,6 +83,8 @@ def check(l, t, q, a1, a2, p, max_s=32):
     for d in (+1, -1):
         want, cells = oracle_ext(t, a1, q, a2, d, p)
         got = emu_ext(l, tk, a1, qk, a2, d, p, max_s)
+        if got[5] == 2 and max_s < 64:          # band too wide for the common kernel: the host reruns it with the wide one
+            got = emu_ext(l, tk, a1, qk, a2, d, p, 64)
         assert got[5] == 0, f'status {got[5]} dir {d} (want {want})'
         assert got[:5] == want, f'dir {d}: emulated kernel {got[:5]} != oracle {want} (kbest {got[7]}, oracle cells {cells}, kernel band cells {got[6]})'
 
