@@ -2,7 +2,11 @@
 """
 bench.py -- measures the hot path on B200 (contract: one JSON line on stdout from rank 0).
 
-  python bench.py --gpus N --steps K --warmup W [--workload cov|self] [--impl b200|reference]
+  python bench.py --gpus N --steps K --warmup W [--workload x|self|map|cov|c5] [--impl b200|reference]
+
+Default workload = BASELINE config 4 (`mimeo x`, 50 Mbp vs 100 Mbp), the largest named config that fits one GPU within the
+driver's time and the one BASELINE.json shards over 8 GPUs; the same job at every N (strong scaling). Configs 1, 2 and 3 are
+measured beside it at N=1 (extra keys); config 5 (`--workload c5`, MB2_C5_MBP to scale it down) is run by hand.
 
 A "step" is one pass of the hot path over one batch of synthetic input.
   value : whole-job throughput with inputs already resident in HBM, timed with CUDA events on the
@@ -124,6 +128,7 @@ class CoverageWorkload:
         out = coverage.coverage_segments(self.pinned[0].numpy(), self.pinned[1].numpy(), self.pinned[2].numpy(),
                                          self.sizes, self.MIN_COV, self.MIN_LEN)
         self.d2h_bytes = sum(a.nbytes for a in out)
+        self.last_e2e = out
         return out
 
     def kernel_bytes(self):
@@ -152,237 +157,313 @@ class CoverageWorkload:
                                       P(oc), P(os_), P(oe), ctypes.c_long(cap))
         dt = time.perf_counter() - t0
         assert k >= 0
+        self.oracle_segments = (oc[:k].copy(), os_[:k].copy(), oe[:k].copy())
         return dt, 1, 'full workload (10M hits / 100 Mbp), arrays already parsed; single-threaded C port of genomecov+merge'
+
+    def parity(self):
+        """Segments of the last e2e step vs the C oracle's, element for element (full config-2 size)."""
+        got = self.last_e2e
+        ok = all(np.array_equal(np.asarray(g), w) for g, w in zip(got, self.oracle_segments))
+        return {'segments_identical': bool(ok), 'segments_compared': int(len(self.oracle_segments[0])),
+                'scope': 'every (scaffold, start, end) segment of the full 10 M-hit table, GPU vs the C restatement of genomecov+merge'}
 
 
 
 def _oracle_pair_job(args):
-    """One (target, query) scaffold pair through the CPU LASTZ-restatement (both strands) -- runs in a worker process."""
-    tcodes, qcodes, hspthresh = args
+    """One (target, query) scaffold pair through the CPU LASTZ-restatement (both strands) -- runs in a worker process.
+    Returns (seconds, rows in mb2_align's row format with the given ids, oracle stage counters)."""
+    ti, tcodes, qi, qcodes, hspthresh = args
     from oracle import lastz_oracle as lo
     st = lo.Stats()
     t0 = time.perf_counter()
     tix = lo.TargetIndex(tcodes)          # LASTZ rebuilds its seed table for every pair: that cost belongs to the baseline
     p = lo.default_params(hspthresh)
-    n = 0
-    for q in (qcodes, lo.revcomp_codes(qcodes)):
-        n += len(lo.align_tile(tix, q, p, st))
-    return time.perf_counter() - t0, n, st.as_dict()
+    rows = []
+    m = len(qcodes)
+    for strand, q in ((0, qcodes), (1, lo.revcomp_codes(qcodes))):
+        for (s1, e1, s2, e2, sc, nm, nc, _a, _b) in lo.align_tile(tix, q, p, st).tolist():
+            qs, qe = (s2 + 1, e2) if strand == 0 else (m - e2 + 1, m - s2)
+            rows.append((ti, qi, strand, s1 + 1, e1, qs, qe, sc, nm, nc))
+    return time.perf_counter() - t0, rows, st.as_dict()
 
 
-class SelfWorkload:
-    """BASELINE config 1: `mimeo self` on a synthetic 5 Mbp genome (10 scaffolds x 500 kbp, 20 planted repeat families of
-    5-30 copies at ~80 % pairwise identity), minIdt 80, minLen 100, minCov 3, intraCov 4, --strictSelf.
-    Under N ranks every rank annotates its own genome of the batch (weak scaling: one genome per GPU, no collective)."""
-    name = 'C1: mimeo self, synthetic 5 Mbp genome (10 x 500 kbp, 20 repeat families at ~80% identity), minIdt 80 minLen 100 minCov 3 intraCov 4 strictSelf'
-    NSCAF, SCAF_LEN, NFAM = 10, 500_000, 20
-    MIN_IDT, MIN_LEN, MIN_COV, INTRA_COV, HSPTHRESH = 80, 100, 3, 4, 3000
+class AlignWorkload:
+    """A `mimeo self / x / map` job on ONE pair of genomes, the pair grid cut into one (target group x query group) block per
+    rank (mimeo_b200.parallel.ShardPlan; strong scaling). Per step every rank aligns its block, filters, all-gathers the hit
+    table over NCCL, thresholds the coverage of the target scaffolds it owns and sends its segments to rank 0."""
     dtype = 'int32'
+    scaling = 'strong'
+    mode = 'self'
+    MIN_IDT, MIN_LEN, MIN_COV, INTRA_COV, HSPTHRESH, STRICT = 80, 100, 3, 4, 3000, True
 
+    # ---- subclasses provide genomes(): (tnames, tseqs, qnames, qseqs) with tnames in C-locale order; q* is t* for self
     def __init__(self, rank):
-        from tests.helpers import synth_genome
-        g = synth_genome(1001 + rank, self.NSCAF, self.SCAF_LEN, self.NFAM, copies=(5, 30), fam_len=(300, 3000), sub=0.106, indel=0.005)
-        self.names = sorted(g, key=lambda s: s.encode())
-        self.seqs = [g[n] for n in self.names]
-        self.sizes = [len(x) for x in self.seqs]
-        self.mbp = sum(self.sizes) / 1e6
+        self.tnames, self.tseqs, self.qnames, self.qseqs = self.genomes()
+        self.same = self.qseqs is self.tseqs
+        self.tsizes = [len(x) for x in self.tseqs]
+        self.qsizes = [len(x) for x in self.qseqs]
+        self.mbp = (sum(self.tsizes) + (0 if self.same else sum(self.qsizes))) / 1e6
+        self.stats = {}
+
+    def covs(self):
+        if self.mode == 'map':
+            return []
+        if self.mode == 'self' and self.STRICT:
+            return [('inter', self.MIN_COV), ('intra', self.INTRA_COV)]
+        return [('inter', self.MIN_COV)]
 
     def to_device(self, torch, dev):
+        import torch.distributed as dist
+        from mimeo_b200 import parallel
         from mimeo_b200.genome import Genome
-        self.pinned = [torch.from_numpy(x.copy()).pin_memory() for x in self.seqs]
-        self.T = Genome(self.names, self.seqs)
-        self.Tboth = self.T.both_strands()
-        self.h2d_bytes = sum(self.sizes)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.plan = parallel.ShardPlan(self.tsizes, self.qsizes, self.world)
+        self.t_idx, self.q_idx = self.plan.block(self.rank)
+        self.pinned_t = [torch.from_numpy(np.ascontiguousarray(self.tseqs[i])).pin_memory() for i in self.t_idx]
+        share = self.same and self.t_idx == self.q_idx
+        self.pinned_q = self.pinned_t if share else [torch.from_numpy(np.ascontiguousarray(self.qseqs[i])).pin_memory() for i in self.q_idx]
+        self.T = Genome([self.tnames[i] for i in self.t_idx], [t.numpy() for t in self.pinned_t])
+        self.Q = self.T if share else Genome([self.qnames[i] for i in self.q_idx], [t.numpy() for t in self.pinned_q])
+        self.Qb = self.Q.both_strands()
+        self.hint = None
+        if self.same and not share:
+            pos = {g: k for k, g in enumerate(self.q_idx)}
+            self.hint = [pos.get(g, -1) for g in self.t_idx]
+        self.h2d_bytes = sum(self.tsizes[i] for i in self.t_idx) + (0 if share else sum(self.qsizes[i] for i in self.q_idx))
+        self.d2h_bytes = 0
+
+    def _annotate(self, hits):
+        from mimeo_b200 import coverage, engine, parallel
+        filt = engine.filter_hits_map if self.mode == 'map' else engine.filter_hits
+        out = parallel.annotate_block(hits, self.t_idx, self.q_idx, self.plan, self.tsizes, self.MIN_IDT, self.MIN_LEN,
+                                      coverage.coverage_segments, self.covs(), filt, strict_self=(self.mode == 'self' and self.STRICT))
+        if out is not None:
+            self.table, self.segs = out
+            self.nhits, self.nseg = len(self.table), sum(len(v) for v in self.segs.values())
+        return out
 
     def step_resident(self):
-        from mimeo_b200 import engine
-        inter, intra, hits, stats = engine.self_segments(self.T, self.Tboth, self.sizes, self.MIN_IDT, self.MIN_LEN, self.MIN_COV,
-                                                         self.INTRA_COV, self.HSPTHRESH, True)
-        self.stats, self.nhits, self.nseg = stats, len(hits['t_id']), len(inter[0]) + len(intra[0])
-        return inter, intra
+        from mimeo_b200 import align as A
+        from mimeo_b200.genome import align_params
+        hits, self.stats = A.align(self.T, self.Q, align_params(self.HSPTHRESH), Q_aux=self.Qb, t_same_q=self.hint)
+        self.raw_hits = hits
+        return self._annotate(hits)
 
     def step_e2e(self):
-        """Host ASCII (pinned) in -> .tab rows and GFF3 rows out, every copy inside."""
+        """Host ASCII (pinned) in -> .tab rows and GFF3 rows out on rank 0, every copy and the collectives inside."""
         from mimeo_b200 import align as A, engine
-        from mimeo_b200.genome import Genome
-        T = Genome(self.names, [t.numpy() for t in self.pinned])
+        from mimeo_b200.genome import Genome, align_params
+        share = self.pinned_q is self.pinned_t
+        T = Genome([self.tnames[i] for i in self.t_idx], [t.numpy() for t in self.pinned_t])
+        Q = T if share else Genome([self.qnames[i] for i in self.q_idx], [t.numpy() for t in self.pinned_q])
         try:
-            inter, intra, hits, stats = engine.self_segments(T, None, self.sizes, self.MIN_IDT, self.MIN_LEN, self.MIN_COV,
-                                                             self.INTRA_COV, self.HSPTHRESH, True)
+            hits, _ = A.align(T, Q, align_params(self.HSPTHRESH), t_same_q=self.hint)
         finally:
+            if Q is not T:
+                Q.close()
             T.close()
-        blocks = A.tab_blocks(hits, self.names, self.names, self.MIN_LEN, self.MIN_IDT)
+        out = self._annotate(hits)
+        if out is None:
+            return None
+        table, segs = out
+        cols = {f: np.ascontiguousarray(table[:, k]) for k, f in enumerate(A.HIT_FIELDS)}
+        blocks = A.tab_blocks(cols, self.tnames, self.qnames, 0, 0) if len(table) else {}      # already filtered: format only
         ntab = sum(len(v) for v in blocks.values())
-        gff = [f'{self.names[int(c)]}\tmimeo-self\tSelf_Repeat\t{int(s)}\t{int(e)}\t.\t+\t.\tID=Self_Repeat_{k + 1:05d}\n'
-               for k, (c, s, e) in enumerate(zip(*inter))]
-        self.d2h_bytes = 40 * len(hits['t_id']) + 12 * (len(inter[0]) + len(intra[0]))
-        return ntab, len(gff)
+        src = {'self': 'mimeo-self', 'x': 'mimeo', 'map': 'mimeo-map'}[self.mode]
+        gff = ''.join(engine.segment_gff_text(v[:, 0], v[:, 1], v[:, 2], self.tnames, src, 'Repeat', 'Repeat') for v in segs.values())
+        self.d2h_bytes = 40 * len(table) + 12 * self.nseg
+        return ntab, gff.count('\n')
 
     def kernel_bytes(self):
-        """Algorithmic bytes of the HBM-bound seeding kernels, per strand-launch."""
-        Q = T = sum(self.sizes)
-        S = self.stats['seed_hits'] / 2.0
-        S_out = self.stats['survivors'] / 2.0
+        """Algorithmic bytes of the HBM-bound seeding kernels per launch; one seed_scan launch covers BOTH
+        strands of a query chunk, so every term counts both strands."""
+        T = sum(self.tsizes[i] for i in self.t_idx)
+        Q2 = 2 * sum(self.qsizes[i] for i in self.q_idx)
+        S, S_out = self.stats['seed_hits'], self.stats['survivors']
         return {
             'seed_table_build': T // 4 * 2 + 4 * T + 2 * 4 * (1 << 24),
-            'seed_scan': Q // 4 + Q * 13 * 4 + 4 * S + 8 * S_out,
+            'seed_scan': Q2 // 4 + Q2 * 13 * 4 + 4 * S + 8 * S_out,          # summed over the launches of a step
         }
 
     def int_cells(self):
         return {'seed_scan': self.stats['stage1_cells'], 'hsp_extend': self.stats['stage2_cells'], 'gapped': self.stats['gapped_cells']}
 
-    def cpu_reference(self, threads, npairs=None):
-        """CPU LASTZ-restatement on a bounded, stratified sample of the 100 ordered scaffold pairs (always includes self
-        pairs in proportion), extrapolated by pair count; plus nothing else (annotation stages are negligible here)."""
+    # ---- CPU side
+    def sample_pairs(self, npairs):
+        """Deterministic sample of the ordered (target, query) scaffold pairs; in self mode every n-th sampled pair is a
+        self pair, like the full schedule (n of n*n)."""
+        nt, nq = len(self.tnames), len(self.qnames)
+        if npairs >= nt * nq:
+            return [(a, b) for a in range(nt) for b in range(nq)]
+        rng = np.random.default_rng(7)
+        flat = rng.choice(nt * nq, size=npairs, replace=False)
+        pairs = [(int(f // nq), int(f % nq)) for f in flat]
+        if self.same:
+            nself = max(1, round(npairs / nt))
+            pairs = [(a, a) for a in rng.choice(nt, size=min(nself, nt), replace=False).tolist()] + [(a, b) for a, b in pairs if a != b][:npairs - nself]
+        return pairs
+
+    def cpu_reference(self, threads, npairs=None, want_rows=False):
+        """The CPU LASTZ-restatement on a bounded sample of the job's scaffold pairs, one oracle process per pair on `threads`
+        processes (the reference runs one LASTZ process per pair, serially). Returns (wall seconds of the sample, threads,
+        description, fraction of the pair grid's area covered, rows or None, oracle gapped cells)."""
         from concurrent.futures import ProcessPoolExecutor
         from oracle import lastz_oracle as lo
-        enc = [lo.encode(x) for x in self.seqs]
-        n = len(enc)
         if npairs is None:
-            npairs = max(2, min(n * n, 2 * threads))
-        # stratified: one self pair per ceil(n) sampled pairs, like the full schedule (n self pairs of n*n)
-        rng = np.random.default_rng(7)
-        pairs = [(0, 0)] + [tuple(map(int, rng.integers(0, n, 2))) for _ in range(npairs - 1)]
-        pairs = [(a, b if (k == 0 or a != b) else (b + 1) % n) for k, (a, b) in enumerate(pairs)]
-        jobs = [(enc[a], enc[b], self.HSPTHRESH) for a, b in pairs]
+            npairs = max(2, 2 * threads)
+        pairs = self.sample_pairs(npairs)
+        tenc = {a: lo.encode(self.tseqs[a]) for a in {a for a, _ in pairs}}
+        qenc = tenc if self.same else {}
+        for _, b in pairs:
+            if b not in qenc:
+                qenc[b] = lo.encode(self.qseqs[b])
+        jobs = [(a, tenc[a], b, qenc[b], self.HSPTHRESH) for a, b in pairs]
         t0 = time.perf_counter()
         if threads > 1:
             with ProcessPoolExecutor(max_workers=threads) as ex:
-                res = list(ex.map(_oracle_pair_job, jobs))
+                res = list(ex.map(_oracle_pair_job, jobs, chunksize=1))
         else:
             res = [_oracle_pair_job(j) for j in jobs]
         wall = time.perf_counter() - t0
-        n_self = sum(1 for a, b in pairs if a == b)
-        t_self = np.mean([r[0] for (a, b), r in zip(pairs, res) if a == b])
-        t_cross = np.mean([r[0] for (a, b), r in zip(pairs, res) if a != b])
-        cpu_seconds_full = n * t_self + n * (n - 1) * t_cross           # all n*n ordered pairs, one core
-        est = cpu_seconds_full / threads if threads > 1 else cpu_seconds_full
-        sample = (f'{len(pairs)} of {n * n} ordered scaffold pairs ({n_self} self) through the C LASTZ-restatement incl. per-pair seed-table '
-                  f'build, both strands; {wall:.1f} s wall on {threads} process(es); full-genome time extrapolated by pair class: '
-                  f'{cpu_seconds_full:.0f} core-seconds')
-        return est, threads, sample
+        area = sum(float(self.tsizes[a]) * float(self.qsizes[b]) for a, b in pairs)
+        frac = area / (float(sum(self.tsizes)) * float(sum(self.qsizes)))
+        core_s = sum(r[0] for r in res)
+        cells = sum(r[2]['gapped_cells'] for r in res)
+        sample = (f'{len(pairs)} of {len(self.tnames) * len(self.qnames)} ordered scaffold pairs ({100 * frac:.2f}% of the pair grid by area) '
+                  f'through the C LASTZ-restatement incl. per-pair seed-table build, both strands, {threads} process(es): {wall:.1f} s wall, '
+                  f'{core_s:.1f} core-seconds; value = job Mbp x sampled fraction / wall')
+        rows = None
+        if want_rows:
+            rows = set()
+            for r in res:
+                rows.update(r[1])
+        return wall, threads, sample, frac, rows, pairs, cells
+
+    def parity(self, oracle_rows, pairs):
+        """Rows of the sampled pairs, GPU (last resident step, before filtering) vs oracle."""
+        from mimeo_b200.align import HIT_FIELDS
+        h = self.raw_hits
+        t = np.asarray(self.t_idx, dtype=np.int64)[h['t_id']] if len(h['t_id']) else h['t_id']
+        q = np.asarray(self.q_idx, dtype=np.int64)[h['q_id']] if len(h['q_id']) else h['q_id']
+        want_pairs = set(pairs)
+        got = {(int(t[k]), int(q[k])) + tuple(int(h[f][k]) for f in HIT_FIELDS[2:]) for k in range(len(t)) if (int(t[k]), int(q[k])) in want_pairs}
+        return got == oracle_rows, len(oracle_rows)
 
 
-class ShardedSelfWorkload(SelfWorkload):
-    """NOT a BASELINE config: a C5-SHAPED genome scaled to 100 Mbp (50 scaffolds x 2 Mbp, 30 repeat families of 20-100
-    copies, 2-10 kbp, ~92 % identity) used to exercise the multi-GPU path: ONE genome, target scaffolds row-sharded over
-    the ranks (strong scaling), hits and segments gathered to rank 0 (the only collective)."""
-    name = 'C5-shaped self-alignment scaled to 100 Mbp (50 x 2 Mbp, 30 families x 20-100 copies of 2-10 kbp at ~92% identity), target scaffolds sharded over ranks'
-    NSCAF, SCAF_LEN, NFAM = 50, 2_000_000, 30
-    scaling = 'strong'
+class SelfWorkload(AlignWorkload):
+    """BASELINE config 1: `mimeo self` on a synthetic 5 Mbp genome (10 scaffolds x 500 kbp, 20 planted repeat families of
+    5-30 copies at ~80 % pairwise identity), minIdt 80, minLen 100, minCov 3, intraCov 4, --strictSelf."""
+    name = 'C1: mimeo self, synthetic 5 Mbp genome (10 x 500 kbp, 20 repeat families at ~80% identity), minIdt 80 minLen 100 minCov 3 intraCov 4 strictSelf'
+    mode = 'self'
+    NSCAF, SCAF_LEN, NFAM = 10, 500_000, 20
 
-    def __init__(self, rank):
+    def genomes(self):
         from tests.helpers import synth_genome
-        g = synth_genome(1005, self.NSCAF, self.SCAF_LEN, self.NFAM, copies=(20, 100), fam_len=(2000, 10000), sub=0.04, indel=0.004)
-        self.names = sorted(g, key=lambda s: s.encode())
-        self.seqs = [g[n] for n in self.names]
-        self.sizes = [len(x) for x in self.seqs]
-        self.mbp = sum(self.sizes) / 1e6
-
-    def to_device(self, torch, dev):
-        from mimeo_b200 import parallel
-        from mimeo_b200.genome import Genome
-        import torch.distributed as dist
-        world = dist.get_world_size() if dist.is_initialized() else 1
-        rank = dist.get_rank() if dist.is_initialized() else 0
-        self.mine = parallel.partition_targets(self.sizes, world)[rank]
-        self.Q = Genome(self.names, self.seqs)
-        self.Qb = self.Q.both_strands()
-        self.T = self.Q if world == 1 else Genome([self.names[i] for i in self.mine], [self.seqs[i] for i in self.mine])
-        self.pinned = []
-        self.h2d_bytes = sum(self.sizes)
-        self.world = world
-
-    def _align_fn(self, t_idx):
-        from mimeo_b200 import align as A
-        from mimeo_b200.genome import align_params
-        hits, stats = A.align(self.T, self.Q, align_params(self.HSPTHRESH), Q_aux=self.Qb, t_same_q=None if self.T is self.Q else self.mine)
-        self.stats = stats
-        return hits
-
-    def step_resident(self):
-        from mimeo_b200 import coverage, engine, parallel
-        out = parallel.self_sharded(self.names, self.seqs, self.MIN_IDT, self.MIN_LEN, self.MIN_COV, self.INTRA_COV, self.HSPTHRESH, True,
-                                    align_fn=self._align_fn, coverage_fn=coverage.coverage_segments, filter_fn=engine.filter_hits)
-        if out is not None:
-            self.nhits, self.nseg = len(out[0]['t_id']), len(out[1]) + len(out[2])
-        return out
-
-    def step_e2e(self):
-        out = self.step_resident()
-        self.d2h_bytes = 0 if out is None else 40 * self.nhits + 12 * self.nseg
-        return out
-
-    def mbp_per_rank(self, world):
-        return self.mbp / world        # strong scaling: the job is one genome
-
-    def cpu_reference(self, threads, npairs=None):
-        return SelfWorkload.cpu_reference(self, threads, npairs=max(2, min(8, threads)))
+        g = synth_genome(1001, self.NSCAF, self.SCAF_LEN, self.NFAM, copies=(5, 30), fam_len=(300, 3000), sub=0.106, indel=0.005)
+        names = sorted(g, key=lambda s: s.encode())
+        seqs = [g[n] for n in names]
+        self.names, self.seqs, self.sizes = names, seqs, [len(x) for x in seqs]
+        return names, seqs, names, seqs
 
 
-class C5Workload(ShardedSelfWorkload):
-    """BASELINE config 5: `mimeo self` on a 1 Gbp synthetic plant-like genome (40 % repeats, 500 scaffolds), one genome whose
-    target scaffolds are row-sharded over the ranks (strong scaling). MB2_C5_MBP scales the genome down for trial runs (the
-    workload name then says so)."""
-    NSCAF = 500
-    scaling = 'strong'
+class XWorkload(AlignWorkload):
+    """BASELINE config 4: `mimeo x`, genome A 50 Mbp (50 x 1 Mbp) annotated by its hits against genome B 100 Mbp (100 x 1 Mbp),
+    40 repeat families 5-30x in B and 1-3x in A at 80-90 % identity, minIdt 80, minLen 100, minCov 5."""
+    name = ('C4: mimeo x, synthetic genome A 50 Mbp (50 x 1 Mbp) vs genome B 100 Mbp (100 x 1 Mbp), 40 repeat families (5-30 copies in B, '
+            '1-3 in A, 80-90% identity), minIdt 80 minLen 100 minCov 5; Mbp = bases of both genomes')
+    mode = 'x'
+    MIN_COV = 5
 
-    def __init__(self, rank):
+    def genomes(self):
+        from tests.helpers import synth_c4
+        a, b = synth_c4(1004)
+        an, bn = sorted(a, key=lambda s: s.encode()), sorted(b, key=lambda s: s.encode())
+        return an, [a[n] for n in an], bn, [b[n] for n in bn]
+
+
+class MapWorkload(AlignWorkload):
+    """BASELINE config 3: `mimeo map`, two 40 Mbp genomes (B = A diverged by 8 % substitutions + 0.5 % indels over 60 % of its
+    length, 10 % of the blocks inverted), minIdt 90, minLen 100, no coverage filter."""
+    name = ('C3: mimeo map, synthetic genome A 40 Mbp (40 x 1 Mbp) vs B = A diverged (8% substitutions, 0.5% indels over 60% of its length, '
+            '10% of blocks inverted), minIdt 90 minLen 100, no coverage filter; Mbp = bases of both genomes')
+    mode = 'map'
+    MIN_IDT = 90
+
+    def genomes(self):
+        from tests.helpers import synth_c3
+        a, b = synth_c3(1003)
+        an, bn = sorted(a, key=lambda s: s.encode()), sorted(b, key=lambda s: s.encode())
+        return an, [a[n] for n in an], bn, [b[n] for n in bn]
+
+
+class C5Workload(AlignWorkload):
+    """BASELINE config 5: `mimeo self` on a 1 Gbp synthetic plant-like genome (40 % repeats, 500 scaffolds). MB2_C5_MBP scales
+    the genome down for trial runs (the workload name then says so)."""
+    mode = 'self'
+
+    def genomes(self):
         from tests.helpers import synth_c5
         mbp = float(os.environ.get('MB2_C5_MBP', '1000'))
-        nscaf = max(8, int(round(self.NSCAF * mbp / 1000.0)))
+        nscaf = max(8, int(round(500 * mbp / 1000.0)))
         g = synth_c5(1005, int(mbp * 1e6), nscaf)
-        self.names = sorted(g, key=lambda s: s.encode())
-        self.seqs = [g[n] for n in self.names]
-        self.sizes = [len(x) for x in self.seqs]
-        self.mbp = sum(self.sizes) / 1e6
+        names = sorted(g, key=lambda s: s.encode())
+        seqs = [g[n] for n in names]
         self.name = ('C5: mimeo self, synthetic plant-like genome %.0f Mbp, %d scaffolds (log-normal lengths), 40%% repeats (families of '
-                     '2-10 kbp, 50-2000 copies, 75-98%% identity), minIdt 80 minLen 100 minCov 3 intraCov 4 strictSelf, targets sharded over ranks'
-                     % (self.mbp, nscaf)) + ('' if mbp == 1000 else ' [SCALED-DOWN TRIAL of the 1 Gbp config]')
+                     '2-10 kbp, 50-2000 copies, 75-98%% identity), minIdt 80 minLen 100 minCov 3 intraCov 4 strictSelf'
+                     % (sum(len(x) for x in seqs) / 1e6, nscaf)) + ('' if mbp == 1000 else ' [SCALED-DOWN TRIAL of the 1 Gbp config]')
+        return names, seqs, names, seqs
 
-WORKLOADS = {'self': SelfWorkload, 'cov': CoverageWorkload, 'c5s': ShardedSelfWorkload, 'c5': C5Workload}
+
+WORKLOADS = {'x': XWorkload, 'self': SelfWorkload, 'map': MapWorkload, 'cov': CoverageWorkload, 'c5': C5Workload}
+METRIC = 'self-alignment Mbp/sec (genome Mbp annotated per second of hot-path time)'
 
 
 # ------------------------------------------------------------------------------------------------- arms
 def run_reference(args):
+    """The reference's CPU path for this job on the box's host cores: the C LASTZ-restatement (no LASTZ binary exists in the
+    image), one process per scaffold pair on every core, each step a bounded sample of the job's pair grid. ms_per_step is
+    the measured wall time of a step; value scales the job's Mbp by the sampled fraction of the grid."""
     rank, _, world = env_rank()
     if rank != 0:
         return
     wl = WORKLOADS[args.workload](0)
-    times = []
+    cores = os.cpu_count() or 1
+    times, frac, sample = [], 1.0, ''
     for i in range(args.warmup + args.steps):
-        dt, cores, sample = wl.cpu_reference(os.cpu_count())
+        if args.workload == 'cov':
+            dt, used, sample = wl.cpu_reference(cores)
+        else:
+            dt, used, sample, frac, _, _, _ = wl.cpu_reference(cores, npairs=args.ref_pairs or None)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
-    val = wl.mbp / (ms / 1e3)
+    val = wl.mbp * frac / (ms / 1e3)
     print(json.dumps({
-        'impl': 'reference', 'metric': 'self-alignment Mbp/sec (annotated genome Mbp per second of hot-path time)',
-        'value': val, 'unit': 'Mbp/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': wl.dtype, 'data': 'synthetic',
-        'config': {'workload': wl.name},
-        'cpu_baseline': {'value': val, 'unit': 'Mbp/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'Mbp/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': getattr(wl, 'scaling', 'weak'), 'vs_baseline': None, 'dtype': wl.dtype,
+        'data': 'synthetic', 'config': {'workload': wl.name},
+        'cpu_baseline': {'value': val, 'unit': 'Mbp/s', 'cores': used, 'kind': 'port', 'sample': sample, 'sample_fraction': frac,
+                         'host_cpu_count': cores},
         'e2e': {'value': val, 'unit': 'Mbp/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
 
 
-def quick_config2(steps=5, warmup=3):
-    """BASELINE config 2 (10 M hits / 100 Mbp) measured by this same script in a fresh process (`--workload cov`): same arms,
-    same timing rules as the headline; the parent holds the GPU idle meanwhile. Returns the child's line, trimmed."""
-    env = dict(os.environ, MB2_BENCH_NO_C2='1')
+def side_config(workload, steps=5, warmup=3, timeout=900):
+    """Another BASELINE config measured by this same script in a fresh process: same arms, same timing rules as the headline;
+    the parent holds the GPU idle meanwhile. Returns the child's line, trimmed."""
+    env = dict(os.environ, MB2_BENCH_NO_SIDE='1')
     for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE'):
         env.pop(k, None)
-    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--workload', 'cov', '--steps', str(steps), '--warmup', str(warmup)],
-                         env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--workload', workload, '--steps', str(steps), '--warmup', str(warmup)],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     if out.returncode != 0:
         raise RuntimeError(f'child exited {out.returncode}: {out.stderr[-200:]}')
     d = json.loads(out.stdout.strip().splitlines()[-1])
-    r = d['roofline']
-    return {'workload': d['config']['workload'], 'steps': d['steps'], 'warmup': d['warmup'], 'ms_per_step': d['ms_per_step'],
-            'value': d['value'], 'unit': d['unit'], 'e2e': d['e2e'], 'gpu_launches': d['gpu_launches'], 'clocks': d['clocks'],
-            'cpu_baseline': d['cpu_baseline'],
-            'roofline': {k: r.get(k) for k in ('kernel', 'achieved', 'peak', 'frac', 'traffic', 'ms_per_launch',
-                                               'algorithmic_bytes_per_launch', 'kernels_ms_per_step', 'stage_survey_model')}}
+    keep = ('value', 'unit', 'ms_per_step', 'steps', 'warmup', 'e2e', 'gpu_launches', 'clocks', 'cpu_baseline', 'roofline', 'gcups', 'parity')
+    r = {k: d[k] for k in keep if k in d}
+    r['workload'] = d['config']['workload']
+    return r
 
 
 def run_b200(args):
@@ -428,7 +509,7 @@ def run_b200(args):
     total_ms = 0.0
     for _ in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (outside the timed interval)
-        torch.cuda.synchronize()
+        barrier()                           # every rank starts the step together: the step contains collectives
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
@@ -445,32 +526,52 @@ def run_b200(args):
     job_mbp = wl.mbp if scaling == 'strong' else world * wl.mbp
     value = job_mbp / (ms_step / 1e3)
 
-    # ---- roofline of the dominant HBM-bound kernel (same timed region, CUDA events on the library stream)
+    # ---- roofline of the dominant kernel (same timed region, CUDA events on the library stream)
     peak, peak_src = measured_peaks()
     kb = wl.kernel_bytes()
-    tags = [t for t in kb if not t.startswith('_')]
-    all_tags = tags + [t for t in ('surv_sort', 'hsp_extend', 'hsp_sort', 'chain', 'gapped', 'gp_forward', 'gp_walk', 'cov_events', 'cov_bin_events', 'cov_tile') if t not in tags]
+    hbm_tags = [t for t in kb if not t.startswith('_')]
+    int_tags = ['hsp_extend', 'gapped'] if hasattr(wl, 'int_cells') else []
+    all_tags = hbm_tags + [t for t in ('surv_sort', 'hsp_extend', 'hsp_sort', 'chain', 'gapped', 'gp_forward', 'cov_events', 'cov_bin_events', 'cov_tile') if t not in hbm_tags]
     prof = {t: _lib.prof_get(t) for t in all_tags}
-    dom = max(tags, key=lambda t: prof[t][0])
-    dms, dcnt = prof[dom]
-    per_launch_ms = dms / max(dcnt, 1)
-    achieved = kb[dom] / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
-    traffic, traffic_src = ncu_traffic(args.workload, dom)
-    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'ms_per_launch': per_launch_ms, 'algorithmic_bytes_per_launch': kb[dom],
-                'kernels_ms_per_step': {t: prof[t][0] / args.steps for t in all_tags if prof[t][1]},
-                'note': 'the dominant HBM-bound launch group of this workload; kernels bound by the integer pipe (x-drop and y-drop '
-                        'extension, the largest share of a self-alignment step) are reported under gcups, not against HBM'}
+    sm = _lib.lib().mb2_sm_count()
+    int_peak = sm * 128 * 1.965e9                                   # INT32 lane-ops/s at max clock
+    budget = {'seed_scan': 6, 'hsp_extend': 6, 'gapped': 12}
+    cells = wl.int_cells() if hasattr(wl, 'int_cells') else {}
+
+    def hbm_roofline(tag):
+        ms, cnt = prof[tag]
+        per_launch_ms = ms / max(cnt, 1)
+        launches_per_step = cnt / max(args.steps, 1)
+        bytes_per_launch = kb[tag] / max(launches_per_step, 1) if tag == 'seed_scan' else kb[tag]
+        achieved = bytes_per_launch / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
+        traffic, traffic_src = ncu_traffic(args.workload, tag)
+        return {'bound': 'hbm', 'kernel': tag, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                'traffic_source': traffic_src, 'peak_source': peak_src, 'ms_per_launch': per_launch_ms, 'launches_per_step': launches_per_step,
+                'algorithmic_bytes_per_launch': bytes_per_launch}
+
+    def int_roofline(tag):
+        ms = prof[tag][0] / args.steps
+        g = cells[tag] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        return {'bound': 'int32 (integer pipe; no tensor cores: not a dense contraction)', 'kernel': tag, 'achieved': g * budget[tag] / 1e3, 'peak': int_peak / 1e12,
+                'unit': 'Tera lane-ops/s at %d ops per cell' % budget[tag], 'frac': g * 1e9 * budget[tag] / int_peak, 'traffic': None,
+                'gcups': g, 'cells_per_step': cells[tag], 'ms_per_step': ms}
+
+    dom = max(hbm_tags, key=lambda t: prof[t][0])
+    roofline = hbm_roofline(dom)                      # `roofline` = the dominant HBM-bound launch group
+    top = max(hbm_tags + int_tags, key=lambda t: prof[t][0])
+    roofline['dominant_kernel_of_step'] = top
+    if int_tags:
+        roofline['int_kernel'] = int_roofline(max(int_tags, key=lambda t: prof[t][0]))
+    roofline['kernels_ms_per_step'] = {t: prof[t][0] / args.steps for t in all_tags if prof[t][1]}
+    roofline['note'] = ('the kernel with the largest share of the step; `hbm_kernels` lists the HBM-bound launch groups against the measured copy '
+                        'peak, `gcups` the integer-pipe kernels (x-drop, y-drop) against the INT32 issue roofline at the SURVEY op budgets')
+    roofline['hbm_kernels'] = {t: {k: v for k, v in hbm_roofline(t).items() if k in ('achieved', 'frac', 'ms_per_launch', 'algorithmic_bytes_per_launch', 'traffic')}
+                               for t in hbm_tags if prof[t][1]}
     if '_stage_survey' in kb:
         roofline['stage_survey_model'] = {'bytes': kb['_stage_survey'], 'achieved': kb['_stage_survey'] / (ms_step / 1e3) / 1e9,
                                           'frac': kb['_stage_survey'] / (ms_step / 1e3) / 1e9 / peak}
     extra = {}
-    if hasattr(wl, 'int_cells'):
-        # integer-pipe kernels: GCUPS = DP/extension cells actually evaluated / kernel seconds
-        cells = wl.int_cells()
-        sm = _lib.lib().mb2_sm_count()
-        int_peak = sm * 128 * 1.965e9                                   # INT32 lane-ops/s at max clock
-        budget = {'seed_scan': 6, 'hsp_extend': 6, 'gapped': 12}
+    if cells:
         gc = {}
         for t, c in cells.items():
             ms = prof[t][0] / args.steps
@@ -479,9 +580,13 @@ def run_b200(args):
                 gc[t] = {'gcups': g, 'cells_per_step': c, 'ms_per_step': ms, 'frac_of_int_roofline': g * 1e9 * budget[t] / int_peak}
         tot_cells = sum(cells.values())
         tot_ms = sum(prof[t][0] for t in cells) / args.steps
-        extra['gcups'] = {'value': tot_cells / (tot_ms / 1e3) / 1e9 if tot_ms > 0 else 0.0, 'unit': 'GCUPS (ungapped + gapped cells / kernel seconds)',
+        extra['gcups'] = {'value': tot_cells / (tot_ms / 1e3) / 1e9 if tot_ms > 0 else 0.0, 'unit': 'GCUPS (ungapped + gapped cells / kernel seconds), this rank',
                           'per_kernel': gc, 'int_roofline_ops_per_s': int_peak, 'ops_per_cell_budget': budget}
         extra['stage_counters'] = wl.stats
+    if hasattr(wl, 'plan'):
+        extra['partition'] = {'grid': f'{wl.plan.gt} target groups x {wl.plan.gq} query groups', 'balance': wl.plan.balance,
+                              'collectives_per_step': 'all-gather of the filtered hit table + gather of segments to rank 0 (NCCL)' if world > 1 else 'none (1 rank)',
+                              'rows_gathered': getattr(wl, 'nhits', None), 'segments': getattr(wl, 'nseg', None)}
 
     # ---- end-to-end arm through the host-buffer C ABI (H2D + D2H inside the timed region)
     for _ in range(max(1, args.warmup // 2)):
@@ -496,31 +601,47 @@ def run_b200(args):
     e2e = {'value': job_mbp / (e2e_ms / 1e3), 'unit': 'Mbp/s', 'ms_per_step': e2e_ms,
            'h2d_bytes_per_step': wl.h2d_bytes, 'd2h_bytes_per_step': wl.d2h_bytes}
 
-    # ---- BASELINE config 2 beside the headline (single GPU, default workload only): the coverage/threshold stage on its own
-    # 10 M-hit table, same timing rules, a few steps; reported as an extra key, never mixed into `value`
-    if rank == 0 and world == 1 and args.workload == 'self' and not os.environ.get('MB2_BENCH_NO_C2'):
-        try:
-            extra['config2_coverage_stage'] = quick_config2()
-        except Exception as e:      # the headline line must not depend on this leg
-            extra['config2_coverage_stage'] = {'error': f'{type(e).__name__}: {e}'[:300]}
+    # ---- the other single-GPU BASELINE configs beside the headline (default workload, 1 GPU only): extra keys, never mixed into `value`
+    if rank == 0 and world == 1 and args.workload == DEFAULT_WORKLOAD and not os.environ.get('MB2_BENCH_NO_SIDE'):
+        for key, w, st in (('config1_self_5Mbp', 'self', 5), ('config2_coverage_stage', 'cov', 5), ('config3_map_40Mbp', 'map', 3)):
+            try:
+                extra[key] = side_config(w, steps=st)
+            except Exception as e:      # the headline line must not depend on these legs
+                extra[key] = {'error': f'{type(e).__name__}: {e}'[:300]}
 
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1:
-        dt, cores, sample = wl.cpu_reference(1)
-        cpu = {'value': wl.mbp / dt, 'unit': 'Mbp/s', 'cores': cores, 'kind': 'port', 'sample': sample, 'seconds': dt}
+        if args.workload == 'cov':
+            dt, cores, sample = wl.cpu_reference(1)
+            cpu = {'value': wl.mbp / dt, 'unit': 'Mbp/s', 'cores': cores, 'kind': 'port', 'sample': sample, 'seconds': dt}
+            parity = wl.parity()
+        else:
+            # full pair grid for C1 (every row of the benchmarked job is compared); a bounded sample elsewhere
+            ncores = os.cpu_count() or 1
+            npairs = len(wl.tnames) * len(wl.qnames) if args.workload == 'self' else 12
+            dt, cores, sample, frac, rows, pairs, ocells = wl.cpu_reference(ncores if args.workload == 'self' else 1, npairs=npairs, want_rows=True)
+            core_s = dt * cores
+            cpu = {'value': wl.mbp * frac / core_s, 'unit': 'Mbp/s', 'cores': 1, 'kind': 'port', 'sample': sample + f'; reported for ONE core, the reference\'s own schedule (serial LASTZ processes): {core_s:.1f} core-seconds',
+                   'seconds': core_s, 'sample_fraction': frac, 'host_cpu_count': ncores, 'oracle_gapped_cells_in_sample': ocells}
+            ok, nrows = wl.parity(rows, pairs)
+            parity = {'rows_identical': bool(ok), 'rows_compared': nrows, 'pairs_compared': len(pairs),
+                      'scope': 'every alignment row (t, q, strand, start1, end1, start2+, end2+, score, matches, columns) of the sampled scaffold pairs, GPU vs oracle'}
 
     if rank == 0:
         print(json.dumps({
-            'metric': 'self-alignment Mbp/sec (annotated genome Mbp per second of hot-path time)',
-            'value': value, 'unit': 'Mbp/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'metric': METRIC, 'value': value, 'unit': 'Mbp/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None,
             'dtype': wl.dtype, 'data': 'synthetic',
             'config': {'workload': wl.name, 'l2': 'flushed between timed steps (256 MiB memset, outside the timed interval)',
-                       'sharding': 'one genome (scaffold group) of the batch per rank, no data-path collective'},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, **extra,
+                       'sharding': ('one job; the (target x query) scaffold pair grid cut into one block per rank; hit tables all-gathered, segments gathered to rank 0 inside the timed step'
+                                    if scaling == 'strong' else 'one scaffold group of the batch per rank, no data-path collective')},
+            'roofline': roofline, 'cpu_baseline': cpu, 'parity': parity, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, **extra,
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+DEFAULT_WORKLOAD = 'x'
 
 
 def main():
@@ -529,7 +650,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='self', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--ref-pairs', type=int, default=0, help='reference arm: scaffold pairs per step (default 2 x host cores)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

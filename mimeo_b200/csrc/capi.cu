@@ -1,5 +1,7 @@
 // capi.cu -- extern "C" boundary of libmimeo_b200.so (see include/mimeo_b200.h).
+#include <algorithm>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "primitives.cuh"
@@ -20,6 +22,77 @@ void ensure_init() {
     int cur = -1;
     if (cudaGetDevice(&cur) != cudaSuccess || cur != g_ctx.device) MB2_CUDA(cudaSetDevice(g_ctx.device));
 }
+
+// ---- scratch allocator (common.cuh)
+namespace {
+struct Slab { char* base; size_t size; };
+struct ScratchState {
+    std::vector<Slab> slabs;
+    std::map<char*, size_t> free_blocks;     // address -> size, coalesced
+    std::map<char*, size_t> used;            // address -> size
+    size_t reserved = 0;
+};
+ScratchState g_scratch;
+constexpr size_t SCRATCH_ALIGN = 512;
+constexpr size_t SCRATCH_MIN_SLAB = (size_t)1 << 30;
+}  // namespace
+
+void* scratch_alloc(size_t bytes) {
+    bytes = (bytes + SCRATCH_ALIGN - 1) / SCRATCH_ALIGN * SCRATCH_ALIGN;
+    ScratchState& st = g_scratch;
+    auto best = st.free_blocks.end();
+    for (auto it = st.free_blocks.begin(); it != st.free_blocks.end(); ++it)
+        if (it->second >= bytes && (best == st.free_blocks.end() || it->second < best->second)) best = it;
+    if (best == st.free_blocks.end()) {
+        // grow: a slab of at least 1 GiB (and at least half of what is reserved so far, so growth stays geometric)
+        size_t want = std::max(bytes, std::max(SCRATCH_MIN_SLAB, st.reserved / 2));
+        char* p = nullptr;
+        cudaError_t e = cudaMalloc((void**)&p, want);
+        if (e != cudaSuccess && want > bytes) { cudaGetLastError(); want = bytes; e = cudaMalloc((void**)&p, want); }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            throw Error(MB2_ERR_TOO_LARGE, "device memory exhausted: cannot reserve " + std::to_string(bytes >> 20) + " MiB of scratch (" +
+                                               std::to_string(st.reserved >> 20) + " MiB reserved)");
+        }
+        st.slabs.push_back({p, want});
+        st.reserved += want;
+        best = st.free_blocks.emplace(p, want).first;
+    }
+    char* p = best->first;
+    const size_t sz = best->second;
+    st.free_blocks.erase(best);
+    if (sz > bytes) st.free_blocks.emplace(p + bytes, sz - bytes);
+    st.used.emplace(p, bytes);
+    return p;
+}
+
+void scratch_free(void* ptr) {
+    ScratchState& st = g_scratch;
+    char* p = static_cast<char*>(ptr);
+    auto u = st.used.find(p);
+    if (u == st.used.end()) return;          // not ours (never happens), or released by scratch_release_all
+    size_t sz = u->second;
+    st.used.erase(u);
+    auto nx = st.free_blocks.lower_bound(p);
+    // coalesce with the following and the preceding free block when they touch AND lie in the same slab
+    auto same_slab = [&](char* a, char* b) {
+        for (const Slab& s : st.slabs) if (a >= s.base && a < s.base + s.size) return b >= s.base && b < s.base + s.size;
+        return false;
+    };
+    if (nx != st.free_blocks.end() && p + sz == nx->first && same_slab(p, nx->first)) { sz += nx->second; nx = st.free_blocks.erase(nx); }
+    if (nx != st.free_blocks.begin()) {
+        auto pv = std::prev(nx);
+        if (pv->first + pv->second == p && same_slab(pv->first, p)) { p = pv->first; sz += pv->second; st.free_blocks.erase(pv); }
+    }
+    st.free_blocks.emplace(p, sz);
+}
+
+void scratch_release_all() {
+    ScratchState& st = g_scratch;
+    for (const Slab& s : st.slabs) cudaFree(s.base);
+    st = ScratchState();
+}
+size_t scratch_reserved_bytes() { return g_scratch.reserved; }
 
 template <typename F>
 static int guarded(F&& f) {
@@ -90,9 +163,10 @@ int mb2_init(int device) {
 
 void mb2_shutdown(void) {
     if (g_ctx.ready) {
+        cudaStreamSynchronize(g_ctx.stream);
         coverage_release_scratch();
         gapped_release_scratch();
-        cudaStreamSynchronize(g_ctx.stream);
+        scratch_release_all();
         cudaStreamDestroy(g_ctx.stream);
         g_ctx.stream = nullptr;
         g_ctx.ready = false;
@@ -208,9 +282,9 @@ int mb2_coverage_segments_into(const int32_t* d_chrom, const int32_t* d_start, c
 void mb2_free_segments(mb2_segments* seg) {
     if (!seg) return;
     if (seg->on_device) {
-        if (seg->chrom) cudaFreeAsync(seg->chrom, g_ctx.stream);
-        if (seg->start) cudaFreeAsync(seg->start, g_ctx.stream);
-        if (seg->end) cudaFreeAsync(seg->end, g_ctx.stream);
+        if (seg->chrom) scratch_free(seg->chrom);
+        if (seg->start) scratch_free(seg->start);
+        if (seg->end) scratch_free(seg->end);
     } else {
         free(seg->chrom); free(seg->start); free(seg->end);
     }

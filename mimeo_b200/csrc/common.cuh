@@ -47,7 +47,16 @@ struct Ctx {
 Ctx& ctx();
 void ensure_init();
 
-// Stream-ordered scratch buffer (cudaMallocAsync on the library stream; pool keeps memory cached).
+// Device scratch allocator of the library: a host-side best-fit allocator over a few large slabs obtained with cudaMalloc
+// and kept until mb2_shutdown. Every user of the memory is enqueued on the ONE library stream, so a freed block may be
+// handed out again at once (stream order protects it), and the steady state of a pipeline makes NO driver calls: driver
+// allocation calls contend with other driver clients (an nvidia-smi poller stalled them for tens of milliseconds per step).
+void* scratch_alloc(size_t bytes);
+void scratch_free(void* p);
+void scratch_release_all();        // mb2_shutdown
+size_t scratch_reserved_bytes();
+
+// Stream-ordered scratch buffer on the library stream.
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -65,10 +74,10 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) MB2_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), ctx().stream));
+        if (count) p = static_cast<T*>(scratch_alloc(count * sizeof(T)));
     }
     void release() {
-        if (p) cudaFreeAsync(p, ctx().stream);
+        if (p) scratch_free(p);
         p = nullptr; n = 0;
     }
     T* get() const { return p; }

@@ -285,9 +285,9 @@ struct Arena {
     void reserve(size_t bytes) {
         used = 0;
         if (bytes <= cap) return;
-        if (p) { cudaFreeAsync(p, ctx().stream); p = nullptr; cap = 0; }
+        if (p) { scratch_free(p); p = nullptr; cap = 0; }
         const size_t want = bytes + bytes / 8;
-        MB2_CUDA(cudaMallocAsync((void**)&p, want, ctx().stream));
+        p = static_cast<uint8_t*>(scratch_alloc(want));
         cap = want;
     }
     template <typename T> T* take(size_t count) {
@@ -299,7 +299,7 @@ struct Arena {
 };
 static Arena g_arena;
 void coverage_release_scratch() {   // mb2_shutdown
-    if (g_arena.p) cudaFreeAsync(g_arena.p, ctx().stream);
+    if (g_arena.p) scratch_free(g_arena.p);
     g_arena.p = nullptr; g_arena.cap = g_arena.used = 0;
 }
 static size_t arena_slot(size_t count, size_t elem) { return (count * elem + 255) & ~(size_t)255; }

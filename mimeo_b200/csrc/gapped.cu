@@ -360,6 +360,7 @@ gp_forward_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restri
                   const uint32_t* __restrict__ tile, yw::Params prm, const int32_t* __restrict__ same_q, yw::Pool pool,
                   yw::ExtResult* __restrict__ res, unsigned long long* __restrict__ counters, uint32_t lay_mask) {
     const int lane = threadIdx.x;
+    uint32_t priv_used = 0;                 // private trace chunks this warp slot has handed out in this launch
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(next_item, 1u);
@@ -381,7 +382,7 @@ gp_forward_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restri
             continue;
         }
         yw::ydrop_forward_warp<MAXS>(T.codes, Q.codes, (int64_t)toff + a1, (int64_t)qoff + a2, dir == 0 ? +1 : -1, prm, pool, item, blockIdx.x,
-                                     &res[item], lay_mask);
+                                     priv_used, &res[item], lay_mask);
         __syncwarp();
         if (lane == 0) {
             const yw::ExtResult r = res[item];
@@ -393,16 +394,8 @@ gp_forward_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restri
     }
 }
 
-// launch order of the round's items: the higher-scoring anchor first (long extensions start early, short ones fill the tail)
-__global__ void __launch_bounds__(256)
-gp_item_keys_kernel(GpWork W, const uint32_t* __restrict__ items, uint32_t nitems, const int32_t* __restrict__ hscore, uint32_t* __restrict__ key) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nitems) return;
-    const int sc = hscore[W.order[items[k] >> 1]];
-    key[k] = 0xffffffu - (uint32_t)min(sc, 0xffffff);
-}
-
-// walk-back of every traced item of the round: one warp per item
+// walk-back of every traced item of the round: one warp per item (the traces of a round stay in the pool until the host
+// resets it for the next round)
 __global__ void __launch_bounds__(128)
 gp_walk_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restrict__ items, uint32_t nitems, const uint32_t* __restrict__ tile,
                yw::Params prm, yw::Pool pool, yw::ExtResult* __restrict__ res, unsigned long long* __restrict__ counters) {
@@ -422,6 +415,15 @@ gp_walk_kernel(GenomeView T, GenomeView Q, GpWork W, const uint32_t* __restrict_
         W.e_score[item] = r.score; W.e_di[item] = r.di; W.e_dj[item] = r.dj; W.e_nm[item] = r.nmatch; W.e_nc[item] = r.ncols;
         if (r.status != yw::ST_OK) atomicAdd(&counters[CNT_ERR], 1ull);
     }
+}
+
+// launch order of the round's items: the higher-scoring anchor first (long extensions start early, short ones fill the tail)
+__global__ void __launch_bounds__(256)
+gp_item_keys_kernel(GpWork W, const uint32_t* __restrict__ items, uint32_t nitems, const int32_t* __restrict__ hscore, uint32_t* __restrict__ key) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nitems) return;
+    const int sc = hscore[W.order[items[k] >> 1]];
+    key[k] = 0xffffffu - (uint32_t)min(sc, 0xffffff);
 }
 
 // Trace pool + re-layout scratch of the extension kernels: one device arena, grown on demand, kept between calls.
@@ -457,7 +459,7 @@ static yw::Pool trace_pool(int nslots) {
     if (!g_trace.base) {
         size_t free_b = 0, total_b = 0;
         MB2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        size_t want = (size_t)16 << 30;                                   // 2 bytes per evaluated DP cell of one round
+        size_t want = (size_t)48 << 30;                                   // 2 bytes per evaluated DP cell of one round (capped at a third of the free memory)
         if (const char* e = getenv("MB2_TRACE_POOL_MB")) { const double v = atof(e); if (v > 0) want = (size_t)(v * 1048576.0); }
         want = std::min(want, free_b / 3);
         size_t nchunks = want / yw::CHUNK_BYTES / yw::NSUB * yw::NSUB;
@@ -475,8 +477,12 @@ static yw::Pool trace_pool(int nslots) {
         g_trace.nslots = nslots;
     }
     yw::Pool p;
-    p.base = g_trace.base; p.meta = g_trace.meta; p.next = g_trace.next; p.per_sub = (uint32_t)(g_trace.nchunks / yw::NSUB);
-    p.scratch = g_trace.scratch;
+    p.base = g_trace.base; p.meta = g_trace.meta; p.next = g_trace.next; p.scratch = g_trace.scratch;
+    // a third of the pool is private (one slice per resident warp: no atomics, reused by every extension of that warp), the
+    // rest is shared by the extensions whose trace outgrows their slice (50 kbp alignments: ~80 MB each)
+    p.priv = (uint32_t)(g_trace.nchunks / 3 / (size_t)nslots);
+    p.shared0 = p.priv * (uint32_t)nslots;
+    p.per_sub = (uint32_t)((g_trace.nchunks - p.shared0) / yw::NSUB);
     return p;
 }
 
@@ -595,9 +601,12 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
             const yw::Params prm{p.gap_open, p.gap_extend, p.ydrop};
             const int nslots = cx.sm_count * GP_WARPS_PER_SM;
             const yw::Pool pool = trace_pool(nslots);
+            yw::Pool pool_wide = pool;
+            pool_wide.priv = 0;              // the wide-band kernel runs in the same round: its traces go to the shared part only
             DevBuf<yw::ExtResult> res(2 * (size_t)nm);
             DevBuf<uint32_t> next_item(2);
             unsigned long long h_nomem_before = 0;
+            uint32_t prev_sched = 0, conc = (uint32_t)nslots;      // items launched last round; CTAs (= concurrent extensions) allowed
             for (uint32_t round = 1;; round++) {
                 MB2_CUDA(cudaMemsetAsync(counts.get(), 0, 2 * sizeof(uint32_t), cx.stream));
                 launch(gp_select_kernel, cdiv((size_t)h_nseg * 32, 128), 128, 0, W, h.tile.get(), nm, seg_start.get(), h_nseg, resume.get(), nkept.get(),
@@ -616,15 +625,19 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
                     cudaEventRecord(ev0, cx.stream);
                 }
                 if (h_counts[0] == 0 && h_counts[1] == 0) break;
-                // every item of the previous round deferred again: one extension alone does not fit the pool
-                MB2_REQUIRE(round == 1 || h_nomem - h_nomem_before < (unsigned long long)(h_counts[0] + h_counts[1]) || h_nomem == h_nomem_before, -3,
+                // items that ran out of trace pool were put back; if NONE of the previous round finished, one extension alone
+                // does not fit the pool. Otherwise run fewer extensions at a time: as many as finished last round.
+                const unsigned long long deferred = h_nomem - h_nomem_before;
+                MB2_REQUIRE(deferred == 0 || deferred < prev_sched || conc > 1, -3,
                             "gapped stage: the trace pool is too small for a single extension (raise MB2_TRACE_POOL_MB)");
+                if (deferred * 2 > prev_sched) conc = std::max<uint32_t>(1, conc / 2);      // most ran out of pool together: fewer at a time
+                prev_sched = h_counts[0] + h_counts[1];
                 h_nomem_before = h_nomem;
                 MB2_CUDA(cudaMemsetAsync(pool.next, 0, yw::NSUB * sizeof(uint32_t), cx.stream));      // previous round's traces are consumed
                 MB2_CUDA(cudaMemsetAsync(next_item.get(), 0, 2 * sizeof(uint32_t), cx.stream));
                 static const uint32_t lay_narrow = layout_mask("MB2_GP_LAYOUTS", "16,24,32"), lay_wide = lay_narrow | (1u << 12) | (1u << 16);
                 static const bool sort_items = !getenv("MB2_GP_NOSORT");
-                static const int occ = getenv("MB2_GP_OCC") ? atoi(getenv("MB2_GP_OCC")) : 20;
+                static const int occ = getenv("MB2_GP_OCC") ? atoi(getenv("MB2_GP_OCC")) : 16;
                 const uint32_t* it_n = items_n.get();
                 DevBuf<uint32_t> sk0, sk1, si1;
                 if (sort_items && h_counts[0] > (uint32_t)nslots) {
@@ -637,15 +650,15 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
                     ProfScope pf("gp_forward");
                     if (h_counts[0]) {
                         auto go = [&](auto kern, int per_sm) {
-                            launch(kern, std::min<uint32_t>(h_counts[0], (uint32_t)(cx.sm_count * per_sm)), 32, 0, tv, qv, W, it_n, h_counts[0],
+                            launch(kern, std::min<uint32_t>(h_counts[0], std::min<uint32_t>(conc, (uint32_t)(cx.sm_count * per_sm))), 32, 0, tv, qv, W, it_n, h_counts[0],
                                    next_item.get(), h.tile.get(), prm, d_same.get(), pool, res.get(), counters, lay_narrow);
                         };
                         if (occ >= 20) go(gp_forward_kernel<32, 20>, 20);
                         else go(gp_forward_kernel<32, 16>, 16);
                     }
                     if (h_counts[1]) {
-                        launch(gp_forward_kernel<64, 4>, std::min<uint32_t>(h_counts[1], (uint32_t)nslots), 32, 0, tv, qv, W, (const uint32_t*)items_w.get(), h_counts[1],
-                               next_item.get() + 1, h.tile.get(), prm, d_same.get(), pool, res.get(), counters, lay_wide);
+                        launch(gp_forward_kernel<64, 4>, std::min<uint32_t>(h_counts[1], std::min<uint32_t>(conc, (uint32_t)(cx.sm_count * 4))), 32, 0, tv, qv, W, (const uint32_t*)items_w.get(), h_counts[1],
+                               next_item.get() + 1, h.tile.get(), prm, d_same.get(), pool_wide, res.get(), counters, lay_wide);
                     }
                 }
                 {

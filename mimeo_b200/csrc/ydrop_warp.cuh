@@ -75,11 +75,17 @@ struct ChunkMeta {        // 32 bytes
     int32_t pad0, pad1;
 };
 
+// Chunk ids [0, nslots * priv) are private: warp slot s owns [s * priv, (s + 1) * priv) and hands them out with a plain
+// counter that runs over all the extensions the slot processes in one launch (no atomics). When the slice is used up the
+// trace continues in the shared part: NSUB bump counters over per_sub chunks each. The host resets both between launches,
+// after the walk-back kernel has consumed the traces.
 struct Pool {
     uint8_t* base;        // nchunks * CHUNK_BYTES
     ChunkMeta* meta;      // nchunks
-    uint32_t* next;       // NSUB counters
-    uint32_t per_sub;     // chunks per sub-pool
+    uint32_t* next;       // NSUB counters of the shared part
+    uint32_t per_sub;     // chunks per shared sub-pool
+    uint32_t priv;        // private chunks per warp slot
+    uint32_t shared0;     // first chunk id of the shared part
     int16_t* scratch;     // per warp slot: 3 * WIN int16 (re-layout scratch)
 };
 
@@ -174,21 +180,22 @@ struct Ctx {
     int status;
     // trace
     Pool pool;
-    uint32_t item;
+    uint32_t item, slot;
+    uint32_t priv_used;   // private chunks handed out to this extension
     uint32_t chunk;       // current chunk id
     int k0, nrows, cap;
     int16_t* scr;         // this warp's scratch: H, D, I each WIN
 };
 
 // ------------------------------------------------------------------------------------------ trace pool
-YW_DEV_NOINLINE uint32_t pool_alloc(uint32_t* next, uint32_t per_sub, uint32_t item) {
+YW_DEV_NOINLINE uint32_t pool_alloc_shared(uint32_t* next, uint32_t per_sub, uint32_t shared0, uint32_t item) {
     uint32_t id = 0xffffffffu;
     if (lane_id() == 0) {
         for (uint32_t t = 0; t < NSUB; t++) {
             const uint32_t sub = (item + t) % NSUB;
             if (*(volatile uint32_t*)&next[sub] >= per_sub) continue;
             const uint32_t idx = atomic_add(&next[sub], 1u);
-            if (idx < per_sub) { id = sub * per_sub + idx; break; }
+            if (idx < per_sub) { id = shared0 + sub * per_sub + idx; break; }
         }
     }
     return shfl(id, 0);
@@ -197,7 +204,9 @@ YW_DEV_NOINLINE uint32_t pool_alloc(uint32_t* next, uint32_t per_sub, uint32_t i
 YW_DEV bool chunk_open(Ctx& c, int k_first, int rows_per_chunk) {
     const uint32_t prev = c.chunk;
     if (prev != 0xffffffffu && lane_id() == 0) c.pool.meta[prev].nrows = c.nrows;
-    const uint32_t id = pool_alloc(c.pool.next, c.pool.per_sub, c.item);
+    uint32_t id;
+    if (c.priv_used < c.pool.priv) id = c.slot * c.pool.priv + c.priv_used++;
+    else id = pool_alloc_shared(c.pool.next, c.pool.per_sub, c.pool.shared0, c.item);
     if (id == 0xffffffffu) { c.status = ST_NOMEM; return false; }
     if (lane_id() == 0) {
         ChunkMeta m;
@@ -545,7 +554,7 @@ YW_DEV void run_layout(Ctx& c, bool first) {
 // this instantiation may use (32: the common kernel; 64: the wide-band kernel, more registers).
 template <int MAXS>
 YW_DEV void ydrop_forward_warp(const uint8_t* tcodes, const uint8_t* qcodes, int64_t ta, int64_t qa, int dir, Params p,
-                               Pool pool, uint32_t item, uint32_t warp_slot, ExtResult* res, uint32_t lay_mask) {
+                               Pool pool, uint32_t item, uint32_t warp_slot, uint32_t& priv_used, ExtResult* res, uint32_t lay_mask) {
     constexpr int max_S = MAXS;
     Ctx c;
     c.tc = tcodes; c.qc = qcodes; c.ta = ta; c.qa = qa; c.dir = dir; c.p = p;
@@ -557,7 +566,7 @@ YW_DEV void ydrop_forward_warp(const uint8_t* tcodes, const uint8_t* qcodes, int
     c.bestT = c.init_best + c.bias + p.E;      // image of best = 0 on anti-diagonal 1
     c.best_real = 0; c.kbest = 0; c.bestv = c.init_best;
     c.dead_steps = 0; c.lo_lane = c.hi_lane = 16; c.cells = 0; c.status = ST_OK;
-    c.pool = pool; c.item = item; c.chunk = 0xffffffffu; c.k0 = 0; c.nrows = 0; c.cap = 0;
+    c.pool = pool; c.item = item; c.slot = warp_slot; c.priv_used = priv_used; c.chunk = 0xffffffffu; c.k0 = 0; c.nrows = 0; c.cap = 0;
     c.scr = pool.scratch + (size_t)warp_slot * 3 * WIN;
     const int lane = lane_id();
     {
@@ -598,6 +607,7 @@ YW_DEV void ydrop_forward_warp(const uint8_t* tcodes, const uint8_t* qcodes, int
         c.S = ns;
         c.rbase = (c.alo - slack) & ~1;
     }
+    priv_used = c.priv_used;
     if (lane == 0) {
         ExtResult r;
         r.score = c.best_real; r.kbest = c.kbest; r.bestv = c.bestv; r.chunk = c.chunk; r.status = c.status;

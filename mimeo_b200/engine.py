@@ -101,6 +101,15 @@ def filter_hits(hits: Dict[str, np.ndarray], minLen, minIdt) -> np.ndarray:
     return keep & (tenths >= 10.0 * float(minIdt))
 
 
+def filter_hits_map(hits: Dict[str, np.ndarray], minLen, minIdt) -> np.ndarray:
+    """`mimeo map`: the rows that survive BOTH the awk filter after LASTZ (filter_hits) and import_Align's own test
+    (wrappers.py:76): int(end1) - int(start1) >= minLen, i.e. one base stricter than length1, and float(identity) >= minIdt."""
+    keep = filter_hits(hits, minLen, minIdt)
+    if len(keep):
+        keep &= (hits['end1'].astype(np.int64) - hits['start1']) >= minLen
+    return keep
+
+
 def self_segments(T: Genome, T_both: Optional[Genome], sizes: Sequence[int], minIdt, minLen, minCov, intraCov, hspthresh=3000,
                   strictSelf=True):
     """`mimeo self` without any text: device genome in, (inter segments, intra segments or None, hits, stats) out.

@@ -11,15 +11,15 @@ namespace yw { EmuWarp* g_warp = nullptr; }
 
 namespace {
 struct Job {
-    const uint8_t *tc, *qc; long ta, qa; int dir; yw::Params p; yw::Pool pool; yw::ExtResult* res; int max_s; int phase; uint32_t lay_mask;
+    const uint8_t *tc, *qc; long ta, qa; int dir; yw::Params p; yw::Pool pool; yw::ExtResult* res; int max_s; int phase; uint32_t lay_mask; uint32_t priv_used = 0;
     yw::WalkCache wc;
 };
 Job* g_job;
 void lane_main() {
     Job& j = *g_job;
     if (j.phase == 0) {
-        if (j.max_s >= 64) yw::ydrop_forward_warp<64>(j.tc, j.qc, j.ta, j.qa, j.dir, j.p, j.pool, 0u, 0u, j.res, j.lay_mask);
-        else yw::ydrop_forward_warp<32>(j.tc, j.qc, j.ta, j.qa, j.dir, j.p, j.pool, 0u, 0u, j.res, j.lay_mask);
+        if (j.max_s >= 64) yw::ydrop_forward_warp<64>(j.tc, j.qc, j.ta, j.qa, j.dir, j.p, j.pool, 0u, 0u, j.priv_used, j.res, j.lay_mask);
+        else yw::ydrop_forward_warp<32>(j.tc, j.qc, j.ta, j.qa, j.dir, j.p, j.pool, 0u, 0u, j.priv_used, j.res, j.lay_mask);
     } else {
         yw::ydrop_walk_warp(j.tc, j.qc, j.ta, j.qa, j.dir, j.p, j.pool, j.res, j.wc);
     }
@@ -53,7 +53,7 @@ void run_warp() {
 
 extern "C" {
 // out: score, di, dj, nmatch, ncols, status, cells, kbest, chunks_used, widest layout, layouts
-int emu_extend(const uint8_t* tc, const uint8_t* qc, long ta, long qa, int dir, int O, int E, int Y, int max_s, int nchunks, unsigned lay_mask, int* out) {
+int emu_extend(const uint8_t* tc, const uint8_t* qc, long ta, long qa, int dir, int O, int E, int Y, int max_s, int nchunks, unsigned lay_mask, int priv, int* out) {
     std::vector<uint8_t> base((size_t)nchunks * yw::CHUNK_BYTES);
     std::vector<yw::ChunkMeta> meta(nchunks);
     std::vector<uint32_t> next(yw::NSUB, 0);
@@ -62,7 +62,8 @@ int emu_extend(const uint8_t* tc, const uint8_t* qc, long ta, long qa, int dir, 
     memset(&res, 0, sizeof(res));
     Job j;
     j.tc = tc; j.qc = qc; j.ta = ta; j.qa = qa; j.dir = dir; j.p = yw::Params{O, E, Y}; j.res = &res; j.max_s = max_s; j.lay_mask = lay_mask;
-    j.pool.base = base.data(); j.pool.meta = meta.data(); j.pool.next = next.data(); j.pool.per_sub = (uint32_t)(nchunks / yw::NSUB);
+    j.pool.base = base.data(); j.pool.meta = meta.data(); j.pool.next = next.data();
+    j.pool.priv = (uint32_t)priv; j.pool.shared0 = (uint32_t)priv; j.pool.per_sub = (uint32_t)((nchunks - priv) / yw::NSUB);
     j.pool.scratch = scratch.data();
     g_job = &j;
     j.phase = 0; run_warp();
@@ -70,7 +71,7 @@ int emu_extend(const uint8_t* tc, const uint8_t* qc, long ta, long qa, int dir, 
     uint32_t used = 0;
     for (uint32_t s = 0; s < (uint32_t)yw::NSUB; s++) used += next[s] < j.pool.per_sub ? next[s] : j.pool.per_sub;
     out[0] = res.score; out[1] = res.di; out[2] = res.dj; out[3] = res.nmatch; out[4] = res.ncols; out[5] = res.status;
-    out[6] = (int)res.cells; out[7] = res.kbest; out[8] = (int)used; out[9] = res.max_s; out[10] = res.nlayouts;
+    out[6] = (int)res.cells; out[7] = res.kbest; out[8] = (int)used + (int)j.pool.priv; out[9] = res.max_s; out[10] = res.nlayouts;
     return 0;
 }
 }

@@ -156,6 +156,58 @@ def synth_c5(seed, total_bp=1_000_000_000, nscaf=500, repeat_frac=0.40, fam_len=
     return {f'scaf{i:04d}': scafs[i] for i in range(nscaf)}
 
 
+def synth_c4(seed=1004, a_scaf=50, b_scaf=100, scaf_len=1_000_000, nfam=40, fam_len=(300, 3000)):
+    """SURVEY 8(d) config-4 generator (`mimeo x`): genome A (50 x 1 Mbp) and genome B (100 x 1 Mbp), uniform random
+    background; 40 repeat families, each present 5-30 times in B and 1-3 times in A, every copy diverged from the family
+    consensus so that two copies are 80-90 % identical (per-copy substitution rate 5-10.6 %, indel rate 0.5 %), random
+    strand, random non-overlapping place. Returns (A, B) as {name: uint8 ASCII array}."""
+    rng = np.random.default_rng(seed)
+    bases = np.frombuffer(b'ACGT', dtype=np.uint8)
+
+    def blank(n, prefix):
+        return [bases[rng.integers(0, 4, scaf_len)] for _ in range(n)], [np.zeros(scaf_len // 64 + 2, dtype=bool) for _ in range(n)], prefix
+    ga, gb = blank(a_scaf, 'A'), blank(b_scaf, 'B')
+
+    def plant(g, cp):
+        scafs, used, _ = g
+        for _try in range(50):
+            s = int(rng.integers(0, len(scafs)))
+            p = int(rng.integers(0, scaf_len - len(cp)))
+            if not used[s][p // 64:(p + len(cp)) // 64 + 1].any():
+                scafs[s][p:p + len(cp)] = cp
+                used[s][p // 64:(p + len(cp)) // 64 + 1] = True
+                return
+    for _ in range(nfam):
+        cons = bases[rng.integers(0, 4, int(rng.integers(fam_len[0], fam_len[1] + 1)))]
+        for g, lo, hi in ((gb, 5, 30), (ga, 1, 3)):
+            for _c in range(int(rng.integers(lo, hi + 1))):
+                cp = mutate(rng, cons, float(rng.uniform(0.05, 0.106)), 0.005)
+                plant(g, revcomp_ascii(cp) if rng.random() < 0.5 else cp)
+    return ({f'A{i:03d}': ga[0][i] for i in range(a_scaf)}, {f'B{i:03d}': gb[0][i] for i in range(b_scaf)})
+
+
+def synth_c3(seed=1003, nscaf=40, scaf_len=1_000_000, block=50_000, keep_frac=0.60, sub=0.08, indel=0.005, inv_frac=0.10):
+    """SURVEY 8(d) config-3 generator (`mimeo map`): genome A (40 x 1 Mbp, uniform random) and genome B = A with 8 %
+    substitutions and 0.5 % indels over 60 % of its length (blocks of 50 kbp; the other blocks are re-randomised), 10 % of
+    the kept blocks inverted. Returns (A, B) as {name: uint8 ASCII array}."""
+    rng = np.random.default_rng(seed)
+    bases = np.frombuffer(b'ACGT', dtype=np.uint8)
+    A, B = {}, {}
+    for i in range(nscaf):
+        a = bases[rng.integers(0, 4, scaf_len)]
+        parts = []
+        for p in range(0, scaf_len, block):
+            blk = a[p:p + block]
+            if rng.random() < keep_frac:
+                m = mutate(rng, blk, sub, indel)
+                parts.append(revcomp_ascii(m) if rng.random() < inv_frac else m)
+            else:
+                parts.append(bases[rng.integers(0, 4, len(blk))])
+        A[f'A{i:03d}'] = a
+        B[f'B{i:03d}'] = np.concatenate(parts)
+    return A, B
+
+
 def odd_genome(rng, k):
     """Small genomes of awkward shapes for parity stress (kind = k % 6): ordinary / tiny scaffolds / tandem array and low
     complexity / N-rich / one dense family / two long near-identical scaffolds."""

@@ -97,3 +97,98 @@ def test_world_size_2_equals_single_rank():
     want = (sorted(zip(*[hits[k].tolist() for k in parallel.HIT_FIELDS])), inter.tolist(), intra.tolist())
     assert got[0] == want[0] and len(want[0]) > 5
     assert got[1] == want[1] and got[2] == want[2] and len(want[1]) + len(want[2]) > 0
+
+
+# ------------------------------------------------------------------------------------------ 2-D block plan
+def test_shard_plan_covers_the_pair_grid_once():
+    tl, ql = [5, 9, 3, 7, 7, 2], [4, 4, 8, 1, 6]
+    for world in (1, 2, 3, 4, 6):
+        plan = parallel.ShardPlan(tl, ql, world)
+        assert plan.gt * plan.gq == world
+        seen = set()
+        for r in range(world):
+            t, q = plan.block(r)
+            for a in t:
+                for b in q:
+                    assert (a, b) not in seen
+                    seen.add((a, b))
+        assert len(seen) == len(tl) * len(ql) and 0 < plan.balance <= 1.0
+    assert parallel.ShardPlan([1] * 50, [1] * 100, 8).balance == pytest.approx(1.0)
+    with pytest.raises(ValueError):
+        parallel.ShardPlan([1], [1], 4)
+
+
+def _block_hits(enc_t, enc_q, t_idx, q_idx, hspthresh=3000):
+    """A rank's block through the oracle (stand-in for mb2_align): rows with LOCAL ids."""
+    from oracle import lastz_oracle as lo
+    cols = {f: [] for f in parallel.HIT_FIELDS}
+    p = lo.default_params(hspthresh)
+    for lt, ti in enumerate(t_idx):
+        tix = lo.TargetIndex(enc_t[ti])
+        for lq, qi in enumerate(q_idx):
+            q = enc_q[qi]
+            m = len(q)
+            for st in (0, 1):
+                qq = q if st == 0 else lo.revcomp_codes(q)
+                for (s1, e1, s2, e2, sc, nm, nc, _a, _b) in lo.align_tile(tix, qq, p).tolist():
+                    qs, qe = (s2 + 1, e2) if st == 0 else (m - e2 + 1, m - s2)
+                    for f, v in zip(parallel.HIT_FIELDS, (lt, lq, st, s1 + 1, e1, qs, qe, sc, nm, nc)):
+                        cols[f].append(v)
+    return {f: np.array(v, dtype=np.int32) for f, v in cols.items()}
+
+
+def _grid_case():
+    from tests.helpers import synth_genome
+    from oracle import lastz_oracle as lo
+    g = synth_genome(62, 4, 15_000, 2, copies=(6, 8), fam_len=(400, 900), sub=0.06, indel=0.003)
+    names = sorted(g)
+    enc = [lo.encode(g[n]) for n in names]
+    return names, enc
+
+
+def _grid_run(world, rank):
+    from mimeo_b200 import engine
+    from oracle import annot_oracle as ao
+    names, enc = _grid_case()
+    sizes = [len(e) for e in enc]
+    plan = parallel.ShardPlan(sizes, sizes, world)
+    t_idx, q_idx = plan.block(rank)
+    hits = _block_hits(enc, enc, t_idx, q_idx)
+    return parallel.annotate_block(hits, t_idx, q_idx, plan, sizes, 80, 100, ao.coverage_segments_arrays, [('inter', 2), ('intra', 2)],
+                                   engine.filter_hits, strict_self=True)
+
+
+def _grid_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = _grid_run(world, rank)
+    if rank == 0:
+        table, segs = out
+        q.put((sorted(map(tuple, table.tolist())), {k: v.tolist() for k, v in segs.items()}))
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_block_grid_with_all_gather_equals_single_rank(world):
+    """The north-star partition on CPU ranks (gloo): (target group x query group) blocks, all-gather of the filtered hit
+    tables, owner-side coverage, segments gathered to rank 0 == the one-rank result."""
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grid_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    table, segs = _grid_run(1, 0)
+    want = (sorted(map(tuple, table.tolist())), {k: v.tolist() for k, v in segs.items()})
+    assert got[0] == want[0] and len(want[0]) > 5
+    assert got[1] == want[1] and sum(len(v) for v in want[1].values()) > 0

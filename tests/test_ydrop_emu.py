@@ -24,7 +24,7 @@ def emu_lib():
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-I', os.path.join(HERE, 'emu'), '-o', SO, srcs[0]])
     l = C.CDLL(SO)
     l.emu_extend.restype = C.c_int
-    l.emu_extend.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p]
+    l.emu_extend.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_void_p]
     return l
 
 
@@ -49,9 +49,10 @@ def oracle_ext(t, a1, q, a2, d, p):
 ALL_LAYOUTS = sum(1 << (s // 4) for s in (8, 12, 16, 20, 24, 32, 48, 64))
 
 
-def emu_ext(l, tk, a1, qk, a2, d, p, max_s=32, nchunks=4096, layouts=ALL_LAYOUTS):
+def emu_ext(l, tk, a1, qk, a2, d, p, max_s=32, nchunks=4096, layouts=ALL_LAYOUTS, priv=7):
+    """priv: chunks of the warp slot's private part of the trace pool (the rest of the trace goes to the shared part)."""
     out = np.zeros(11, np.int32)
-    l.emu_extend(tk.ctypes.data, qk.ctypes.data, PAD + a1, PAD + a2, d, p.gap_open, p.gap_extend, p.ydrop, max_s, nchunks, layouts, out.ctypes.data)
+    l.emu_extend(tk.ctypes.data, qk.ctypes.data, PAD + a1, PAD + a2, d, p.gap_open, p.gap_extend, p.ydrop, max_s, nchunks, layouts, priv, out.ctypes.data)
     return out.tolist()
 
 
