@@ -204,6 +204,7 @@ class AlignWorkload:
         self.qsizes = [len(x) for x in self.qseqs]
         self.mbp = (sum(self.tsizes) + (0 if self.same else sum(self.qsizes))) / 1e6
         self.stats = {}
+        self.keep_raw = False        # parity leg: also keep the unfiltered rows of the last step
 
     def covs(self):
         if self.mode == 'map':
@@ -234,31 +235,42 @@ class AlignWorkload:
         self.d2h_bytes = 0
 
     def _annotate(self, hits):
-        from mimeo_b200 import coverage, engine, parallel
-        filt = engine.filter_hits_map if self.mode == 'map' else engine.filter_hits
+        """hits: rows of this rank's block, already filtered and sorted on the device."""
+        from mimeo_b200 import coverage, parallel
+        keep_all = lambda h, minLen, minIdt: np.ones(len(h['t_id']), dtype=bool)
         out = parallel.annotate_block(hits, self.t_idx, self.q_idx, self.plan, self.tsizes, self.MIN_IDT, self.MIN_LEN,
-                                      coverage.coverage_segments, self.covs(), filt, strict_self=(self.mode == 'self' and self.STRICT))
+                                      coverage.coverage_segments, self.covs(), keep_all, strict_self=(self.mode == 'self' and self.STRICT))
         if out is not None:
             self.table, self.segs = out
             self.nhits, self.nseg = len(self.table), sum(len(v) for v in self.segs.values())
         return out
 
-    def step_resident(self):
+    def _align_filter(self, T, Q, Qb):
+        """alignment + device-side filter / compaction / sort (`mb2_filter_sort`); only the surviving rows cross PCIe."""
         from mimeo_b200 import align as A
         from mimeo_b200.genome import align_params
-        hits, self.stats = A.align(self.T, self.Q, align_params(self.HSPTHRESH), Q_aux=self.Qb, t_same_q=self.hint)
-        self.raw_hits = hits
-        return self._annotate(hits)
+        dh = A.align_device(T, Q, align_params(self.HSPTHRESH), Q_aux=Qb, t_same_q=self.hint)
+        try:
+            if self.keep_raw:
+                self.raw_hits, _ = dh.download()
+            dh.filter_sort(self.MIN_LEN, self.MIN_IDT, map_rule=(self.mode == 'map'))
+            hits, self.stats = dh.download()
+        finally:
+            dh.close()
+        return hits
+
+    def step_resident(self):
+        return self._annotate(self._align_filter(self.T, self.Q, self.Qb))
 
     def step_e2e(self):
         """Host ASCII (pinned) in -> .tab rows and GFF3 rows out on rank 0, every copy and the collectives inside."""
         from mimeo_b200 import align as A, engine
-        from mimeo_b200.genome import Genome, align_params
+        from mimeo_b200.genome import Genome
         share = self.pinned_q is self.pinned_t
         T = Genome([self.tnames[i] for i in self.t_idx], [t.numpy() for t in self.pinned_t])
         Q = T if share else Genome([self.qnames[i] for i in self.q_idx], [t.numpy() for t in self.pinned_q])
         try:
-            hits, _ = A.align(T, Q, align_params(self.HSPTHRESH), t_same_q=self.hint)
+            hits = self._align_filter(T, Q, None)
         finally:
             if Q is not T:
                 Q.close()
@@ -299,6 +311,9 @@ class AlignWorkload:
         rng = np.random.default_rng(7)
         flat = rng.choice(nt * nq, size=npairs, replace=False)
         pairs = [(int(f // nq), int(f % nq)) for f in flat]
+        if self.mode == 'map':       # scaffold i of B descends from scaffold i of A: a third of the sample are such pairs
+            nd = max(1, npairs // 3)
+            pairs = [(int(a), int(a)) for a in rng.choice(min(nt, nq), size=min(nd, nt, nq), replace=False)] + [(a, b) for a, b in pairs if a != b][:npairs - nd]
         if self.same:
             nself = max(1, round(npairs / nt))
             pairs = [(a, a) for a in rng.choice(nt, size=min(nself, nt), replace=False).tolist()] + [(a, b) for a, b in pairs if a != b][:npairs - nself]
@@ -471,9 +486,11 @@ def run_b200(args):
     import torch.distributed as dist
     from mimeo_b200 import _lib
     rank, local_rank, world = env_rank()
+    # rank 0 prints ONE JSON line: whatever native libraries write to fd 1 meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -619,14 +636,20 @@ def run_b200(args):
             # full pair grid for C1 (every row of the benchmarked job is compared); a bounded sample elsewhere
             ncores = os.cpu_count() or 1
             npairs = len(wl.tnames) * len(wl.qnames) if args.workload == 'self' else 12
-            dt, cores, sample, frac, rows, pairs, ocells = wl.cpu_reference(ncores if args.workload == 'self' else 1, npairs=npairs, want_rows=True)
+            dt, cores, sample, frac, rows, pairs, ocells = wl.cpu_reference(min(ncores, npairs), npairs=npairs, want_rows=True)
             core_s = dt * cores
             cpu = {'value': wl.mbp * frac / core_s, 'unit': 'Mbp/s', 'cores': 1, 'kind': 'port', 'sample': sample + f'; reported for ONE core, the reference\'s own schedule (serial LASTZ processes): {core_s:.1f} core-seconds',
                    'seconds': core_s, 'sample_fraction': frac, 'host_cpu_count': ncores, 'oracle_gapped_cells_in_sample': ocells}
+            wl.keep_raw = True
+            wl.step_resident()
+            wl.keep_raw = False
             ok, nrows = wl.parity(rows, pairs)
             parity = {'rows_identical': bool(ok), 'rows_compared': nrows, 'pairs_compared': len(pairs),
                       'scope': 'every alignment row (t, q, strand, start1, end1, start2+, end2+, score, matches, columns) of the sampled scaffold pairs, GPU vs oracle'}
 
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': 'Mbp/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

@@ -159,6 +159,30 @@ MB2_API int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome
                       const int32_t* t_same_q, mb2_hits* out);
 MB2_API void mb2_free_hits(mb2_hits* h);
 
+/* ---- the hit table kept in HBM between the stages ------------------------------------------------ */
+/* mb2_align with the rows left on the device (same columns, same coordinates); the handle owns them. */
+typedef struct mb2_hits_dev mb2_hits_dev;
+MB2_API int mb2_align_dev(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux, const mb2_align_params* p, int strands,
+                          const int32_t* t_same_q, mb2_hits_dev** out);
+MB2_API void mb2_hits_dev_free(mb2_hits_dev* h);
+MB2_API uint64_t mb2_hits_dev_count(const mb2_hits_dev* h);
+/* Kernel (d) part 1, in place on the device table. Replaces the filter that follows every LASTZ call in the reference's
+ * script (wrappers.py:1044-1056; map: 665-675; x: 805-817): keep length1 >= min_len and the PRINTED identity ('%.1f' of
+ * 100*nmatch/ncols, as awk compares it) >= min_idt; map_rule != 0 adds import_Align's own test end1 - start1 >= min_len
+ * (wrappers.py:76). Survivors are compacted and sorted by (t_id, q_id, start1, end1) -- the order of `sort -k 1,1 -k 3n,4n`
+ * inside every scaffold-pair block; rows equal in all four keys keep their order (the text formatter breaks those ties). */
+MB2_API int mb2_filter_sort(mb2_hits_dev* h, double min_len, double min_idt, int map_rule, uint64_t* n_kept);
+/* Coverage stage straight from the device table (no host round trip of the BED projection, wrappers.py:1120-1128):
+ * which = 0 every row, 1 rows with t_id != q_id (the .tab of --strictSelf), 2 rows with t_id == q_id (_intra.tab,
+ * wrappers.py:1016). Segments are returned in HOST arrays (free with mb2_free_segments). */
+MB2_API int mb2_hits_dev_coverage(const mb2_hits_dev* h, int which, const int64_t* chrom_sizes, int nchrom, int min_cov, int min_len,
+                                  mb2_segments* out);
+/* A device table from HOST columns (e.g. the rows of a recycled .tab, or a table gathered from other ranks); nt / nq = number of
+ * target / query scaffolds the ids refer to. */
+MB2_API int mb2_hits_dev_upload(const mb2_hits* in, int nt, int nq, mb2_hits_dev** out);
+/* The (surviving) rows as HOST arrays, e.g. for the .tab text (free with mb2_free_hits). */
+MB2_API int mb2_hits_dev_download(const mb2_hits_dev* h, mb2_hits* out);
+
 /* ---- native text ingest (host side, no GPU needed) --------------------------------------------- */
 /* The BED projection of a LASTZ-style .tab file, i.e. what `awk '!/^#/ {print $1,$3,$4;}'` hands to
  * sort | bedtools genomecov (wrappers.py:1120-1128, x: 827-835, self intra: 1201-1220): one (name, start1, end1)

@@ -84,6 +84,13 @@ SIGNATURES = {
     'mb2_test_hsps': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(AlignParams), C.POINTER(Hsps), C.c_void_p]),
     'mb2_align': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AlignParams), C.c_int, C.c_void_p, C.POINTER(Hits)]),
     'mb2_free_hits': (None, [C.POINTER(Hits)]),
+    'mb2_align_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(AlignParams), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    'mb2_hits_dev_free': (None, [C.c_void_p]),
+    'mb2_hits_dev_count': (C.c_uint64, [C.c_void_p]),
+    'mb2_filter_sort': (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_uint64)]),
+    'mb2_hits_dev_coverage': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Segments)]),
+    'mb2_hits_dev_upload': (C.c_int, [C.POINTER(Hits), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    'mb2_hits_dev_download': (C.c_int, [C.c_void_p, C.POINTER(Hits)]),
     'mb2_tab_project': (C.c_int, [C.c_char_p, C.c_int, C.POINTER(TabHits)]),
     'mb2_free_tab_hits': (None, [C.POINTER(TabHits)]),
     'mb2_fasta_read': (C.c_int, [C.c_char_p, C.c_int, C.POINTER(Fasta)]),

@@ -43,6 +43,90 @@ def align(T: Genome, Q: Genome, params: Optional[_lib.AlignParams] = None, stran
     return cols, stats
 
 
+def _hits_to_numpy(h) -> Tuple[Dict[str, np.ndarray], Dict[str, int]]:
+    n = int(h.n)
+    cols = {f: (np.ctypeslib.as_array(getattr(h, f), shape=(n,)).copy() if n else np.zeros(0, np.int32)) for f in HIT_FIELDS}
+    stats = {name: int(h.stats[i]) for i, name in enumerate(STAT_NAMES)}
+    return cols, stats
+
+
+class DeviceHits:
+    """The hit table of one alignment job kept in HBM (`mb2_hits_dev`): filter + sort, coverage and the projection onto the
+    coverage stage run on it without the rows crossing PCIe; `download()` brings the (surviving) rows to the host for the
+    .tab text."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    @classmethod
+    def from_host(cls, cols: Dict[str, np.ndarray], nt: int, nq: int) -> 'DeviceHits':
+        _lib.init()
+        arrs = [np.ascontiguousarray(cols[f], dtype=np.int32) for f in HIT_FIELDS]
+        h = _lib.Hits()
+        for f, a in zip(HIT_FIELDS, arrs):
+            setattr(h, f, a.ctypes.data_as(_lib.c_i32p))
+        h.n = len(arrs[0])
+        out = C.c_void_p()
+        _lib.check(_lib.lib().mb2_hits_dev_upload(C.byref(h), int(nt), int(nq), C.byref(out)))
+        return cls(out)
+
+    def __len__(self):
+        return int(_lib.lib().mb2_hits_dev_count(self.handle))
+
+    def filter_sort(self, minLen, minIdt, map_rule: bool = False) -> int:
+        """The awk filters + per-pair sort of wrappers.py:1044-1056 on the device, in place. Returns the rows kept."""
+        n = C.c_uint64(0)
+        _lib.check(_lib.lib().mb2_filter_sort(self.handle, float(minLen), float(minIdt), 1 if map_rule else 0, C.byref(n)))
+        return int(n.value)
+
+    def coverage(self, which: int, sizes, cov: int, minLen: int):
+        """Segments (chrom, start, end) of the rows selected by `which` (0 all, 1 t != q, 2 t == q)."""
+        sz = np.ascontiguousarray(sizes, dtype=np.int64)
+        seg = _lib.Segments()
+        _lib.check(_lib.lib().mb2_hits_dev_coverage(self.handle, int(which), sz.ctypes.data, len(sz), int(cov), int(minLen), C.byref(seg)))
+        try:
+            n = int(seg.n)
+            if n == 0:
+                z = np.zeros(0, dtype=np.int32)
+                return z, z.copy(), z.copy()
+            return tuple(np.ctypeslib.as_array(p, shape=(n,)).copy() for p in (seg.chrom, seg.start, seg.end))
+        finally:
+            _lib.lib().mb2_free_segments(C.byref(seg))
+
+    def download(self) -> Tuple[Dict[str, np.ndarray], Dict[str, int]]:
+        h = _lib.Hits()
+        _lib.check(_lib.lib().mb2_hits_dev_download(self.handle, C.byref(h)))
+        try:
+            return _hits_to_numpy(h)
+        finally:
+            _lib.lib().mb2_free_hits(C.byref(h))
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            _lib.lib().mb2_hits_dev_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def align_device(T: Genome, Q: Genome, params: Optional[_lib.AlignParams] = None, strands: int = 3,
+                 Q_aux: Optional[Genome] = None, t_same_q=None) -> DeviceHits:
+    """`align()` with the rows left in HBM."""
+    if params is None:
+        params = align_params()
+    same = None if t_same_q is None else np.ascontiguousarray(t_same_q, dtype=np.int32)
+    if same is not None and len(same) != len(T.names):
+        raise ValueError('t_same_q needs one entry per target scaffold')
+    out = C.c_void_p()
+    _lib.check(_lib.lib().mb2_align_dev(T.handle, Q.handle, Q_aux.handle if Q_aux is not None else None, C.byref(params),
+                                        int(strands), same.ctypes.data if same is not None else None, C.byref(out)))
+    return DeviceHits(out)
+
+
 def pct_text(nmatch: int, ncols: int) -> str:
     """LASTZ prints the identity percentage with '%.1f' of 100*n/d evaluated in double precision."""
     return '%.1f' % (100.0 * nmatch / ncols) if ncols else '0.0'

@@ -98,25 +98,15 @@ void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& 
     }
 }
 
-static void append_alns(const AlnSet& a, HostAlns& out) {
-    const size_t n = a.n;
-    if (!n) return;
-    Ctx& cx = ctx();
-    const size_t base = out.tile.size();
-    out.tile.resize(base + n); out.s1.resize(base + n); out.e1.resize(base + n); out.s2.resize(base + n); out.e2.resize(base + n);
-    out.score.resize(base + n); out.nmatch.resize(base + n); out.ncols.resize(base + n);
-    auto d2h = [&](void* dst, const void* src) { MB2_CUDA(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, cx.stream)); };
-    d2h(out.tile.data() + base, a.tile.get()); d2h(out.s1.data() + base, a.s1.get()); d2h(out.e1.data() + base, a.e1.get());
-    d2h(out.s2.data() + base, a.s2.get()); d2h(out.e2.data() + base, a.e2.get()); d2h(out.score.data() + base, a.score.get());
-    d2h(out.nmatch.data() + base, a.nmatch.get()); d2h(out.ncols.data() + base, a.ncols.get());
-    MB2_CUDA(cudaStreamSynchronize(cx.stream));
-}
-
-// Full pipeline for one strand-oriented query genome: alignments in strand-local, scaffold-local coordinates (host).
-void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, HostAlns& alns,
+// Full pipeline for one strand-oriented query genome; the alignments of every query chunk are appended to the device hit
+// table `out` in LASTZ's output columns.
+void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, DevHits& out, int nq, int strands,
                   unsigned long long* h_counters) {
     Ctx& cx = ctx();
     MB2_REQUIRE(T.G + Q.G < 0xffffffffull, -3, "align: target + query exceed 2^32 padded positions");
+    // tile ids (target scaffold * query scaffolds + query scaffold) are 32-bit throughout the stage
+    MB2_REQUIRE((uint64_t)T.nscaf * (uint64_t)Q.nscaf < (1ull << 32), -3,
+                "align: target scaffolds x query scaffolds (both strands) must stay below 2^32 tiles; align the target in scaffold groups");
     unsigned long long acc[CNT_N] = {0};
     uint32_t maxlen = 0;
     for (int s = 0; s < T.nscaf; s++) maxlen = std::max(maxlen, T.len[s]);
@@ -174,7 +164,7 @@ void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const 
         MB2_CUDA(cudaStreamSynchronize(cx.stream));
         acc[CNT_HSPS] += hsps.n; acc[CNT_EXTENDED] += c2[CNT_EXTENDED]; acc[CNT_S2_CELLS] += c2[CNT_S2_CELLS];
         acc[CNT_GAPPED_CELLS] += c2[CNT_GAPPED_CELLS]; acc[CNT_ANCHORS] += c2[CNT_ANCHORS]; acc[CNT_ALNS] += a.n;
-        append_alns(a, alns);
+        out.append(a, Q, nq, strands);
     }
     if (h_counters) for (int k = 0; k < CNT_N; k++) h_counters[k] = acc[k];
 }

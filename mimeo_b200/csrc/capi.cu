@@ -385,62 +385,137 @@ void mb2_free_hits(mb2_hits* h) {
     std::memset(h, 0, sizeof(*h));
 }
 
+}  // extern "C"
+
+struct mb2_hits_dev { DevHits h; int nt = 0, nq = 0; };
+
+// every `lastz T Q` of the job: rows of all (target scaffold, query scaffold, strand) tiles appended to a device table
+static void align_into(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux, const mb2_align_params* p, int strands,
+                       const int32_t* t_same_q, mb2_hits_dev& out) {
+    MB2_REQUIRE(T && Q && T->g && Q->g, MB2_ERR_INVALID_ARG, "align: null argument");
+    MB2_REQUIRE(strands >= 1 && strands <= 3, MB2_ERR_INVALID_ARG, "align: strands must be 1, 2 or 3");
+    const AlignParams ap = to_params(p);
+    const int nq = Q->g->nscaf;
+    // the query actually aligned: Q (+), revcomp(Q) (-), or both strands as one 2n-scaffold genome
+    const Genome* q = Q->g;
+    Genome* own = nullptr;
+    if (strands != 1) {
+        if (Q_aux && Q_aux->g) {
+            q = Q_aux->g;
+            MB2_REQUIRE(q->nscaf == (strands == 3 ? 2 * nq : nq), MB2_ERR_INVALID_ARG, "align: Q_aux does not match Q and strands");
+        } else {
+            own = strands == 3 ? genome_both_strands(*Q->g) : genome_revcomp(*Q->g);
+            q = own;
+        }
+    }
+    try {
+        align_strand(*T->g, *q, ap, (strands & 1) ? t_same_q : nullptr, out.h, nq, strands, out.h.stats);
+        MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));     // `own` is free to go
+    } catch (...) { delete own; throw; }
+    delete own;
+    out.nt = T->g->nscaf; out.nq = nq;
+}
+
+static void download_hits(const DevHits& h, mb2_hits* out) {
+    std::memset(out, 0, sizeof(*out));
+    const size_t n = h.n;
+    out->n = n;
+    for (int k = 0; k < CNT_N; k++) out->stats[k] = h.stats[k];
+    int32_t** dst[10] = {&out->t_id, &out->q_id, &out->strand, &out->start1, &out->end1, &out->start2, &out->end2,
+                         &out->score, &out->nmatch, &out->ncols};
+    for (int c = 0; c < 10; c++) {
+        *dst[c] = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
+        MB2_REQUIRE(*dst[c] != nullptr, MB2_ERR_INTERNAL, "align: host allocation failed");
+        if (n) MB2_CUDA(cudaMemcpyAsync(*dst[c], h.col[c].get(), n * sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+    }
+    MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+}
+
+extern "C" {
+
 int mb2_align(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux, const mb2_align_params* p, int strands,
               const int32_t* t_same_q, mb2_hits* out) {
     return guarded([&] {
         ensure_init();
-        MB2_REQUIRE(T && Q && out && T->g && Q->g, MB2_ERR_INVALID_ARG, "align: null argument");
-        MB2_REQUIRE(strands >= 1 && strands <= 3, MB2_ERR_INVALID_ARG, "align: strands must be 1, 2 or 3");
+        MB2_REQUIRE(out != nullptr, MB2_ERR_INVALID_ARG, "align: null argument");
         std::memset(out, 0, sizeof(*out));
-        const AlignParams ap = to_params(p);
-        const int nq = Q->g->nscaf;
-        // the query actually aligned: Q (+), revcomp(Q) (-), or both strands as one 2n-scaffold genome
-        const Genome* q = Q->g;
-        Genome* own = nullptr;
-        if (strands != 1) {
-            if (Q_aux && Q_aux->g) {
-                q = Q_aux->g;
-                MB2_REQUIRE(q->nscaf == (strands == 3 ? 2 * nq : nq), MB2_ERR_INVALID_ARG, "align: Q_aux does not match Q and strands");
-            } else {
-                own = strands == 3 ? genome_both_strands(*Q->g) : genome_revcomp(*Q->g);
-                q = own;
-            }
+        mb2_hits_dev d;
+        align_into(T, Q, Q_aux, p, strands, t_same_q, d);
+        download_hits(d.h, out);
+    });
+}
+
+int mb2_align_dev(const mb2_genome* T, const mb2_genome* Q, const mb2_genome* Q_aux, const mb2_align_params* p, int strands,
+                  const int32_t* t_same_q, mb2_hits_dev** out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(out != nullptr, MB2_ERR_INVALID_ARG, "align_dev: null argument");
+        *out = nullptr;
+        mb2_hits_dev* d = new mb2_hits_dev();
+        try { align_into(T, Q, Q_aux, p, strands, t_same_q, *d); } catch (...) { delete d; throw; }
+        *out = d;
+    });
+}
+void mb2_hits_dev_free(mb2_hits_dev* h) { delete h; }
+uint64_t mb2_hits_dev_count(const mb2_hits_dev* h) { return h ? (uint64_t)h->h.n : 0; }
+
+int mb2_filter_sort(mb2_hits_dev* h, double min_len, double min_idt, int map_rule, uint64_t* n_kept) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(h != nullptr, MB2_ERR_INVALID_ARG, "filter_sort: null argument");
+        hits_filter_sort(h->h, min_len, min_idt, map_rule != 0, h->nt, h->nq);
+        if (n_kept) *n_kept = h->h.n;
+    });
+}
+
+int mb2_hits_dev_coverage(const mb2_hits_dev* h, int which, const int64_t* chrom_sizes, int nchrom, int min_cov, int min_len, mb2_segments* out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(h && out && chrom_sizes, MB2_ERR_INVALID_ARG, "hits_dev_coverage: null argument");
+        MB2_REQUIRE(which >= 0 && which <= 2, MB2_ERR_INVALID_ARG, "hits_dev_coverage: which must be 0 (all), 1 (t != q) or 2 (t == q)");
+        std::memset(out, 0, sizeof(*out));
+        CoverageResult res;
+        hits_coverage(h->h, which, chrom_sizes, nchrom, min_cov, min_len, res);
+        out->n = res.n;
+        out->on_device = 0;
+        if (res.n) {
+            out->chrom = (int32_t*)malloc(res.n * sizeof(int32_t));
+            out->start = (int32_t*)malloc(res.n * sizeof(int32_t));
+            out->end = (int32_t*)malloc(res.n * sizeof(int32_t));
+            MB2_REQUIRE(out->chrom && out->start && out->end, MB2_ERR_INTERNAL, "coverage: host allocation failed");
+            MB2_CUDA(cudaMemcpyAsync(out->chrom, res.chrom.get(), res.n * sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+            MB2_CUDA(cudaMemcpyAsync(out->start, res.start.get(), res.n * sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+            MB2_CUDA(cudaMemcpyAsync(out->end, res.end.get(), res.n * sizeof(int32_t), cudaMemcpyDeviceToHost, g_ctx.stream));
         }
-        std::vector<int32_t> cols[10];
+        MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    });
+}
+
+int mb2_hits_dev_upload(const mb2_hits* in, int nt, int nq, mb2_hits_dev** out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(in && out, MB2_ERR_INVALID_ARG, "hits_dev_upload: null argument");
+        *out = nullptr;
+        mb2_hits_dev* d = new mb2_hits_dev();
         try {
-            HostAlns a;
-            unsigned long long cnt[CNT_N];
-            align_strand(*T->g, *q, ap, (strands & 1) ? t_same_q : nullptr, a, cnt);
-            for (int k = 0; k < CNT_N; k++) out->stats[k] = cnt[k];
-            const size_t n = a.tile.size();
-            if (n) {
-                const std::vector<uint32_t>& tile = a.tile;
-                const std::vector<int32_t>&s1 = a.s1, &e1 = a.e1, &s2 = a.s2, &e2 = a.e2, &sc = a.score, &nm = a.nmatch, &nc = a.ncols;
-                const uint32_t nq2 = (uint32_t)q->nscaf;
-                for (int c = 0; c < 10; c++) cols[c].reserve(n);
-                for (size_t k = 0; k < n; k++) {
-                    const int32_t q2 = (int32_t)(tile[k] % nq2), ti = (int32_t)(tile[k] / nq2);
-                    const int st = strands == 3 ? (q2 >= nq ? 1 : 0) : (strands == 2 ? 1 : 0);
-                    const int32_t qi = q2 >= nq ? q2 - nq : q2;
-                    const int32_t m = (int32_t)Q->g->len[qi];
-                    cols[0].push_back(ti); cols[1].push_back(qi); cols[2].push_back(st);
-                    cols[3].push_back(s1[k] + 1); cols[4].push_back(e1[k]);
-                    if (st == 0) { cols[5].push_back(s2[k] + 1); cols[6].push_back(e2[k]); }
-                    else { cols[5].push_back(m - e2[k] + 1); cols[6].push_back(m - s2[k]); }   // back to the + strand of the query
-                    cols[7].push_back(sc[k]); cols[8].push_back(nm[k]); cols[9].push_back(nc[k]);
-                }
+            const int32_t* src[10] = {in->t_id, in->q_id, in->strand, in->start1, in->end1, in->start2, in->end2, in->score, in->nmatch, in->ncols};
+            d->h.reserve(in->n ? in->n : 1);
+            for (int c = 0; c < 10 && in->n; c++) {
+                MB2_REQUIRE(src[c] != nullptr, MB2_ERR_INVALID_ARG, "hits_dev_upload: null column");
+                MB2_CUDA(cudaMemcpyAsync(d->h.col[c].get(), src[c], in->n * sizeof(int32_t), cudaMemcpyHostToDevice, g_ctx.stream));
             }
-        } catch (...) { delete own; throw; }
-        delete own;
-        const size_t n = cols[0].size();
-        out->n = n;
-        int32_t** dst[10] = {&out->t_id, &out->q_id, &out->strand, &out->start1, &out->end1, &out->start2, &out->end2,
-                             &out->score, &out->nmatch, &out->ncols};
-        for (int c = 0; c < 10; c++) {
-            *dst[c] = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
-            MB2_REQUIRE(*dst[c] != nullptr, MB2_ERR_INTERNAL, "align: host allocation failed");
-            if (n) std::memcpy(*dst[c], cols[c].data(), n * sizeof(int32_t));
-        }
+            d->h.n = in->n; d->nt = nt; d->nq = nq;
+            MB2_CUDA(cudaStreamSynchronize(g_ctx.stream));
+        } catch (...) { delete d; throw; }
+        *out = d;
+    });
+}
+
+int mb2_hits_dev_download(const mb2_hits_dev* h, mb2_hits* out) {
+    return guarded([&] {
+        ensure_init();
+        MB2_REQUIRE(h && out, MB2_ERR_INVALID_ARG, "hits_dev_download: null argument");
+        download_hits(h->h, out);
     });
 }
 

@@ -6,6 +6,8 @@
 
 namespace mb2 {
 
+constexpr int CNT_N_DECL = 16;
+
 // ---- coverage.cu
 struct CoverageResult {
     DevBuf<int32_t> chrom, start, end;   // library-owned result (unused when the caller supplies its own arrays)
@@ -69,11 +71,25 @@ struct AlnSet {   // strand-local, scaffold-local, 0-based half-open
 void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevBuf<uint8_t>& in_chain, const AlignParams& p,
                    const int32_t* h_same_q, AlnSet& out, unsigned long long* counters);
 
+// hits.cu : the hit table in HBM (LASTZ's output columns, one row per alignment)
+struct HitCols { int32_t* c[10]; };     // t_id, q_id, strand, start1, end1, start2+, end2+, score, nmatch, ncols
+struct DevHits {
+    DevBuf<int32_t> col[10];
+    size_t n = 0, cap = 0;
+    unsigned long long stats[CNT_N_DECL] = {0};
+    void reserve(size_t want);
+    HitCols view() const;
+    void append(const AlnSet& a, const Genome& Q, int nq, int strands);    // strand-local alignments -> output columns
+};
+void hits_filter_sort(DevHits& h, double min_len, double min_idt, bool map_rule, int nt, int nq);
+void hits_coverage(const DevHits& h, int which, const int64_t* h_sizes, int nchrom, int min_cov, int min_len, CoverageResult& res);
+
 // align.cu
 void align_hsps(const Genome& T, const Genome& Q, const AlignParams& p, HspSet& hsps, unsigned long long* h_counters);
 
-struct HostAlns { std::vector<uint32_t> tile; std::vector<int32_t> s1, e1, s2, e2, score, nmatch, ncols; };
-void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, HostAlns& alns, unsigned long long* h_counters);
+// whole pipeline for one (strand-oriented) query genome; rows are appended to `out` (nq, strands: see DevHits::append)
+void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const int32_t* h_same_q, DevHits& out, int nq, int strands,
+                  unsigned long long* h_counters);
 
 // hostio.cu : native text ingest (no device work)
 struct TabHits {                       // BED projection of a .tab file: columns 1, 3, 4 of every non-'#' line

@@ -46,12 +46,20 @@ def load_files(paths: Sequence[str]) -> Tuple[List[str], List[np.ndarray], Dict[
     return names, seqs, index
 
 
-def align_genomes(tnames, tseqs, qnames, qseqs, hspthresh=3000, same=False):
-    """Device genomes + all-pairs alignment. Returns (hits dict, stats dict)."""
+def align_genomes(tnames, tseqs, qnames, qseqs, hspthresh=3000, same=False, minLen=None, minIdt=None):
+    """Device genomes + all-pairs alignment. Returns (hits dict, stats dict). With minLen / minIdt the rows are filtered and
+    sorted on the device (`mb2_filter_sort`) and only the survivors are returned."""
     T = Genome(tnames, tseqs)
     Q = T if same else Genome(qnames, qseqs)
     try:
-        return _align.align(T, Q, align_params(hspthresh))
+        if minLen is None:
+            return _align.align(T, Q, align_params(hspthresh))
+        dh = _align.align_device(T, Q, align_params(hspthresh))
+        try:
+            dh.filter_sort(minLen, minIdt)
+            return dh.download()
+        finally:
+            dh.close()
     finally:
         if Q is not T:
             Q.close()
@@ -70,8 +78,8 @@ def align_pairs(pairs: Sequence[Tuple[str, str]], outtab: str, minIdt, minLen, h
         qnames, qseqs, qidx = tnames, tseqs, tidx
     else:
         qnames, qseqs, qidx = load_files(qpaths)
-    hits, stats = align_genomes(tnames, tseqs, qnames, qseqs, hspthresh, same)
-    blocks = _align.tab_blocks(hits, tnames, qnames, minLen, minIdt)
+    hits, stats = align_genomes(tnames, tseqs, qnames, qseqs, hspthresh, same, minLen, minIdt)     # filtered on the device
+    blocks = _align.tab_blocks(hits, tnames, qnames, minLen, minIdt)                                  # text + whole-line tie-break
     with open(outtab, 'a') as ft:
         fi = open(outtab_intra, 'a') if outtab_intra else None
         try:
@@ -112,17 +120,18 @@ def filter_hits_map(hits: Dict[str, np.ndarray], minLen, minIdt) -> np.ndarray:
 
 def self_segments(T: Genome, T_both: Optional[Genome], sizes: Sequence[int], minIdt, minLen, minCov, intraCov, hspthresh=3000,
                   strictSelf=True):
-    """`mimeo self` without any text: device genome in, (inter segments, intra segments or None, hits, stats) out.
-    Scaffold index order must already be the C-locale name order (it defines the GFF row order)."""
-    hits, stats = _align.align(T, T, align_params(hspthresh), Q_aux=T_both)
-    keep = filter_hits(hits, minLen, minIdt)
-    intra_mask = (hits['t_id'] == hits['q_id']) & keep if strictSelf else np.zeros(len(keep), dtype=bool)
-    inter_mask = keep & ~intra_mask
-
-    def seg(mask, cov):
-        return _coverage.coverage_segments(hits['t_id'][mask], hits['start1'][mask], hits['end1'][mask], sizes, cov, minLen)
-    inter = seg(inter_mask, minCov)
-    intra = seg(intra_mask, intraCov) if strictSelf else None
+    """`mimeo self` without any text: device genome in, (inter segments, intra segments or None, kept hits, stats) out.
+    The hit table stays in HBM from the alignment through the filter (`mb2_filter_sort`) to both coverage passes; only the
+    surviving rows come back (for the .tab text). Scaffold index order must already be the C-locale name order (it defines
+    the GFF row order)."""
+    dh = _align.align_device(T, T, align_params(hspthresh), Q_aux=T_both)
+    try:
+        dh.filter_sort(minLen, minIdt)
+        inter = dh.coverage(1 if strictSelf else 0, sizes, minCov, minLen)
+        intra = dh.coverage(2, sizes, intraCov, minLen) if strictSelf else None
+        hits, stats = dh.download()
+    finally:
+        dh.close()
     return inter, intra, hits, stats
 
 

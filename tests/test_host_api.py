@@ -194,7 +194,7 @@ def _oracle_device_stubs(monkeypatch):
     from oracle import lastz_oracle as lo
     from mimeo_b200 import align, coverage, engine
 
-    def align_stub(tnames, tseqs, qnames, qseqs, hspthresh=3000, same=False):
+    def align_stub(tnames, tseqs, qnames, qseqs, hspthresh=3000, same=False, minLen=None, minIdt=None):   # unfiltered: the formatter filters too
         p = lo.default_params(hspthresh)
         cols = {f: [] for f in align.HIT_FIELDS}
         qenc = [lo.encode(np.asarray(s)) for s in qseqs]
