@@ -167,18 +167,63 @@ def align_tile(t: TargetIndex, q: np.ndarray, p: Params, stats: Optional[Stats] 
     return out[:n].copy()
 
 
+_FLIB = None
+
+
+def faithful_lib():
+    """oracle/lastz_faithful.c: the sequential, order-dependent second statement (measures the effect of deviations D1-D5)."""
+    global _FLIB
+    if _FLIB is None:
+        so = os.path.join(HERE, '_build', 'liblastz_faithful.so')
+        srcs = [os.path.join(HERE, 'lastz_faithful.c'), os.path.join(HERE, 'lastz_oracle.c')]
+        if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(x) for x in srcs):
+            subprocess.check_call(['make', '-C', HERE, '_build/liblastz_faithful.so'], stdout=subprocess.DEVNULL)
+        l = C.CDLL(so)
+        l.lzf_align_tile_ix.restype = C.c_long
+        l.lzf_align_tile_ix.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(Params), C.c_void_p, C.c_long, C.POINTER(Stats)]
+        l.lzo_index_build.restype = C.c_void_p
+        l.lzo_index_build.argtypes = [C.c_void_p, C.c_long]
+        l.lzo_index_free.argtypes = [C.c_void_p]
+        _FLIB = l
+    return _FLIB
+
+
+def align_tile_faithful(tcodes: np.ndarray, q: np.ndarray, p: Params, stats: Optional[Stats] = None) -> np.ndarray:
+    """align_tile() through the sequential second statement (its own index handle: the two libraries do not share memory)."""
+    l = faithful_lib()
+    tcodes = np.ascontiguousarray(tcodes, dtype=np.uint8)
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    ix = l.lzo_index_build(tcodes.ctypes.data, len(tcodes))
+    try:
+        cap = 1 << 14
+        while True:
+            out = np.zeros((cap, 9), dtype=np.int32)
+            st = Stats()
+            n = l.lzf_align_tile_ix(ix, tcodes.ctypes.data, len(tcodes), q.ctypes.data, len(q), C.byref(p), out.ctypes.data, cap, C.byref(st))
+            if n < cap:
+                break
+            cap *= 4
+    finally:
+        l.lzo_index_free(ix)
+    if stats is not None:
+        stats.add(st)
+    return out[:n].copy()
+
+
 def pct_str(nmatch: int, ncols: int) -> str:
     """LASTZ prints identity as '%.1f%%' of 100*n/d computed in double precision."""
     return '%.1f' % (100.0 * nmatch / ncols) if ncols else '0.0'
 
 
-def lastz_general(tname: str, t: TargetIndex, qname: str, qcodes: np.ndarray, p: Params, stats: Optional[Stats] = None) -> List[str]:
+def lastz_general(tname: str, t: TargetIndex, qname: str, qcodes: np.ndarray, p: Params, stats: Optional[Stats] = None,
+                  faithful: bool = False) -> List[str]:
     """The text `lastz T Q ... --format=general:... --markend --strand=both` writes (13 columns, '%' present)."""
     out = ['#name1\tstrand1\tstart1\tend1\tlength1\tname2\tstrand2\tstart2+\tend2+\tlength2\tscore\tidentity\tidPct\n']
     m = len(qcodes)
     for strand in '+-':
         q = qcodes if strand == '+' else revcomp_codes(qcodes)
-        for (s1, e1, s2, e2, score, nm, nc, _a1, _a2) in align_tile(t, q, p, stats).tolist():
+        rows = align_tile_faithful(t.codes, q, p, stats) if faithful else align_tile(t, q, p, stats)
+        for (s1, e1, s2, e2, score, nm, nc, _a1, _a2) in rows.tolist():
             if strand == '+':
                 qs, qe = s2 + 1, e2
             else:
@@ -198,8 +243,10 @@ def _pairs(anames: Sequence[str], bnames: Optional[Sequence[str]]):
 def _pair_job(args):
     """One `lastz T Q ...` process of the reference's script (target table built per pair, both strands) -- pool worker."""
     a, tcodes, b, qcodes, hspthresh, kw = args
+    kw = dict(kw)
+    faithful = bool(kw.pop('faithful', False))
     st = Stats()
-    lines = lastz_general(a, TargetIndex(tcodes), b, qcodes, default_params(hspthresh, **kw), st)
+    lines = lastz_general(a, TargetIndex(tcodes), b, qcodes, default_params(hspthresh, **kw), st, faithful=faithful)
     return (a, b), lines, st.as_dict()
 
 
