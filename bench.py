@@ -579,6 +579,13 @@ def run_b200(args):
     roofline['dominant_kernel_of_step'] = top
     if int_tags:
         roofline['int_kernel'] = int_roofline(max(int_tags, key=lambda t: prof[t][0]))
+    if dom == 'seed_scan' and cells.get('seed_scan'):
+        # the scan's lookups are HBM-shaped but its time goes to the fused first-stage x-drop (ncu: issue-bound, DRAM < 10 % busy):
+        # the same launch against the integer roofline, 6 lane-ops per scored column
+        ms = prof['seed_scan'][0] / args.steps
+        g = cells['seed_scan'] / (ms / 1e3) / 1e9
+        roofline['same_kernel_vs_int_roofline'] = {'gcups': g, 'cells_per_step': cells['seed_scan'], 'frac': g * 1e9 * budget['seed_scan'] / int_peak,
+                                                   'ops_per_cell': budget['seed_scan'], 'peak_lane_ops_per_s': int_peak}
     roofline['kernels_ms_per_step'] = {t: prof[t][0] / args.steps for t in all_tags if prof[t][1]}
     roofline['note'] = ('the kernel with the largest share of the step; `hbm_kernels` lists the HBM-bound launch groups against the measured copy '
                         'peak, `gcups` the integer-pipe kernels (x-drop, y-drop) against the INT32 issue roofline at the SURVEY op budgets')

@@ -630,7 +630,9 @@ void gapped_extend(const Genome& T, const Genome& Q, const HspSet& h, const DevB
                 const unsigned long long deferred = h_nomem - h_nomem_before;
                 MB2_REQUIRE(deferred == 0 || deferred < prev_sched || conc > 1, -3,
                             "gapped stage: the trace pool is too small for a single extension (raise MB2_TRACE_POOL_MB)");
-                if (deferred * 2 > prev_sched) conc = std::max<uint32_t>(1, conc / 2);      // most ran out of pool together: fewer at a time
+                // Deferred items are normal (a round's traces fill the pool, the rest fail fast and come back). Only when NOT ONE
+                // extension of a round finished were the extensions in flight too long to fit side by side: run fewer at a time.
+                if (prev_sched && deferred >= prev_sched) conc = std::max<uint32_t>(1, conc / 2);
                 prev_sched = h_counts[0] + h_counts[1];
                 h_nomem_before = h_nomem;
                 MB2_CUDA(cudaMemsetAsync(pool.next, 0, yw::NSUB * sizeof(uint32_t), cx.stream));      // previous round's traces are consumed

@@ -15,12 +15,12 @@ __device__ __forceinline__ uint32_t code_byte(uint32_t base, uint32_t bad, uint3
 // one thread packs 32 bases -> one uint64 of 2-bit codes + one uint32 of N flags
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm,
-            uint8_t* __restrict__ codes) {
+            uint32_t* __restrict__ sm, uint8_t* __restrict__ codes) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     const uint4* src = reinterpret_cast<const uint4*>(ascii + (size_t)w * 32);
     uint64_t bits = 0;
-    uint32_t nflag = 0, padflag = 0;
+    uint32_t nflag = 0, padflag = 0, lowflag = 0;
 #pragma unroll
     for (int v = 0; v < 2; v++) {
         const uint4 x = src[v];
@@ -37,11 +37,13 @@ pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __rest
                 bits |= (uint64_t)code << (2 * idx);
                 nflag |= bad << idx;
                 padflag |= (raw == 0u ? 1u : 0u) << idx;                      // pad positions of the ASCII image are NUL bytes
+                lowflag |= ((raw >= 'a' && raw <= 'z') ? 1u : 0u) << idx;        // soft-masked: not seeded, still extended through
             }
         }
     }
     pk[w] = bits;
     nm[w] = nflag;
+    sm[w] = nflag | lowflag;
     uint32_t out[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -60,7 +62,7 @@ pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __rest
 
 // reverse complement every scaffold in place of its own slot (same offsets, same lengths)
 __global__ void __launch_bounds__(256)
-revcomp_kernel(GenomeView src, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm, uint8_t* __restrict__ codes, uint32_t nwords) {
+revcomp_kernel(GenomeView src, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm, uint32_t* __restrict__ sm, uint8_t* __restrict__ codes, uint32_t nwords) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     const uint32_t p0 = w * 32;
@@ -69,21 +71,24 @@ revcomp_kernel(GenomeView src, uint64_t* __restrict__ pk, uint32_t* __restrict__
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (src.off[mid] <= p0 + 31) lo = mid; else hi = mid; }
     const uint32_t so = src.off[lo], sl = src.len[lo];
     uint64_t bits = 0;
-    uint32_t nflag = 0;
+    uint32_t nflag = 0, sflag = 0;
     for (int c = 0; c < 32; c++) {
         const uint32_t p = p0 + c;
-        uint32_t code = 0, bad = 1;
+        uint32_t code = 0, bad = 1, soft = 1;
         if (p >= so && p < so + sl) {
             const uint32_t sp = so + (sl - 1 - (p - so));
             bad = isn_at(src.nm, sp);
+            soft = isn_at(src.sm, sp);
             code = bad ? 0u : 3u - base_at(src.pk, sp);
         }
         bits |= (uint64_t)code << (2 * c);
         nflag |= bad << c;
+        sflag |= soft << c;
         codes[(size_t)p0 + c] = (uint8_t)code_byte(code, bad, (p >= so && p < so + sl) ? 0u : 1u);
     }
     pk[w] = bits;
     nm[w] = nflag;
+    sm[w] = sflag;
 }
 
 // nfree[s] = 1 iff scaffold s has no non-ACGT base (one CTA per scaffold scans its mask words)
@@ -134,11 +139,11 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         for (int s = 0; s < n; s++)
             if (lens[s]) MB2_CUDA(cudaMemcpyAsync(d_ascii.get() + g->off[s], seqs[s], lens[s], cudaMemcpyHostToDevice, cx.stream));
         const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
-        g->pk.alloc(nwords); g->nm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
+        g->pk.alloc(nwords); g->nm.alloc(nwords); g->sm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
         g->d_off.alloc(n); g->d_len.alloc(n);
         MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), g->off.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
         MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), g->len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
-        launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get(), g->codes.get());
+        launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get(), g->sm.get(), g->codes.get());
         g->d_nfree.alloc(n);
         launch(nfree_kernel, n, 256, 0, g->nm.get(), g->d_off.get(), g->d_len.get(), g->d_nfree.get());
         MB2_CUDA(cudaStreamSynchronize(cx.stream));      // the caller's buffers are free again after this
@@ -152,14 +157,14 @@ Genome* genome_revcomp(const Genome& src) {
     try {
         g->nscaf = src.nscaf; g->off = src.off; g->len = src.len; g->G = src.G; g->nbases = src.nbases; g->is_rc = !src.is_rc;
         const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
-        g->pk.alloc(nwords); g->nm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
+        g->pk.alloc(nwords); g->nm.alloc(nwords); g->sm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
         g->d_off.alloc(src.nscaf); g->d_len.alloc(src.nscaf);
         Ctx& cx = ctx();
         MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), src.d_off.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
         MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), src.d_len.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
         g->d_nfree.alloc(src.nscaf);
         MB2_CUDA(cudaMemcpyAsync(g->d_nfree.get(), src.d_nfree.get(), src.nscaf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
-        launch(revcomp_kernel, cdiv(nwords, 256), 256, 0, view(src), g->pk.get(), g->nm.get(), g->codes.get(), nwords);
+        launch(revcomp_kernel, cdiv(nwords, 256), 256, 0, view(src), g->pk.get(), g->nm.get(), g->sm.get(), g->codes.get(), nwords);
         g->id = next_genome_id(); g->fwd_src_id = 0; g->nfwd = 0;
     } catch (...) { delete g; throw; }
     return g;
@@ -169,7 +174,7 @@ Genome* genome_revcomp(const Genome& src) {
 // alignment pipeline cover --strand=both (tile = target x (scaffold, strand)), so the two strands share every launch.
 __global__ void __launch_bounds__(256)
 both_strands_kernel(GenomeView src, const uint32_t* __restrict__ noff, const uint32_t* __restrict__ nlen, int n2,
-                    uint64_t* __restrict__ pk, uint32_t* __restrict__ nm, uint8_t* __restrict__ codes, uint32_t nwords) {
+                    uint64_t* __restrict__ pk, uint32_t* __restrict__ nm, uint32_t* __restrict__ sm, uint8_t* __restrict__ codes, uint32_t nwords) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     const uint32_t p0 = w * 32;
@@ -179,22 +184,24 @@ both_strands_kernel(GenomeView src, const uint32_t* __restrict__ noff, const uin
     const int n = n2 >> 1;
     const bool rc = lo >= n;
     const uint32_t srco = src.off[rc ? lo - n : lo];
-    uint64_t bits = 0; uint32_t nflag = 0;
+    uint64_t bits = 0; uint32_t nflag = 0, sflag = 0;
     uint32_t cw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int c = 0; c < 32; c++) {
         const uint32_t p = p0 + c;
-        uint32_t code = 0, bad = 1;
+        uint32_t code = 0, bad = 1, soft = 1;
         if (p >= so && p < so + sl) {
             const uint32_t k = p - so;
             const uint32_t sp = srco + (rc ? sl - 1 - k : k);
             bad = isn_at(src.nm, sp);
+            soft = isn_at(src.sm, sp);
             code = bad ? 0u : (rc ? 3u - base_at(src.pk, sp) : base_at(src.pk, sp));
         }
         bits |= (uint64_t)code << (2 * c);
         nflag |= bad << c;
+        sflag |= soft << c;
         cw[c >> 2] |= code_byte(code, bad, (p >= so && p < so + sl) ? 0u : 1u) << (8 * (c & 3));
     }
-    pk[w] = bits; nm[w] = nflag;
+    pk[w] = bits; nm[w] = nflag; sm[w] = sflag;
     uint4* dst = reinterpret_cast<uint4*>(codes + (size_t)w * 32);
     dst[0] = make_uint4(cw[0], cw[1], cw[2], cw[3]);
     dst[1] = make_uint4(cw[4], cw[5], cw[6], cw[7]);
@@ -208,7 +215,7 @@ Genome* genome_both_strands(const Genome& src) {
         for (int s = 0; s < n; s++) lens[s] = lens[n + s] = src.len[s];
         layout(*g, lens.data(), 2 * n);
         const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
-        g->pk.alloc(nwords); g->nm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
+        g->pk.alloc(nwords); g->nm.alloc(nwords); g->sm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
         g->d_off.alloc(2 * n); g->d_len.alloc(2 * n); g->d_nfree.alloc(2 * n);
         Ctx& cx = ctx();
         MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), g->off.data(), 2 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
@@ -216,7 +223,7 @@ Genome* genome_both_strands(const Genome& src) {
         MB2_CUDA(cudaMemcpyAsync(g->d_nfree.get(), src.d_nfree.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
         MB2_CUDA(cudaMemcpyAsync(g->d_nfree.get() + n, src.d_nfree.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cx.stream));
         launch(both_strands_kernel, cdiv(nwords, 256), 256, 0, view(src), g->d_off.get(), g->d_len.get(), 2 * n, g->pk.get(), g->nm.get(),
-               g->codes.get(), nwords);
+               g->sm.get(), g->codes.get(), nwords);
         MB2_CUDA(cudaStreamSynchronize(cx.stream));   // g->off/len host vectors were copy sources
         g->id = next_genome_id(); g->fwd_src_id = src.fwd_src_id == src.id ? src.id : 0; g->nfwd = src.fwd_src_id == src.id ? n : 0;
     } catch (...) { delete g; throw; }

@@ -33,7 +33,7 @@ seed_keys_kernel(GenomeView T, uint32_t p_lo, uint32_t n, uint32_t* __restrict__
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t p = p_lo + k;
-    const uint32_t nw = nwindow32(T.nm, p) & SEED_WINDOW_MASK19;
+    const uint32_t nw = nwindow32(T.sm, p) & SEED_WINDOW_MASK19;    // non-ACGT or soft-masked: no seed word
     keys[k] = nw ? KEY_INVALID : seed_key(window32(T.pk, p));
     pos[k] = p;
 }
@@ -146,7 +146,7 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
             step++;
             const uint32_t jrel = round * 32 + lane;
             const uint32_t j = q_lo + jrel;
-            const bool jvalid = jrel < q_n && (nwindow32(Q.nm, j) & SEED_WINDOW_MASK19) == 0;
+            const bool jvalid = jrel < q_n && (nwindow32(Q.sm, j) & SEED_WINDOW_MASK19) == 0;
             uint32_t key = 0;
             if (jvalid) key = seed_key(window32(Q.pk, j));
             uint32_t b0[SC_HALF], cnt[SC_HALF];
@@ -206,7 +206,7 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
         uint32_t ln = 1, rn = 0, fn = 0;
         if (live) {
             lt = window32(T.pk, hi - 1); lq = window32(Q.pk, hj - 1);
-            ln = (nwindow32(Q.nm, hj - 1) | nwindow32(T.nm, hi - 1)) & SEED_WINDOW_MASK19;
+            ln = (nwindow32(Q.sm, hj - 1) | nwindow32(T.sm, hi - 1)) & SEED_WINDOW_MASK19;
             rt = window32(T.pk, hi + SEED_SPAN); rq = window32(Q.pk, hj + SEED_SPAN);
             rn = (nwindow32(T.nm, hi + SEED_SPAN) | nwindow32(Q.nm, hj + SEED_SPAN)) & S1_WINDOW_MASK;
             ft = window32(T.pk, hi + SEED_SPAN - 32); fq = window32(Q.pk, hj + SEED_SPAN - 32);
@@ -364,7 +364,7 @@ seed_scan2_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, 
                 step++;
                 const uint32_t jrel = round * 32 + lane;
                 const uint32_t j = q_lo + jrel;
-                const bool jvalid = jrel < q_n && (nwindow32(Q.nm, j) & SEED_WINDOW_MASK19) == 0;
+                const bool jvalid = jrel < q_n && (nwindow32(Q.sm, j) & SEED_WINDOW_MASK19) == 0;
                 uint32_t key = 0;
                 if (jvalid) key = seed_key(window32(Q.pk, j));
                 uint32_t b0[SC_HALF], cnt[SC_HALF];
@@ -417,7 +417,7 @@ seed_scan2_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, 
                     hi = pos[rb[lo & (SC_RING - 1)] + (h - rc[lo & (SC_RING - 1)])];
                     hj = rj[lo & (SC_RING - 1)];
                     const uint64_t lt = window32(T.pk, hi - 1), lq = window32(Q.pk, hj - 1);
-                    const uint32_t ln = (nwindow32(Q.nm, hj - 1) | nwindow32(T.nm, hi - 1)) & SEED_WINDOW_MASK19;
+                    const uint32_t ln = (nwindow32(Q.sm, hj - 1) | nwindow32(T.sm, hi - 1)) & SEED_WINDOW_MASK19;
                     if (ln == 0 && seed_match(lt, lq, transition != 0)) live = false; else n_lead++;
                 }
                 const uint32_t lm = __ballot_sync(0xffffffffu, live);

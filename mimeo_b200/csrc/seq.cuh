@@ -7,7 +7,9 @@
 //     non-ACGT character, so ten of them end the extension without changing its maximum,
 //   * unaligned 64-bit window reads one word past a scaffold are always in bounds.
 // Storage: pk  = 2 bits/base, 32 bases per uint64 word, base p in bits [2(p%32), 2(p%32)+1];
-//          nm  = 1 bit/base, 32 bases per uint32 word, 1 = not A/C/G/T (N, IUPAC, pad).
+//          nm  = 1 bit/base, 32 bases per uint32 word, 1 = not A/C/G/T (N, IUPAC, pad): scores -100 in every extension;
+//          sm  = nm | soft-mask: lower-case input is excluded from SEEDING on both sequences, as LASTZ does without
+//                [unmask] (a 19-mer window holding such a base is no seed word), but is extended through by its base.
 #pragma once
 #include "common.cuh"
 
@@ -24,6 +26,7 @@ struct Genome {
     uint64_t nbases = 0;              // sum of scaffold lengths
     DevBuf<uint64_t> pk;              // G/32 + 2 words
     DevBuf<uint32_t> nm;              // G/32 + 2 words
+    DevBuf<uint32_t> sm;              // G/32 + 2 words: 1 = not seedable (non-ACGT, pad, or soft-masked = lower case in the input)
     DevBuf<uint8_t> codes;            // 1 byte/base for the gapped DP: base | parity << 2, 8 = other, 12 = pad (genome.cu:code_byte)
     DevBuf<uint32_t> d_off, d_len;
     DevBuf<uint32_t> d_nfree;         // per scaffold: 1 = every base is A/C/G/T
@@ -38,6 +41,7 @@ uint64_t next_genome_id();
 struct GenomeView {   // what kernels receive
     const uint64_t* __restrict__ pk;
     const uint32_t* __restrict__ nm;
+    const uint32_t* __restrict__ sm;
     const uint8_t* __restrict__ codes;
     const uint32_t* __restrict__ off;
     const uint32_t* __restrict__ len;
@@ -45,7 +49,7 @@ struct GenomeView {   // what kernels receive
     int nscaf;
     uint32_t G;
 };
-inline GenomeView view(const Genome& g) { return GenomeView{g.pk.get(), g.nm.get(), g.codes.get(), g.d_off.get(), g.d_len.get(), g.d_nfree.get(), g.nscaf, (uint32_t)g.G}; }
+inline GenomeView view(const Genome& g) { return GenomeView{g.pk.get(), g.nm.get(), g.sm.get(), g.codes.get(), g.d_off.get(), g.d_len.get(), g.d_nfree.get(), g.nscaf, (uint32_t)g.G}; }
 
 // HOXD70 as LASTZ's default, row = target base, col = query base (index t*4+q)
 static __constant__ int c_sub[16] = {91, -114, -31, -123, -114, 100, -125, -31, -31, -125, 100, -114, -123, -31, -114, 91};

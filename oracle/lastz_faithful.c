@@ -42,7 +42,7 @@ static void xdrop_extend_stop(const uint8_t *t, long n, const uint8_t *q, long m
     int run = 0, best = 0;
     long be = c1;
     while (c1 < n && c2 < m) {
-        run += SUB[t[c1]][q[c2]];
+        run += SUB[BASE(t[c1])][BASE(q[c2])];
         c1++; c2++; (*cells)++;
         if (run > best) { best = run; be = c1; }
         else if (run < best - X) break;
@@ -52,7 +52,7 @@ static void xdrop_extend_stop(const uint8_t *t, long n, const uint8_t *q, long m
     int runl = 0, bestl = 0;
     long bs = i + SEED_SPAN;
     while (c1 >= 0 && c2 >= 0) {
-        runl += SUB[t[c1]][q[c2]];
+        runl += SUB[BASE(t[c1])][BASE(q[c2])];
         (*cells)++;
         if (runl > bestl) { bestl = runl; bs = c1; }
         else if (runl < bestl - X) break;
@@ -89,7 +89,7 @@ long lzf_hsps(const lzo_index *ix, const uint8_t *t, long n, const uint8_t *q, l
                 st->hsps_raw++;
                 if (p->entropy) {
                     uint32_t cnt[4] = {0, 0, 0, 0};
-                    for (long c = bs; c < be; c++) if (t[c] == q[c - (i - j)] && t[c] < 4) cnt[t[c]]++;
+                    for (long c = bs; c < be; c++) if (BASE(t[c]) == BASE(q[c - (i - j)]) && BASE(t[c]) < 4) cnt[BASE(t[c])]++;
                     score = (int)((double)score * entropy_double(cnt));          /* F3 */
                     if (score < p->hspthresh) continue;
                 }
@@ -158,7 +158,7 @@ static fext_t rowwise_extend(const uint8_t *t, long a1, long tn, const uint8_t *
             int mval = NEG_INF;
             if (i == 0 && j == 0) mval = 0;
             else if (hd > NEG_INF && i >= 1 && j >= 1) {
-                int a = dir > 0 ? t[a1 + i - 1] : t[a1 - i], b = dir > 0 ? q[a2 + j - 1] : q[a2 - j];
+                int a = BASE(dir > 0 ? t[a1 + i - 1] : t[a1 - i]), b = BASE(dir > 0 ? q[a2 + j - 1] : q[a2 - j]);
                 mval = hd + SUB[a][b];
             }
             int h, hsel;
@@ -202,7 +202,7 @@ static fext_t rowwise_extend(const uint8_t *t, long a1, long tn, const uint8_t *
             if (state == 0) {
                 int hs = b & 3;
                 if (hs == 0) {
-                    int a = dir > 0 ? t[a1 + i - 1] : t[a1 - i], c = dir > 0 ? q[a2 + j - 1] : q[a2 - j];
+                    int a = BASE(dir > 0 ? t[a1 + i - 1] : t[a1 - i]), c = BASE(dir > 0 ? q[a2 + j - 1] : q[a2 - j]);
                     r.ncols++; if (a == c && a < 4) r.nmatch++;
                     i--; j--;
                 } else state = hs;

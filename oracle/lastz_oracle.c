@@ -45,7 +45,8 @@
  *       best is the maximum over all earlier anti-diagonals. (LASTZ prunes row by row.)
  *   D5  "inside a reported alignment" is tested on the alignment's bounding box, and extensions
  *       are not clipped by earlier alignments; no traceback-memory truncation exists.
- *   D6  lower-case (soft-masked) input is treated as upper case.
+ *   (D6 of round 1 -- soft-masking ignored -- is gone: lower-case bases are excluded from seeding on both sequences and
+ *   extended through by their base, as LASTZ does without [unmask].)
  *
  * Coordinates inside this file: 0-based, half-open, on the strand that was aligned (the caller
  * reverse-complements the query for the minus strand and converts back).
@@ -61,6 +62,9 @@
 #define SEED_SPAN 19
 #define NEG_INF (INT_MIN / 4)
 
+/* Codes: 0..3 = A,C,G,T, 4 = anything else; bit 3 set = soft-masked (lower case in the input). A soft-masked base is
+ * never part of a seed word (every test below that asks "code > 3" rejects it) but is extended through by its base. */
+#define BASE(x) ((x) & 7)
 static const int SUB[5][5] = {
     {91, -114, -31, -123, -100},
     {-114, 100, -125, -31, -100},
@@ -159,7 +163,7 @@ static void xdrop_extend(const uint8_t *t, long n, const uint8_t *q, long m, lon
     int run = 0, best = 0;
     long be = c1;
     while (c1 < n && c2 < m) {
-        run += SUB[t[c1]][q[c2]];
+        run += SUB[BASE(t[c1])][BASE(q[c2])];
         c1++; c2++; (*cells)++;
         if (run > best) { best = run; be = c1; }
         else if (run < best - X) break;
@@ -168,7 +172,7 @@ static void xdrop_extend(const uint8_t *t, long n, const uint8_t *q, long m, lon
     int runl = 0, bestl = 0;
     long bs = i + SEED_SPAN;
     while (c1 >= 0 && c2 >= 0) {
-        runl += SUB[t[c1]][q[c2]];
+        runl += SUB[BASE(t[c1])][BASE(q[c2])];
         (*cells)++;
         if (runl > bestl) { bestl = runl; bs = c1; }
         else if (runl < bestl - X) break;
@@ -239,7 +243,7 @@ long lzo_hsps_ix(const lzo_index *ix_in, const uint8_t *t, long n, const uint8_t
                 st->hsps_raw++;
                 if (p->entropy) {
                     uint32_t cnt[4] = {0, 0, 0, 0};
-                    for (long c = bs; c < be; c++) if (t[c] == q[c - (i - j)] && t[c] < 4) cnt[t[c]]++;
+                    for (long c = bs; c < be; c++) if (BASE(t[c]) == BASE(q[c - (i - j)]) && BASE(t[c]) < 4) cnt[BASE(t[c])]++;
                     uint32_t h = lzo_entropy_q24(cnt);
                     score = (int)(((int64_t)score * (int64_t)h) >> 24);
                     if (score < p->hspthresh) continue;
@@ -343,10 +347,10 @@ void lzo_anchor(const uint8_t *t, const uint8_t *q, const lzo_hsp *h, int32_t *a
     if (h->len <= 31) off = h->len / 2;
     else {
         int sum = 0;
-        for (int c = 0; c < 31; c++) sum += SUB[t[h->s1 + c]][q[h->s2 + c]];
+        for (int c = 0; c < 31; c++) sum += SUB[BASE(t[h->s1 + c])][BASE(q[h->s2 + c])];
         int best = sum, bw = 0;
         for (int w = 1; w + 31 <= h->len; w++) {
-            sum += SUB[t[h->s1 + w + 30]][q[h->s2 + w + 30]] - SUB[t[h->s1 + w - 1]][q[h->s2 + w - 1]];
+            sum += SUB[BASE(t[h->s1 + w + 30])][BASE(q[h->s2 + w + 30])] - SUB[BASE(t[h->s1 + w - 1])][BASE(q[h->s2 + w - 1])];
             if (sum > best) { best = sum; bw = w; }
         }
         off = bw + 15;
@@ -420,7 +424,7 @@ static ext_t ydrop_extend(const uint8_t *t, long a1, long tn, const uint8_t *q, 
                 if (i >= 1 && j >= 1 && i - 1 >= lo2 && i - 1 <= hi2) {
                     const cell_t *dg = &p2[i - 1 - lo2];
                     if (dg->h > NEG_INF) {
-                        int a = dir > 0 ? t[a1 + i - 1] : t[a1 - i], b = dir > 0 ? q[a2 + j - 1] : q[a2 - j];
+                        int a = BASE(dir > 0 ? t[a1 + i - 1] : t[a1 - i]), b = BASE(dir > 0 ? q[a2 + j - 1] : q[a2 - j]);
                         mval = dg->h + SUB[a][b]; mm = dg->hm + (a == b && a < 4); mc = dg->hc + 1;
                     }
                 }
@@ -531,7 +535,7 @@ long lzo_align_tile_ix(const lzo_index *ix, const uint8_t *t, long n, const uint
             if (nout >= cap) { nout = -1; break; }
             lzo_aln *o = &out[nout++];
             o->s1 = h[x].s1; o->e1 = h[x].s1 + h[x].len; o->s2 = h[x].s2; o->e2 = h[x].s2 + h[x].len; o->score = h[x].score;
-            int nm = 0; for (int c = 0; c < h[x].len; c++) nm += (t[h[x].s1 + c] == q[h[x].s2 + c] && t[h[x].s1 + c] < 4);
+            int nm = 0; for (int c = 0; c < h[x].len; c++) nm += (BASE(t[h[x].s1 + c]) == BASE(q[h[x].s2 + c]) && BASE(t[h[x].s1 + c]) < 4);
             o->nmatch = nm; o->ncols = h[x].len; o->a1 = o->s1; o->a2 = o->s2;
         }
     }
@@ -548,6 +552,6 @@ long lzo_align_tile(const uint8_t *t, long n, const uint8_t *q, long m, const lz
 /* helpers for the Python side */
 void lzo_revcomp(const uint8_t *s, long n, uint8_t *out)
 {
-    for (long i = 0; i < n; i++) { uint8_t b = s[n - 1 - i]; out[i] = b < 4 ? (uint8_t)(3 - b) : b; }
+    for (long i = 0; i < n; i++) { uint8_t b = s[n - 1 - i]; out[i] = BASE(b) < 4 ? (uint8_t)((3 - BASE(b)) | (b & 8)) : b; }
 }
-int lzo_sub(int a, int b) { return SUB[a][b]; }
+int lzo_sub(int a, int b) { return SUB[BASE(a)][BASE(b)]; }

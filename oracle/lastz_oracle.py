@@ -92,7 +92,10 @@ def default_params(hspthresh=3000, **kw) -> Params:
 _ENC = np.full(256, 4, dtype=np.uint8)
 for _i, _c in enumerate('ACGT'):
     _ENC[ord(_c)] = _i
-    _ENC[ord(_c.lower())] = _i          # D6: soft-masking is ignored
+    _ENC[ord(_c.lower())] = _i | 8      # soft-masked: same base, bit 3 set (never seeded, still extended through)
+for _c in range(ord('a'), ord('z') + 1):
+    if _ENC[_c] == 4:
+        _ENC[_c] = 4 | 8
 
 
 def encode(seq) -> np.ndarray:
@@ -106,8 +109,8 @@ def encode(seq) -> np.ndarray:
 
 def revcomp_codes(codes: np.ndarray) -> np.ndarray:
     r = codes[::-1].copy()
-    m = r < 4
-    r[m] = 3 - r[m]
+    m = (r & 7) < 4
+    r[m] = (3 - (r[m] & 7)) | (r[m] & 8)
     return r
 
 

@@ -184,3 +184,24 @@ def test_awkward_genomes_bit_exact_vs_oracle(M, kind):
     hits, _ = A.align(T, T, G.align_params(3000))
     want = oracle_rows(g, g, lo.default_params(3000))
     assert gpu_rows(hits) == want and len(want) >= 2
+
+
+def test_soft_masked_bases_are_not_seeded_but_extended_through(M):
+    """Lower-case input (soft-masking, e.g. RepeatMasker -xsmall) is excluded from seeding on both sequences and still scored
+    by its base in every extension, as LASTZ does without [unmask]; GPU rows == oracle rows, and masking changes the output."""
+    A, G = M
+    g = synth_genome(71, 3, 30_000, 3, copies=(4, 7), fam_len=(400, 1800), sub=0.08, indel=0.004)
+    rng = np.random.default_rng(5)
+    masked = {}
+    for name, seq in g.items():
+        s = seq.copy()
+        for _ in range(12):                      # lower-case stretches of 50-1500 bases, some swallow whole repeat copies
+            p0 = int(rng.integers(0, len(s) - 1600)); n = int(rng.integers(50, 1500))
+            s[p0:p0 + n] |= 0x20
+        masked[name] = s
+    T = G.Genome.from_dict(masked)
+    hits, stats = A.align(T, T, G.align_params(3000))
+    want = oracle_rows(masked, masked, lo.default_params(3000))
+    assert gpu_rows(hits) == want and len(want) > 10
+    plain = oracle_rows(g, g, lo.default_params(3000))
+    assert plain != want                          # the mask matters on this input

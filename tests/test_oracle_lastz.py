@@ -197,3 +197,22 @@ def test_minus_strand_coordinates():
     r = rows[0]
     assert r[6] == '-' and abs(int(r[2]) - 2001) <= 25 and abs(int(r[3]) - 2600) <= 25
     assert abs(int(r[7]) - 1001) <= 25 and abs(int(r[8]) - 1600) <= 25 and float(r[12].strip().rstrip('%')) >= 99.0
+
+
+def test_soft_masked_windows_are_never_seeds_but_score_by_base():
+    """A lower-case base makes every 19-mer window that holds it a non-seed on either sequence; extensions score it as its base."""
+    rng = np.random.default_rng(9)
+    seq = rng.integers(0, 4, 400).astype(np.uint8)
+    soft = seq.copy()
+    soft[100:130] |= 8
+    l = lo.lib()
+    for i in range(60, 150):
+        clean = not (i <= 129 and i + 19 > 100)
+        assert bool(l.lzo_seed_at(soft.ctypes.data, 400, seq.ctypes.data, 400, i, i, 1)) == clean
+        assert bool(l.lzo_seed_at(seq.ctypes.data, 400, soft.ctypes.data, 400, i, i, 1)) == clean
+    p = lo.default_params(3000)
+    a = lo.align_tile(lo.TargetIndex(seq), seq, p)
+    b = lo.align_tile(lo.TargetIndex(soft), seq, p)
+    assert a.tolist() == b.tolist() and len(a) == 1 and a[0][5] == 400     # seeded elsewhere, extended through the masked stretch: 400 matches
+    assert lo.revcomp_codes(lo.revcomp_codes(soft)).tolist() == soft.tolist()
+    assert lo.encode('acgtnACGTN').tolist() == [8, 9, 10, 11, 12, 0, 1, 2, 3, 4]
