@@ -459,9 +459,9 @@ static yw::Pool trace_pool(int nslots) {
     if (!g_trace.base) {
         size_t free_b = 0, total_b = 0;
         MB2_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        size_t want = (size_t)48 << 30;                                   // 2 bytes per evaluated DP cell of one round (capped at a third of the free memory)
+        size_t want = (size_t)96 << 30;                                   // 2 bytes per evaluated DP cell of one round (capped at 45 % of the free memory)
         if (const char* e = getenv("MB2_TRACE_POOL_MB")) { const double v = atof(e); if (v > 0) want = (size_t)(v * 1048576.0); }
-        want = std::min(want, free_b / 3);
+        want = std::min(want, free_b / 20 * 9);
         size_t nchunks = want / yw::CHUNK_BYTES / yw::NSUB * yw::NSUB;
         MB2_REQUIRE(nchunks >= (size_t)yw::NSUB, -3, "gapped stage: not enough device memory for the trace pool");
         MB2_CUDA(cudaStreamSynchronize(cx.stream));

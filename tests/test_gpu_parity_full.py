@@ -64,3 +64,23 @@ def test_c2_full_segments_equal_oracle():
     assert len(want[0]) >= 50          # 70x mean depth: every scaffold is one segment, clipped at its ends
     for g, w in zip(got, want):
         assert np.array_equal(np.asarray(g), np.asarray(w))
+
+
+def test_c5_shaped_genome_every_row():
+    """BASELINE config 5's generator (plant-like: 40 % of the bases from repeat families, log-normal scaffold lengths) at a size
+    the oracle finishes in seconds (1.5 Mbp, 6 scaffolds, 126 k HSPs, 1.1 k alignments): every row of every tile equal. The
+    1 Gbp run itself (profiles/r2_c5_1Gbp_n8.json) is the same kernels on the same generator."""
+    from mimeo_b200 import align as A, genome as G
+    from tests.helpers import synth_c5
+    g = synth_c5(1005, 1_500_000, 6, fam_len=(1000, 4000), copies=(10, 60))
+    names = sorted(g, key=lambda s: s.encode())
+    enc = {n: lo.encode(g[n]) for n in names}
+    st = lo.Stats()
+    general = lo.general_all_pairs(enc, None, 3000, workers=os.cpu_count() or 1, stats=st)
+    want = lo.general_rows(general, names, names)
+    T = G.Genome(names, [g[n] for n in names])
+    hits, stats = A.align(T, T, G.align_params(3000))
+    T.close()
+    got = set(zip(*[hits[f].tolist() for f in A.HIT_FIELDS]))
+    assert len(want) > 1000 and got == want, f'{len(got - want)} rows only on the GPU, {len(want - got)} only in the oracle'
+    assert stats['hsps'] == st.hsps_kept and stats['seed_hits'] == st.seed_hits
