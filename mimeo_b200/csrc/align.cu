@@ -120,6 +120,10 @@ void align_strand(const Genome& T, const Genome& Q, const AlignParams& p, const 
     DevBuf<unsigned long long> counters(CNT_N);
     DevBuf<uint64_t> s0, s1;
     const std::vector<int32_t> same = same_scaffold_map(T, Q, h_same_q);
+    // scores are 32-bit (as LASTZ's score type): the trivial alignment of a scaffold with itself scores up to 100 per base
+    for (int t = 0; t < T.nscaf; t++)
+        MB2_REQUIRE(same[t] < 0 || T.len[t] < 21000000u, -3,
+                    "align: a scaffold of 21 Mbp or more aligned to itself: the score of the trivial self-alignment does not fit 32 bits");
     DevBuf<int32_t> d_same(T.nscaf);
     MB2_CUDA(cudaMemcpyAsync(d_same.get(), same.data(), T.nscaf * sizeof(int32_t), cudaMemcpyHostToDevice, cx.stream));
     MB2_CUDA(cudaStreamSynchronize(cx.stream));

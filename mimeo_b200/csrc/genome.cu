@@ -15,7 +15,7 @@ __device__ __forceinline__ uint32_t code_byte(uint32_t base, uint32_t bad, uint3
 // one thread packs 32 bases -> one uint64 of 2-bit codes + one uint32 of N flags
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __restrict__ pk, uint32_t* __restrict__ nm,
-            uint32_t* __restrict__ sm, uint8_t* __restrict__ codes) {
+            uint32_t* __restrict__ sm, uint8_t* __restrict__ codes, int* __restrict__ any_soft) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwords) return;
     const uint4* src = reinterpret_cast<const uint4*>(ascii + (size_t)w * 32);
@@ -44,6 +44,7 @@ pack_kernel(const uint8_t* __restrict__ ascii, uint32_t nwords, uint64_t* __rest
     pk[w] = bits;
     nm[w] = nflag;
     sm[w] = nflag | lowflag;
+    if (lowflag & ~nflag) atomicOr(any_soft, 1);      // rare: only soft-masked assemblies take this
     uint32_t out[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -143,10 +144,16 @@ Genome* genome_from_ascii(const uint8_t* const* seqs, const uint64_t* lens, int 
         g->d_off.alloc(n); g->d_len.alloc(n);
         MB2_CUDA(cudaMemcpyAsync(g->d_off.get(), g->off.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
         MB2_CUDA(cudaMemcpyAsync(g->d_len.get(), g->len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, cx.stream));
-        launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get(), g->sm.get(), g->codes.get());
+        DevBuf<int> d_soft(1);
+        MB2_CUDA(cudaMemsetAsync(d_soft.get(), 0, sizeof(int), cx.stream));
+        launch(pack_kernel, cdiv(nwords, 256), 256, 0, d_ascii.get(), nwords, g->pk.get(), g->nm.get(), g->sm.get(), g->codes.get(), d_soft.get());
+        int h_soft = 0;
+        MB2_CUDA(cudaMemcpyAsync(&h_soft, d_soft.get(), sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
         g->d_nfree.alloc(n);
         launch(nfree_kernel, n, 256, 0, g->nm.get(), g->d_off.get(), g->d_len.get(), g->d_nfree.get());
         MB2_CUDA(cudaStreamSynchronize(cx.stream));      // the caller's buffers are free again after this
+        g->has_soft = h_soft != 0;
+        if (!g->has_soft) g->sm.release();               // identical to nm: view() hands kernels nm
         g->id = next_genome_id(); g->fwd_src_id = g->id; g->nfwd = n;
     } catch (...) { delete g; throw; }
     return g;
@@ -156,6 +163,7 @@ Genome* genome_revcomp(const Genome& src) {
     Genome* g = new Genome();
     try {
         g->nscaf = src.nscaf; g->off = src.off; g->len = src.len; g->G = src.G; g->nbases = src.nbases; g->is_rc = !src.is_rc;
+        g->has_soft = src.has_soft;
         const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
         g->pk.alloc(nwords); g->nm.alloc(nwords); g->sm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
         g->d_off.alloc(src.nscaf); g->d_len.alloc(src.nscaf);
@@ -214,6 +222,7 @@ Genome* genome_both_strands(const Genome& src) {
         std::vector<uint64_t> lens(2 * n);
         for (int s = 0; s < n; s++) lens[s] = lens[n + s] = src.len[s];
         layout(*g, lens.data(), 2 * n);
+        g->has_soft = src.has_soft;
         const uint32_t nwords = (uint32_t)(g->G / 32) + 2;
         g->pk.alloc(nwords); g->nm.alloc(nwords); g->sm.alloc(nwords); g->codes.alloc((size_t)nwords * 32);
         g->d_off.alloc(2 * n); g->d_len.alloc(2 * n); g->d_nfree.alloc(2 * n);

@@ -97,6 +97,48 @@ __device__ __forceinline__ void xdrop_window30(const uint32_t* __restrict__ tab,
     if (slow) D = d_keep;
 }
 
+// 128 columns of one sequence in registers, starting at the 64-column boundary at or below `first`: packed bases, non-ACGT
+// flags and (when the genome is soft-masked) the not-seedable flags; any 32-column window that starts in [c0, c0 + 96) is
+// cut out with selects and a funnel shift.
+struct SeqBlock {
+    uint64_t w[4];
+    uint32_t n[4], s[4];
+    uint32_t c0;
+    __device__ __forceinline__ uint64_t bases(uint32_t p) const {
+        const uint32_t off = p - c0, i = off >> 5, sh = (off & 31u) * 2u;
+        const uint64_t lo = i == 0 ? w[0] : (i == 1 ? w[1] : w[2]), hi = i == 0 ? w[1] : (i == 1 ? w[2] : w[3]);
+        return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+    }
+    __device__ __forceinline__ uint32_t flags(uint32_t p) const {
+        const uint32_t off = p - c0, i = off >> 5;
+        const uint32_t lo = i == 0 ? n[0] : (i == 1 ? n[1] : n[2]), hi = i == 0 ? n[1] : (i == 1 ? n[2] : n[3]);
+        return __funnelshift_r(lo, hi, off & 31u);
+    }
+    __device__ __forceinline__ uint32_t soft(uint32_t p) const {
+        const uint32_t off = p - c0, i = off >> 5;
+        const uint32_t lo = i == 0 ? s[0] : (i == 1 ? s[1] : s[2]), hi = i == 0 ? s[1] : (i == 1 ? s[2] : s[3]);
+        return __funnelshift_r(lo, hi, off & 31u);
+    }
+};
+__device__ __forceinline__ SeqBlock load_block(const uint64_t* __restrict__ pk, const uint32_t* __restrict__ nm, const uint32_t* __restrict__ sm,
+                                               uint32_t first) {
+    SeqBlock b;
+    b.c0 = first & ~63u;
+    const uint32_t w0 = b.c0 >> 5;                                 // even: 16-byte aligned in pk, 8-byte aligned in nm / sm
+    const uint4 a = *reinterpret_cast<const uint4*>(pk + w0), c = *reinterpret_cast<const uint4*>(pk + w0 + 2);
+    b.w[0] = (uint64_t)a.x | ((uint64_t)a.y << 32); b.w[1] = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    b.w[2] = (uint64_t)c.x | ((uint64_t)c.y << 32); b.w[3] = (uint64_t)c.z | ((uint64_t)c.w << 32);
+    const uint2 n0 = *reinterpret_cast<const uint2*>(nm + w0), n1 = *reinterpret_cast<const uint2*>(nm + w0 + 2);
+    b.n[0] = n0.x; b.n[1] = n0.y; b.n[2] = n1.x; b.n[3] = n1.y;
+    if (sm != nm) {                                                // uniform: a genome without lower case hands out nm for both
+        const uint2 s0 = *reinterpret_cast<const uint2*>(sm + w0), s1 = *reinterpret_cast<const uint2*>(sm + w0 + 2);
+        b.s[0] = s0.x; b.s[1] = s0.y; b.s[2] = s1.x; b.s[3] = s1.y;
+    } else {
+        b.s[0] = b.n[0]; b.s[1] = b.n[1]; b.s[2] = b.n[2]; b.s[3] = b.n[3];
+    }
+    return b;
+}
+
 // ---- load-balanced scan --------------------------------------------------------------------------------------
 // Every WARP works on its own: no CTA barrier after the table build. A warp takes 32 consecutive query positions per
 // round (lane = position). Phase A: the 13 bucket ranges of each position are looked up, the non-empty ones are
@@ -114,7 +156,7 @@ constexpr int SC_STEPS = (SC_NPROBE + SC_HALF - 1) / SC_HALF;   // steps per rou
 constexpr int SC_RING = 128;               // descriptors per warp: < 32 pending (every descriptor holds >= 1 hit) + 96 new
                                            // (a small ring keeps shared memory low, which leaves the SM more L1 for the gathers)
 
-__global__ void __launch_bounds__(SC_NT)
+__global__ void __launch_bounds__(SC_NT, 4)
 seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, const uint32_t* __restrict__ pos,
                  uint32_t q_lo, uint32_t q_n, int X, int K, int transition, uint32_t diag_bias,
                  uint64_t* __restrict__ surv, uint32_t surv_cap, unsigned long long* __restrict__ counters) {
@@ -200,17 +242,21 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
             hi = pos[rb[lo & (SC_RING - 1)] + (h - rc[lo & (SC_RING - 1)])];
             hj = rj[lo & (SC_RING - 1)];
         }
-        // everything the batch needs that does not depend on the x-drop outcome: leader windows, first right window,
-        // first left window (T side is a random gather; issue them back to back)
+        // Everything the batch needs that does not depend on the x-drop outcome: leader window (p - 1), first right window
+        // (p + 19) and first left window (p - 13). All three lie inside the 128 columns that start at the 64-column boundary
+        // below p - 13, so each sequence is fetched as ONE aligned block (32 bytes of packed bases, 16 of flags: four load
+        // instructions per sequence instead of twelve) and the windows are cut out of registers. The scan is bound by the L1
+        // wavefronts of its divergent gathers, not by issue slots or DRAM (ncu, profiles/r2_seed_scan_c4_ncu_summary.txt).
         uint64_t lt = 0, lq = 0, rt = 0, rq = 0, ft = 0, fq = 0;
         uint32_t ln = 1, rn = 0, fn = 0;
         if (live) {
-            lt = window32(T.pk, hi - 1); lq = window32(Q.pk, hj - 1);
-            ln = (nwindow32(Q.sm, hj - 1) | nwindow32(T.sm, hi - 1)) & SEED_WINDOW_MASK19;
-            rt = window32(T.pk, hi + SEED_SPAN); rq = window32(Q.pk, hj + SEED_SPAN);
-            rn = (nwindow32(T.nm, hi + SEED_SPAN) | nwindow32(Q.nm, hj + SEED_SPAN)) & S1_WINDOW_MASK;
-            ft = window32(T.pk, hi + SEED_SPAN - 32); fq = window32(Q.pk, hj + SEED_SPAN - 32);
-            fn = __brev(nwindow32(T.nm, hi + SEED_SPAN - 32) | nwindow32(Q.nm, hj + SEED_SPAN - 32)) & S1_WINDOW_MASK;
+            const SeqBlock bt = load_block(T.pk, T.nm, T.sm, hi - 13), bq = load_block(Q.pk, Q.nm, Q.sm, hj - 13);
+            lt = bt.bases(hi - 1); lq = bq.bases(hj - 1);
+            ln = (bq.soft(hj - 1) | bt.soft(hi - 1)) & SEED_WINDOW_MASK19;
+            rt = bt.bases(hi + SEED_SPAN); rq = bq.bases(hj + SEED_SPAN);
+            rn = (bt.flags(hi + SEED_SPAN) | bq.flags(hj + SEED_SPAN)) & S1_WINDOW_MASK;
+            ft = bt.bases(hi + SEED_SPAN - 32); fq = bq.bases(hj + SEED_SPAN - 32);
+            fn = __brev(bt.flags(hi + SEED_SPAN - 32) | bq.flags(hj + SEED_SPAN - 32)) & S1_WINDOW_MASK;
             // spec D1: only run leaders are candidates
             if (ln == 0 && seed_match(lt, lq, transition != 0)) live = false; else n_lead++;
         }

@@ -27,6 +27,7 @@ struct Genome {
     DevBuf<uint64_t> pk;              // G/32 + 2 words
     DevBuf<uint32_t> nm;              // G/32 + 2 words
     DevBuf<uint32_t> sm;              // G/32 + 2 words: 1 = not seedable (non-ACGT, pad, or soft-masked = lower case in the input)
+    bool has_soft = false;            // false: no lower-case base anywhere, sm == nm bit for bit and kernels are handed nm (one plane to gather from)
     DevBuf<uint8_t> codes;            // 1 byte/base for the gapped DP: base | parity << 2, 8 = other, 12 = pad (genome.cu:code_byte)
     DevBuf<uint32_t> d_off, d_len;
     DevBuf<uint32_t> d_nfree;         // per scaffold: 1 = every base is A/C/G/T
@@ -49,7 +50,7 @@ struct GenomeView {   // what kernels receive
     int nscaf;
     uint32_t G;
 };
-inline GenomeView view(const Genome& g) { return GenomeView{g.pk.get(), g.nm.get(), g.sm.get(), g.codes.get(), g.d_off.get(), g.d_len.get(), g.d_nfree.get(), g.nscaf, (uint32_t)g.G}; }
+inline GenomeView view(const Genome& g) { return GenomeView{g.pk.get(), g.nm.get(), g.has_soft ? g.sm.get() : g.nm.get(), g.codes.get(), g.d_off.get(), g.d_len.get(), g.d_nfree.get(), g.nscaf, (uint32_t)g.G}; }
 
 // HOXD70 as LASTZ's default, row = target base, col = query base (index t*4+q)
 static __constant__ int c_sub[16] = {91, -114, -31, -123, -114, 100, -125, -31, -31, -125, 100, -114, -123, -31, -114, 91};

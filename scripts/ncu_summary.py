@@ -8,6 +8,7 @@ row = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[0]
+units = dict(zip(hdr, rows[1]))
 d = dict(zip(hdr, rows[2 + row]))
 keys = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'sm__cycles_active.avg', 'sm__cycles_elapsed.max',
@@ -20,7 +21,7 @@ print(title)
 print('kernel:', d.get('Kernel Name', '')[:150])
 for k in keys:
     if k in d:
-        print('  %-75s %s' % (k, d[k]))
+        print('  %-75s %s %s' % (k, d[k], units.get(k, '')))
 for k in d:
     if 'stalled' in k and 'per_issue_active.ratio' in k and float(d[k] or 0) > 0.1:
         print('  stall %-69s %s' % (k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''), d[k]))

@@ -36,10 +36,10 @@ def test_pack_and_revcomp_roundtrip(G):
     dev = G.Genome.from_dict(g)
     rc = dev.revcomp()
     for i, (n, s) in enumerate(g.items()):
-        want = lo.encode(s)
+        want = lo.encode(s) & 7                  # decode reports bases; the soft-mask bit of the oracle's codes is not a base
         assert (dev.decode(i) == want).all()
         assert (rc.decode(i) == lo.revcomp_codes(want)).all()
-    assert (rc.revcomp().decode(3) == lo.encode(g['odd'])).all()
+    assert (rc.revcomp().decode(3) == (lo.encode(g['odd']) & 7)).all()
 
 
 @pytest.mark.parametrize('seed,strand', [(11, '+'), (12, '-'), (13, '+')])
