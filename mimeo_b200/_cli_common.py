@@ -13,8 +13,3 @@ def add_loglevel(parser):
     parser.add_argument('--loglevel', type=str, default='INFO', choices=['DEBUG', 'INFO', 'WARNING', 'ERROR', 'CRITICAL'],
                         help='Set the logging level.')
 
-
-def warn_missing(tools):
-    """The reference only warns when lastz/bedtools are missing (run_self.py:191-201). Here both are replaced by the
-    GPU library, so the paths are accepted for compatibility and nothing is checked."""
-    return []

@@ -140,9 +140,9 @@ def test_query_chunking_is_invisible(M, monkeypatch):
         assert s1[k] == s2[k], k
 
 
-def test_long_alignment_takes_the_exact_wide_payload_path(M):
-    """One alignment of > 65536 columns (a scaffold with a single N against itself: no closed form) must leave the
-    16+16-bit payload kernel, be redone with 32+32-bit payloads and still equal the oracle bit for bit."""
+def test_very_long_alignment_many_frame_moves_and_trace_chunks(M):
+    """One alignment of ~150 000 columns (a scaffold with a single N against itself: no closed form): 300 000 anti-diagonals,
+    hundreds of frame moves of the 16-bit scores and ~2 000 trace chunks walked back, equal to the oracle bit for bit."""
     A, G = M
     rng = np.random.default_rng(48)
     n = 150_000

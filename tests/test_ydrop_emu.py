@@ -125,3 +125,47 @@ def test_ydrop_kernel_source_long_gaps_and_frame_moves():
     # long alignment (several frame moves, layout changes 16 -> 24 -> 32) with gaps up to 120 bases
     t, q = make_case(rng, [200, 200, 200, 200], 5000, 0.05, 0.004, maxgap=120)
     check(l, t, q, 200 + 2500, min(len(q) - 1, 200 + 2500), p)
+
+
+ASAN_CHILD = r'''
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+from tests import test_ydrop_emu as T
+from oracle import lastz_oracle as lo
+T.SO = %(so)r
+l = T.emu_lib()
+p = lo.default_params(3000)
+for seed in range(8):
+    rng = np.random.default_rng(900 + seed)
+    core = int(rng.integers(50, 2500)); flank = [int(rng.integers(0, 900)) for _ in range(4)]
+    t, q = T.make_case(rng, flank, core, float(rng.uniform(0, 0.25)), float(rng.uniform(0, 0.03)), int(rng.choice([1, 3, 30, 150])), n_frac=float(rng.choice([0, 0.01])))
+    a1 = min(len(t) - 1, flank[0] + core // 2); a2 = min(len(q) - 1, flank[2] + core // 2)
+    tk, qk = T.kernel_codes(t), T.kernel_codes(q)
+    for d in (1, -1):
+        want, _ = T.oracle_ext(t, a1, q, a2, d, p)
+        got = T.emu_ext(l, tk, a1, qk, a2, d, p, 64 if seed %% 2 else 32, 2048, T.ALL_LAYOUTS, priv=int(rng.integers(0, 9)))
+        if got[5] == 2:
+            got = T.emu_ext(l, tk, a1, qk, a2, d, p, 64, 2048)
+        assert got[:5] == want and got[5] == 0, (seed, d, want, got)
+print('ASAN-SWEEP-OK')
+'''
+
+
+def test_ydrop_kernel_source_under_address_sanitizer():
+    """Memory safety of the kernel source (trace pool chunks, re-layout scratch, sequence windows): the same sweep with the
+    emulator built -fsanitize=address. The GPU pool has no compute-sanitizer; this is the bounds check the source gets."""
+    import sys
+    asan = subprocess.run(['g++', '-print-file-name=libasan.so'], capture_output=True, text=True).stdout.strip()
+    if not asan or not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip('libasan not installed')
+    so = os.path.join(HERE, 'emu', '_build', 'libydrop_emu_asan.so')
+    srcs = [os.path.join(HERE, 'emu', 'ydrop_emu.cpp'), os.path.join(HERE, 'emu', 'ydrop_emu.h'),
+            os.path.join(ROOT, 'mimeo_b200', 'csrc', 'ydrop_warp.cuh')]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(['g++', '-O1', '-g', '-fsanitize=address', '-fno-omit-frame-pointer', '-std=c++17', '-shared', '-fPIC',
+                               '-I', os.path.join(HERE, 'emu'), '-o', so, srcs[0]])
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS='detect_leaks=0:abort_on_error=0')
+    r = subprocess.run([sys.executable, '-c', ASAN_CHILD % dict(root=ROOT, so=so)], env=env, capture_output=True, text=True, timeout=900)
+    assert 'ERROR: AddressSanitizer' not in r.stderr, r.stderr[-3000:]
+    assert r.returncode == 0 and 'ASAN-SWEEP-OK' in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
