@@ -60,17 +60,37 @@ void build_seed_table(const Genome& T, uint32_t p_lo, uint32_t p_hi, SeedTable& 
     tab.p_lo = p_lo; tab.p_hi = p_hi;
 }
 
-// A finished lane of the first-stage x-drop parks at D = S1_DONE, where every later chunk is a no-op on best
-// (state (best, D) and table layout: xdrop_table.cuh).
+// First-stage table: the three-column entry of xdrop_table.cuh with the x-drop baked in and no argmax field, so that a chunk
+// costs no constant arithmetic:  bits 22..31 = s0+s1+s2 (signed), bits 13..21 = 125 + max prefix sum,
+// bits 0..12 = 125 + X + min prefix sum.  State of a lane: (best, D) with D = (best - run) + 125 >= 125; a chunk is
+//   terminate iff min_field < D;   DM = max(D, max_field);   best += DM - D;   D = DM - sum
+// (the rule of xdrop_table.cuh with D shifted by X - 250). A finished lane parks at D = S1_DONE, where every later chunk is
+// a no-op on best.
 constexpr int S1_DONE = 1 << 24;
+constexpr int S1_D0 = 125;                     // run = best = 0
+constexpr int S1_MAX_XDROP = 8191 - 125 - 300; // min field fits 13 bits
+__device__ __forceinline__ uint32_t s1_entry(uint32_t idx, int X) {
+    const uint32_t q6 = idx >> 6, t6 = idx & 63;
+    int sum = 0, mx = INT_MIN, mn = INT_MAX;
+    for (int c = 0; c < 3; c++) {
+        sum += sub_lut((((t6 >> (2 * c)) & 3u) << 2) | ((q6 >> (2 * c)) & 3u));
+        mx = max(mx, sum); mn = min(mn, sum);
+    }
+    return ((uint32_t)sum << 22) | ((uint32_t)(mx + 125) << 13) | (uint32_t)(mn + X + 125);
+}
+// bits [s, s + 32) of the 64-bit word (hi:lo) for a compile-time s in (-32, 64); negative s shifts left
+__device__ __forceinline__ uint32_t s1_bits(uint32_t lo, uint32_t hi, int s) {
+    return s <= 0 ? lo << (-s) : (s < 32 ? __funnelshift_r(lo, hi, s) : hi >> (s - 32));
+}
 // 30 columns (first column in the low bits of wt / wq / an); updates (best, D) of the lane exactly as the
 // column-by-column rule would. Lanes whose window holds a non-ACGT column take the per-column path.
-__device__ __forceinline__ void xdrop_window30(const uint32_t* __restrict__ tab, uint64_t wt, uint64_t wq, uint32_t an, int X,
+// tab_sa = shared-space address of the table. nchunks counts the chunks a lane entered while still open.
+__device__ __forceinline__ void xdrop_window30(uint32_t tab_sa, uint64_t wt, uint64_t wq, uint32_t an, int X,
                                                int& best, int& D, uint32_t& nchunks) {
     int d_keep = 0;
     bool slow = false;
     if (D < S1_DONE / 2 && an) {
-        int run = best - (D - 375 + X);
+        int run = best - (D - 125);
         bool term = false;
         for (int c = 0; c < S1_WINDOW && !term; c++) {
             const int sc = (an & 1u) ? SCORE_N : sub_lut((uint32_t)((wt & 3) << 2 | (wq & 3)));
@@ -79,21 +99,26 @@ __device__ __forceinline__ void xdrop_window30(const uint32_t* __restrict__ tab,
             if (run > best) best = run; else if (run < best - X) term = true;
         }
         nchunks += S1_WINDOW / 3;
-        d_keep = term ? S1_DONE : (best - run) + 375 - X;
+        d_keep = term ? S1_DONE : (best - run) + 125;
         slow = true; D = S1_DONE;              // the window is consumed: the table loop below is a no-op for this lane
     }
     const uint32_t tl = (uint32_t)wt, th = (uint32_t)(wt >> 32), ql = (uint32_t)wq, qh = (uint32_t)(wq >> 32);
-    const int c2 = 250 - X;
+    uint32_t parked = 0;                       // sum of D at chunk entry: S1_DONE per parked chunk + (< 2^24 in total) for the open ones
+    int entered = S1_WINDOW / 3;
 #pragma unroll
     for (int k = 0; k < S1_WINDOW / 3; k++) {
-        if (k == 3 || k == 6 || k == 8) { if (__all_sync(0xffffffffu, D >= S1_DONE / 2)) break; }
-        const uint32_t e = tab[xt_index(tl, th, ql, qh, k)];
-        nchunks += D < S1_DONE / 2 ? 1u : 0u;
-        const bool term = xt_minf(e) < D;
-        const int dm = max(D, xt_maxf(e) + c2);
+        if (k == 3 || k == 6 || k == 8) { if (__all_sync(0xffffffffu, D >= S1_DONE / 2)) { entered = k; break; } }
+        // byte address = table + (q6 << 8 | t6 << 2)
+        const uint32_t addr = ((s1_bits(tl, th, 6 * k - 2) & 0xFCu) | (s1_bits(ql, qh, 6 * k - 8) & 0x3F00u)) + tab_sa;
+        uint32_t e;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(addr));
+        parked += (uint32_t)D;
+        const bool term = (int)(e & 0x1FFFu) < D;
+        const int dm = max(D, (int)((e >> 13) & 511u));
         best += dm - D;
-        D = term ? S1_DONE : dm - xt_sum(e);
+        D = term ? S1_DONE : dm - ((int)e >> 22);
     }
+    nchunks += (uint32_t)entered - (parked >> 24);
     if (slow) D = d_keep;
 }
 
@@ -156,7 +181,8 @@ constexpr int SC_STEPS = (SC_NPROBE + SC_HALF - 1) / SC_HALF;   // steps per rou
 constexpr int SC_RING = 128;               // descriptors per warp: < 32 pending (every descriptor holds >= 1 hit) + 96 new
                                            // (a small ring keeps shared memory low, which leaves the SM more L1 for the gathers)
 
-__global__ void __launch_bounds__(SC_NT, 4)
+template <int MINB>
+__global__ void __launch_bounds__(SC_NT, MINB)
 seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, const uint32_t* __restrict__ pos,
                  uint32_t q_lo, uint32_t q_n, int X, int K, int transition, uint32_t diag_bias,
                  uint64_t* __restrict__ surv, uint32_t surv_cap, unsigned long long* __restrict__ counters) {
@@ -164,7 +190,8 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
     __shared__ uint32_t r_cum[SC_WARPS][SC_RING], r_b0[SC_WARPS][SC_RING], r_j[SC_WARPS][SC_RING];
     __shared__ unsigned long long sh_stat[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < S1_TAB; e += SC_NT) s1tab[e] = xt_entry((uint32_t)e);
+    for (int e = tid; e < S1_TAB; e += SC_NT) s1tab[e] = s1_entry((uint32_t)e, X);
+    const uint32_t s1tab_sa = (uint32_t)__cvta_generic_to_shared(s1tab);
     if (tid < 3) sh_stat[tid] = 0;
     __syncthreads();
     uint32_t* __restrict__ rc = r_cum[warp];
@@ -245,8 +272,10 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
         // Everything the batch needs that does not depend on the x-drop outcome: leader window (p - 1), first right window
         // (p + 19) and first left window (p - 13). All three lie inside the 128 columns that start at the 64-column boundary
         // below p - 13, so each sequence is fetched as ONE aligned block (32 bytes of packed bases, 16 of flags: four load
-        // instructions per sequence instead of twelve) and the windows are cut out of registers. The scan is bound by the L1
-        // wavefronts of its divergent gathers, not by issue slots or DRAM (ncu, profiles/r2_seed_scan_c4_ncu_summary.txt).
+        // instructions per sequence instead of twelve) and the windows are cut out of registers. After the bank fix of the
+        // extension table (xdrop_table.cuh) the scan is bound by the integer ALU pipe (ncu on C4: alu pipe 74 % busy, L1 data
+        // pipe 65 %, DRAM 11 %; profiles/r2_seed_scan_c4_v2_ncu_summary.txt); taking the pos[] and target gathers of the next
+        // batch off the critical path (a pipelined variant, measured) changed nothing and was dropped.
         uint64_t lt = 0, lq = 0, rt = 0, rq = 0, ft = 0, fq = 0;
         uint32_t ln = 1, rn = 0, fn = 0;
         if (live) {
@@ -261,7 +290,7 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
             if (ln == 0 && seed_match(lt, lq, transition != 0)) live = false; else n_lead++;
         }
         // right of the seed: up to S1_RIGHT_WINDOWS windows of 30 columns; a warp stops as soon as all its lanes are done
-        const int d_start = live ? 375 - X : S1_DONE;      // run = best = 0
+        const int d_start = live ? S1_D0 : S1_DONE;
         int best_r = 0, dr = d_start;
         uint32_t nchunks = 0;
 #pragma unroll 1
@@ -273,7 +302,7 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
                 wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
                 an = (nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            xdrop_window30(s1tab, wt, wq, an, X, best_r, dr, nchunks);
+            xdrop_window30(s1tab_sa, wt, wq, an, X, best_r, dr, nchunks);
         }
         const bool open_r = dr < S1_DONE / 2;
         // left, from the last seed column downwards: windows are reversed so that the same forward-order table applies
@@ -287,7 +316,7 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
                 wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
                 an = __brev(nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            xdrop_window30(s1tab, rev2groups(wt), rev2groups(wq), an, X, best_l, dl, nchunks);
+            xdrop_window30(s1tab_sa, rev2groups(wt), rev2groups(wq), an, X, best_l, dl, nchunks);
         }
         const bool open_l = dl < S1_DONE / 2;
         n_cells += 3ull * nchunks;
@@ -581,6 +610,7 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
     const uint32_t n = q_hi - q_lo;
     if (n == 0) return;
     MB2_REQUIRE(p.xdrop >= XT_MIN_XDROP, -2, "x-drop below 251 is not supported by the three-column extension table");
+    MB2_REQUIRE(p.xdrop <= S1_MAX_XDROP, -2, "x-drop above 7766 is not supported by the first-stage extension table");
     ProfScope ps("seed_scan");
     // MB2_SCAN_V2=1 selects the experimental second-generation scan (measured slower: DESIGN.md, profiles/r2_seed_scan2_*)
     static const bool use_v2 = getenv("MB2_SCAN_V2") != nullptr;
@@ -597,17 +627,18 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
                p.hspthresh, p.transition, (uint32_t)Q.G, surv, surv_cap, counters);
         return;
     }
-    static int ctas_per_sm = 0;
-    if (!ctas_per_sm) {
-        if (getenv("MB2_SCAN_CARVEOUT"))
-            MB2_CUDA(cudaFuncSetAttribute(seed_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("MB2_SCAN_CARVEOUT"))));
-        MB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, seed_scan_kernel, SC_NT, 0));
-        if (getenv("MB2_SCAN_CTAS")) ctas_per_sm = atoi(getenv("MB2_SCAN_CTAS"));
-    }
-    // persistent: exactly one resident wave of CTAs; every warp strides over the 32-position rounds
-    const unsigned grid = std::min<unsigned>(cdiv(nrounds, SC_WARPS), (unsigned)ctx().sm_count * (unsigned)std::max(1, ctas_per_sm));
-    launch(seed_scan_kernel, grid, SC_NT, 0, view(T), view(Q), tab.off.get(), tab.pos.get(), q_lo, n, p.xdrop,
-           p.hspthresh, p.transition, (uint32_t)Q.G, surv, surv_cap, counters);
+    // resident CTAs per SM: 3 (79 registers, no spill; default) or 4 (64 registers, 28 bytes of spill = 104 GB of local-memory
+    // write-through per C4 launch); the kernel is bound by the integer ALU pipe, so the two are within 1 % (MB2_SCAN_MINB overrides)
+    static const int minb = getenv("MB2_SCAN_MINB") ? atoi(getenv("MB2_SCAN_MINB")) : 3;
+    auto go = [&](auto kern) {
+        int per_sm = 0;
+        MB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SC_NT, 0));
+        // persistent: exactly one resident wave of CTAs; every warp strides over the 32-position rounds
+        const unsigned grid = std::min<unsigned>(cdiv(nrounds, SC_WARPS), (unsigned)ctx().sm_count * (unsigned)std::max(1, per_sm));
+        launch(kern, grid, SC_NT, 0, view(T), view(Q), tab.off.get(), tab.pos.get(), q_lo, n, p.xdrop,
+               p.hspthresh, p.transition, (uint32_t)Q.G, surv, surv_cap, counters);
+    };
+    if (minb <= 3) go(seed_scan_kernel<3>); else go(seed_scan_kernel<4>);
 }
 
 }  // namespace mb2

@@ -1,7 +1,9 @@
 // xdrop_table.cuh -- exact gap-free x-drop at three columns per shared-memory table lookup (used by the first-stage
 // filter of seed.cu and the thread-per-diagonal HSP extension of hsp.cu).
 //
-// Entry for target bases t0 t1 t2 / query bases q0 q1 q2 (index = t6 << 6 | q6, first column in the low bits):
+// Entry for target bases t0 t1 t2 / query bases q0 q1 q2 (index = q6 << 6 | t6, first column in the low bits; the shared-memory
+// bank comes from the TARGET bases: the 32 hits of a seed-scan batch mostly share one query position, so with the query bits in
+// the bank they collided 7.75 ways per lookup (ncu, profiles/r2_seed_scan_c4_ncu_summary.txt)):
 //   bits 22..31 = s0+s1+s2 (signed), bits 18..19 = index (0..2) of the FIRST column that reaches the maximum prefix sum,
 //   bits 9..17 = 125 + max prefix sum, bits 0..8 = 375 + min prefix sum.
 // Exactness of the chunked rule: prefix sums inside a chunk differ by at most 2*125 < xdrop (callers require
@@ -28,7 +30,7 @@ __device__ __forceinline__ int sub_lut(uint32_t idx) {
 }
 
 __device__ __forceinline__ uint32_t xt_entry(uint32_t idx) {
-    const uint32_t t6 = idx >> 6, q6 = idx & 63;
+    const uint32_t q6 = idx >> 6, t6 = idx & 63;
     int sum = 0, mx = INT_MIN, mn = INT_MAX, at = 0;
     for (int c = 0; c < 3; c++) {
         sum += sub_lut((((t6 >> (2 * c)) & 3u) << 2) | ((q6 >> (2 * c)) & 3u));
@@ -54,7 +56,7 @@ __device__ __forceinline__ uint32_t xt_index(uint32_t tl, uint32_t th, uint32_t 
     if (sh + 6 <= 32) { t6 = (tl >> sh) & 63u; q6 = (ql >> sh) & 63u; }
     else if (sh >= 32) { t6 = (th >> (sh - 32)) & 63u; q6 = (qh >> (sh - 32)) & 63u; }
     else { t6 = __funnelshift_r(tl, th, sh) & 63u; q6 = __funnelshift_r(ql, qh, sh) & 63u; }
-    return (t6 << 6) | q6;
+    return (q6 << 6) | t6;
 }
 
 }  // namespace mb2

@@ -16,7 +16,10 @@ keys = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'smsp__issue_active
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum',
         'smsp__sass_inst_executed_op_local_ld.sum', 'smsp__sass_inst_executed_op_local_st.sum', 'launch__registers_per_thread',
-        'launch__grid_size', 'launch__block_size']
+        'launch__grid_size', 'launch__block_size',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_lgds.sum', 'smsp__sass_inst_executed_op_shared_ld.sum', 'smsp__sass_inst_executed_op_global_ld.sum',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'dram__throughput.avg.pct_of_peak_sustained_elapsed']
 print(title)
 print('kernel:', d.get('Kernel Name', '')[:150])
 for k in keys:
