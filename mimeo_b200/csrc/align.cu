@@ -47,6 +47,7 @@ static bool scan_chunk(const Genome& T, const Genome& Q, const SeedTable& tab, u
     for (int attempt = 0; attempt < 2; attempt++) {
         if (s0.n < cap) s0.alloc(cap);
         MB2_CUDA(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), cx.stream));
+        MB2_CUDA(cudaMemsetAsync(counters + CNT_WORK, 0, sizeof(unsigned long long), cx.stream));      // the scan's round dispenser
         seed_scan(T, Q, tab, q_lo, q_hi, p, s0.get(), (uint32_t)std::min<uint64_t>(cap, 0xffffffffull), counters);
         unsigned long long h[4];
         MB2_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, cx.stream));

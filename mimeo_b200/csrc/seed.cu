@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t s1_bits(uint32_t lo, uint32_t hi, int s) {
 // 30 columns (first column in the low bits of wt / wq / an); updates (best, D) of the lane exactly as the
 // column-by-column rule would. Lanes whose window holds a non-ACGT column take the per-column path.
 // tab_sa = shared-space address of the table. nchunks counts the chunks a lane entered while still open.
-__device__ __forceinline__ void xdrop_window30(uint32_t tab_sa, uint64_t wt, uint64_t wq, uint32_t an, int X,
+__device__ __forceinline__ void xdrop_window30(uint32_t tab_sa, uint32_t m10, uint32_t m9, uint64_t wt, uint64_t wq, uint32_t an, int X,
                                                int& best, int& D, uint32_t& nchunks) {
     int d_keep = 0;
     bool slow = false;
@@ -113,10 +113,13 @@ __device__ __forceinline__ void xdrop_window30(uint32_t tab_sa, uint64_t wt, uin
         uint32_t e;
         asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(addr));
         parked += (uint32_t)D;
+        // The max-prefix and sum fields are cut out with multiplies (fma pipe) instead of shifts and masks (alu pipe, the busier
+        // one): (e * 2^10) hi-multiplied by 2^9 = bits 13..21, e hi-multiplied by 2^10 = e >> 22 (signed). The multipliers arrive
+        // in registers so that they stay multiplies.
         const bool term = (int)(e & 0x1FFFu) < D;
-        const int dm = max(D, (int)((e >> 13) & 511u));
+        const int dm = max(D, (int)__umulhi(e * m10, m9));
         best += dm - D;
-        D = term ? S1_DONE : dm - ((int)e >> 22);
+        D = term ? S1_DONE : dm - __mulhi((int)e, (int)m10);
     }
     nchunks += (uint32_t)entered - (parked >> 24);
     if (slow) D = d_keep;
@@ -192,6 +195,7 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int e = tid; e < S1_TAB; e += SC_NT) s1tab[e] = s1_entry((uint32_t)e, X);
     const uint32_t s1tab_sa = (uint32_t)__cvta_generic_to_shared(s1tab);
+    const uint32_t s1_m10 = q_n ? 1024u : 0u, s1_m9 = q_n ? 512u : 0u;     // 2^10, 2^9 (q_n > 0 always; see xdrop_window30)
     if (tid < 3) sh_stat[tid] = 0;
     __syncthreads();
     uint32_t* __restrict__ rc = r_cum[warp];
@@ -199,20 +203,28 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
     uint32_t* __restrict__ rj = r_j[warp];
     const int nprobe = transition ? SC_NPROBE : 1;
     const uint32_t nrounds = (q_n + 31) / 32;
-    const uint32_t nwarps = gridDim.x * SC_WARPS, gw = blockIdx.x * SC_WARPS + warp;
-    // a warp's step = (round, part): SC_HALF probes of the round's 32 positions at a time
-    const uint32_t my_rounds = gw < nrounds ? (nrounds - gw + nwarps - 1) / nwarps : 0;
-    const uint32_t nsteps = my_rounds * SC_STEPS;
-    uint32_t step = 0;
+    // Rounds are handed out dynamically (counters[CNT_WORK], zeroed by the caller): hits per round vary by orders of magnitude
+    // between unique sequence and repeat families, and with a static stride the resident warps ran dry one after another
+    // (ncu: 40 % warps active of a theoretical 50 %; C4 scan 480 -> 407 ms). A warp's step = (round, part): SC_HALF probes of
+    // the round's 32 positions at a time.
+    uint32_t round = 0;
+    int part = SC_STEPS;                    // SC_STEPS: the current round is used up
+    bool exhausted = false;
     uint32_t head = 0, tail = 0;            // ring positions (monotone, used modulo SC_RING)
     uint32_t cum_tail = 0, consumed = 0;    // hits appended / processed so far (wrapping arithmetic)
     unsigned long long n_lead = 0, n_cells = 0, n_hits = 0;
     for (;;) {
         // ---------------- phase A: append half rounds until a full batch is pending
-        while (cum_tail - consumed < 32u && step < nsteps) {
-            const uint32_t round = gw + (step / SC_STEPS) * nwarps;
-            const int p0 = (int)(step % SC_STEPS) * SC_HALF, p1 = min(SC_NPROBE, p0 + SC_HALF);
-            step++;
+        while (cum_tail - consumed < 32u && !exhausted) {
+            if (part == SC_STEPS) {
+                unsigned long long r = 0;
+                if (lane == 0) r = atomicAdd(&counters[CNT_WORK], 1ull);
+                r = __shfl_sync(0xffffffffu, r, 0);
+                if (r >= nrounds) { exhausted = true; break; }
+                round = (uint32_t)r; part = 0;
+            }
+            const int p0 = part * SC_HALF, p1 = min(SC_NPROBE, p0 + SC_HALF);
+            part++;
             const uint32_t jrel = round * 32 + lane;
             const uint32_t j = q_lo + jrel;
             const bool jvalid = jrel < q_n && (nwindow32(Q.sm, j) & SEED_WINDOW_MASK19) == 0;
@@ -228,6 +240,8 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
                     const uint32_t kk = pr == 0 ? key : key ^ (2u << (2 * (pr - 1)));
                     b = off[kk];
                     c = off[kk + 1] - b;
+                    // the bucket's positions are gathered a few batches from now: start their trip from DRAM to L2 already
+                    if (c) asm volatile("prefetch.global.L2 [%0];" :: "l"(pos + b));
                 }
                 b0[q] = b; cnt[q] = c;
                 mine += c; nne += c ? 1u : 0u;
@@ -302,7 +316,7 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
                 wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
                 an = (nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            xdrop_window30(s1tab_sa, wt, wq, an, X, best_r, dr, nchunks);
+            xdrop_window30(s1tab_sa, s1_m10, s1_m9, wt, wq, an, X, best_r, dr, nchunks);
         }
         const bool open_r = dr < S1_DONE / 2;
         // left, from the last seed column downwards: windows are reversed so that the same forward-order table applies
@@ -316,7 +330,7 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
                 wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
                 an = __brev(nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            xdrop_window30(s1tab_sa, rev2groups(wt), rev2groups(wq), an, X, best_l, dl, nchunks);
+            xdrop_window30(s1tab_sa, s1_m10, s1_m9, rev2groups(wt), rev2groups(wq), an, X, best_l, dl, nchunks);
         }
         const bool open_l = dl < S1_DONE / 2;
         n_cells += 3ull * nchunks;
@@ -627,9 +641,9 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
                p.hspthresh, p.transition, (uint32_t)Q.G, surv, surv_cap, counters);
         return;
     }
-    // resident CTAs per SM: 3 (79 registers, no spill; default) or 4 (64 registers, 28 bytes of spill = 104 GB of local-memory
-    // write-through per C4 launch); the kernel is bound by the integer ALU pipe, so the two are within 1 % (MB2_SCAN_MINB overrides)
-    static const int minb = getenv("MB2_SCAN_MINB") ? atoi(getenv("MB2_SCAN_MINB")) : 3;
+    // resident CTAs per SM: 4 (61 registers, no spill; default) or 3; the scan hides its gather latencies with resident warps,
+    // C4: 407 ms with 4, 429 ms with 3 (MB2_SCAN_MINB overrides)
+    static const int minb = getenv("MB2_SCAN_MINB") ? atoi(getenv("MB2_SCAN_MINB")) : 4;
     auto go = [&](auto kern) {
         int per_sm = 0;
         MB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SC_NT, 0));
