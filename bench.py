@@ -57,6 +57,15 @@ def ncu_traffic(workload, kernel):
         return None, None
 
 
+def ncu_pipes(workload, kernel):
+    """Pipe utilisation of `kernel` on this workload from the committed ncu capture (profiles/roofline_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
+            return json.load(f)[workload][kernel].get('pipes')
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
@@ -580,12 +589,14 @@ def run_b200(args):
     if int_tags:
         roofline['int_kernel'] = int_roofline(max(int_tags, key=lambda t: prof[t][0]))
     if dom == 'seed_scan' and cells.get('seed_scan'):
-        # the scan's lookups are HBM-shaped but its time goes to the fused first-stage x-drop (ncu: issue-bound, DRAM < 10 % busy):
+        # the scan's lookups are HBM-shaped but its time goes to the fused first-stage x-drop (ncu: ALU pipe, issue slots and L1 data pipe each ~74 % busy, DRAM 13 %):
         # the same launch against the integer roofline, 6 lane-ops per scored column
         ms = prof['seed_scan'][0] / args.steps
         g = cells['seed_scan'] / (ms / 1e3) / 1e9
         roofline['same_kernel_vs_int_roofline'] = {'gcups': g, 'cells_per_step': cells['seed_scan'], 'frac': g * 1e9 * budget['seed_scan'] / int_peak,
                                                    'ops_per_cell': budget['seed_scan'], 'peak_lane_ops_per_s': int_peak}
+        if ncu_pipes(args.workload, 'seed_scan'):
+            roofline['same_kernel_vs_int_roofline']['ncu_pipe_utilisation'] = ncu_pipes(args.workload, 'seed_scan')
     roofline['kernels_ms_per_step'] = {t: prof[t][0] / args.steps for t in all_tags if prof[t][1]}
     roofline['note'] = ('the kernel with the largest share of the step; `hbm_kernels` lists the HBM-bound launch groups against the measured copy '
                         'peak, `gcups` the integer-pipe kernels (x-drop, y-drop) against the INT32 issue roofline at the SURVEY op budgets')

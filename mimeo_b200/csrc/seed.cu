@@ -240,8 +240,6 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
                     const uint32_t kk = pr == 0 ? key : key ^ (2u << (2 * (pr - 1)));
                     b = off[kk];
                     c = off[kk + 1] - b;
-                    // the bucket's positions are gathered a few batches from now: start their trip from DRAM to L2 already
-                    if (c) asm volatile("prefetch.global.L2 [%0];" :: "l"(pos + b));
                 }
                 b0[q] = b; cnt[q] = c;
                 mine += c; nne += c ? 1u : 0u;
