@@ -126,26 +126,34 @@ __device__ __forceinline__ void xdrop_window30(uint32_t tab_sa, uint32_t m10, ui
 }
 
 // 128 columns of one sequence in registers, starting at the 64-column boundary at or below `first`: packed bases, non-ACGT
-// flags and (when the genome is soft-masked) the not-seedable flags; any 32-column window that starts in [c0, c0 + 96) is
-// cut out with selects and a funnel shift.
+// flags and (when the genome is soft-masked) the not-seedable flags.
 struct SeqBlock {
     uint64_t w[4];
     uint32_t n[4], s[4];
     uint32_t c0;
-    __device__ __forceinline__ uint64_t bases(uint32_t p) const {
-        const uint32_t off = p - c0, i = off >> 5, sh = (off & 31u) * 2u;
-        const uint64_t lo = i == 0 ? w[0] : (i == 1 ? w[1] : w[2]), hi = i == 0 ? w[1] : (i == 1 ? w[2] : w[3]);
-        return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
-    }
-    __device__ __forceinline__ uint32_t flags(uint32_t p) const {
-        const uint32_t off = p - c0, i = off >> 5;
-        const uint32_t lo = i == 0 ? n[0] : (i == 1 ? n[1] : n[2]), hi = i == 0 ? n[1] : (i == 1 ? n[2] : n[3]);
-        return __funnelshift_r(lo, hi, off & 31u);
-    }
-    __device__ __forceinline__ uint32_t soft(uint32_t p) const {
-        const uint32_t off = p - c0, i = off >> 5;
-        const uint32_t lo = i == 0 ? s[0] : (i == 1 ? s[1] : s[2]), hi = i == 0 ? s[1] : (i == 1 ? s[2] : s[3]);
-        return __funnelshift_r(lo, hi, off & 31u);
+    // The three windows a batch needs, cut out together: f = 32 columns from p (p = hit - 13: the first left window),
+    // l = from p + 12 (the leader window, hit - 1), r = from p + 32 (the first right window, hit + 19); non-ACGT flags of f
+    // and r, not-seedable flags of l. p lies in [c0, c0 + 64). The eight 32-bit words of the block are shifted by whole
+    // words with two levels of selects (shared between the outputs), then by bits with funnel shifts.
+    __device__ __forceinline__ void windows(uint32_t p, uint64_t& f, uint64_t& l, uint64_t& r, uint32_t& fn, uint32_t& rn, uint32_t& ls) const {
+        const uint32_t off = p - c0, sh = (off & 15u) * 2u;
+        const bool b0 = off & 16u, b1 = off & 32u;
+        uint32_t x[8], a[7], y[5];
+#pragma unroll
+        for (int m = 0; m < 4; m++) { x[2 * m] = (uint32_t)w[m]; x[2 * m + 1] = (uint32_t)(w[m] >> 32); }
+#pragma unroll
+        for (int m = 0; m < 7; m++) a[m] = b0 ? x[m + 1] : x[m];
+#pragma unroll
+        for (int m = 0; m < 5; m++) y[m] = b1 ? a[m + 2] : a[m];
+        const uint32_t f0 = __funnelshift_r(y[0], y[1], sh), f1 = __funnelshift_r(y[1], y[2], sh);
+        const uint32_t r0 = __funnelshift_r(y[2], y[3], sh), r1 = __funnelshift_r(y[3], y[4], sh);
+        f = (uint64_t)f0 | ((uint64_t)f1 << 32); r = (uint64_t)r0 | ((uint64_t)r1 << 32);
+        l = (uint64_t)__funnelshift_r(f0, f1, 24) | ((uint64_t)__funnelshift_r(f1, r0, 24) << 32);
+        const uint32_t sn = off & 31u;
+        const uint32_t n0 = b1 ? n[1] : n[0], n1 = b1 ? n[2] : n[1], n2 = b1 ? n[3] : n[2];
+        fn = __funnelshift_r(n0, n1, sn); rn = __funnelshift_r(n1, n2, sn);
+        const uint32_t s0 = b1 ? s[1] : s[0], s1 = b1 ? s[2] : s[1], s2 = b1 ? s[3] : s[2];
+        ls = __funnelshift_r(__funnelshift_r(s0, s1, sn), __funnelshift_r(s1, s2, sn), 12);
     }
 };
 __device__ __forceinline__ SeqBlock load_block(const uint64_t* __restrict__ pk, const uint32_t* __restrict__ nm, const uint32_t* __restrict__ sm,
@@ -271,15 +279,22 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
         bool live = (uint32_t)lane < nb;
         const uint32_t h = consumed + (uint32_t)lane;
         uint32_t hi = 0, hj = 0, e_last = head;
-        if (live) {
-            uint32_t lo = head, hi_d = tail;                        // last descriptor with cum <= h (wrapping compare)
-            while (hi_d - lo > 1) {
-                const uint32_t mid = lo + ((hi_d - lo) >> 1);
-                if ((int32_t)(h - rc[mid & (SC_RING - 1)]) >= 0) lo = mid; else hi_d = mid;
+        {
+            // Descriptor of every hit of the batch without a search: rc[head] <= consumed < rc[head + 1] (invariant of `head`) and
+            // every descriptor holds at least one hit, so the batch lies inside descriptors head .. head + 31. Lane i looks at
+            // descriptor head + i; the ones that START inside the batch (at offset 1..31) set a bit at their offset; the
+            // descriptor of the hit at offset l is head + (bits at or below l).
+            const uint32_t di = head + (uint32_t)lane;
+            const bool dv = (int32_t)(tail - di) > 0;
+            const uint32_t ci = dv ? rc[di & (SC_RING - 1)] : 0u;
+            const uint32_t first = ci - consumed;                   // wrapping; >= 1 for lane > 0
+            const uint32_t starts = __reduce_or_sync(0xffffffffu, (dv && lane > 0 && first < 32u) ? (1u << first) : 0u);
+            if (live) {
+                const uint32_t lo = head + (uint32_t)__popc(starts & ((2u << lane) - 1u));
+                e_last = lo;
+                hi = pos[rb[lo & (SC_RING - 1)] + (h - rc[lo & (SC_RING - 1)])];
+                hj = rj[lo & (SC_RING - 1)];
             }
-            e_last = lo;
-            hi = pos[rb[lo & (SC_RING - 1)] + (h - rc[lo & (SC_RING - 1)])];
-            hj = rj[lo & (SC_RING - 1)];
         }
         // Everything the batch needs that does not depend on the x-drop outcome: leader window (p - 1), first right window
         // (p + 19) and first left window (p - 13). All three lie inside the 128 columns that start at the 64-column boundary
@@ -292,12 +307,12 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
         uint32_t ln = 1, rn = 0, fn = 0;
         if (live) {
             const SeqBlock bt = load_block(T.pk, T.nm, T.sm, hi - 13), bq = load_block(Q.pk, Q.nm, Q.sm, hj - 13);
-            lt = bt.bases(hi - 1); lq = bq.bases(hj - 1);
-            ln = (bq.soft(hj - 1) | bt.soft(hi - 1)) & SEED_WINDOW_MASK19;
-            rt = bt.bases(hi + SEED_SPAN); rq = bq.bases(hj + SEED_SPAN);
-            rn = (bt.flags(hi + SEED_SPAN) | bq.flags(hj + SEED_SPAN)) & S1_WINDOW_MASK;
-            ft = bt.bases(hi + SEED_SPAN - 32); fq = bq.bases(hj + SEED_SPAN - 32);
-            fn = __brev(bt.flags(hi + SEED_SPAN - 32) | bq.flags(hj + SEED_SPAN - 32)) & S1_WINDOW_MASK;
+            uint32_t tfn, trn, tls, qfn, qrn, qls;
+            bt.windows(hi - 13, ft, lt, rt, tfn, trn, tls);
+            bq.windows(hj - 13, fq, lq, rq, qfn, qrn, qls);
+            ln = (tls | qls) & SEED_WINDOW_MASK19;
+            rn = (trn | qrn) & S1_WINDOW_MASK;
+            fn = __brev(tfn | qfn) & S1_WINDOW_MASK;
             // spec D1: only run leaders are candidates
             if (ln == 0 && seed_match(lt, lq, transition != 0)) live = false; else n_lead++;
         }
@@ -639,8 +654,8 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
                p.hspthresh, p.transition, (uint32_t)Q.G, surv, surv_cap, counters);
         return;
     }
-    // resident CTAs per SM: 4 (61 registers, no spill; default) or 3; the scan hides its gather latencies with resident warps,
-    // C4: 407 ms with 4, 429 ms with 3 (MB2_SCAN_MINB overrides)
+    // resident CTAs per SM: 4 (56 registers, no spill; default) or 3; the scan hides its gather latencies with resident warps
+    // (C4: 5 % slower with 3; 5 CTAs at 48 registers: no faster). MB2_SCAN_MINB overrides.
     static const int minb = getenv("MB2_SCAN_MINB") ? atoi(getenv("MB2_SCAN_MINB")) : 4;
     auto go = [&](auto kern) {
         int per_sm = 0;
