@@ -589,7 +589,7 @@ def run_b200(args):
     if int_tags:
         roofline['int_kernel'] = int_roofline(max(int_tags, key=lambda t: prof[t][0]))
     if dom == 'seed_scan' and cells.get('seed_scan'):
-        # the scan's lookups are HBM-shaped but its time goes to the fused first-stage x-drop (ncu: ALU pipe, issue slots and L1 data pipe each ~74 % busy, DRAM 13 %):
+        # the scan's lookups are HBM-shaped but its time goes to the fused first-stage x-drop (ncu: ALU pipe and L1 data pipe ~75 % busy, DRAM 11 %):
         # the same launch against the integer roofline, 6 lane-ops per scored column
         ms = prof['seed_scan'][0] / args.steps
         g = cells['seed_scan'] / (ms / 1e3) / 1e9
