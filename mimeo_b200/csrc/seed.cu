@@ -85,6 +85,7 @@ __device__ __forceinline__ uint32_t s1_bits(uint32_t lo, uint32_t hi, int s) {
 // 30 columns (first column in the low bits of wt / wq / an); updates (best, D) of the lane exactly as the
 // column-by-column rule would. Lanes whose window holds a non-ACGT column take the per-column path.
 // tab_sa = shared-space address of the table. nchunks counts the chunks a lane entered while still open.
+template <uint32_t VOTES>
 __device__ __forceinline__ void xdrop_window30(uint32_t tab_sa, uint32_t m10, uint32_t m9, uint64_t wt, uint64_t wq, uint32_t an, int X,
                                                int& best, int& D, uint32_t& nchunks) {
     int d_keep = 0;
@@ -107,7 +108,7 @@ __device__ __forceinline__ void xdrop_window30(uint32_t tab_sa, uint32_t m10, ui
     int entered = S1_WINDOW / 3;
 #pragma unroll
     for (int k = 0; k < S1_WINDOW / 3; k++) {
-        if (k == 3 || k == 6 || k == 8) { if (__all_sync(0xffffffffu, D >= S1_DONE / 2)) { entered = k; break; } }
+        if ((VOTES >> k) & 1u) { if (__all_sync(0xffffffffu, D >= S1_DONE / 2)) { entered = k; break; } }
         // byte address = table + (q6 << 8 | t6 << 2)
         const uint32_t addr = ((s1_bits(tl, th, 6 * k - 2) & 0xFCu) | (s1_bits(ql, qh, 6 * k - 8) & 0x3F00u)) + tab_sa;
         uint32_t e;
@@ -192,7 +193,7 @@ constexpr int SC_STEPS = (SC_NPROBE + SC_HALF - 1) / SC_HALF;   // steps per rou
 constexpr int SC_RING = 128;               // descriptors per warp: < 32 pending (every descriptor holds >= 1 hit) + 96 new
                                            // (a small ring keeps shared memory low, which leaves the SM more L1 for the gathers)
 
-template <int MINB>
+template <int MINB, uint32_t TAILVOTES>
 __global__ void __launch_bounds__(SC_NT, MINB)
 seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, const uint32_t* __restrict__ pos,
                  uint32_t q_lo, uint32_t q_n, int X, int K, int transition, uint32_t diag_bias,
@@ -316,34 +317,38 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
             // spec D1: only run leaders are candidates
             if (ln == 0 && seed_match(lt, lq, transition != 0)) live = false; else n_lead++;
         }
-        // right of the seed: up to S1_RIGHT_WINDOWS windows of 30 columns; a warp stops as soon as all its lanes are done
+        // Right of the seed: up to S1_RIGHT_WINDOWS windows of 30 columns. Left, from the last seed column downwards: up to
+        // S1_LEFT_WINDOWS windows, reversed so that the same forward-order table applies. The first window of either side comes
+        // out of the blocks above and runs without polling (some lane of 32 is practically always still open at its end; on the
+        // left its first 19 columns are the seed itself); in the later windows a warp leaves as soon as all its lanes are done.
         const int d_start = live ? S1_D0 : S1_DONE;
         int best_r = 0, dr = d_start;
         uint32_t nchunks = 0;
+        xdrop_window30<0u>(s1tab_sa, s1_m10, s1_m9, rt, rq, rn, X, best_r, dr, nchunks);
 #pragma unroll 1
-        for (int b = 0; b < S1_RIGHT_WINDOWS; b++) {
+        for (int b = 1; b < S1_RIGHT_WINDOWS; b++) {
             if (__all_sync(0xffffffffu, dr >= S1_DONE / 2)) break;
-            uint64_t wt = rt, wq = rq; uint32_t an = rn;
-            if (b > 0 && dr < S1_DONE / 2) {
+            uint64_t wt = 0, wq = 0; uint32_t an = 0;
+            if (dr < S1_DONE / 2) {
                 const uint32_t ct = hi + SEED_SPAN + S1_WINDOW * b, cq = hj + SEED_SPAN + S1_WINDOW * b;
                 wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
                 an = (nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            xdrop_window30(s1tab_sa, s1_m10, s1_m9, wt, wq, an, X, best_r, dr, nchunks);
+            xdrop_window30<TAILVOTES>(s1tab_sa, s1_m10, s1_m9, wt, wq, an, X, best_r, dr, nchunks);
         }
         const bool open_r = dr < S1_DONE / 2;
-        // left, from the last seed column downwards: windows are reversed so that the same forward-order table applies
         int best_l = 0, dl = d_start;
+        xdrop_window30<0u>(s1tab_sa, s1_m10, s1_m9, rev2groups(ft), rev2groups(fq), fn, X, best_l, dl, nchunks);
 #pragma unroll 1
-        for (int b = 0; b < S1_LEFT_WINDOWS; b++) {
+        for (int b = 1; b < S1_LEFT_WINDOWS; b++) {
             if (__all_sync(0xffffffffu, dl >= S1_DONE / 2)) break;
-            uint64_t wt = ft, wq = fq; uint32_t an = fn;
-            if (b > 0 && dl < S1_DONE / 2) {
+            uint64_t wt = 0, wq = 0; uint32_t an = 0;
+            if (dl < S1_DONE / 2) {
                 const uint32_t ct = hi + SEED_SPAN - S1_WINDOW * b - 32, cq = hj + SEED_SPAN - S1_WINDOW * b - 32;
                 wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
                 an = __brev(nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & S1_WINDOW_MASK;
             }
-            xdrop_window30(s1tab_sa, s1_m10, s1_m9, rev2groups(wt), rev2groups(wq), an, X, best_l, dl, nchunks);
+            xdrop_window30<TAILVOTES>(s1tab_sa, s1_m10, s1_m9, rev2groups(wt), rev2groups(wq), an, X, best_l, dl, nchunks);
         }
         const bool open_l = dl < S1_DONE / 2;
         n_cells += 3ull * nchunks;
@@ -665,7 +670,8 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
         launch(kern, grid, SC_NT, 0, view(T), view(Q), tab.off.get(), tab.pos.get(), q_lo, n, p.xdrop,
                p.hspthresh, p.transition, (uint32_t)Q.G, surv, surv_cap, counters);
     };
-    if (minb <= 3) go(seed_scan_kernel<3>); else go(seed_scan_kernel<4>);
+    // later windows are polled before chunks 3, 6 and 8 (measured on C4: 4/7, 2/4/6/8 and 1/3/5/7/9 are all within 0.6 %)
+    if (minb <= 3) go(seed_scan_kernel<3, 0x148u>); else go(seed_scan_kernel<4, 0x148u>);
 }
 
 }  // namespace mb2
