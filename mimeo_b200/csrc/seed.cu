@@ -379,263 +379,6 @@ seed_scan_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, c
     if (tid < 3 && sh_stat[tid]) atomicAdd(&counters[1 + tid], sh_stat[tid]);
 }
 
-// ---- second generation of the scan (EXPERIMENT, off by default: MB2_SCAN_V2=1) ---------------------------------
-// Measured on C1 (profiles/r2_seed_scan2_v1_ncu_summary.txt): identical survivors and the same 2.4e9 warp instructions as the
-// first generation, but 8.5 ms instead of 3.3 ms -- the 128 KB table costs 1.5e8 shared-memory bank conflicts per launch and
-// leaves room for only 24 warps per SM, so the four window gathers of every 15-column quantum are exposed (issue 26 %).
-// Same contract as seed_scan_kernel (same survivors, same counters except the evaluated-cell count), different machine:
-//   * the first-stage x-drop advances FIVE columns per shared-memory lookup: HOXD70 is a function of (t ^ q, parity(t))
-//     per column, so five columns index a 2^15-entry table (x-or bits | parity bits << 10) of {sum, max prefix, min prefix};
-//     the chunk rule of xdrop_table.cuh holds for any chunk whose prefix sums span less than the x-drop (4 * 125 < X);
-//   * extensions do not run in lock step to the slowest lane of a batch: every run leader becomes a work item on a
-//     per-warp stack in shared memory and is advanced by QUANTA of 15 columns; a quantum always takes 32 items (any mix of
-//     rightward and leftward work), items that are still open afterwards go back on the stack. The right side goes
-//     first, then the same item turns into its left side; the survivor test sees both.
-constexpr int S2_C = 5;                          // columns per lookup
-constexpr int S2_QCH = 3;                        // lookups per quantum
-constexpr int S2_QCOLS = S2_C * S2_QCH;          // 15 columns per quantum
-constexpr int S2_RQ = 4, S2_LQ = 6;              // bounds: 60 columns right, 90 left (as the first generation)
-constexpr int S2_TAB = 1 << (3 * S2_C);          // 32768 entries
-constexpr int S2_PLUT = 1 << (2 * S2_C);         // parity compaction: 10 bits (5 useful) -> 5 bits << 10
-constexpr int S2_MINB = 125 * S2_C;              // bias of the min-prefix field
-constexpr int S2_NT = 768, S2_WARPS = S2_NT / 32;
-constexpr int S2_STACK = 64;                     // items per warp: < 32 waiting + 32 new
-constexpr int S2_MIN_XDROP = 125 * (S2_C - 1) + 1;
-
-__device__ __forceinline__ uint32_t s2_entry(uint32_t idx) {
-    const uint32_t xb = idx & (S2_PLUT - 1), pb = idx >> (2 * S2_C);
-    int sum = 0, mx = INT_MIN, mn = INT_MAX;
-    for (int c = 0; c < S2_C; c++) {
-        const uint32_t x = (xb >> (2 * c)) & 3u, par = (pb >> c) & 1u;
-        const int sc = x == 0 ? (par ? 100 : 91) : (x == 1 ? -114 : (x == 2 ? -31 : (par ? -125 : -123)));
-        sum += sc;
-        mx = max(mx, sum); mn = min(mn, sum);
-    }
-    return ((uint32_t)sum << 21) | ((uint32_t)(mx + 125) << 11) | (uint32_t)(mn + S2_MINB);
-}
-__device__ __forceinline__ int s2_sum(uint32_t e) { return (int)e >> 21; }
-__device__ __forceinline__ int s2_maxf(uint32_t e) { return (int)((e >> 11) & 1023u); }
-__device__ __forceinline__ int s2_minf(uint32_t e) { return (int)(e & 1023u); }
-
-struct S2Shared {
-    uint32_t tab[S2_TAB];
-    uint16_t plut[S2_PLUT];
-    uint32_t r_cum[S2_WARPS][SC_RING], r_b0[S2_WARPS][SC_RING], r_j[S2_WARPS][SC_RING];
-    // work stack, struct of arrays: target pos, query pos, meta (quanta done | left << 8 | right side open << 9), best, D, best of the right side
-    uint32_t k_hi[S2_WARPS][S2_STACK], k_hj[S2_WARPS][S2_STACK], k_meta[S2_WARPS][S2_STACK];
-    int k_best[S2_WARPS][S2_STACK], k_d[S2_WARPS][S2_STACK], k_br[S2_WARPS][S2_STACK];
-    unsigned long long stat[3];
-};
-
-__global__ void __launch_bounds__(S2_NT, 1)
-seed_scan2_kernel(GenomeView T, GenomeView Q, const uint32_t* __restrict__ off, const uint32_t* __restrict__ pos,
-                  uint32_t q_lo, uint32_t q_n, int X, int K, int transition, uint32_t diag_bias,
-                  uint64_t* __restrict__ surv, uint32_t surv_cap, unsigned long long* __restrict__ counters) {
-    extern __shared__ __align__(16) unsigned char s2_raw[];
-    S2Shared& sm = *reinterpret_cast<S2Shared*>(s2_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < S2_TAB; e += S2_NT) sm.tab[e] = s2_entry((uint32_t)e);
-    for (int e = tid; e < S2_PLUT; e += S2_NT) {
-        uint32_t c = 0;
-        for (int b = 0; b < S2_C; b++) c |= ((e >> (2 * b)) & 1u) << b;
-        sm.plut[e] = (uint16_t)(c << (2 * S2_C));
-    }
-    if (tid < 3) sm.stat[tid] = 0;
-    __syncthreads();
-    uint32_t* __restrict__ rc = sm.r_cum[warp];
-    uint32_t* __restrict__ rb = sm.r_b0[warp];
-    uint32_t* __restrict__ rj = sm.r_j[warp];
-    uint32_t* __restrict__ khi = sm.k_hi[warp];
-    uint32_t* __restrict__ khj = sm.k_hj[warp];
-    uint32_t* __restrict__ kme = sm.k_meta[warp];
-    int* __restrict__ kbe = sm.k_best[warp];
-    int* __restrict__ kd = sm.k_d[warp];
-    int* __restrict__ kbr = sm.k_br[warp];
-    const int nprobe = transition ? SC_NPROBE : 1;
-    const uint32_t nrounds = (q_n + 31) / 32;
-    const uint32_t nwarps = gridDim.x * S2_WARPS, gw = blockIdx.x * S2_WARPS + warp;
-    const uint32_t my_rounds = gw < nrounds ? (nrounds - gw + nwarps - 1) / nwarps : 0;
-    const uint32_t nsteps = my_rounds * SC_STEPS;
-    uint32_t step = 0;
-    uint32_t head = 0, tail = 0, cum_tail = 0, consumed = 0;
-    uint32_t top = 0;                                   // items on the stack
-    unsigned long long n_lead = 0, n_cells = 0, n_hits = 0;
-    const int D0 = S2_MINB - X, c2 = S2_MINB - 125 - X;
-    const uint32_t qmask = (1u << S2_QCOLS) - 1u, xmask = (1u << (2 * S2_C)) - 1u;
-    for (;;) {
-        if (top < 32u && (cum_tail - consumed > 0u || step < nsteps)) {
-            // ---------------- phase A: append probe results until a batch of hits is pending (or the input ends)
-            while (cum_tail - consumed < 32u && step < nsteps) {
-                const uint32_t round = gw + (step / SC_STEPS) * nwarps;
-                const int p0 = (int)(step % SC_STEPS) * SC_HALF, p1 = min(SC_NPROBE, p0 + SC_HALF);
-                step++;
-                const uint32_t jrel = round * 32 + lane;
-                const uint32_t j = q_lo + jrel;
-                const bool jvalid = jrel < q_n && (nwindow32(Q.sm, j) & SEED_WINDOW_MASK19) == 0;
-                uint32_t key = 0;
-                if (jvalid) key = seed_key(window32(Q.pk, j));
-                uint32_t b0[SC_HALF], cnt[SC_HALF];
-                uint32_t mine = 0, nne = 0;
-#pragma unroll
-                for (int q = 0; q < SC_HALF; q++) {
-                    const int pr = p0 + q;
-                    uint32_t c = 0, b = 0;
-                    if (jvalid && pr < p1 && pr < nprobe) {
-                        const uint32_t kk = pr == 0 ? key : key ^ (2u << (2 * (pr - 1)));
-                        b = off[kk];
-                        c = off[kk + 1] - b;
-                    }
-                    b0[q] = b; cnt[q] = c;
-                    mine += c; nne += c ? 1u : 0u;
-                }
-                uint32_t sh = mine, sn = nne;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t th = __shfl_up_sync(0xffffffffu, sh, d), tn = __shfl_up_sync(0xffffffffu, sn, d);
-                    if (lane >= d) { sh += th; sn += tn; }
-                }
-                const uint32_t tot_h = __shfl_sync(0xffffffffu, sh, 31), tot_n = __shfl_sync(0xffffffffu, sn, 31);
-                uint32_t run = cum_tail + sh - mine, slot = tail + sn - nne;
-#pragma unroll
-                for (int q = 0; q < SC_HALF; q++) {
-                    if (cnt[q]) {
-                        const uint32_t w = slot & (SC_RING - 1);
-                        rc[w] = run; rb[w] = b0[q]; rj[w] = j;
-                        run += cnt[q]; slot++;
-                    }
-                }
-                tail += tot_n; cum_tail += tot_h; n_hits += (lane == 0) ? tot_h : 0;
-                __syncwarp();
-            }
-            // ---------------- fetch: up to 32 hits -> run-leader test (spec D1) -> new rightward items on the stack
-            const uint32_t pending = cum_tail - consumed;
-            if (pending) {
-                const uint32_t nb = min(pending, 32u);
-                bool live = (uint32_t)lane < nb;
-                const uint32_t h = consumed + (uint32_t)lane;
-                uint32_t hi = 0, hj = 0, e_last = head;
-                if (live) {
-                    uint32_t lo = head, hi_d = tail;
-                    while (hi_d - lo > 1) {
-                        const uint32_t mid = lo + ((hi_d - lo) >> 1);
-                        if ((int32_t)(h - rc[mid & (SC_RING - 1)]) >= 0) lo = mid; else hi_d = mid;
-                    }
-                    e_last = lo;
-                    hi = pos[rb[lo & (SC_RING - 1)] + (h - rc[lo & (SC_RING - 1)])];
-                    hj = rj[lo & (SC_RING - 1)];
-                    const uint64_t lt = window32(T.pk, hi - 1), lq = window32(Q.pk, hj - 1);
-                    const uint32_t ln = (nwindow32(Q.sm, hj - 1) | nwindow32(T.sm, hi - 1)) & SEED_WINDOW_MASK19;
-                    if (ln == 0 && seed_match(lt, lq, transition != 0)) live = false; else n_lead++;
-                }
-                const uint32_t lm = __ballot_sync(0xffffffffu, live);
-                if (live) {
-                    const uint32_t sl = top + __popc(lm & ((1u << lane) - 1u));
-                    khi[sl] = hi; khj[sl] = hj; kme[sl] = 0u; kbe[sl] = 0; kd[sl] = D0; kbr[sl] = 0;
-                }
-                top += __popc(lm);
-                consumed += nb;
-                const uint32_t e = __shfl_sync(0xffffffffu, e_last, (int)nb - 1);
-                const uint32_t next_cum = (e + 1 < tail) ? rc[(e + 1) & (SC_RING - 1)] : cum_tail;
-                head = ((int32_t)(next_cum - consumed) > 0) ? e : e + 1;
-                __syncwarp();
-            }
-            continue;
-        }
-        if (top == 0) break;
-        // ---------------- one quantum: the 32 topmost items (all of them at the very end) advance 15 columns
-        const uint32_t nb = min(top, 32u);
-        top -= nb;
-        const bool have = (uint32_t)lane < nb;
-        uint32_t hi = 0, hj = 0, meta = 0;
-        int best = 0, D = S1_DONE, br = 0;
-        if (have) { const uint32_t sl = top + lane; hi = khi[sl]; hj = khj[sl]; meta = kme[sl]; best = kbe[sl]; D = kd[sl]; br = kbr[sl]; }
-        __syncwarp();
-        const uint32_t qd = meta & 0xffu;
-        const bool left = (meta >> 8) & 1u;
-        uint32_t xw = 0, pw = 0, an = 0;
-        uint64_t wt = 0, wq = 0;
-        if (have) {
-            if (!left) {
-                const uint32_t ct = hi + SEED_SPAN + S2_QCOLS * qd, cq = hj + SEED_SPAN + S2_QCOLS * qd;
-                wt = window32(T.pk, ct); wq = window32(Q.pk, cq);
-                an = (nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & qmask;
-            } else {
-                const uint32_t ct = hi + SEED_SPAN - 32 - S2_QCOLS * qd, cq = hj + SEED_SPAN - 32 - S2_QCOLS * qd;
-                wt = rev2groups(window32(T.pk, ct)); wq = rev2groups(window32(Q.pk, cq));
-                an = __brev(nwindow32(T.nm, ct) | nwindow32(Q.nm, cq)) & qmask;
-            }
-            xw = (uint32_t)(wt ^ wq);
-            pw = ((uint32_t)wt ^ ((uint32_t)wt >> 1)) & 0x55555555u;
-        }
-        const bool slow = have && an != 0;
-        int d_keep = 0;
-        if (slow) {
-            // a non-ACGT column in sight: column by column (rare); the table loop below is then a no-op for this lane
-            int run = best - (D - S2_MINB + X);
-            bool term = false;
-            uint64_t t2 = wt, q2 = wq; uint32_t a2 = an;
-            for (int c = 0; c < S2_QCOLS && !term; c++) {
-                const int sc = (a2 & 1u) ? SCORE_N : sub_lut((uint32_t)((t2 & 3) << 2 | (q2 & 3)));
-                t2 >>= 2; q2 >>= 2; a2 >>= 1;
-                run += sc; n_cells++;
-                if (run > best) best = run; else if (run < best - X) term = true;
-            }
-            d_keep = term ? S1_DONE : (best - run) + S2_MINB - X;
-            D = S1_DONE;
-        }
-#pragma unroll
-        for (int k = 0; k < S2_QCH; k++) {
-            if (k > 0 && __all_sync(0xffffffffu, D >= S1_DONE / 2)) break;
-            const uint32_t idx = ((xw >> (2 * S2_C * k)) & xmask) | sm.plut[(pw >> (2 * S2_C * k)) & xmask];
-            const uint32_t e = sm.tab[idx];
-            const bool alive = D < S1_DONE / 2;
-            n_cells += alive ? (unsigned)S2_C : 0u;
-            const bool term = s2_minf(e) < D;
-            const int dm = max(D, s2_maxf(e) + c2);
-            best += alive ? dm - D : 0;
-            D = (term || !alive) ? S1_DONE : dm - s2_sum(e);
-        }
-        if (slow) D = d_keep;
-        // ---------------- what becomes of the item
-        const bool termd = D >= S1_DONE / 2;
-        const bool at_bound = qd + 1 >= (uint32_t)(left ? S2_LQ : S2_RQ);
-        const bool side_done = have && (termd || at_bound);
-        const bool side_open = have && !termd && at_bound;
-        bool again = have && !side_done;                      // same side, next quantum
-        bool survivor = false;
-        uint32_t nmeta = meta + 1u;
-        if (side_done && !left) {
-            if (side_open) survivor = true;                   // still open at the bound: a survivor whatever the left side does
-            else { br = best; nmeta = 1u << 8; best = 0; D = D0; again = true; }   // the item turns into its left side
-        } else if (side_done && left) {
-            const bool open_r = (meta >> 9) & 1u;
-            survivor = open_r || side_open || (br + best >= K);   // dead iff both sides ended inside their bounds with a total below K
-        }
-        const uint32_t am = __ballot_sync(0xffffffffu, again);
-        if (again) {
-            const uint32_t sl = top + __popc(am & ((1u << lane) - 1u));
-            khi[sl] = hi; khj[sl] = hj; kme[sl] = nmeta; kbe[sl] = best; kd[sl] = D; kbr[sl] = br;
-        }
-        top += __popc(am);
-        const uint32_t smask = __ballot_sync(0xffffffffu, survivor);
-        if (smask) {
-            unsigned long long basev = 0;
-            if (lane == __ffs(smask) - 1) basev = atomicAdd(&counters[0], (unsigned long long)__popc(smask));
-            basev = __shfl_sync(0xffffffffu, basev, __ffs(smask) - 1);
-            if (survivor) {
-                const unsigned long long slot = basev + __popc(smask & ((1u << lane) - 1u));
-                if (slot < surv_cap) surv[slot] = ((uint64_t)(hi - hj + diag_bias) << 32) | hj;
-            }
-        }
-        __syncwarp();
-    }
-    if (n_lead) atomicAdd(&sm.stat[1], n_lead);
-    if (n_cells) atomicAdd(&sm.stat[2], n_cells);
-    if (n_hits) atomicAdd(&sm.stat[0], n_hits);
-    __syncthreads();
-    if (tid < 3 && sm.stat[tid]) atomicAdd(&counters[1 + tid], sm.stat[tid]);
-}
-
 // Enqueue the scan of query positions [q_lo, q_hi) against a built table. Survivors are appended to surv.
 void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t q_lo, uint32_t q_hi, const AlignParams& p,
                uint64_t* surv, uint32_t surv_cap, unsigned long long* counters) {
@@ -644,21 +387,7 @@ void seed_scan(const Genome& T, const Genome& Q, const SeedTable& tab, uint32_t 
     MB2_REQUIRE(p.xdrop >= XT_MIN_XDROP, -2, "x-drop below 251 is not supported by the three-column extension table");
     MB2_REQUIRE(p.xdrop <= S1_MAX_XDROP, -2, "x-drop above 7766 is not supported by the first-stage extension table");
     ProfScope ps("seed_scan");
-    // MB2_SCAN_V2=1 selects the experimental second-generation scan (measured slower: DESIGN.md, profiles/r2_seed_scan2_*)
-    static const bool use_v2 = getenv("MB2_SCAN_V2") != nullptr;
     const unsigned nrounds = cdiv(n, 32);
-    if (use_v2 && p.xdrop >= S2_MIN_XDROP) {
-        static bool configured = false;
-        if (!configured) {
-            MB2_CUDA(cudaFuncSetAttribute(seed_scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2Shared)));
-            configured = true;
-        }
-        // persistent: one CTA per SM (its 128 KB lookup table fills most of the shared memory); every warp strides over the rounds
-        const unsigned grid = std::min<unsigned>(cdiv(nrounds, S2_WARPS), (unsigned)ctx().sm_count);
-        launch(seed_scan2_kernel, grid, S2_NT, sizeof(S2Shared), view(T), view(Q), tab.off.get(), tab.pos.get(), q_lo, n, p.xdrop,
-               p.hspthresh, p.transition, (uint32_t)Q.G, surv, surv_cap, counters);
-        return;
-    }
     // resident CTAs per SM: 4 (56 registers, no spill; default) or 3; the scan hides its gather latencies with resident warps
     // (C4: 5 % slower with 3; 5 CTAs at 48 registers: no faster). MB2_SCAN_MINB overrides.
     static const int minb = getenv("MB2_SCAN_MINB") ? atoi(getenv("MB2_SCAN_MINB")) : 4;
