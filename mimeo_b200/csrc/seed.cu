@@ -178,10 +178,10 @@ __device__ __forceinline__ SeqBlock load_block(const uint64_t* __restrict__ pk, 
 
 // ---- load-balanced scan --------------------------------------------------------------------------------------
 // Every WARP works on its own: no CTA barrier after the table build. A warp takes 32 consecutive query positions per
-// round (lane = position). Phase A: the 13 bucket ranges of each position are looked up, the non-empty ones are
+// round (lane = position); rounds are handed out by an atomic counter. Phase A: the 13 bucket ranges of each position are looked up, the non-empty ones are
 // compacted (warp scans, three probes at a time) into the warp's ring of descriptors {first hit number, first index in pos[], query position};
 // hit numbers are cumulative over the warp's whole life. Phase B: whenever 32 hits are pending, lane l takes hit
-// `consumed + l`, finds its descriptor by binary search in the ring, and runs the leader test and the bounded x-drop
+// `consumed + l`, finds its descriptor (one OR-reduction over the next 32 descriptors + a popcount), and runs the leader test and the bounded x-drop
 // (30-column windows, 3 columns per table lookup). Leftover hits (< 32) wait for the next round, so batches are always
 // full except for the very last one of a warp. All loads of a batch that do not depend on the x-drop outcome (leader
 // windows, first right and left windows) are issued together.
